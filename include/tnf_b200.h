@@ -1,0 +1,168 @@
+/*
+ * tnf_b200.h - C ABI of libtnf_b200.so: the ThermoNeRF volumetric-render hot path
+ * as hand-written sm_100a CUDA.
+ *
+ * Boundary contract:
+ *   - plain pointers and sizes only; no torch types.  Every buffer is owned by the
+ *     caller (a PyTorch CUDA tensor in the Python host layer): contiguous, fp32
+ *     (int64 for camera indices), 16-byte aligned.  The library never allocates or
+ *     frees caller-visible memory and keeps no state between calls except a
+ *     thread-local error string.
+ *   - every entry point returns TNF_OK (0) or a negative TnfStatus and never throws;
+ *     tnf_last_error() describes the last failure on the calling thread.
+ *   - all work is enqueued on the cudaStream_t passed as `stream` (opaque void*);
+ *     nothing synchronises the device.
+ *
+ * Reference interface each entry point replaces (paths relative to the reference
+ * repo Schindler-EPFL-Lab/thermo-nerf; the arithmetic itself lives in
+ * nerfstudio==1.1.5, reference pyproject.toml:11):
+ *
+ *   tnf_render_forward   <- ThermalNerfModel.get_outputs
+ *                           thermo_nerf/thermal_nerf/thermal_nerf_model.py:210-275
+ *                           (proposal sampler :222-224, field.forward :225-227 =
+ *                           thermal_field.py:108-201, get_weights :233, renderers
+ *                           :237-243, prop depths :267-270, ThermalRenderer :271 =
+ *                           thermal_renderer.py:113-149), plus the NearFarCollider
+ *                           built at thermal_nerf_model.py:182-184.
+ *   tnf_render_backward  <- autograd of the same function as driven by
+ *                           get_loss_dict, thermal_nerf_model.py:277-326.
+ *   tnf_adam_step        <- the Adam optimisers configured at
+ *                           thermo_nerf/thermal_nerf/config_thermal_nerf.py:32-45.
+ */
+#ifndef TNF_B200_H_
+#define TNF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TNF_ABI_VERSION 1
+
+#define TNF_MAX_LEVELS 16      /* hash levels of the field grid (fixed: 16)          */
+#define TNF_MAX_PROP_LEVELS 8  /* max hash levels of a proposal density grid          */
+#define TNF_MAX_SAMPLES 256    /* max samples per ray of any level                    */
+#define TNF_NUM_PROP 2         /* proposal iterations (nerfacto default, fixed)       */
+
+typedef enum TnfStatus {
+  TNF_OK = 0,
+  TNF_ERR_INVALID_ARGUMENT = -1,   /* null / misaligned pointer, negative size       */
+  TNF_ERR_UNSUPPORTED_CONFIG = -2, /* architecture outside what the kernels compile  */
+  TNF_ERR_WORKSPACE_TOO_SMALL = -3,
+  TNF_ERR_CUDA = -4                /* a CUDA runtime call failed; see tnf_last_error */
+} TnfStatus;
+
+/* How the 32-d appearance embedding is chosen (thermal_field.py:124-137). */
+typedef enum TnfAppearanceMode {
+  TNF_APPEARANCE_ZEROS = 0,  /* eval, use_average_appearance_embedding=False        */
+  TNF_APPEARANCE_MEAN = 1,   /* eval, mean over all training cameras                 */
+  TNF_APPEARANCE_LOOKUP = 2  /* training: embedding[camera_indices]                  */
+} TnfAppearanceMode;
+
+/* Arithmetic used for the 64-wide field MLPs. Hashing, sampling, the proposal MLPs
+ * and compositing are fp32 in both modes. */
+typedef enum TnfPrecision {
+  TNF_PRECISION_FP32 = 0,    /* fp32 FFMA everywhere                                  */
+  TNF_PRECISION_TC_FP16 = 1  /* fp16 operands, fp32 accumulate on the tensor cores    */
+} TnfPrecision;
+
+/* nerfstudio HashEncoding, torch layout: table [num_levels << log2_size, 2] fp32,
+ * level-major; `scalings` is the registered buffer (host copy). */
+typedef struct TnfHashGrid {
+  const float* table;
+  float scalings[TNF_MAX_LEVELS];
+  int32_t num_levels;
+  int32_t log2_size;
+} TnfHashGrid;
+
+/* torch.nn.Linear: weight [out, in] row-major, bias [out]. */
+typedef struct TnfLinear {
+  const float* weight;
+  const float* bias;
+} TnfLinear;
+
+/* HashMLPDensityField (thermal_nerf_model.py:127-148): grid -> 16 -> 1. */
+typedef struct TnfDensityNet {
+  TnfHashGrid grid;
+  TnfLinear l0; /* [16, 2*num_levels] */
+  TnfLinear l1; /* [1, 16]            */
+} TnfDensityNet;
+
+/* ThermalNerfactoTField (thermal_field.py:33-106). */
+typedef struct TnfField {
+  TnfHashGrid grid;        /* 16 levels x 2 features                              */
+  TnfLinear base0;         /* mlp_base.mlp.layers.0        [64, 32]               */
+  TnfLinear base1;         /* mlp_base.mlp.layers.1        [16, 64] (1 | 15 geo)  */
+  TnfLinear rgb0;          /* mlp_head.layers.0            [64, 63] sh|geo|app    */
+  TnfLinear rgb1;          /* mlp_head.layers.1            [64, 64]               */
+  TnfLinear rgb2;          /* mlp_head.layers.2            [3, 64]                */
+  TnfLinear th0;           /* mlp_thermal.layers.0         [64, 15]               */
+  TnfLinear th1;           /* mlp_thermal.layers.1         [64, 64] (sigmoid out) */
+  TnfLinear th2;           /* field_head_thermal.net       [1, 64]                */
+  const float* appearance; /* embedding_appearance weight  [num_images, 32]       */
+  int32_t num_images;
+  int32_t _pad;
+} TnfField;
+
+typedef struct TnfModel {
+  TnfDensityNet prop[TNF_NUM_PROP];
+  TnfField field;
+  int32_t num_samples[TNF_NUM_PROP + 1]; /* (256, 96, 48) by default; each <= 256, last <= 64 */
+  int32_t training;        /* 0: eval renderers (nan_to_num + clamp[0,1]); 1: training        */
+  float near_plane;        /* used when rays.nears == NULL                                    */
+  float far_plane;         /* used when rays.fars  == NULL                                    */
+  float anneal;            /* ProposalNetworkSampler._anneal (1.0 for a fresh/eval sampler)   */
+  int32_t use_contraction; /* 1: L-inf scene contraction; 0: aabb normalisation               */
+  float aabb[6];           /* min xyz, max xyz (only for use_contraction == 0)                */
+  int32_t appearance_mode; /* TnfAppearanceMode                                               */
+  int32_t precision;       /* TnfPrecision                                                    */
+} TnfModel;
+
+typedef struct TnfRays {
+  const float* origins;          /* [R,3]                                                     */
+  const float* directions;       /* [R,3]                                                     */
+  const int64_t* camera_indices; /* [R]   (required for TNF_APPEARANCE_LOOKUP, else may be 0) */
+  const float* nears;            /* [R] or NULL                                               */
+  const float* fars;             /* [R] or NULL                                               */
+  const float* jitter;           /* [3,R] single-jitter draws in [0,1) (training) or NULL     */
+  int64_t num_rays;
+} TnfRays;
+
+typedef struct TnfOutputs {
+  float* rgb;            /* [R,3] */
+  float* thermal;        /* [R,1] */
+  float* depth;          /* [R,1] median depth                                              */
+  float* expected_depth; /* [R,1] clipped to the per-chunk [min,max] of sample mid-points   */
+  float* accumulation;   /* [R,1] */
+  float* prop_depth[TNF_NUM_PROP]; /* [R,1] each                                            */
+  /* optional (NULL to skip) - the training-only outputs of get_outputs: */
+  float* weights[TNF_NUM_PROP + 1]; /* weights_list[k]           [R, S_k]                   */
+  float* sdist[TNF_NUM_PROP + 1];   /* spacing bins of level k   [R, S_k + 1]               */
+} TnfOutputs;
+
+/* ABI version of the loaded library (== TNF_ABI_VERSION of the header it was built from). */
+int tnf_version(void);
+
+/* Description of the last error on the calling thread ("" if none). */
+const char* tnf_last_error(void);
+
+/* Bytes of device scratch tnf_render_forward needs for `num_rays` rays when the
+ * expected-depth clip is evaluated per `depth_clip_chunk` rays (<= 0: whole call). */
+size_t tnf_forward_workspace_bytes(int64_t num_rays, int64_t depth_clip_chunk);
+
+/*
+ * One pass of get_outputs over `rays`.  `depth_clip_chunk` reproduces the
+ * reference's chunk-dependent expected-depth clip (nerfstudio clips to the min/max
+ * sample mid-point of each forward call, i.e. of each eval_num_rays_per_chunk slice,
+ * config_thermal_nerf.py:30): rays [k*chunk, (k+1)*chunk) share one clip range.
+ */
+int tnf_render_forward(const TnfModel* model, const TnfRays* rays, const TnfOutputs* out,
+                       int64_t depth_clip_chunk, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TNF_B200_H_ */

@@ -1,0 +1,19 @@
+"""thermo_nerf_b200: the ThermoNeRF volumetric-render hot path as hand-written sm_100a CUDA.
+
+Layout: ``csrc/`` (kernels + C ABI, built into ``lib/libtnf_b200.so``), ``_lib`` (ctypes
+binding of ``include/tnf_b200.h``), ``functional`` (tensor-level entry points),
+``modules`` / ``model`` (host-side mirror of the reference's nerfstudio plugin surface).
+"""
+
+from . import _lib
+from .functional import ModelTensors, render_forward
+from .model import ThermalNerfModel, ThermalNerfModelConfig
+from .modules import (CameraOptimizer, FieldHeadNames, FieldHeadNamesT, HashMLPDensityField, ThermalFieldHead,
+                      ThermalNerfactoTField)
+from .rays import PinholeCameras, RayBundle, orbit_cameras
+
+__all__ = [
+    "ModelTensors", "render_forward", "ThermalNerfModel", "ThermalNerfModelConfig", "CameraOptimizer",
+    "FieldHeadNames", "FieldHeadNamesT", "HashMLPDensityField", "ThermalFieldHead", "ThermalNerfactoTField",
+    "PinholeCameras", "RayBundle", "orbit_cameras",
+]

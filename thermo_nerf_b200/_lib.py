@@ -1,0 +1,170 @@
+"""ctypes binding of ``libtnf_b200.so`` (C ABI declared in ``include/tnf_b200.h``).
+
+The structures below mirror the header field for field.  There is no fallback: if the
+shared library is missing or does not load, every compute entry point raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+from typing import Optional
+
+TNF_ABI_VERSION = 1
+TNF_MAX_LEVELS = 16
+TNF_MAX_PROP_LEVELS = 8
+TNF_MAX_SAMPLES = 256
+TNF_MAX_FIELD_SAMPLES = 64
+TNF_NUM_PROP = 2
+
+TNF_OK = 0
+TNF_ERR_INVALID_ARGUMENT = -1
+TNF_ERR_UNSUPPORTED_CONFIG = -2
+TNF_ERR_WORKSPACE_TOO_SMALL = -3
+TNF_ERR_CUDA = -4
+
+APPEARANCE_ZEROS, APPEARANCE_MEAN, APPEARANCE_LOOKUP = 0, 1, 2
+PRECISION_FP32, PRECISION_TC_FP16 = 0, 1
+
+_fp = C.c_void_p  # device pointers cross the ABI as plain addresses
+
+
+class TnfHashGrid(C.Structure):
+    _fields_ = [
+        ("table", _fp),
+        ("scalings", C.c_float * TNF_MAX_LEVELS),
+        ("num_levels", C.c_int32),
+        ("log2_size", C.c_int32),
+    ]
+
+
+class TnfLinear(C.Structure):
+    _fields_ = [("weight", _fp), ("bias", _fp)]
+
+
+class TnfDensityNet(C.Structure):
+    _fields_ = [("grid", TnfHashGrid), ("l0", TnfLinear), ("l1", TnfLinear)]
+
+
+class TnfField(C.Structure):
+    _fields_ = [
+        ("grid", TnfHashGrid),
+        ("base0", TnfLinear),
+        ("base1", TnfLinear),
+        ("rgb0", TnfLinear),
+        ("rgb1", TnfLinear),
+        ("rgb2", TnfLinear),
+        ("th0", TnfLinear),
+        ("th1", TnfLinear),
+        ("th2", TnfLinear),
+        ("appearance", _fp),
+        ("num_images", C.c_int32),
+        ("_pad", C.c_int32),
+    ]
+
+
+class TnfModel(C.Structure):
+    _fields_ = [
+        ("prop", TnfDensityNet * TNF_NUM_PROP),
+        ("field", TnfField),
+        ("num_samples", C.c_int32 * (TNF_NUM_PROP + 1)),
+        ("training", C.c_int32),
+        ("near_plane", C.c_float),
+        ("far_plane", C.c_float),
+        ("anneal", C.c_float),
+        ("use_contraction", C.c_int32),
+        ("aabb", C.c_float * 6),
+        ("appearance_mode", C.c_int32),
+        ("precision", C.c_int32),
+    ]
+
+
+class TnfRays(C.Structure):
+    _fields_ = [
+        ("origins", _fp),
+        ("directions", _fp),
+        ("camera_indices", _fp),
+        ("nears", _fp),
+        ("fars", _fp),
+        ("jitter", _fp),
+        ("num_rays", C.c_int64),
+    ]
+
+
+class TnfOutputs(C.Structure):
+    _fields_ = [
+        ("rgb", _fp),
+        ("thermal", _fp),
+        ("depth", _fp),
+        ("expected_depth", _fp),
+        ("accumulation", _fp),
+        ("prop_depth", _fp * TNF_NUM_PROP),
+        ("weights", _fp * (TNF_NUM_PROP + 1)),
+        ("sdist", _fp * (TNF_NUM_PROP + 1)),
+    ]
+
+
+# every symbol include/tnf_b200.h declares (tests check the library exports all of them)
+EXPORTED_SYMBOLS = (
+    "tnf_version",
+    "tnf_last_error",
+    "tnf_forward_workspace_bytes",
+    "tnf_render_forward",
+)
+
+
+class TnfError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libtnf_b200 error {code}: {message}")
+        self.code = code
+
+
+def library_path() -> Path:
+    env = os.environ.get("TNF_B200_LIB")
+    if env:
+        return Path(env)
+    return Path(__file__).resolve().parent / "lib" / "libtnf_b200.so"
+
+
+_LIB: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once).  Raises if it is absent - there is no CPU path."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not path.exists():
+        raise ImportError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  thermo_nerf_b200 has no CPU or PyTorch fallback."
+        )
+    lib = C.CDLL(str(path))
+    lib.tnf_version.restype = C.c_int
+    lib.tnf_version.argtypes = []
+    lib.tnf_last_error.restype = C.c_char_p
+    lib.tnf_last_error.argtypes = []
+    lib.tnf_forward_workspace_bytes.restype = C.c_size_t
+    lib.tnf_forward_workspace_bytes.argtypes = [C.c_int64, C.c_int64]
+    lib.tnf_render_forward.restype = C.c_int
+    lib.tnf_render_forward.argtypes = [
+        C.POINTER(TnfModel),
+        C.POINTER(TnfRays),
+        C.POINTER(TnfOutputs),
+        C.c_int64,
+        C.c_void_p,
+        C.c_size_t,
+        C.c_void_p,
+    ]
+    got = lib.tnf_version()
+    if got != TNF_ABI_VERSION:
+        raise ImportError(f"{path}: ABI version {got}, binding expects {TNF_ABI_VERSION}")
+    _LIB = lib
+    return lib
+
+
+def check(code: int) -> None:
+    if code != TNF_OK:
+        raise TnfError(code, load().tnf_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,907 @@
+// Fused forward of ThermalNerfModel.get_outputs
+// (thermo_nerf/thermal_nerf/thermal_nerf_model.py:210-275) for sm_100a.
+//
+// One persistent kernel; one warp owns one ray from the first proposal sample to the
+// composited pixel.  Nothing per-sample ever reaches HBM in eval mode:
+//
+//   level 0  256 piecewise-lindisp samples -> proposal net 0 (hash 5x2 -> 16 -> 1) -> weights
+//   level 1  inverse-CDF resample (96)     -> proposal net 1                      -> weights
+//   level 2  inverse-CDF resample (48)     -> field (hash 16x2 -> 64 -> 16 | rgb head | thermal head)
+//   composite rgb / thermal (last-sample background), accumulation, median + expected depth
+//
+// Lanes map to consecutive samples of the ray so the 8 corner gathers of a level hit
+// neighbouring (often identical) table cells -> few L1 wavefronts per load.  Weights, CDFs
+// and bins live in a per-warp shared-memory scratch; MLP weights are staged once per CTA.
+// TNF_PRECISION_TC_FP16 runs the 64-wide field MLPs on the tensor cores with
+// register-resident activations (C fragments of one layer are the A fragments of the next).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "tnf_device.cuh"
+
+namespace tnf {
+
+// ------------------------------------------------------------------------------------
+// shared-memory images of the field MLPs
+// ------------------------------------------------------------------------------------
+struct FieldCommon {
+  float rgb0sh_t[16 * 64];   // [k][n] SH block of mlp_head.layers.0 (cols 0..15)
+  float rgb0app_t[32 * 64];  // [j][n] appearance block (cols 31..62)
+  float rgb0b[64];           // bias (+ folded constant appearance part in eval)
+  float app_const[32];
+};
+
+struct FieldW32 {
+  float base0t[32 * 64];
+  float base0b[64];
+  float base1t[64 * 16];
+  float base1b[16];
+  float rgb0geo_t[16 * 64];  // row 0 = 0 (density slot), rows 1..15 = geo block (cols 16..30)
+  float rgb1t[64 * 64];
+  float rgb1b[64];
+  float rgb2t[64 * 4];
+  float rgb2b[4];
+  float th0t[16 * 64];  // row 0 = 0
+  float th0b[64];
+  float th1t[64 * 64];
+  float th1b[64];
+  float th2[64];
+  float th2b[4];
+};
+
+// mma.m16n8k16 B fragments, [k-tile][n-tile][lane]
+struct FieldWTC {
+  uint2 base0[2][8][32];
+  uint2 base1[4][2][32];
+  uint2 geo0[1][16][32];  // n-tiles 0..7: rgb0 geo block, 8..15: mlp_thermal.layers.0
+  uint2 rgb1[4][8][32];
+  uint2 rgb2[4][1][32];
+  uint2 th1[4][8][32];
+  uint2 th2[4][1][32];
+  float base0b[64];
+  float base1b[16];
+  float rgb1b[64];
+  float rgb2b[8];
+  float th0b[64];
+  float th1b[64];
+  float th2b[8];
+};
+
+template <int PREC>
+struct Smem;
+template <>
+struct Smem<TNF_PRECISION_FP32> {
+  PropW prop[TNF_NUM_PROP];
+  FieldCommon fc;
+  FieldW32 fw;
+  WarpScratch ws[kWarpsPerCta];
+  float act[kWarpsPerCta][64 * 32];  // per-lane activation column: act[k*32 + lane]
+  float geo[kWarpsPerCta][16 * 32];
+};
+template <>
+struct Smem<TNF_PRECISION_TC_FP16> {
+  PropW prop[TNF_NUM_PROP];
+  FieldCommon fc;
+  FieldWTC fw;
+  WarpScratch ws[kWarpsPerCta];
+};
+
+// ------------------------------------------------------------------------------------
+// weight staging (once per CTA; weights are tiny and L2 resident)
+// ------------------------------------------------------------------------------------
+__device__ void stage_prop(PropW& W, const TnfDensityNet& net, int tid) {
+  const int K = 2 * net.grid.num_levels;
+  for (int i = tid; i < 256; i += kThreads) {
+    const int k = i >> 4, j = i & 15;
+    W.w0t[i] = (k < K) ? net.l0.weight[j * K + k] : 0.f;
+  }
+  if (tid < 16) {
+    W.b0[tid] = net.l0.bias[tid];
+    W.w1[tid] = net.l1.weight[tid];
+  }
+  if (tid == 0) W.b1 = net.l1.bias[0];
+}
+
+// logical [K][N] views (zero padded) of the torch [out,in] matrices
+struct ViewPlain {  // W[k][n] = w[n*ld + k], k < kv, n < nv
+  const float* w;
+  int ld, kv, nv;
+  __device__ float operator()(int k, int n) const { return (k < kv && n < nv) ? w[n * ld + k] : 0.f; }
+};
+struct ViewShift {  // row 0 is the (unused) density slot: W[k][n] = w[n*ld + col0 + k-1] for 1 <= k <= kv
+  const float* w;
+  int ld, col0, kv, nv;
+  __device__ float operator()(int k, int n) const {
+    return (k >= 1 && k <= kv && n < nv) ? w[n * ld + col0 + k - 1] : 0.f;
+  }
+};
+struct ViewGeo0 {  // n < 64: rgb0 geo block, n >= 64: thermal layer 0
+  ViewShift rgb, th;
+  __device__ float operator()(int k, int n) const { return n < 64 ? rgb(k, n) : th(k, n - 64); }
+};
+
+template <typename V>
+__device__ void stage_t(float* dst, int K, int N, const V& v, int tid) {
+  for (int i = tid; i < K * N; i += kThreads) dst[i] = v(i / N, i % N);
+}
+template <typename V>
+__device__ void stage_frag(uint2* dst, int KT, int NT, const V& v, int tid) {
+  for (int i = tid; i < KT * NT * 32; i += kThreads) {
+    const int lane = i & 31, nt = (i >> 5) % NT, kt = (i >> 5) / NT;
+    const int g = lane >> 2, q = lane & 3;
+    const int n = nt * 8 + g, k = kt * 16 + 2 * q;
+    dst[i] = make_uint2(pack_half2(v(k, n), v(k + 1, n)), pack_half2(v(k + 8, n), v(k + 9, n)));
+  }
+}
+__device__ void stage_vec(float* dst, const float* src, int n, int npad, int tid) {
+  for (int i = tid; i < npad; i += kThreads) dst[i] = i < n ? src[i] : 0.f;
+}
+
+__device__ void stage_common(FieldCommon& C, const TnfField& f, bool fold_appearance, int tid) {
+  stage_t(C.rgb0sh_t, 16, 64, ViewPlain{f.rgb0.weight, 63, 16, 64}, tid);
+  stage_t(C.rgb0app_t, 32, 64, ViewPlain{f.rgb0.weight + 31, 63, 32, 64}, tid);
+  if (tid < 64) {
+    float b = f.rgb0.bias[tid];
+    if (fold_appearance) {
+      for (int j = 0; j < 32; ++j) b = fmaf(C.app_const[j], f.rgb0.weight[tid * 63 + 31 + j], b);
+    }
+    C.rgb0b[tid] = b;
+  }
+}
+
+__device__ void stage_field(FieldW32& W, const TnfField& f, int tid) {
+  stage_t(W.base0t, 32, 64, ViewPlain{f.base0.weight, 32, 32, 64}, tid);
+  stage_t(W.base1t, 64, 16, ViewPlain{f.base1.weight, 64, 64, 16}, tid);
+  stage_t(W.rgb0geo_t, 16, 64, ViewShift{f.rgb0.weight, 63, 16, 15, 64}, tid);
+  stage_t(W.rgb1t, 64, 64, ViewPlain{f.rgb1.weight, 64, 64, 64}, tid);
+  stage_t(W.rgb2t, 64, 4, ViewPlain{f.rgb2.weight, 64, 64, 3}, tid);
+  stage_t(W.th0t, 16, 64, ViewShift{f.th0.weight, 15, 0, 15, 64}, tid);
+  stage_t(W.th1t, 64, 64, ViewPlain{f.th1.weight, 64, 64, 64}, tid);
+  stage_vec(W.base0b, f.base0.bias, 64, 64, tid);
+  stage_vec(W.base1b, f.base1.bias, 16, 16, tid);
+  stage_vec(W.rgb1b, f.rgb1.bias, 64, 64, tid);
+  stage_vec(W.rgb2b, f.rgb2.bias, 3, 4, tid);
+  stage_vec(W.th0b, f.th0.bias, 64, 64, tid);
+  stage_vec(W.th1b, f.th1.bias, 64, 64, tid);
+  stage_vec(W.th2, f.th2.weight, 64, 64, tid);
+  stage_vec(W.th2b, f.th2.bias, 1, 4, tid);
+}
+
+__device__ void stage_field(FieldWTC& W, const TnfField& f, int tid) {
+  stage_frag(&W.base0[0][0][0], 2, 8, ViewPlain{f.base0.weight, 32, 32, 64}, tid);
+  stage_frag(&W.base1[0][0][0], 4, 2, ViewPlain{f.base1.weight, 64, 64, 16}, tid);
+  stage_frag(&W.geo0[0][0][0], 1, 16,
+             ViewGeo0{ViewShift{f.rgb0.weight, 63, 16, 15, 64}, ViewShift{f.th0.weight, 15, 0, 15, 64}}, tid);
+  stage_frag(&W.rgb1[0][0][0], 4, 8, ViewPlain{f.rgb1.weight, 64, 64, 64}, tid);
+  stage_frag(&W.rgb2[0][0][0], 4, 1, ViewPlain{f.rgb2.weight, 64, 64, 3}, tid);
+  stage_frag(&W.th1[0][0][0], 4, 8, ViewPlain{f.th1.weight, 64, 64, 64}, tid);
+  stage_frag(&W.th2[0][0][0], 4, 1, ViewPlain{f.th2.weight, 64, 64, 1}, tid);
+  stage_vec(W.base0b, f.base0.bias, 64, 64, tid);
+  stage_vec(W.base1b, f.base1.bias, 16, 16, tid);
+  stage_vec(W.rgb1b, f.rgb1.bias, 64, 64, tid);
+  stage_vec(W.rgb2b, f.rgb2.bias, 3, 8, tid);
+  stage_vec(W.th0b, f.th0.bias, 64, 64, tid);
+  stage_vec(W.th1b, f.th1.bias, 64, 64, tid);
+  stage_vec(W.th2b, f.th2.bias, 1, 8, tid);
+}
+
+// ------------------------------------------------------------------------------------
+// per-ray state
+// ------------------------------------------------------------------------------------
+struct RayCtx {
+  float ox, oy, oz, dx, dy, dz;
+  float s_near, s_far;
+};
+
+__device__ __forceinline__ void sample_geometry(const RayCtx& rc, float s0, float s1, float& mid, float& delta) {
+  const float t0 = to_euclid(s0, rc.s_near, rc.s_far);
+  const float t1 = to_euclid(s1, rc.s_near, rc.s_far);
+  mid = (t0 + t1) * 0.5f;
+  delta = t1 - t0;
+}
+
+// Running alpha-compositing state of one level (RaySamples.get_weights + median depth).
+struct Compositor {
+  float carry = 0.f;     // sum of delta*sigma of all previous samples
+  float cw = 0.f;        // cumulative weight
+  float median = 0.f;    // DepthRenderer("median")
+  bool found = false;
+  __device__ __forceinline__ float step(float ds, float mid, bool active, int lane) {
+    const float incl = warp_incl_scan(ds, lane);
+    float excl = __shfl_up_sync(kFull, incl, 1);
+    if (lane == 0) excl = 0.f;
+    const float T = expf(-(carry + excl));
+    const float alpha = 1.f - expf(-ds);
+    const float w = active ? nan_to_num(alpha * T) : 0.f;
+    carry += __shfl_sync(kFull, incl, 31);
+    const float cwi = warp_incl_scan(w, lane) + cw;
+    const unsigned hit = __ballot_sync(kFull, active && cwi >= 0.5f);
+    if (!found && hit) {
+      median = __shfl_sync(kFull, mid, __ffs(hit) - 1);
+      found = true;
+    }
+    cw = __shfl_sync(kFull, cwi, 31);
+    return w;
+  }
+};
+
+// ------------------------------------------------------------------------------------
+// proposal level: HashMLPDensityField.density_fn on S samples -> weights in ws.w
+// ------------------------------------------------------------------------------------
+template <int LVL>
+__device__ __forceinline__ float proposal_level(const TnfModel& m, const PropW& W, WarpScratch& ws,
+                                                const RayCtx& rc, const int S, const bool stratified,
+                                                const float jit, const int lane, float* __restrict__ out_w,
+                                                float* __restrict__ out_sdist) {
+  const TnfDensityNet& net = m.prop[LVL];
+  const int L = net.grid.num_levels;
+  const uint32_t mask = (1u << net.grid.log2_size) - 1u;
+  const float2* __restrict__ tab = reinterpret_cast<const float2*>(net.grid.table);
+  auto sb = [&](int i) -> float { return LVL == 0 ? initial_sbin(i, S, stratified, jit) : ws.bins[i]; };
+
+  Compositor comp;
+  float last_mid = 0.f;
+  for (int base = 0; base < S; base += 32) {
+    const int i = base + lane;
+    const bool active = i < S;
+    const int ii = active ? i : S - 1;
+    float mid, delta;
+    sample_geometry(rc, sb(ii), sb(ii + 1), mid, delta);
+    float px, py, pz;
+    const float sel = normalise_position(m, fmaf(rc.dx, mid, rc.ox), fmaf(rc.dy, mid, rc.oy),
+                                         fmaf(rc.dz, mid, rc.oz), px, py, pz);
+    float feat[2 * TNF_MAX_PROP_LEVELS];
+#pragma unroll
+    for (int l = 0; l < TNF_MAX_PROP_LEVELS; ++l) {
+      float2 f = make_float2(0.f, 0.f);
+      if (l < L) f = hash_level(tab + ((size_t)l << net.grid.log2_size), px, py, pz, net.grid.scalings[l], mask);
+      feat[2 * l] = f.x;
+      feat[2 * l + 1] = f.y;
+    }
+    float h[16];
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(&W.b0[j]);
+      h[j] = b.x; h[j + 1] = b.y; h[j + 2] = b.z; h[j + 3] = b.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 2 * TNF_MAX_PROP_LEVELS; ++k) {
+      if (k < 2 * L) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 w = *reinterpret_cast<const float4*>(&W.w0t[k * 16 + j]);
+          h[j] = fmaf(feat[k], w.x, h[j]);
+          h[j + 1] = fmaf(feat[k], w.y, h[j + 1]);
+          h[j + 2] = fmaf(feat[k], w.z, h[j + 2]);
+          h[j + 3] = fmaf(feat[k], w.w, h[j + 3]);
+        }
+      }
+    }
+    float o = W.b1;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o = fmaf(fmaxf(h[j], 0.f), W.w1[j], o);
+    const float density = expf(o) * sel;  // average_init_density == 1.0
+    const float w = comp.step(active ? delta * density : 0.f, mid, active, lane);
+    if (active) {
+      ws.w[i] = w;
+      if (out_w) out_w[i] = w;
+    }
+    if (base + 32 >= S) last_mid = __shfl_sync(kFull, mid, (S - 1) & 31);
+  }
+  if (out_sdist) {
+    for (int i = lane; i <= S; i += 32) out_sdist[i] = sb(i);
+  }
+  __syncwarp();
+  return comp.found ? comp.median : last_mid;
+}
+
+// ------------------------------------------------------------------------------------
+// PDFSampler (include_original=False, histogram_padding=0.01, eps=1e-5): ws.w (weights of
+// the previous level, consumed) -> `dst` (Snew+1 spacing bins).  `exist` = previous level's
+// spacing bins, or nullptr when they are the analytic initial bins.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdf_resample(WarpScratch& ws, const int Sprev, const int Snew, const float anneal,
+                                             const bool stratified, const float jit_prev, const float jit_new,
+                                             const float* exist, float* dst, const int lane) {
+  float part = 0.f;
+  for (int i = lane; i < Sprev; i += 32) {
+    float w = ws.w[i];
+    if (anneal != 1.f) w = powf(w, anneal);
+    w += 0.01f;
+    ws.w[i] = w;
+    part += w;
+  }
+  float sum = warp_sum(part);
+  const float padding = fmaxf(1e-5f - sum, 0.f);
+  const float padw = padding / (float)Sprev;
+  sum += padding;
+  float carry = 0.f;
+  if (lane == 0) ws.cdf[0] = 0.f;
+  for (int base = 0; base < Sprev; base += 32) {
+    const int i = base + lane;
+    const float p = (i < Sprev) ? (ws.w[i] + padw) / sum : 0.f;
+    const float inc = warp_incl_scan(p, lane) + carry;
+    if (i < Sprev) ws.cdf[i + 1] = fminf(1.f, inc);
+    carry = __shfl_sync(kFull, inc, 31);
+  }
+  __syncwarp();
+  const int nb = Snew + 1;
+  const float u_end = (float)(1.0 - 1.0 / (double)nb);
+  const float u_off = stratified ? jit_new / (float)nb : (float)(1.0 / (double)(2 * nb));
+  auto ex = [&](int i) -> float { return exist ? exist[i] : initial_sbin(i, Sprev, stratified, jit_prev); };
+  for (int j = lane; j < nb; j += 32) {
+    const float u = linspace_at(j, nb, 0.f, u_end) + u_off;
+    int lo = 0, hi = Sprev + 1;  // searchsorted(cdf, u, side="right")
+    while (lo < hi) {
+      const int midx = (lo + hi) >> 1;
+      if (ws.cdf[midx] <= u) lo = midx + 1; else hi = midx;
+    }
+    const int below = min(max(lo - 1, 0), Sprev);
+    const int above = min(max(lo, 0), Sprev);
+    const float c0 = ws.cdf[below], c1 = ws.cdf[above];
+    const float b0 = ex(below), b1 = ex(above);
+    float t = (u - c0) / (c1 - c0);
+    t = isnan(t) ? 0.f : t;
+    t = fminf(fmaxf(t, 0.f), 1.f);
+    dst[j] = b0 + t * (b1 - b0);
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------
+// field level, fp32: lane per sample, activations in a per-lane shared-memory column
+// ------------------------------------------------------------------------------------
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2 };
+
+template <int K, int N, int ACT>
+__device__ __forceinline__ void dense_col(const float* __restrict__ wt, const float* __restrict__ bias,
+                                          const float* xin, float (&y)[N]) {
+#pragma unroll
+  for (int n = 0; n < N; n += 4) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + n);
+    y[n] = b.x; y[n + 1] = b.y; y[n + 2] = b.z; y[n + 3] = b.w;
+  }
+#pragma unroll 2
+  for (int k = 0; k < K; ++k) {
+    const float x = xin[k * 32];
+#pragma unroll
+    for (int n = 0; n < N; n += 4) {
+      const float4 w = *reinterpret_cast<const float4*>(wt + k * N + n);
+      y[n] = fmaf(x, w.x, y[n]);
+      y[n + 1] = fmaf(x, w.y, y[n + 1]);
+      y[n + 2] = fmaf(x, w.z, y[n + 2]);
+      y[n + 3] = fmaf(x, w.w, y[n + 3]);
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    if (ACT == ACT_RELU) y[n] = fmaxf(y[n], 0.f);
+    if (ACT == ACT_SIGMOID) y[n] = sigmoidf(y[n]);
+  }
+}
+template <int N>
+__device__ __forceinline__ void store_col(float* xout, const float (&y)[N]) {
+#pragma unroll
+  for (int n = 0; n < N; ++n) xout[n * 32] = y[n];
+}
+
+__device__ __forceinline__ void field_level(const TnfModel& m, Smem<TNF_PRECISION_FP32>& S, WarpScratch& ws,
+                                            const RayCtx& rc, const int S2, const int lane, const int warp) {
+  const FieldW32& W = S.fw;
+  float* a = &S.act[warp][lane];
+  float* geo = &S.geo[warp][lane];
+  const TnfHashGrid& grid = m.field.grid;
+  const uint32_t mask = (1u << grid.log2_size) - 1u;
+  const float2* __restrict__ tab = reinterpret_cast<const float2*>(grid.table);
+  for (int base = 0; base < S2; base += 32) {
+    const int i = base + lane;
+    const bool active = i < S2;
+    const int ii = active ? i : S2 - 1;
+    float mid, delta;
+    sample_geometry(rc, ws.w[ii], ws.w[ii + 1], mid, delta);
+    float px, py, pz;
+    const float sel = normalise_position(m, fmaf(rc.dx, mid, rc.ox), fmaf(rc.dy, mid, rc.oy),
+                                         fmaf(rc.dz, mid, rc.oz), px, py, pz);
+#pragma unroll 4
+    for (int l = 0; l < TNF_MAX_LEVELS; ++l) {
+      const float2 f = hash_level(tab + ((size_t)l << grid.log2_size), px, py, pz, grid.scalings[l], mask);
+      a[(2 * l) * 32] = f.x;
+      a[(2 * l + 1) * 32] = f.y;
+    }
+    {
+      float y[64];
+      dense_col<32, 64, ACT_RELU>(W.base0t, W.base0b, a, y);
+      store_col(a, y);
+    }
+    float dba;
+    {
+      float y[16];
+      dense_col<64, 16, ACT_NONE>(W.base1t, W.base1b, a, y);
+      dba = y[0];
+      y[0] = 0.f;  // density slot; its weight rows are zero
+      store_col(geo, y);
+    }
+    float rgb[4];
+    {
+      float y[64];
+      dense_col<16, 64, ACT_RELU>(W.rgb0geo_t, ws.rayb, geo, y);
+      store_col(a, y);
+      dense_col<64, 64, ACT_RELU>(W.rgb1t, W.rgb1b, a, y);
+      store_col(a, y);
+      dense_col<64, 4, ACT_SIGMOID>(W.rgb2t, W.rgb2b, a, rgb);
+    }
+    float th;
+    {
+      float y[64];
+      dense_col<16, 64, ACT_RELU>(W.th0t, W.th0b, geo, y);
+      store_col(a, y);
+      dense_col<64, 64, ACT_SIGMOID>(W.th1t, W.th1b, a, y);
+      th = W.th2b[0];
+#pragma unroll
+      for (int k = 0; k < 64; ++k) th = fmaf(y[k], W.th2[k], th);
+    }
+    if (active) {
+      ws.sigma[i] = expf(dba) * sel;
+      ws.r[i] = rgb[0];
+      ws.g[i] = rgb[1];
+      ws.b[i] = rgb[2];
+      ws.th[i] = th;
+    }
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------
+// field level, tensor cores: 16-sample tiles, mma.m16n8k16, activations stay in registers
+// ------------------------------------------------------------------------------------
+template <int NT, int KT>
+__device__ __forceinline__ void mma_layer(float (&c)[NT][4], const uint32_t (&a)[KT][4], const uint2* __restrict__ w,
+                                          const int nt0, const int ntw, const int lane) {
+  // w is [KT][ntw][32]; uses n-tiles nt0 .. nt0+NT-1
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) mma_16816(c[nt], a[kt], w[(kt * ntw + nt0 + nt) * 32 + lane]);
+}
+template <int NT>
+__device__ __forceinline__ void init_bias(float (&c)[NT][4], const float* bias, const int q) {
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const float2 b = *reinterpret_cast<const float2*>(bias + nt * 8 + 2 * q);
+    c[nt][0] = b.x; c[nt][1] = b.y; c[nt][2] = b.x; c[nt][3] = b.y;
+  }
+}
+template <int NT, int ACT>
+__device__ __forceinline__ void act_pack(const float (&c)[NT][4], uint32_t (&a)[NT / 2][4]) {
+#pragma unroll
+  for (int kt = 0; kt < NT / 2; ++kt) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        v[e] = c[2 * kt + h][e];
+        if (ACT == ACT_RELU) v[e] = fmaxf(v[e], 0.f);
+        if (ACT == ACT_SIGMOID) v[e] = sigmoidf(v[e]);
+      }
+      a[kt][2 * h] = pack_half2(v[0], v[1]);      // row g
+      a[kt][2 * h + 1] = pack_half2(v[2], v[3]);  // row g+8
+    }
+  }
+}
+
+__device__ __forceinline__ void field_level(const TnfModel& m, Smem<TNF_PRECISION_TC_FP16>& S, WarpScratch& ws,
+                                            const RayCtx& rc, const int S2, const int lane, const int warp) {
+  const FieldWTC& W = S.fw;
+  const TnfHashGrid& grid = m.field.grid;
+  const uint32_t mask = (1u << grid.log2_size) - 1u;
+  const float2* __restrict__ tab = reinterpret_cast<const float2*>(grid.table);
+  const int g = lane >> 2, q = lane & 3;
+  for (int base = 0; base < S2; base += 16) {
+    const int r0 = base + g, r1 = base + g + 8;
+    float p[2][3], sel[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int ii = min(h ? r1 : r0, S2 - 1);
+      float mid, delta;
+      sample_geometry(rc, ws.w[ii], ws.w[ii + 1], mid, delta);
+      sel[h] = normalise_position(m, fmaf(rc.dx, mid, rc.ox), fmaf(rc.dy, mid, rc.oy), fmaf(rc.dz, mid, rc.oz),
+                                  p[h][0], p[h][1], p[h][2]);
+    }
+    // hash encode straight into A-fragment layout: this lane owns levels q, q+4, q+8, q+12
+    uint32_t a0[2][4];
+#pragma unroll
+    for (int kt = 0; kt < 2; ++kt) {
+#pragma unroll
+      for (int hl = 0; hl < 2; ++hl) {
+        const int l = kt * 8 + hl * 4 + q;
+        const float2* lt = tab + ((size_t)l << grid.log2_size);
+        const float sc = grid.scalings[l];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float2 f = hash_level(lt, p[h][0], p[h][1], p[h][2], sc, mask);
+          a0[kt][2 * hl + h] = pack_half2(f.x, f.y);
+        }
+      }
+    }
+    uint32_t hid[4][4];
+    {
+      float c[8][4];
+      init_bias(c, W.base0b, q);
+      mma_layer<8, 2>(c, a0, &W.base0[0][0][0], 0, 8, lane);
+      act_pack<8, ACT_RELU>(c, hid);
+    }
+    float dba0, dba1;
+    uint32_t ga[1][4];
+    {
+      float c[2][4];
+      init_bias(c, W.base1b, q);
+      mma_layer<2, 4>(c, hid, &W.base1[0][0][0], 0, 2, lane);
+      dba0 = c[0][0];
+      dba1 = c[0][2];
+      if (q == 0) { c[0][0] = 0.f; c[0][2] = 0.f; }  // density slot (zero weight rows downstream)
+      act_pack<2, ACT_NONE>(c, ga);
+    }
+    float rgb[1][4];
+    {
+      float c[8][4];
+      init_bias(c, ws.rayb, q);
+      mma_layer<8, 1>(c, ga, &W.geo0[0][0][0], 0, 16, lane);
+      act_pack<8, ACT_RELU>(c, hid);
+      init_bias(c, W.rgb1b, q);
+      mma_layer<8, 4>(c, hid, &W.rgb1[0][0][0], 0, 8, lane);
+      act_pack<8, ACT_RELU>(c, hid);
+      init_bias(rgb, W.rgb2b, q);
+      mma_layer<1, 4>(rgb, hid, &W.rgb2[0][0][0], 0, 1, lane);
+    }
+    float th[1][4];
+    {
+      float c[8][4];
+      init_bias(c, W.th0b, q);
+      mma_layer<8, 1>(c, ga, &W.geo0[0][0][0], 8, 16, lane);
+      act_pack<8, ACT_RELU>(c, hid);
+      init_bias(c, W.th1b, q);
+      mma_layer<8, 4>(c, hid, &W.th1[0][0][0], 0, 8, lane);
+      act_pack<8, ACT_SIGMOID>(c, hid);
+      init_bias(th, W.th2b, q);
+      mma_layer<1, 4>(th, hid, &W.th2[0][0][0], 0, 1, lane);
+    }
+    if (q == 0) {
+      if (r0 < S2) {
+        ws.sigma[r0] = expf(dba0) * sel[0];
+        ws.r[r0] = sigmoidf(rgb[0][0]);
+        ws.g[r0] = sigmoidf(rgb[0][1]);
+        ws.th[r0] = th[0][0];
+      }
+      if (r1 < S2) {
+        ws.sigma[r1] = expf(dba1) * sel[1];
+        ws.r[r1] = sigmoidf(rgb[0][2]);
+        ws.g[r1] = sigmoidf(rgb[0][3]);
+        ws.th[r1] = th[0][2];
+      }
+    } else if (q == 1) {
+      if (r0 < S2) ws.b[r0] = sigmoidf(rgb[0][0]);
+      if (r1 < S2) ws.b[r1] = sigmoidf(rgb[0][2]);
+    }
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------
+template <int PREC>
+__global__ void __launch_bounds__(kThreads, PREC == TNF_PRECISION_TC_FP16 ? 2 : 1)
+    tnf_forward_kernel(const __grid_constant__ TnfModel m, const __grid_constant__ TnfRays rays,
+                       const __grid_constant__ TnfOutputs out, const long long chunk,
+                       unsigned* __restrict__ clip_min, unsigned* __restrict__ clip_max) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<PREC>& S = *reinterpret_cast<Smem<PREC>*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // ---- stage weights
+  if (warp == 0) {
+    float e = 0.f;
+    if (m.appearance_mode == TNF_APPEARANCE_MEAN) {
+      for (int i = 0; i < m.field.num_images; ++i) e += m.field.appearance[i * 32 + lane];
+      e /= (float)m.field.num_images;
+    }
+    S.fc.app_const[lane] = e;
+  }
+  stage_prop(S.prop[0], m.prop[0], tid);
+  stage_prop(S.prop[1], m.prop[1], tid);
+  stage_field(S.fw, m.field, tid);
+  __syncthreads();
+  const bool lookup = m.appearance_mode == TNF_APPEARANCE_LOOKUP;
+  stage_common(S.fc, m.field, !lookup, tid);
+  __syncthreads();
+
+  WarpScratch& ws = S.ws[warp];
+  const bool train = m.training != 0;
+  const bool stratified = train && rays.jitter != nullptr;
+  const int S0 = m.num_samples[0], S1 = m.num_samples[1], S2 = m.num_samples[2];
+  const long long R = rays.num_rays;
+  long long cur_chunk = -1;
+  float cmin = FLT_MAX, cmax = 0.f;
+
+  for (long long ray = (long long)blockIdx.x * kWarpsPerCta + warp; ray < R;
+       ray += (long long)gridDim.x * kWarpsPerCta) {
+    RayCtx rc;
+    rc.ox = __ldg(rays.origins + ray * 3 + 0);
+    rc.oy = __ldg(rays.origins + ray * 3 + 1);
+    rc.oz = __ldg(rays.origins + ray * 3 + 2);
+    rc.dx = __ldg(rays.directions + ray * 3 + 0);
+    rc.dy = __ldg(rays.directions + ray * 3 + 1);
+    rc.dz = __ldg(rays.directions + ray * 3 + 2);
+    const float near = rays.nears ? __ldg(rays.nears + ray) : m.near_plane;
+    const float far = rays.fars ? __ldg(rays.fars + ray) : m.far_plane;
+    rc.s_near = spacing_fn(near);
+    rc.s_far = spacing_fn(far);
+    float jit0 = 0.f, jit1 = 0.f, jit2 = 0.f;
+    if (stratified) {
+      jit0 = __ldg(rays.jitter + ray);
+      jit1 = __ldg(rays.jitter + R + ray);
+      jit2 = __ldg(rays.jitter + 2 * R + ray);
+    }
+
+    // ---- per-ray first-layer bias of the colour head: bias + W_sh * SH((d+1)/2) [+ W_app * e_cam]
+    {
+      float sh[16];
+      sh4((rc.dx + 1.f) * 0.5f, (rc.dy + 1.f) * 0.5f, (rc.dz + 1.f) * 0.5f, sh);
+      float b0 = S.fc.rgb0b[lane], b1 = S.fc.rgb0b[lane + 32];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        b0 = fmaf(sh[k], S.fc.rgb0sh_t[k * 64 + lane], b0);
+        b1 = fmaf(sh[k], S.fc.rgb0sh_t[k * 64 + lane + 32], b1);
+      }
+      if (lookup) {
+        const long long cam = rays.camera_indices[ray];
+        const float e = __ldg(m.field.appearance + cam * 32 + lane);
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+          const float ej = __shfl_sync(kFull, e, j);
+          b0 = fmaf(ej, S.fc.rgb0app_t[j * 64 + lane], b0);
+          b1 = fmaf(ej, S.fc.rgb0app_t[j * 64 + lane + 32], b1);
+        }
+      }
+      ws.rayb[lane] = b0;
+      ws.rayb[lane + 32] = b1;
+    }
+
+    // ---- level 0
+    const float pd0 = proposal_level<0>(m, S.prop[0], ws, rc, S0, stratified, jit0, lane,
+                                        out.weights[0] ? out.weights[0] + ray * S0 : nullptr,
+                                        out.sdist[0] ? out.sdist[0] + ray * (S0 + 1) : nullptr);
+    pdf_resample(ws, S0, S1, m.anneal, stratified, jit0, jit1, nullptr, ws.bins, lane);
+    // ---- level 1
+    const float pd1 = proposal_level<1>(m, S.prop[1], ws, rc, S1, stratified, jit1, lane,
+                                        out.weights[1] ? out.weights[1] + ray * S1 : nullptr,
+                                        out.sdist[1] ? out.sdist[1] + ray * (S1 + 1) : nullptr);
+    pdf_resample(ws, S1, S2, m.anneal, stratified, jit1, jit2, ws.bins, ws.w, lane);
+    // ---- level 2: field; its spacing bins now live in ws.w[0..S2]
+    field_level(m, S, ws, rc, S2, lane, warp);
+
+    // ---- composite (get_weights + RGB/Thermal/Accumulation/Depth renderers)
+    Compositor comp;
+    float sr = 0.f, sg = 0.f, sb = 0.f, st = 0.f, sw = 0.f, swt = 0.f;
+    float first_mid = 0.f, last_mid = 0.f;
+    for (int base = 0; base < S2; base += 32) {
+      const int i = base + lane;
+      const bool active = i < S2;
+      const int ii = active ? i : S2 - 1;
+      float mid, delta;
+      sample_geometry(rc, ws.w[ii], ws.w[ii + 1], mid, delta);
+      const float w = comp.step(active ? delta * ws.sigma[ii] : 0.f, mid, active, lane);
+      float cr = ws.r[ii], cg = ws.g[ii], cb = ws.b[ii], ct = ws.th[ii];
+      if (!train) { cr = nan_to_num(cr); cg = nan_to_num(cg); cb = nan_to_num(cb); ct = nan_to_num(ct); }
+      sr = fmaf(w, cr, sr);
+      sg = fmaf(w, cg, sg);
+      sb = fmaf(w, cb, sb);
+      st = fmaf(w, ct, st);
+      sw += w;
+      swt = fmaf(w, mid, swt);
+      if (active && out.weights[2]) out.weights[2][ray * S2 + i] = w;
+      if (base == 0) first_mid = __shfl_sync(kFull, mid, 0);
+      if (base + 32 >= S2) last_mid = __shfl_sync(kFull, mid, (S2 - 1) & 31);
+    }
+    if (out.sdist[2]) {
+      for (int i = lane; i <= S2; i += 32) out.sdist[2][ray * (S2 + 1) + i] = ws.w[i];
+    }
+    sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb); st = warp_sum(st);
+    sw = warp_sum(sw); swt = warp_sum(swt);
+    if (lane == 0) {
+      float lr = ws.r[S2 - 1], lg = ws.g[S2 - 1], lb = ws.b[S2 - 1], lt = ws.th[S2 - 1];
+      if (!train) { lr = nan_to_num(lr); lg = nan_to_num(lg); lb = nan_to_num(lb); lt = nan_to_num(lt); }
+      const float bgw = 1.f - sw;  // background_color = "last_sample" (thermal_renderer.py:49)
+      float r = sr + lr * bgw, g = sg + lg * bgw, b = sb + lb * bgw, t = st + lt * bgw;
+      if (!train) {
+        r = fminf(fmaxf(r, 0.f), 1.f); g = fminf(fmaxf(g, 0.f), 1.f);
+        b = fminf(fmaxf(b, 0.f), 1.f); t = fminf(fmaxf(t, 0.f), 1.f);
+      }
+      out.rgb[ray * 3 + 0] = r;
+      out.rgb[ray * 3 + 1] = g;
+      out.rgb[ray * 3 + 2] = b;
+      out.thermal[ray] = t;
+      out.accumulation[ray] = sw;
+      out.depth[ray] = comp.found ? comp.median : last_mid;
+      out.expected_depth[ray] = swt / (sw + 1e-10f);  // clipped by tnf_clip_kernel
+      out.prop_depth[0][ray] = pd0;
+      out.prop_depth[1][ray] = pd1;
+    }
+    // ---- per-chunk min/max of the sample mid-points (tensor-global clip of DepthRenderer("expected"))
+    const long long c = chunk > 0 ? ray / chunk : 0;
+    if (c != cur_chunk) {
+      if (cur_chunk >= 0 && lane == 0) {
+        atomicMin(clip_min + cur_chunk, __float_as_uint(cmin));
+        atomicMax(clip_max + cur_chunk, __float_as_uint(cmax));
+      }
+      cur_chunk = c;
+      cmin = FLT_MAX;
+      cmax = 0.f;
+    }
+    if (first_mid == first_mid) cmin = fminf(cmin, first_mid);
+    if (last_mid == last_mid) cmax = fmaxf(cmax, last_mid);
+    __syncwarp();
+  }
+  if (cur_chunk >= 0 && lane == 0) {
+    atomicMin(clip_min + cur_chunk, __float_as_uint(cmin));
+    atomicMax(clip_max + cur_chunk, __float_as_uint(cmax));
+  }
+}
+
+__global__ void tnf_clip_kernel(float* __restrict__ expected_depth, const long long R, const long long chunk,
+                                const unsigned* __restrict__ clip_min, const unsigned* __restrict__ clip_max) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const long long c = chunk > 0 ? r / chunk : 0;
+  const float lo = __uint_as_float(clip_min[c]), hi = __uint_as_float(clip_max[c]);
+  const float e = expected_depth[r];
+  if (e == e) expected_depth[r] = fminf(fmaxf(e, lo), hi);
+}
+
+}  // namespace tnf
+
+// ====================================================================================
+// C ABI
+// ====================================================================================
+namespace {
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_linear(const TnfLinear& l, const char* name) {
+  if (!l.weight || !l.bias) return fail(TNF_ERR_INVALID_ARGUMENT, "%s: null weight/bias", name);
+  return TNF_OK;
+}
+
+int check_model(const TnfModel* m) {
+  if (!m) return fail(TNF_ERR_INVALID_ARGUMENT, "model is null");
+  for (int k = 0; k < TNF_NUM_PROP; ++k) {
+    const TnfDensityNet& n = m->prop[k];
+    if (!n.grid.table) return fail(TNF_ERR_INVALID_ARGUMENT, "prop[%d].grid.table is null", k);
+    if (n.grid.num_levels < 1 || n.grid.num_levels > TNF_MAX_PROP_LEVELS)
+      return fail(TNF_ERR_UNSUPPORTED_CONFIG, "prop[%d]: num_levels=%d not in [1,%d]", k, n.grid.num_levels,
+                  TNF_MAX_PROP_LEVELS);
+    if (n.grid.log2_size < 1 || n.grid.log2_size > 24)
+      return fail(TNF_ERR_UNSUPPORTED_CONFIG, "prop[%d]: log2_size=%d not in [1,24]", k, n.grid.log2_size);
+    if (int e = check_linear(n.l0, "prop.l0")) return e;
+    if (int e = check_linear(n.l1, "prop.l1")) return e;
+  }
+  const TnfField& f = m->field;
+  if (!f.grid.table) return fail(TNF_ERR_INVALID_ARGUMENT, "field.grid.table is null");
+  if (f.grid.num_levels != TNF_MAX_LEVELS)
+    return fail(TNF_ERR_UNSUPPORTED_CONFIG, "field: num_levels=%d, kernels are built for %d", f.grid.num_levels,
+                TNF_MAX_LEVELS);
+  if (f.grid.log2_size < 1 || f.grid.log2_size > 24)
+    return fail(TNF_ERR_UNSUPPORTED_CONFIG, "field: log2_size=%d not in [1,24]", f.grid.log2_size);
+  const TnfLinear* ls[] = {&f.base0, &f.base1, &f.rgb0, &f.rgb1, &f.rgb2, &f.th0, &f.th1, &f.th2};
+  for (const TnfLinear* l : ls)
+    if (int e = check_linear(*l, "field linear")) return e;
+  if (m->appearance_mode != TNF_APPEARANCE_ZEROS && (!f.appearance || f.num_images < 1))
+    return fail(TNF_ERR_INVALID_ARGUMENT, "field.appearance is required for appearance_mode=%d",
+                m->appearance_mode);
+  if (m->appearance_mode < 0 || m->appearance_mode > 2)
+    return fail(TNF_ERR_INVALID_ARGUMENT, "appearance_mode=%d", m->appearance_mode);
+  for (int k = 0; k <= TNF_NUM_PROP; ++k) {
+    const int lim = (k == TNF_NUM_PROP) ? tnf::kMaxFieldS : TNF_MAX_SAMPLES;
+    if (m->num_samples[k] < 1 || m->num_samples[k] > lim)
+      return fail(TNF_ERR_UNSUPPORTED_CONFIG, "num_samples[%d]=%d not in [1,%d]", k, m->num_samples[k], lim);
+  }
+  if (m->precision != TNF_PRECISION_FP32 && m->precision != TNF_PRECISION_TC_FP16)
+    return fail(TNF_ERR_INVALID_ARGUMENT, "precision=%d", m->precision);
+  return TNF_OK;
+}
+
+template <int PREC>
+int launch_forward(const TnfModel& m, const TnfRays& r, const TnfOutputs& o, long long chunk, unsigned* cmin,
+                   unsigned* cmax, cudaStream_t stream) {
+  static thread_local int configured_dev = -1;
+  static thread_local int num_sms = 0;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+  const size_t smem = sizeof(tnf::Smem<PREC>);
+  if (configured_dev != dev) {
+    e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
+    e = cudaFuncSetAttribute(tnf::tnf_forward_kernel<PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess)
+      return fail(TNF_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
+    configured_dev = dev;
+  }
+  const int ctas_per_sm = PREC == TNF_PRECISION_TC_FP16 ? 2 : 1;
+  long long want = (r.num_rays + tnf::kWarpsPerCta - 1) / tnf::kWarpsPerCta;
+  const long long cap = (long long)num_sms * ctas_per_sm;
+  const int grid = (int)(want < cap ? want : cap);
+  tnf::tnf_forward_kernel<PREC><<<grid, tnf::kThreads, smem, stream>>>(m, r, o, chunk, cmin, cmax);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "forward kernel launch: %s", cudaGetErrorString(e));
+  return TNF_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int tnf_version(void) { return TNF_ABI_VERSION; }
+
+const char* tnf_last_error(void) { return g_err; }
+
+size_t tnf_forward_workspace_bytes(int64_t num_rays, int64_t depth_clip_chunk) {
+  if (num_rays <= 0) return 16;
+  const int64_t chunks = depth_clip_chunk > 0 ? (num_rays + depth_clip_chunk - 1) / depth_clip_chunk : 1;
+  return (size_t)(2 * chunks * sizeof(unsigned) + 16);
+}
+
+int tnf_render_forward(const TnfModel* model, const TnfRays* rays, const TnfOutputs* out, int64_t depth_clip_chunk,
+                       void* workspace, size_t workspace_bytes, void* stream_) {
+  g_err[0] = 0;
+  if (int e = check_model(model)) return e;
+  if (!rays || !out) return fail(TNF_ERR_INVALID_ARGUMENT, "rays/out is null");
+  if (rays->num_rays < 0) return fail(TNF_ERR_INVALID_ARGUMENT, "num_rays=%lld", (long long)rays->num_rays);
+  if (rays->num_rays == 0) return TNF_OK;
+  if (!rays->origins || !rays->directions) return fail(TNF_ERR_INVALID_ARGUMENT, "origins/directions is null");
+  if (model->appearance_mode == TNF_APPEARANCE_LOOKUP && !rays->camera_indices)
+    return fail(TNF_ERR_INVALID_ARGUMENT, "camera_indices required for TNF_APPEARANCE_LOOKUP");
+  if (!out->rgb || !out->thermal || !out->depth || !out->expected_depth || !out->accumulation ||
+      !out->prop_depth[0] || !out->prop_depth[1])
+    return fail(TNF_ERR_INVALID_ARGUMENT, "a required output pointer is null");
+  if (!aligned16(rays->origins) || !aligned16(rays->directions) || !aligned16(out->rgb))
+    return fail(TNF_ERR_INVALID_ARGUMENT, "ray/output buffers must be 16-byte aligned");
+  const size_t need = tnf_forward_workspace_bytes(rays->num_rays, depth_clip_chunk);
+  if (!workspace || workspace_bytes < need)
+    return fail(TNF_ERR_WORKSPACE_TOO_SMALL, "workspace %zu < %zu bytes", workspace_bytes, need);
+
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const long long chunk = depth_clip_chunk > 0 ? depth_clip_chunk : 0;
+  const long long chunks = chunk > 0 ? (rays->num_rays + chunk - 1) / chunk : 1;
+  unsigned* cmin = static_cast<unsigned*>(workspace);
+  unsigned* cmax = cmin + chunks;
+  cudaError_t e = cudaMemsetAsync(cmin, 0x7f, chunks * sizeof(unsigned), stream);  // 3.39e38: above any depth
+  if (e == cudaSuccess) e = cudaMemsetAsync(cmax, 0, chunks * sizeof(unsigned), stream);
+  if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+
+  int rc;
+  if (model->precision == TNF_PRECISION_TC_FP16)
+    rc = launch_forward<TNF_PRECISION_TC_FP16>(*model, *rays, *out, chunk, cmin, cmax, stream);
+  else
+    rc = launch_forward<TNF_PRECISION_FP32>(*model, *rays, *out, chunk, cmin, cmax, stream);
+  if (rc != TNF_OK) return rc;
+
+  const int tb = 256;
+  const long long nb = (rays->num_rays + tb - 1) / tb;
+  tnf::tnf_clip_kernel<<<(unsigned)nb, tb, 0, stream>>>(out->expected_depth, rays->num_rays, chunk, cmin, cmax);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "clip kernel launch: %s", cudaGetErrorString(e));
+  return TNF_OK;
+}
+
+}  // extern "C"

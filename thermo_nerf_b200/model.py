@@ -1,0 +1,308 @@
+"""B200 ThermoNeRF model: the reference's ``ThermalNerfModel`` plugin surface over the fused
+sm_100a kernels.
+
+Mirrors thermo_nerf/thermal_nerf/thermal_nerf_model.py (config :46-56, ctor :67-84,
+populate_modules :86-208, get_outputs :210-275, get_loss_dict :277-326) and the pieces of
+nerfstudio's ``Model`` / ``NerfactoModel`` the reference's callers use
+(``forward``, ``get_outputs_for_camera_ray_bundle``, ``get_param_groups``,
+``get_training_callbacks``, ``get_metrics_dict``).  Same names, argument meaning, output
+keys/shapes and error behaviour; the arithmetic is one call into libtnf_b200.so.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Any, Callable, Dict, List, Literal, Optional, Tuple, Type
+
+import numpy as np
+import torch
+from torch import Tensor, nn
+
+from . import _lib as L
+from . import functional as F
+from .modules import CameraOptimizer, HashMLPDensityField, ThermalNerfactoTField
+from .rays import RayBundle
+
+
+@dataclass
+class ThermalNerfModelConfig:
+    """ThermalNerfModelConfig (thermal_nerf_model.py:46-56) + ThermalNerfactoModelConfig
+    (nerfacto_config/thermal_nerfacto.py:13-25) + the NerfactoModelConfig defaults they
+    inherit."""
+
+    _target: Type = field(default_factory=lambda: ThermalNerfModel)
+    # ThermalNerfactoModelConfig
+    max_temperature: float = 1.0
+    min_temperature: float = 0.0
+    cold: bool = False
+    camera_optimizer_mode: Literal["off", "SO3xR3"] = "SO3xR3"
+    # ThermalNerfModelConfig
+    use_transient_embedding: bool = False
+    thermal_loss_weight: float = 1.0  # declared but unused by the reference (thermal_nerf_model.py:53 vs :321-324)
+    pass_thermal_gradients: bool = True
+    # NerfactoModelConfig
+    near_plane: float = 0.05
+    far_plane: float = 1000.0
+    background_color: str = "last_sample"
+    hidden_dim: int = 64
+    hidden_dim_color: int = 64
+    hidden_dim_transient: int = 64
+    num_levels: int = 16
+    base_res: int = 16
+    max_res: int = 2048
+    log2_hashmap_size: int = 19
+    features_per_level: int = 2
+    num_proposal_samples_per_ray: Tuple[int, ...] = (256, 96)
+    num_nerf_samples_per_ray: int = 48
+    proposal_update_every: int = 5
+    proposal_warmup: int = 5000
+    num_proposal_iterations: int = 2
+    use_same_proposal_network: bool = False
+    proposal_net_args_list: List[Dict] = field(
+        default_factory=lambda: [
+            {"hidden_dim": 16, "log2_hashmap_size": 17, "num_levels": 5, "max_res": 128, "use_linear": False},
+            {"hidden_dim": 16, "log2_hashmap_size": 17, "num_levels": 5, "max_res": 256, "use_linear": False},
+        ]
+    )
+    proposal_initial_sampler: Literal["piecewise", "uniform"] = "piecewise"
+    interlevel_loss_mult: float = 1.0
+    distortion_loss_mult: float = 0.002
+    use_proposal_weight_anneal: bool = True
+    use_average_appearance_embedding: bool = True
+    proposal_weights_anneal_slope: float = 10.0
+    proposal_weights_anneal_max_num_iters: int = 1000
+    use_single_jitter: bool = True
+    predict_normals: bool = False
+    disable_scene_contraction: bool = False
+    use_gradient_scaling: bool = False
+    appearance_embed_dim: int = 32
+    implementation: str = "b200"
+    eval_num_rays_per_chunk: int = 1 << 16  # config_thermal_nerf.py:30
+    # B200 specific
+    precision: Literal["fp32", "tc_fp16"] = "tc_fp16"
+
+    def setup(self, **kwargs) -> Any:
+        return self._target(self, **kwargs)
+
+
+@dataclass
+class TrainingCallback:
+    """Shape of nerfstudio's TrainingCallback (where_to_run / update_every_num_iters / func)."""
+
+    where_to_run: List[str]
+    update_every_num_iters: int
+    func: Callable
+
+    def run_callback(self, step: int) -> None:
+        if step % self.update_every_num_iters == 0:
+            self.func(step)
+
+
+BEFORE_TRAIN_ITERATION = "BEFORE_TRAIN_ITERATION"
+AFTER_TRAIN_ITERATION = "AFTER_TRAIN_ITERATION"
+
+
+class _SceneBox:
+    def __init__(self, aabb: Tensor) -> None:
+        self.aabb = aabb
+
+
+class ThermalNerfModel(nn.Module):
+    """ThermalNerfModel on libtnf_b200 (see module docstring)."""
+
+    config: ThermalNerfModelConfig
+
+    def __init__(self, config: ThermalNerfModelConfig, metadata: dict, scene_box, num_train_data: int,
+                 **kwargs) -> None:
+        if "thermal" not in metadata.keys():  # thermal_nerf_model.py:75-76
+            raise ValueError("Thermal images not found in metadata.")
+        super().__init__()
+        self.config = config
+        self.scene_box = scene_box if hasattr(scene_box, "aabb") else _SceneBox(torch.as_tensor(scene_box))
+        self.num_train_data = num_train_data
+        self.kwargs = kwargs
+        self.max_temperature = config.max_temperature
+        self.min_temperature = config.min_temperature
+        self.device_indicator_param = nn.Parameter(torch.empty(0))
+        self.populate_modules()
+        self._tensors: Optional[F.ModelTensors] = None
+
+    # ------------------------------------------------------------------ construction
+    def populate_modules(self) -> None:
+        cfg = self.config
+        if cfg.predict_normals or cfg.use_transient_embedding or cfg.use_gradient_scaling:
+            raise ValueError("predict_normals / use_transient_embedding / use_gradient_scaling are not on the "
+                             "thermal-nerf hot path and are not built into libtnf_b200")
+        if cfg.proposal_initial_sampler != "piecewise" or not cfg.use_single_jitter:
+            raise ValueError("libtnf_b200 implements the default piecewise initial sampler with single jitter")
+        if cfg.num_proposal_iterations != L.TNF_NUM_PROP or cfg.use_same_proposal_network:
+            raise ValueError("libtnf_b200 is built for 2 distinct proposal networks (nerfacto default)")
+        if cfg.background_color != "last_sample":
+            raise ValueError("libtnf_b200 implements background_color='last_sample' (nerfacto default)")
+        aabb = torch.as_tensor(self.scene_box.aabb, dtype=torch.float32)
+        self.field = ThermalNerfactoTField(
+            aabb, num_images=self.num_train_data, hidden_dim=cfg.hidden_dim, num_levels=cfg.num_levels,
+            max_res=cfg.max_res, base_res=cfg.base_res, features_per_level=cfg.features_per_level,
+            log2_hashmap_size=cfg.log2_hashmap_size, hidden_dim_color=cfg.hidden_dim_color,
+            hidden_dim_transient=cfg.hidden_dim_transient,
+            use_average_appearance_embedding=cfg.use_average_appearance_embedding,
+            appearance_embedding_dim=cfg.appearance_embed_dim, pass_thermal_gradients=cfg.pass_thermal_gradients)
+        self.camera_optimizer = CameraOptimizer(self.num_train_data, cfg.camera_optimizer_mode)
+        self.proposal_networks = nn.ModuleList()
+        for i in range(cfg.num_proposal_iterations):
+            a = dict(cfg.proposal_net_args_list[min(i, len(cfg.proposal_net_args_list) - 1)])
+            if a.pop("use_linear", False):
+                raise ValueError("use_linear proposal networks are not built into libtnf_b200")
+            self.proposal_networks.append(HashMLPDensityField(aabb, **a))
+        # ProposalNetworkSampler state (annealing + update schedule)
+        self._anneal = 1.0
+        self._steps_since_update = 0
+        self._step = 0
+        self.step = 0
+
+    @property
+    def device(self) -> torch.device:
+        return self.device_indicator_param.device
+
+    def _apply(self, fn, *a, **k):  # parameters may move: re-resolve tensor references
+        self._tensors = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, state_dict, strict: bool = True, **k):  # type: ignore[override]
+        self._tensors = None
+        return super().load_state_dict(state_dict, strict=strict, **k)
+
+    def tensors(self) -> F.ModelTensors:
+        if self._tensors is None:
+            self._tensors = F.ModelTensors.from_module(self)
+        return self._tensors
+
+    # ------------------------------------------------------------------ nerfstudio Model surface
+    def get_param_groups(self) -> Dict[str, List[nn.Parameter]]:
+        groups: Dict[str, List[nn.Parameter]] = {
+            "proposal_networks": list(self.proposal_networks.parameters()),
+            "fields": list(self.field.parameters()),
+        }
+        self.camera_optimizer.get_param_groups(param_groups=groups)
+        return groups
+
+    def update_schedule(self, step: int) -> float:  # thermal_nerf_model.py:152-161
+        return float(np.clip(np.interp(step, [0, self.config.proposal_warmup], [0, self.config.proposal_update_every]),
+                             1, self.config.proposal_update_every))
+
+    def get_training_callbacks(self, training_callback_attributes=None) -> List[TrainingCallback]:
+        callbacks = []
+        if self.config.use_proposal_weight_anneal:
+            N = self.config.proposal_weights_anneal_max_num_iters
+
+            def set_anneal(step: int) -> None:
+                self.step = step
+                train_frac = float(np.clip(step / N, 0, 1))
+                b = self.config.proposal_weights_anneal_slope
+                self._anneal = b * train_frac / ((b - 1) * train_frac + 1)
+
+            callbacks.append(TrainingCallback([BEFORE_TRAIN_ITERATION], 1, set_anneal))
+
+        def step_cb(step: int) -> None:  # ProposalNetworkSampler.step_cb
+            self._step = step
+            self._steps_since_update += 1
+
+        callbacks.append(TrainingCallback([AFTER_TRAIN_ITERATION], 1, step_cb))
+        return callbacks
+
+    def _precision(self) -> int:
+        return L.PRECISION_FP32 if self.config.precision == "fp32" else L.PRECISION_TC_FP16
+
+    def _appearance_mode(self) -> int:
+        if self.training:
+            return L.APPEARANCE_LOOKUP
+        return L.APPEARANCE_MEAN if self.config.use_average_appearance_embedding else L.APPEARANCE_ZEROS
+
+    def _collider_near(self) -> float:
+        # NearFarCollider(reset_near_plane=True): eval renders from t=0
+        return self.config.near_plane if self.training else 0.0
+
+    def forward(self, ray_bundle) -> Dict[str, Any]:
+        """Model.forward: collider (thermal_nerf_model.py:182-184) then get_outputs.  The
+        NearFarCollider only writes two constants per ray, so they travel as kernel
+        arguments instead of [R,1] tensors (a caller-supplied nears/fars still wins)."""
+        return self.get_outputs(ray_bundle)
+
+    def get_outputs(self, ray_bundle, depth_clip_chunk: int = 0) -> Dict[str, Any]:
+        """thermal_nerf_model.py:210-275 as one fused kernel launch."""
+        cfg = self.config
+        if self.training:
+            self.camera_optimizer.apply_to_raybundle(ray_bundle)
+        shape = tuple(ray_bundle.origins.shape[:-1])
+        o = ray_bundle.origins.reshape(-1, 3).contiguous().float()
+        d = ray_bundle.directions.reshape(-1, 3).contiguous().float()
+        R = o.shape[0]
+        cam = ray_bundle.camera_indices
+        if self.training and cam is None:
+            raise AttributeError("Camera indices are not provided.")  # thermal_field.py:113-114
+        jitter = torch.rand((L.TNF_NUM_PROP + 1, R), device=o.device) if self.training else None
+        nears = ray_bundle.nears.reshape(-1).contiguous().float() if ray_bundle.nears is not None else None
+        fars = ray_bundle.fars.reshape(-1).contiguous().float() if ray_bundle.fars is not None else None
+        res = F.render_forward(
+            self.tensors(), o, d, cam.reshape(-1) if cam is not None else None, nears, fars, jitter,
+            num_samples=(*cfg.num_proposal_samples_per_ray, cfg.num_nerf_samples_per_ray),
+            training=self.training, near_plane=self._collider_near(), far_plane=cfg.far_plane, anneal=self._anneal,
+            use_contraction=not cfg.disable_scene_contraction,
+            aabb=[float(x) for x in torch.as_tensor(self.scene_box.aabb).reshape(-1).tolist()],
+            appearance_mode=self._appearance_mode(), precision=self._precision(),
+            depth_clip_chunk=depth_clip_chunk, return_samples=self.training)
+        outputs: Dict[str, Any] = {
+            "rgb": res["rgb"].view(*shape, 3),
+            "accumulation": res["accumulation"].view(*shape, 1),
+            "depth": res["depth"].view(*shape, 1),
+            "expected_depth": res["expected_depth"].view(*shape, 1),
+        }
+        if self.training:
+            outputs["weights_list"] = res["weights_list"]
+            outputs["ray_samples_list"] = res["sdist_list"]  # spacing bins [R,S+1] per level
+        for i in range(cfg.num_proposal_iterations):
+            outputs[f"prop_depth_{i}"] = res[f"prop_depth_{i}"].view(*shape, 1)
+        outputs["thermal"] = res["thermal"].view(*shape, 1)
+        return outputs
+
+    @torch.no_grad()
+    def get_outputs_for_camera_ray_bundle(self, camera_ray_bundle) -> Dict[str, Tensor]:
+        """nerfstudio Model.get_outputs_for_camera_ray_bundle (called at renderer.py:185,
+        evaluator.py:79).  The reference loops over eval_num_rays_per_chunk slices; here the
+        whole image is ONE launch and the only chunk-dependent quantity (the expected-depth
+        clip range) is evaluated per chunk inside the kernel, so results are identical."""
+        input_device = camera_ray_bundle.directions.device
+        image_shape = tuple(camera_ray_bundle.origins.shape[:-1])
+        flat = RayBundle(
+            origins=camera_ray_bundle.origins.reshape(-1, 3).to(self.device),
+            directions=camera_ray_bundle.directions.reshape(-1, 3).to(self.device),
+            camera_indices=(camera_ray_bundle.camera_indices.reshape(-1, 1).to(self.device)
+                            if camera_ray_bundle.camera_indices is not None else None),
+            nears=camera_ray_bundle.nears.reshape(-1, 1).to(self.device) if camera_ray_bundle.nears is not None else None,
+            fars=camera_ray_bundle.fars.reshape(-1, 1).to(self.device) if camera_ray_bundle.fars is not None else None,
+        )
+        if flat.nears is None or flat.fars is None:
+            flat.nears, flat.fars = None, None  # constants are folded into the kernel arguments
+        was_training = self.training
+        outputs = self.get_outputs(flat, depth_clip_chunk=self.config.eval_num_rays_per_chunk)
+        assert was_training == self.training
+        res = {}
+        for k, v in outputs.items():
+            if not isinstance(v, Tensor):
+                continue  # nerfstudio skips non-tensor outputs (weights_list etc.)
+            res[k] = v.view(*image_shape, -1).to(input_device)
+        return res
+
+    # ------------------------------------------------------------------ metrics (pure torch, as in the reference)
+    def get_metrics_dict(self, outputs, batch) -> Dict[str, Tensor]:
+        gt_rgb = batch["image"].to(self.device)
+        mse = torch.mean((outputs["rgb"] - gt_rgb[..., :3]) ** 2)
+        return {"psnr": -10.0 * torch.log10(mse)}
+
+    def mae_thermal(self, gt: Tensor, pred: Tensor, threshold: Optional[float] = None) -> Tensor:
+        """thermal_metrics.py:5-34."""
+        if threshold:
+            idx = torch.where(gt < threshold) if self.config.cold else torch.where(gt > threshold)
+            gt, pred = gt[idx], pred[idx]
+        span = self.max_temperature - self.min_temperature
+        return torch.mean(torch.abs((gt * span + self.min_temperature) - (pred * span + self.min_temperature)))
