@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""Benchmark of the ThermoNeRF volumetric-render hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (libtnf_b200.so)
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: the path's own
+                                                             # PyTorch implementation (oracle port)
+                                                             # on the box's host cores
+
+One "step" = one pass of the hot path over one batch of synthetic ThermoScenes-shaped rays:
+  --mode render : one 800x800 frame (640 000 rays) through get_outputs_for_camera_ray_bundle
+                  (BASELINE.json configs[4]; metric render Mpix/s, 1 ray = 1 pixel)
+Weights are random "trained-like" (no datasets/checkpoints offline); data is synthetic.
+Prints ONE JSON line on rank 0 (contract in the task statement).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+HW = 800
+FOCAL = 1111.1
+NUM_IMAGES = 100
+ALGO_BYTES_PER_RAY = 161_876  # fp32 hash-gather bytes (161 792) + ray I/O (84)
+ALGO_FLOP_PER_RAY = 1.709e6
+
+
+def env_int(name: str, default: int) -> int:
+    return int(os.environ.get(name, default))
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int) -> None:
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self) -> None:
+        try:
+            f = tempfile.NamedTemporaryFile(prefix="tnf_clocks_", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1]))
+                    mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------- model / data
+def randomise_trained_like(model, seed: int = 0) -> None:
+    """Synthetic 'trained-like' weights: N(0, 0.5^2) hash entries and sharpened density heads so
+    that the proposal PDFs are peaked (samples cluster as they do around real surfaces)."""
+    g = torch.Generator().manual_seed(seed + 1234)
+    with torch.no_grad():
+        encs = [model.field.mlp_base.encoder] + [p.encoding for p in model.proposal_networks]
+        for enc in encs:
+            enc.hash_table.copy_(torch.randn(enc.hash_table.shape, generator=g) * 0.5)
+        for p in model.proposal_networks:
+            p.mlp_base[1].layers[1].weight.mul_(6.0)
+        model.field.mlp_base.mlp.layers[1].weight[0].mul_(6.0)
+
+
+def build_b200_model(device, precision: str):
+    from thermo_nerf_b200 import ThermalNerfModel, ThermalNerfModelConfig
+
+    torch.manual_seed(0)
+    cfg = ThermalNerfModelConfig(precision=precision)
+    model = ThermalNerfModel(cfg, {"thermal": []}, torch.tensor([[-1.0, -1, -1], [1, 1, 1]]), NUM_IMAGES)
+    randomise_trained_like(model, 0)
+    return model.to(device).eval()
+
+
+def frame_bundles(n_frames: int, device, rank: int, world: int):
+    """Distinct orbit frames; rank r renders frames r, r+world, ... (frames shard with no collective)."""
+    from thermo_nerf_b200 import orbit_cameras
+
+    cams = orbit_cameras(max(n_frames * world, 1), hw=HW, focal=FOCAL, device=device)
+    return [cams.generate_rays(rank + i * world) for i in range(n_frames)]
+
+
+class L2Flusher:
+    def __init__(self, device, nbytes: int = 256 << 20) -> None:
+        self.buf = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+
+    def __call__(self) -> None:
+        self.buf.fill_(1.0)
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args, rank: int, world: int) -> None:
+    """The path's own PyTorch implementation (nerfstudio torch semantics; oracle port since
+    nerfstudio is not installable offline) on the host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle import OracleConfig, OracleThermalNerf, make_synthetic_rays
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample = args.ref_rays
+    model = OracleThermalNerf(OracleConfig(), NUM_IMAGES, seed=0)
+    randomise_trained_like(model, 0)
+    rays = make_synthetic_rays(sample, num_images=NUM_IMAGES, seed=1, contiguous_pixels=True)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            model.get_outputs(rays, training=False)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            model.get_outputs(rays, training=False)
+        dt = time.perf_counter() - t0
+    mpix = sample * args.steps / dt / 1e6
+    desc = f"{sample} contiguous rays of an 800x800 frame per step, eval forward, fp32, torch {torch.__version__}"
+    line = {
+        "impl": "reference", "metric": "render_mpix_per_s", "value": mpix, "unit": "Mpix/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "render 800x800 ThermoScenes-shaped frame, eval chunk 65536, samples 256/96/48",
+                   "sample": desc},
+        "cpu_baseline": {"value": mpix, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": mpix, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="render", choices=["render"])
+    ap.add_argument("--precision", default="tc_fp16", choices=["tc_fp16", "fp32"])
+    ap.add_argument("--ref-rays", type=int, default=4096, help="rays per step of the CPU reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-cuda-baseline", action="store_true",
+                    help="opt-in context number: the PyTorch restatement run eagerly on the GPU")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl b200) needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    from thermo_nerf_b200 import RayBundle
+
+    model = build_b200_model(device, args.precision)
+    n_distinct = 4
+    bundles = frame_bundles(n_distinct, device, rank, world)
+    flush = L2Flusher(device)
+    rays_per_step = HW * HW
+    out_keys = ("rgb", "thermal", "depth", "accumulation")
+
+    def step(i: int):
+        return model.get_outputs_for_camera_ray_bundle(bundles[i % n_distinct])
+
+    # ---- device-resident throughput ("value")
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local)
+    sampler.start()
+    for i in range(args.steps):
+        flush()
+        evs[i][0].record()
+        step(i)
+        evs[i][1].record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs))
+    ms_per_step = ms_total / args.steps
+    value = world * rays_per_step / (ms_per_step * 1e-3) / 1e6
+
+    # ---- dominant kernel alone (roofline): tnf_render_forward on device-resident flat rays
+    from thermo_nerf_b200 import functional as F
+    from thermo_nerf_b200 import _lib as L
+
+    flat = bundles[0].flatten()
+    o, d = flat.origins.contiguous(), flat.directions.contiguous()
+    kw = dict(near_plane=0.0, far_plane=1000.0, appearance_mode=L.APPEARANCE_MEAN,
+              precision=L.PRECISION_FP32 if args.precision == "fp32" else L.PRECISION_TC_FP16,
+              depth_clip_chunk=1 << 16)
+    for _ in range(3):
+        F.render_forward(model.tensors(), o, d, **kw)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+    for a, b in kev:
+        flush()
+        a.record()
+        F.render_forward(model.tensors(), o, d, **kw)
+        b.record()
+    torch.cuda.synchronize()
+    k_ms = sum(a.elapsed_time(b) for a, b in kev) / len(kev)
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = rays_per_step * ALGO_BYTES_PER_RAY / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "forward_traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.load(open(tp)).get(args.precision, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "tnf_forward_kernel", "kernel_ms": k_ms, "peak_source": peak_src,
+                "algorithmic_bytes_per_ray": ALGO_BYTES_PER_RAY,
+                "note": "tables (74 MiB fp32) are L2-resident, so DRAM traffic is far below algorithmic gather bytes"}
+
+    # ---- end to end through the public API with HOST buffers (pinned) in the timed region
+    host_in = []
+    for b in bundles:
+        f = b.flatten()
+        host_in.append((f.origins.cpu().pin_memory(), f.directions.cpu().pin_memory(),
+                        f.camera_indices.cpu().pin_memory()))
+    host_out = {k: torch.empty((HW, HW, 3 if k == "rgb" else 1), dtype=torch.float32).pin_memory() for k in out_keys}
+    h2d = sum(t.numel() * t.element_size() for t in host_in[0])
+    d2h = sum(t.numel() * t.element_size() for t in host_out.values())
+
+    def e2e_step(i: int):
+        ho, hd, hc = host_in[i % n_distinct]
+        rb = RayBundle(origins=ho.to(device, non_blocking=True).view(HW, HW, 3),
+                       directions=hd.to(device, non_blocking=True).view(HW, HW, 3),
+                       camera_indices=hc.to(device, non_blocking=True).view(HW, HW, 1))
+        out = model.get_outputs_for_camera_ray_bundle(rb)
+        for k in out_keys:
+            host_out[k].copy_(out[k], non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller consumes the frame on the host
+
+    for i in range(args.warmup):
+        e2e_step(i)
+    barrier()
+    t_e2e = 0.0
+    for i in range(args.steps):
+        flush()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e2e_step(i)
+        t_e2e += time.perf_counter() - t0
+    barrier()
+    t_e2e = max_over_ranks(t_e2e)
+    e2e_val = world * rays_per_step * args.steps / t_e2e / 1e6
+
+    line = {
+        "metric": "render_mpix_per_s", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "fp32 hash/sampling/compositing" + (" + fp16-operand/fp32-accumulate mma field MLPs"
+                                                      if args.precision == "tc_fp16" else " + fp32 MLPs"),
+        "data": "synthetic",
+        "config": {"workload": "render 800x800 ThermoScenes-shaped frame per step (640000 rays, samples 256/96/48, "
+                               "eval chunk 65536), rgb+thermal+depth+accumulation in one pass; frames shard "
+                               "round-robin over ranks, no collective",
+                   "l2": "flushed between timed iterations (256 MiB write)", "rays_per_second": value * 1e6,
+                   "weights": "random trained-like, full-size tables (field 2^19x16, proposals 2^17x5)"},
+        "clocks": clocks, "gpu_launches": 2 * args.steps,
+        "e2e": {"value": e2e_val, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "note": "pinned host rays -> H2D -> get_outputs_for_camera_ray_bundle -> D2H rgb/thermal/depth/acc"},
+        "roofline": roofline,
+    }
+
+    if rank == 0 and world == 1 and args.torch_cuda_baseline:
+        line["torch_cuda_baseline"] = torch_cuda_baseline(device)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args.ref_rays)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(sample: int) -> dict:
+    from oracle import OracleConfig, OracleThermalNerf, make_synthetic_rays
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = OracleThermalNerf(OracleConfig(), NUM_IMAGES, seed=0)
+    randomise_trained_like(model, 0)
+    rays = make_synthetic_rays(sample, num_images=NUM_IMAGES, seed=1, contiguous_pixels=True)
+    with torch.no_grad():
+        model.get_outputs(rays, training=False)
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            model.get_outputs(rays, training=False)
+        dt = (time.perf_counter() - t0) / reps
+    return {"value": sample / dt / 1e6, "unit": "Mpix/s", "cores": cores, "kind": "port",
+            "sample": f"{sample} contiguous rays of an 800x800 frame, eval forward fp32, oracle port on CPU, "
+                      f"{reps} reps"}
+
+
+def torch_cuda_baseline(device) -> dict:
+    """Context only (not the reference arm): the same PyTorch restatement run eagerly on the GPU =
+    what a stock install of the reference executes on CUDA (tinycudann absent from uv.lock)."""
+    from oracle import OracleConfig, OracleRays, OracleThermalNerf, make_synthetic_rays
+
+    try:
+        model = OracleThermalNerf(OracleConfig(), NUM_IMAGES, seed=0)
+        randomise_trained_like(model, 0)
+        model = model.to(device)
+        r = make_synthetic_rays(1 << 16, num_images=NUM_IMAGES, seed=1, contiguous_pixels=True)
+        rays = OracleRays(r.origins.to(device), r.directions.to(device), r.camera_indices.to(device))
+        with torch.no_grad():
+            for _ in range(2):
+                model.get_outputs(rays, training=False)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            reps = 5
+            for _ in range(reps):
+                model.get_outputs(rays, training=False)
+            b.record()
+            torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        return {"value": (1 << 16) / (ms * 1e-3) / 1e6, "unit": "Mpix/s", "kind": "oracle port, eager PyTorch on cuda, fp32",
+                "sample": "one 65536-ray eval chunk"}
+    except Exception as e:  # context only: never fail the bench on it
+        return {"error": repr(e)[:200]}
+
+
+if __name__ == "__main__":
+    main()

@@ -201,9 +201,9 @@ class _ThermalField(nn.Module):
         if training:
             app = self.embedding_appearance(camera_indices)
         elif cfg.use_average_appearance_embedding:
-            app = torch.ones((*shape, cfg.appearance_embed_dim)) * self.embedding_appearance.mean(dim=0)
+            app = torch.ones((*shape, cfg.appearance_embed_dim), device=directions.device) * self.embedding_appearance.mean(dim=0)
         else:
-            app = torch.zeros((*shape, cfg.appearance_embed_dim))
+            app = torch.zeros((*shape, cfg.appearance_embed_dim), device=directions.device)
         h = torch.cat([d, geo.reshape(-1, cfg.geo_feat_dim), app.reshape(-1, cfg.appearance_embed_dim)], dim=-1)
         rgb = self.mlp_head(h).view(*shape, -1)
         th_in = geo.reshape(-1, cfg.geo_feat_dim)
@@ -276,7 +276,7 @@ class OracleThermalNerf(nn.Module):
         to_euclid = M.make_spacing_to_euclid(nears, fars)
         n_prop = len(cfg.num_proposal_samples_per_ray)
         if training and jitter is None:
-            jitter = torch.rand((n_prop + 1, R, 1))
+            jitter = torch.rand((n_prop + 1, R, 1), device=rays.origins.device)
 
         weights_list: List[Tensor] = []
         sdist_list: List[Tensor] = []
@@ -288,7 +288,7 @@ class OracleThermalNerf(nn.Module):
             S = cfg.num_proposal_samples_per_ray[lvl] if is_prop else cfg.num_nerf_samples_per_ray
             tr = jitter[lvl] if training else None
             if lvl == 0:
-                sbins = M.piecewise_initial_bins(R, S, tr)
+                sbins = M.piecewise_initial_bins(R, S, tr, device=rays.origins.device)
             else:
                 annealed = torch.pow(weights, self.anneal)
                 sbins = M.pdf_resample_bins(annealed[..., 0], sbins, S, tr)

@@ -1,0 +1,109 @@
+"""The C-ABI library loads without a GPU, exports every symbol include/tnf_b200.h declares,
+its ctypes mirror has the same struct layout as the C header, and argument validation
+works before any CUDA call.  No compute calls here."""
+
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = ROOT / "include" / "tnf_b200.h"
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+
+    g.build()
+    from thermo_nerf_b200 import _lib
+
+    return _lib.load()
+
+
+def declared_symbols():
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    return sorted(set(re.findall(r"\b(tnf_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    from thermo_nerf_b200 import _lib
+
+    syms = declared_symbols()
+    assert syms, "no declarations found in the header"
+    assert sorted(_lib.EXPORTED_SYMBOLS) == syms
+    for s in syms:
+        assert hasattr(lib, s), s
+
+
+def test_abi_version_and_error_string(lib):
+    assert lib.tnf_version() == 1
+    assert isinstance(lib.tnf_last_error(), bytes)
+
+
+def test_ctypes_layout_matches_c_header(tmp_path):
+    from thermo_nerf_b200 import _lib
+
+    names = ["TnfHashGrid", "TnfLinear", "TnfDensityNet", "TnfField", "TnfModel", "TnfRays", "TnfOutputs"]
+    probes = {
+        "TnfModel": ["field", "num_samples", "training", "near_plane", "anneal", "use_contraction", "aabb",
+                     "appearance_mode", "precision"],
+        "TnfField": ["grid", "base0", "th2", "appearance", "num_images"],
+        "TnfRays": ["jitter", "num_rays"],
+        "TnfOutputs": ["prop_depth", "weights", "sdist"],
+        "TnfHashGrid": ["scalings", "num_levels", "log2_size"],
+    }
+    src = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
+    for n in names:
+        src.append(f'printf("{n} %zu\\n", sizeof({n}));')
+        for f in probes.get(n, []):
+            src.append(f'printf("{n}.{f} %zu\\n", offsetof({n}, {f}));')
+    src.append("return 0;}")
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-o", str(exe), str(c)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    for line in out.strip().splitlines():
+        key, val = line.split()
+        if "." in key:
+            s, f = key.split(".")
+            assert getattr(getattr(_lib, s), f).offset == int(val), key
+        else:
+            assert C.sizeof(getattr(_lib, key)) == int(val), key
+
+
+def test_workspace_size(lib):
+    assert lib.tnf_forward_workspace_bytes(0, 0) >= 8
+    assert lib.tnf_forward_workspace_bytes(640000, 65536) >= 2 * 10 * 4
+    assert lib.tnf_forward_workspace_bytes(100, 0) >= 8
+
+
+def test_argument_validation_happens_before_any_cuda_call(lib):
+    from thermo_nerf_b200 import _lib
+
+    m, r, o = _lib.TnfModel(), _lib.TnfRays(), _lib.TnfOutputs()
+    rc = lib.tnf_render_forward(C.byref(m), C.byref(r), C.byref(o), 0, None, 0, None)
+    assert rc == _lib.TNF_ERR_INVALID_ARGUMENT
+    assert b"null" in lib.tnf_last_error()
+    rc = lib.tnf_render_forward(None, C.byref(r), C.byref(o), 0, None, 0, None)
+    assert rc == _lib.TNF_ERR_INVALID_ARGUMENT
+    # unsupported architecture is reported as such
+    for k in range(2):
+        m.prop[k].grid.table = 16
+        m.prop[k].grid.num_levels = 99
+    rc = lib.tnf_render_forward(C.byref(m), C.byref(r), C.byref(o), 0, None, 0, None)
+    assert rc == _lib.TNF_ERR_UNSUPPORTED_CONFIG
+    with pytest.raises(_lib.TnfError):
+        _lib.check(rc)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from thermo_nerf_b200 import _lib
+
+    monkeypatch.setenv("TNF_B200_LIB", str(tmp_path / "nope.so"))
+    monkeypatch.setattr(_lib, "_LIB", None)
+    with pytest.raises(ImportError):
+        _lib.load()

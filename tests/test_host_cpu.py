@@ -1,0 +1,139 @@
+"""Host-side mirror of the reference plugin surface (no GPU): constructor/error behaviour,
+state-dict key compatibility with the oracle/nerfstudio tree, param groups, training
+callbacks, ray-bundle shim, and that the product path refuses to run off-GPU."""
+
+import pytest
+import torch
+
+from tests.helpers import make_pair
+
+
+def small_pair(**kw):
+    return make_pair(device="cpu", log2_field=10, log2_prop=8, num_images=4, **kw)
+
+
+def test_constructor_raises_without_thermal_metadata():
+    from thermo_nerf_b200 import ThermalNerfModel, ThermalNerfModelConfig
+
+    with pytest.raises(ValueError, match="Thermal images not found"):
+        ThermalNerfModel(ThermalNerfModelConfig(log2_hashmap_size=8), {}, torch.tensor([[-1.0, -1, -1], [1, 1, 1]]), 4)
+
+
+def test_config_target_round_trip():
+    from thermo_nerf_b200 import ThermalNerfModel, ThermalNerfModelConfig
+
+    cfg = ThermalNerfModelConfig(log2_hashmap_size=8,
+                                 proposal_net_args_list=[{"hidden_dim": 16, "log2_hashmap_size": 8, "num_levels": 5,
+                                                          "max_res": 128, "use_linear": False}])
+    m = cfg.setup(metadata={"thermal": []}, scene_box=torch.tensor([[-1.0, -1, -1], [1, 1, 1]]), num_train_data=3)
+    assert isinstance(m, ThermalNerfModel)
+    assert m.max_temperature == 1.0 and m.min_temperature == 0.0
+    assert m.field.pass_rgb_gradients is True and m.field.pass_thermal_gradients is True
+    assert m.config.num_proposal_iterations == 2
+
+
+def test_state_dict_keys_match_reference_tree():
+    oracle, model = small_pair()
+    ok = set(oracle.state_dict().keys())
+    mk = set(model.state_dict().keys())
+    assert mk - ok == {"device_indicator_param"}
+    assert ok - mk == set()
+    # the names a nerfstudio-trained ThermoNeRF checkpoint carries after its `_model.` prefix
+    for k in ("field.mlp_base.encoder.hash_table", "field.mlp_base.mlp.layers.1.weight",
+              "field.mlp_head.layers.2.bias", "field.mlp_thermal.layers.0.weight",
+              "field.field_head_thermal.net.weight", "field.embedding_appearance.embedding.weight",
+              "proposal_networks.0.encoding.hash_table", "proposal_networks.1.mlp_base.1.layers.0.weight",
+              "camera_optimizer.pose_adjustment"):
+        assert k in mk, k
+
+
+def test_param_groups_and_callbacks():
+    _, model = small_pair()
+    groups = model.get_param_groups()
+    assert set(groups) == {"proposal_networks", "fields", "camera_opt"}
+    n = sum(p.numel() for g in groups.values() for p in g)
+    assert n == sum(p.numel() for p in model.parameters())  # nothing but the empty device indicator is left out
+    cbs = model.get_training_callbacks()
+    assert len(cbs) == 2
+    before = [c for c in cbs if c.where_to_run == ["BEFORE_TRAIN_ITERATION"]][0]
+    before.run_callback(0)
+    assert model._anneal == 0.0
+    before.run_callback(500)
+    assert model._anneal == pytest.approx(10 * 0.5 / (9 * 0.5 + 1))
+    before.run_callback(5000)
+    assert model._anneal == pytest.approx(1.0)
+    assert model.update_schedule(0) == 1 and model.update_schedule(5000) == 5 and model.update_schedule(2500) == 2.5
+
+
+def test_unsupported_configurations_are_rejected():
+    from thermo_nerf_b200 import ThermalNerfModel, ThermalNerfModelConfig
+
+    box = torch.tensor([[-1.0, -1, -1], [1, 1, 1]])
+    for kw in (dict(predict_normals=True), dict(num_levels=8), dict(hidden_dim=32), dict(background_color="black"),
+               dict(use_same_proposal_network=True), dict(proposal_initial_sampler="uniform")):
+        with pytest.raises(ValueError):
+            ThermalNerfModel(ThermalNerfModelConfig(log2_hashmap_size=8, **kw), {"thermal": []}, box, 2)
+
+
+def test_parameter_containers_have_no_torch_fallback():
+    _, model = small_pair()
+    with pytest.raises(RuntimeError, match="no PyTorch fallback"):
+        model.field(torch.zeros(1, 3))
+    with pytest.raises(RuntimeError, match="no PyTorch fallback"):
+        model.proposal_networks[0](torch.zeros(1, 3))
+
+
+def test_get_outputs_on_cpu_fails_loudly():
+    from thermo_nerf_b200 import RayBundle
+
+    _, model = small_pair()
+    rb = RayBundle(origins=torch.zeros(4, 3), directions=torch.ones(4, 3),
+                   camera_indices=torch.zeros(4, 1, dtype=torch.int64))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        model.get_outputs(rb)
+
+
+def test_camera_optimizer_matches_oracle():
+    from oracle import OracleRays
+
+    oracle, model = small_pair()
+    o = torch.randn(16, 3)
+    d = torch.nn.functional.normalize(torch.randn(16, 3), dim=-1)
+    cam = torch.randint(0, 4, (16, 1))
+    a = OracleRays(o.clone(), d.clone(), cam)
+    oracle.camera_optimizer.apply_to_raybundle(a)
+    from thermo_nerf_b200 import RayBundle
+
+    b = RayBundle(origins=o.clone(), directions=d.clone(), camera_indices=cam)
+    model.camera_optimizer.apply_to_raybundle(b)
+    assert torch.allclose(a.origins, b.origins, atol=1e-6) and torch.allclose(a.directions, b.directions, atol=1e-6)
+
+
+def test_ray_bundle_shim_and_pinhole_cameras():
+    from thermo_nerf_b200 import orbit_cameras
+
+    cams = orbit_cameras(3, hw=8, focal=10.0)
+    rb = cams.generate_rays(2)
+    assert rb.shape == (8, 8) and rb.origins.shape == (8, 8, 3) and rb.camera_indices.shape == (8, 8, 1)
+    assert torch.allclose(rb.directions.norm(dim=-1), torch.ones(8, 8), atol=1e-6)
+    assert int(rb.camera_indices[0, 0, 0]) == 2
+    # centre ray looks at the origin
+    centre = rb.directions[3:5, 3:5].mean(dim=(0, 1))
+    to_origin = -rb.origins[0, 0] / rb.origins[0, 0].norm()
+    assert torch.dot(centre / centre.norm(), to_origin) > 0.999
+    flat = rb.flatten()
+    assert len(flat) == 64 and flat.get_row_major_sliced_ray_bundle(8, 24).origins.shape == (16, 3)
+    assert flat.reshape((8, 8)).directions.shape == (8, 8, 3)
+
+
+def test_model_tensors_validate_architecture():
+    from thermo_nerf_b200 import ModelTensors
+
+    _, model = small_pair()
+    t = ModelTensors.from_module(model)
+    assert t.field_grid.num_levels == 16 and t.field_grid.log2_size == 10
+    assert [g.log2_size for g in t.prop_grids] == [8, 8]
+    assert t.field_grid.scalings[-1] == 2047.0
+    model.field.mlp_head.layers[0] = torch.nn.Linear(10, 64)
+    with pytest.raises(ValueError, match="fixed architecture"):
+        ModelTensors.from_module(model)

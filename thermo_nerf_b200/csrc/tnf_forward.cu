@@ -194,6 +194,12 @@ struct RayCtx {
   float s_near, s_far;
 };
 
+// frustums.get_positions(): origins + directions * (starts + ends) / 2, rounded like ATen (separate
+// multiply and add, no FMA contraction) so that the discontinuous selector sees the same point.
+__device__ __forceinline__ float ray_x(const RayCtx& rc, float mid) { return __fadd_rn(rc.ox, __fmul_rn(rc.dx, mid)); }
+__device__ __forceinline__ float ray_y(const RayCtx& rc, float mid) { return __fadd_rn(rc.oy, __fmul_rn(rc.dy, mid)); }
+__device__ __forceinline__ float ray_z(const RayCtx& rc, float mid) { return __fadd_rn(rc.oz, __fmul_rn(rc.dz, mid)); }
+
 __device__ __forceinline__ void sample_geometry(const RayCtx& rc, float s0, float s1, float& mid, float& delta) {
   const float t0 = to_euclid(s0, rc.s_near, rc.s_far);
   const float t1 = to_euclid(s1, rc.s_near, rc.s_far);
@@ -249,8 +255,7 @@ __device__ __forceinline__ float proposal_level(const TnfModel& m, const PropW& 
     float mid, delta;
     sample_geometry(rc, sb(ii), sb(ii + 1), mid, delta);
     float px, py, pz;
-    const float sel = normalise_position(m, fmaf(rc.dx, mid, rc.ox), fmaf(rc.dy, mid, rc.oy),
-                                         fmaf(rc.dz, mid, rc.oz), px, py, pz);
+    const float sel = normalise_position(m, ray_x(rc, mid), ray_y(rc, mid), ray_z(rc, mid), px, py, pz);
     float feat[2 * TNF_MAX_PROP_LEVELS];
 #pragma unroll
     for (int l = 0; l < TNF_MAX_PROP_LEVELS; ++l) {
@@ -401,8 +406,7 @@ __device__ __forceinline__ void field_level(const TnfModel& m, Smem<TNF_PRECISIO
     float mid, delta;
     sample_geometry(rc, ws.w[ii], ws.w[ii + 1], mid, delta);
     float px, py, pz;
-    const float sel = normalise_position(m, fmaf(rc.dx, mid, rc.ox), fmaf(rc.dy, mid, rc.oy),
-                                         fmaf(rc.dz, mid, rc.oz), px, py, pz);
+    const float sel = normalise_position(m, ray_x(rc, mid), ray_y(rc, mid), ray_z(rc, mid), px, py, pz);
 #pragma unroll 4
     for (int l = 0; l < TNF_MAX_LEVELS; ++l) {
       const float2 f = hash_level(tab + ((size_t)l << grid.log2_size), px, py, pz, grid.scalings[l], mask);
@@ -506,8 +510,7 @@ __device__ __forceinline__ void field_level(const TnfModel& m, Smem<TNF_PRECISIO
       const int ii = min(h ? r1 : r0, S2 - 1);
       float mid, delta;
       sample_geometry(rc, ws.w[ii], ws.w[ii + 1], mid, delta);
-      sel[h] = normalise_position(m, fmaf(rc.dx, mid, rc.ox), fmaf(rc.dy, mid, rc.oy), fmaf(rc.dz, mid, rc.oz),
-                                  p[h][0], p[h][1], p[h][2]);
+      sel[h] = normalise_position(m, ray_x(rc, mid), ray_y(rc, mid), ray_z(rc, mid), p[h][0], p[h][1], p[h][2]);
     }
     // hash encode straight into A-fragment layout: this lane owns levels q, q+4, q+8, q+12
     uint32_t a0[2][4];
