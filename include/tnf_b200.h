@@ -26,6 +26,9 @@
  *                           built at thermal_nerf_model.py:182-184.
  *   tnf_render_backward  <- autograd of the same function as driven by
  *                           get_loss_dict, thermal_nerf_model.py:277-326.
+ *   tnf_losses           <- ThermalNerfModel.get_loss_dict, thermal_nerf_model.py:277-326
+ *                           (rgb MSE :295-296, interlevel :298-301, distortion :303-305,
+ *                           thermal MSE :319-324).
  *   tnf_adam_step        <- the Adam optimisers configured at
  *                           thermo_nerf/thermal_nerf/config_thermal_nerf.py:32-45.
  */
@@ -39,7 +42,7 @@
 extern "C" {
 #endif
 
-#define TNF_ABI_VERSION 1
+#define TNF_ABI_VERSION 2
 
 #define TNF_MAX_LEVELS 16      /* hash levels of the field grid (fixed: 16)          */
 #define TNF_MAX_PROP_LEVELS 8  /* max hash levels of a proposal density grid          */
@@ -118,6 +121,9 @@ typedef struct TnfModel {
   float aabb[6];           /* min xyz, max xyz (only for use_contraction == 0)                */
   int32_t appearance_mode; /* TnfAppearanceMode                                               */
   int32_t precision;       /* TnfPrecision                                                    */
+  int32_t detach_thermal_geo; /* 1: pass_thermal_gradients == False (thermal_field.py:173-175): the
+                                 thermal head's gradient stops at the geo feature                */
+  int32_t _pad;
 } TnfModel;
 
 typedef struct TnfRays {
@@ -140,6 +146,10 @@ typedef struct TnfOutputs {
   /* optional (NULL to skip) - the training-only outputs of get_outputs: */
   float* weights[TNF_NUM_PROP + 1]; /* weights_list[k]           [R, S_k]                   */
   float* sdist[TNF_NUM_PROP + 1];   /* spacing bins of level k   [R, S_k + 1]               */
+  /* optional (NULL to skip) - saved for tnf_render_backward: */
+  void* field_features;  /* [R*S_2, 32] hash features of the field samples; fp32 for
+                            TNF_PRECISION_FP32, fp16 for TNF_PRECISION_TC_FP16                 */
+  float* field_samples;  /* [R*S_2, 5] per-sample field outputs (sigma, r, g, b, thermal)      */
 } TnfOutputs;
 
 /* ABI version of the loaded library (== TNF_ABI_VERSION of the header it was built from). */
@@ -161,6 +171,111 @@ size_t tnf_forward_workspace_bytes(int64_t num_rays, int64_t depth_clip_chunk);
 int tnf_render_forward(const TnfModel* model, const TnfRays* rays, const TnfOutputs* out,
                        int64_t depth_clip_chunk, void* workspace, size_t workspace_bytes,
                        void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Training: backward of tnf_render_forward, the losses of get_loss_dict, Adam.
+ * ------------------------------------------------------------------------------------ */
+
+/* Gradient buffers, same shapes as the parameters.  Every entry point ACCUMULATES (+=)
+ * into them; the caller zeroes them (tnf_adam_step can do so after consuming them). */
+typedef struct TnfLinearGrad {
+  float* weight;
+  float* bias;
+} TnfLinearGrad;
+
+typedef struct TnfDensityNetGrad {
+  float* table; /* NULL: skip this proposal level entirely (the reference's no_grad steps,
+                   ProposalNetworkSampler `updated == False`) */
+  TnfLinearGrad l0;
+  TnfLinearGrad l1;
+} TnfDensityNetGrad;
+
+typedef struct TnfFieldGrad {
+  float* table;
+  TnfLinearGrad base0, base1, rgb0, rgb1, rgb2, th0, th1, th2;
+  float* appearance; /* [num_images, 32]; may be NULL unless TNF_APPEARANCE_LOOKUP */
+} TnfFieldGrad;
+
+typedef struct TnfModelGrad {
+  TnfDensityNetGrad prop[TNF_NUM_PROP];
+  TnfFieldGrad field;
+} TnfModelGrad;
+
+/* What tnf_render_forward wrote in training mode (same pointers as in TnfOutputs). */
+typedef struct TnfSaved {
+  const float* sdist[TNF_NUM_PROP + 1];
+  const float* weights[TNF_NUM_PROP + 1];
+  const void* field_features;
+  const float* field_samples;
+} TnfSaved;
+
+/* dLoss/dOutput; any pointer may be NULL (= zero gradient). */
+typedef struct TnfOutputGrads {
+  const float* rgb;                     /* [R,3] */
+  const float* thermal;                 /* [R]   */
+  const float* accumulation;            /* [R]   */
+  const float* weights[TNF_NUM_PROP + 1]; /* [R,S_k]: from the interlevel (k<2) and distortion (k=2) losses */
+} TnfOutputGrads;
+
+size_t tnf_backward_workspace_bytes(const TnfModel* model, int64_t num_rays);
+
+/* Backward of tnf_render_forward w.r.t. every parameter (sample positions are detached
+ * as in PDFSampler; depth outputs carry no gradient).  `model` and `rays` must be the
+ * ones of the forward call (same jitter). */
+int tnf_render_backward(const TnfModel* model, const TnfRays* rays, const TnfSaved* saved,
+                        const TnfOutputGrads* gout, const TnfModelGrad* grads, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* get_loss_dict (thermal_nerf_model.py:277-326) + the inherited distortion metric:
+ *   losses[0] rgb_loss        = MSE(gt_rgb, rgb)                       (if use_rgb_loss)
+ *   losses[1] interlevel_loss = interlevel_mult * sum_k mean(outer-measure loss of level k)
+ *   losses[2] distortion_loss = distortion_mult * mean_r(distortion of the final level)
+ *   losses[3] thermal         = MSE(thermal, gt_thermal)               (if use_thermal_loss)
+ * and, when the g_* pointers are non-NULL, d(loss_i)/d(input) * grad_scale for the one
+ * loss each input feeds (rgb <- 0, weights[0..1] <- 1, weights[2] <- 2, thermal <- 3).
+ * `losses` (4 floats, device) is overwritten. */
+typedef struct TnfLossArgs {
+  const float* weights[TNF_NUM_PROP + 1];
+  const float* sdist[TNF_NUM_PROP + 1];
+  const float* rgb;        /* [R,3] */
+  const float* thermal;    /* [R]   */
+  const float* gt_rgb;     /* [R,3] */
+  const float* gt_thermal; /* [R]   */
+  int64_t num_rays;
+  int32_t num_samples[TNF_NUM_PROP + 1];
+  float interlevel_mult;
+  float distortion_mult;
+  int32_t use_rgb_loss;
+  int32_t use_thermal_loss;
+  float grad_scale;
+  float* losses;                       /* [4] */
+  float* g_rgb;                        /* [R,3] or NULL */
+  float* g_thermal;                    /* [R]   or NULL */
+  float* g_weights[TNF_NUM_PROP + 1];  /* [R,S_k] or NULL */
+} TnfLossArgs;
+
+int tnf_losses(const TnfLossArgs* args, void* stream);
+
+/* torch.optim.Adam (amsgrad=False, weight_decay=0, maximize=False) over a list of tensors
+ * in ONE launch.  grad is first multiplied by inv_grad_scale (host value) and, if grad_scale
+ * (device float, may be NULL) is given, divided by *grad_scale; if found_inf (device float,
+ * may be NULL) is non-zero the update is skipped (torch.amp.GradScaler protocol of optimisers
+ * with _step_supports_amp_scaling); with zero_grads != 0 the gradients are zeroed after use
+ * (also on a skipped step). */
+#define TNF_ADAM_MAX_TENSORS 48
+typedef struct TnfAdamTensor {
+  float* param;
+  float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t numel;
+  float lr;
+  int32_t _pad;
+} TnfAdamTensor;
+
+int tnf_adam_step(const TnfAdamTensor* tensors, int32_t num_tensors, float beta1, float beta2, float eps,
+                  int64_t step, float inv_grad_scale, const float* grad_scale, const float* found_inf,
+                  int32_t zero_grads, void* stream);
 
 #ifdef __cplusplus
 }

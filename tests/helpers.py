@@ -55,6 +55,7 @@ def make_pair(log2_field=15, log2_prop=12, num_images=8, seed=0, trained_like=Tr
         disable_scene_contraction=not contraction,
         use_average_appearance_embedding=cfg.use_average_appearance_embedding,
         camera_optimizer_mode=cfg.camera_optimizer_mode,
+        pass_thermal_gradients=cfg.pass_thermal_gradients,
         precision=precision,
     )
     model = ThermalNerfModel(mcfg, {"thermal": []}, torch.tensor([[-1.0, -1, -1], [1, 1, 1]]), num_images)

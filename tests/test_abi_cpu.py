@@ -39,20 +39,30 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_abi_version_and_error_string(lib):
-    assert lib.tnf_version() == 1
+    from thermo_nerf_b200 import _lib
+
+    assert lib.tnf_version() == _lib.TNF_ABI_VERSION == 2
     assert isinstance(lib.tnf_last_error(), bytes)
 
 
 def test_ctypes_layout_matches_c_header(tmp_path):
     from thermo_nerf_b200 import _lib
 
-    names = ["TnfHashGrid", "TnfLinear", "TnfDensityNet", "TnfField", "TnfModel", "TnfRays", "TnfOutputs"]
+    names = ["TnfHashGrid", "TnfLinear", "TnfDensityNet", "TnfField", "TnfModel", "TnfRays", "TnfOutputs",
+             "TnfLinearGrad", "TnfDensityNetGrad", "TnfFieldGrad", "TnfModelGrad", "TnfSaved", "TnfOutputGrads",
+             "TnfLossArgs", "TnfAdamTensor"]
     probes = {
         "TnfModel": ["field", "num_samples", "training", "near_plane", "anneal", "use_contraction", "aabb",
-                     "appearance_mode", "precision"],
+                     "appearance_mode", "precision", "detach_thermal_geo"],
         "TnfField": ["grid", "base0", "th2", "appearance", "num_images"],
         "TnfRays": ["jitter", "num_rays"],
-        "TnfOutputs": ["prop_depth", "weights", "sdist"],
+        "TnfOutputs": ["prop_depth", "weights", "sdist", "field_features", "field_samples"],
+        "TnfModelGrad": ["field"],
+        "TnfFieldGrad": ["th2", "appearance"],
+        "TnfSaved": ["weights", "field_features", "field_samples"],
+        "TnfOutputGrads": ["accumulation", "weights"],
+        "TnfLossArgs": ["num_rays", "num_samples", "interlevel_mult", "grad_scale", "losses", "g_weights"],
+        "TnfAdamTensor": ["numel", "lr"],
         "TnfHashGrid": ["scalings", "num_levels", "log2_size"],
     }
     src = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
@@ -107,3 +117,26 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "_LIB", None)
     with pytest.raises(ImportError):
         _lib.load()
+
+
+def test_training_entry_points_validate_arguments(lib):
+    from thermo_nerf_b200 import _lib
+
+    rc = lib.tnf_losses(None, None)
+    assert rc == _lib.TNF_ERR_INVALID_ARGUMENT
+    a = _lib.TnfLossArgs()
+    rc = lib.tnf_losses(C.byref(a), None)
+    assert rc == _lib.TNF_ERR_INVALID_ARGUMENT and b"losses" in lib.tnf_last_error()
+    rc = lib.tnf_adam_step(None, 3, 0.9, 0.999, 1e-15, 1, 1.0, None, None, 0, None)
+    assert rc == _lib.TNF_ERR_INVALID_ARGUMENT
+    rc = lib.tnf_adam_step(None, 0, 0.9, 0.999, 1e-15, 1, 1.0, None, None, 0, None)
+    assert rc == _lib.TNF_OK  # nothing to do
+    t = (_lib.TnfAdamTensor * 1)()
+    t[0].param = t[0].grad = t[0].exp_avg = t[0].exp_avg_sq = 256
+    t[0].numel = 16
+    rc = lib.tnf_adam_step(t, 1, 0.9, 0.999, 1e-15, 0, 1.0, None, None, 0, None)
+    assert rc == _lib.TNF_ERR_INVALID_ARGUMENT and b"step" in lib.tnf_last_error()
+    m, r = _lib.TnfModel(), _lib.TnfRays()
+    rc = lib.tnf_render_backward(C.byref(m), C.byref(r), None, None, None, None, 0, None)
+    assert rc == _lib.TNF_ERR_INVALID_ARGUMENT
+    assert lib.tnf_backward_workspace_bytes(None, 10) >= 16

@@ -1,0 +1,243 @@
+"""GPU parity tests of the training path: tnf_losses, tnf_render_backward (through the autograd node)
+and tnf_adam_step against the CPU oracle's autograd / torch.optim.Adam on identical inputs.
+
+Tolerances:
+* losses: 1e-5 relative (fp32 both sides; summation order differs)
+* gradients, precision="fp32": per-tensor rel-L2 error <= 2e-3 (atomics reorder fp32 sums;
+  the oracle's autograd runs the same math on the CPU)
+* gradients, precision="tc_fp16" (fp16 forward operands, bf16 backward operands, fp32 accumulate):
+  per-tensor rel-L2 <= 5e-2 and cosine >= 0.998 against the fp32 oracle
+* Adam: 1e-6 relative after 5 steps
+"""
+
+import pytest
+import torch
+
+from oracle import OracleRays, make_synthetic_rays
+from oracle import nerfstudio_math as M
+from tests.helpers import make_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def _train_pair(precision="fp32", R=192, seed=21, **kw):
+    oracle, model = make_pair(trained_like=True, precision=precision, log2_field=12, log2_prop=10,
+                              camera_optimizer_mode="off", **kw)
+    rays = make_synthetic_rays(R, num_images=8, seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    jitter = torch.rand((3, R, 1), generator=g)
+    gt_rgb = torch.rand((R, 3), generator=g)
+    gt_th = torch.rand((R, 1), generator=g)
+    return oracle, model, rays, jitter, gt_rgb, gt_th
+
+
+def _oracle_grads(oracle, rays, jitter, gt_rgb, gt_th, anneal, mults, prop_grad=True):
+    oracle.anneal = anneal
+    oracle.cfg.interlevel_loss_mult, oracle.cfg.distortion_loss_mult = mults
+    oracle.zero_grad()
+    out = oracle.get_outputs(rays, training=True, jitter=jitter, prop_grad=prop_grad)
+    ld = oracle.get_loss_dict(out, gt_rgb, gt_th, training=True)
+    sum(ld.values()).backward()
+    return out, ld, {k: (p.grad.clone() if p.grad is not None else None) for k, p in oracle.named_parameters()}
+
+
+def _ours(model, rays, jitter, gt_rgb, gt_th, anneal, mults, prop_grad=True):
+    from thermo_nerf_b200 import functional as F
+    from thermo_nerf_b200 import _lib as L
+
+    model.train()
+    model.zero_grad()
+    prec = L.PRECISION_FP32 if model.config.precision == "fp32" else L.PRECISION_TC_FP16
+    out = F.render(model.tensors(), rays.origins.cuda(), rays.directions.cuda(), rays.camera_indices.cuda(),
+                   None, None, jitter.cuda().reshape(3, -1), prop_grad=prop_grad, num_samples=(256, 96, 48),
+                   near_plane=0.05, far_plane=1000.0, anneal=anneal, appearance_mode=L.APPEARANCE_LOOKUP,
+                   precision=prec)
+    ld = F.losses(out, gt_rgb.cuda(), gt_th.cuda(), interlevel_mult=mults[0], distortion_mult=mults[1])
+    sum(ld.values()).backward()
+    torch.cuda.synchronize()
+    return out, ld, {k: (p.grad.detach().cpu() if p.grad is not None else None) for k, p in model.named_parameters()}
+
+
+def _rel_l2(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
+
+
+def test_losses_and_their_gradients_match_oracle():
+    from thermo_nerf_b200 import functional as F
+
+    oracle, model, rays, jitter, gt_rgb, gt_th = _train_pair()
+    with torch.no_grad():
+        out = oracle.get_outputs(rays, training=True, jitter=jitter)
+    w = [x.detach().clone().requires_grad_(True) for x in out["weights_list"]]
+    rgb = out["rgb"].detach().clone().requires_grad_(True)
+    th = out["thermal"].detach().clone().requires_grad_(True)
+    ref = {
+        "rgb_loss": torch.nn.functional.mse_loss(gt_rgb, rgb),
+        "interlevel_loss": 1.0 * M.interlevel_loss(w, out["sdist_list"]),
+        "distortion_loss": 0.5 * M.distortion_loss(w, out["sdist_list"]),
+        "thermal": torch.nn.functional.mse_loss(th, gt_th),
+    }
+    sum(ref.values()).backward()
+    losses, g = F.losses_forward_backward([x.detach().cuda() for x in w], [s.cuda() for s in out["sdist_list"]],
+                                          rgb.detach().cuda(), th.detach().cuda(), gt_rgb.cuda(), gt_th.cuda(),
+                                          interlevel_mult=1.0, distortion_mult=0.5)
+    torch.cuda.synchronize()
+    for i, k in enumerate(F.LOSS_NAMES):
+        assert losses[i].item() == pytest.approx(ref[k].item(), rel=1e-5, abs=1e-9), k
+    assert _rel_l2(g["rgb"].cpu(), rgb.grad) <= 1e-5
+    assert _rel_l2(g["thermal"].cpu(), th.grad.reshape(-1)) <= 1e-5
+    for k in range(3):
+        assert _rel_l2(g["weights_list"][k].cpu(), w[k].grad[..., 0]) <= 2e-4, k
+
+
+@pytest.mark.parametrize("anneal", [1.0, 0.35])
+def test_backward_fp32_matches_oracle_autograd(anneal):
+    oracle, model, rays, jitter, gt_rgb, gt_th = _train_pair("fp32")
+    mults = (1.0, 0.5)  # a distortion weight large enough for its gradient to matter in the comparison
+    o_out, o_ld, o_g = _oracle_grads(oracle, rays, jitter, gt_rgb, gt_th, anneal, mults)
+    out, ld, g = _ours(model, rays, jitter, gt_rgb, gt_th, anneal, mults)
+    for k in o_ld:
+        assert ld[k].item() == pytest.approx(o_ld[k].item(), rel=2e-3, abs=1e-7), k
+    checked = 0
+    for k, ref in o_g.items():
+        if k.startswith("camera_optimizer"):
+            continue
+        assert g[k] is not None, k
+        if ref is None or ref.norm() == 0:
+            assert g[k].abs().max().item() <= 1e-7, k
+            continue
+        err = _rel_l2(g[k], ref)
+        assert err <= 2e-3, (k, err)
+        checked += 1
+    assert checked >= 27
+
+
+def test_backward_without_proposal_update_step():
+    """ProposalNetworkSampler `updated == False`: proposal nets get no gradient at all."""
+    oracle, model, rays, jitter, gt_rgb, gt_th = _train_pair("fp32", R=64)
+    _, _, o_g = _oracle_grads(oracle, rays, jitter, gt_rgb, gt_th, 1.0, (1.0, 0.002), prop_grad=False)
+    _, _, g = _ours(model, rays, jitter, gt_rgb, gt_th, 1.0, (1.0, 0.002), prop_grad=False)
+    for k, v in g.items():
+        if k.startswith("proposal_networks"):
+            assert v is None and o_g[k] is None, k
+    assert _rel_l2(g["field.mlp_base.encoder.hash_table"], o_g["field.mlp_base.encoder.hash_table"]) <= 2e-3
+
+
+def test_detached_thermal_gradients():
+    """pass_thermal_gradients=False (thermal_field.py:173-175): the thermal head does not move the trunk."""
+    oracle, model, rays, jitter, gt_rgb, gt_th = _train_pair("fp32", R=64, pass_thermal_gradients=False)
+    from thermo_nerf_b200 import functional as F
+    from thermo_nerf_b200 import _lib as L
+
+    oracle.zero_grad()
+    out = oracle.get_outputs(rays, training=True, jitter=jitter)
+    torch.nn.functional.mse_loss(out["thermal"], gt_th).backward()
+    ref = {k: p.grad for k, p in oracle.named_parameters()}
+    model.train()
+    model.zero_grad()
+    o = F.render(model.tensors(), rays.origins.cuda(), rays.directions.cuda(), rays.camera_indices.cuda(), None, None,
+                 jitter.cuda().reshape(3, -1), near_plane=0.05, appearance_mode=L.APPEARANCE_LOOKUP,
+                 precision=L.PRECISION_FP32, detach_thermal_geo=True)
+    torch.nn.functional.mse_loss(o["thermal"], gt_th.cuda()).backward()
+    torch.cuda.synchronize()
+    g = {k: p.grad for k, p in model.named_parameters()}
+    assert _rel_l2(g["field.mlp_thermal.layers.0.weight"].cpu(), ref["field.mlp_thermal.layers.0.weight"]) <= 2e-3
+    assert _rel_l2(g["field.field_head_thermal.net.weight"].cpu(), ref["field.field_head_thermal.net.weight"]) <= 2e-3
+    # the density still reaches the trunk through the weights; the oracle says how much
+    assert _rel_l2(g["field.mlp_base.mlp.layers.1.weight"].cpu(), ref["field.mlp_base.mlp.layers.1.weight"]) <= 2e-3
+
+
+def test_backward_tensor_core_matches_oracle_autograd():
+    oracle, model, rays, jitter, gt_rgb, gt_th = _train_pair("tc_fp16", R=256)
+    mults = (1.0, 0.5)
+    _, o_ld, o_g = _oracle_grads(oracle, rays, jitter, gt_rgb, gt_th, 1.0, mults)
+    _, ld, g = _ours(model, rays, jitter, gt_rgb, gt_th, 1.0, mults)
+    for k in o_ld:
+        assert ld[k].item() == pytest.approx(o_ld[k].item(), rel=3e-2, abs=1e-5), k
+    for k, ref in o_g.items():
+        if k.startswith("camera_optimizer") or ref is None or ref.norm() == 0:
+            continue
+        err = _rel_l2(g[k], ref)
+        cos = torch.nn.functional.cosine_similarity(g[k].flatten(), ref.flatten(), dim=0).item()
+        assert err <= 5e-2 and cos >= 0.998, (k, err, cos)
+
+
+def test_adam_matches_torch_adam():
+    from thermo_nerf_b200 import FusedAdam
+
+    g = torch.Generator().manual_seed(3)
+    shapes = [(5 * 1024 + 3, 2), (64, 63), (1,), (4096 * 3,)]
+    ps = [torch.randn(s, generator=g).cuda() for s in shapes]
+    a = [p.clone().requires_grad_(True) for p in ps]
+    b = [p.clone().requires_grad_(True) for p in ps]
+    oa = FusedAdam(a, lr=1e-2, eps=1e-15)
+    ob = torch.optim.Adam(b, lr=1e-2, eps=1e-15)
+    for step in range(5):
+        for x, y in zip(a, b):
+            gr = torch.randn(x.shape, generator=g).cuda() * (10.0 ** (step - 3))
+            x.grad, y.grad = gr.clone(), gr.clone()
+        oa.step()
+        ob.step()
+    torch.cuda.synchronize()
+    for x, y in zip(a, b):
+        assert torch.allclose(x, y, rtol=1e-6, atol=1e-7), (x - y).abs().max()
+        assert torch.allclose(oa.state[x]["exp_avg_sq"], ob.state[y]["exp_avg_sq"], rtol=1e-6, atol=1e-12)
+
+
+def test_adam_grad_scaler_protocol_and_skip():
+    from thermo_nerf_b200 import functional as F
+
+    p = torch.ones(5000, device="cuda")
+    gr = torch.full((5000,), 64.0, device="cuda")
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    F.adam_step([p], [gr], [m], [v], [0.1], step=1, grad_scale=torch.tensor([64.0], device="cuda"),
+                found_inf=torch.zeros(1, device="cuda"), zero_grads=True)
+    torch.cuda.synchronize()
+    assert torch.allclose(p, torch.full_like(p, 0.9), atol=1e-6)  # first Adam step moves by lr * sign(g)
+    assert gr.abs().max().item() == 0.0
+    gr.fill_(float("inf"))
+    F.adam_step([p], [gr], [m], [v], [0.1], step=2, found_inf=torch.ones(1, device="cuda"), zero_grads=True)
+    torch.cuda.synchronize()
+    assert torch.allclose(p, torch.full_like(p, 0.9), atol=1e-6)  # skipped
+    assert gr.abs().max().item() == 0.0  # but the gradients were consumed
+
+
+def test_model_api_training_steps_reduce_loss():
+    """Plugin surface end to end: model(ray_bundle) -> get_metrics_dict -> get_loss_dict -> backward ->
+    FusedAdam, with the training callbacks; the loss on a fixed batch must go down."""
+    from thermo_nerf_b200 import FusedAdam, RayBundle
+
+    _, model = make_pair(trained_like=False, precision="tc_fp16", log2_field=14, log2_prop=12)
+    model.train()
+    rays = make_synthetic_rays(1024, num_images=8, seed=5)
+    gen = torch.Generator().manual_seed(1)
+    batch = {"image": torch.rand((1024, 3), generator=gen).mul(0.2).add(0.4).cuda(),
+             "thermal": torch.rand((1024, 1), generator=gen).mul(0.2).add(0.6)}  # thermal GT stays on the host
+    groups = model.get_param_groups()
+    opts = [FusedAdam(groups["proposal_networks"], lr=1e-2, eps=1e-15),
+            FusedAdam(groups["fields"], lr=1e-2, eps=1e-15)]
+    cbs = model.get_training_callbacks()
+    first = last = None
+    for step in range(30):
+        for c in cbs:
+            if c.where_to_run == ["BEFORE_TRAIN_ITERATION"]:
+                c.run_callback(step)
+        rb = RayBundle(origins=rays.origins.cuda(), directions=rays.directions.cuda(),
+                       camera_indices=rays.camera_indices.cuda())
+        for o in opts:
+            o.zero_grad()
+        out = model(rb)
+        metrics = model.get_metrics_dict(out, batch)
+        ld = model.get_loss_dict(out, batch, metrics)
+        assert set(ld) == {"rgb_loss", "interlevel_loss", "distortion_loss", "thermal"}
+        loss = sum(ld.values())
+        loss.backward()
+        for o in opts:
+            o.step()
+        for c in cbs:
+            if c.where_to_run == ["AFTER_TRAIN_ITERATION"]:
+                c.run_callback(step)
+        val = (ld["rgb_loss"] + ld["thermal"]).item()
+        first = val if first is None else first
+        last = val
+    assert last < 0.5 * first, (first, last)

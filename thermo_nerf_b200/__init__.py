@@ -6,14 +6,15 @@ binding of ``include/tnf_b200.h``), ``functional`` (tensor-level entry points),
 """
 
 from . import _lib
-from .functional import ModelTensors, render_forward
+from .functional import ModelTensors, adam_step, losses, render, render_forward
 from .model import ThermalNerfModel, ThermalNerfModelConfig
+from .optim import FusedAdam
 from .modules import (CameraOptimizer, FieldHeadNames, FieldHeadNamesT, HashMLPDensityField, ThermalFieldHead,
                       ThermalNerfactoTField)
 from .rays import PinholeCameras, RayBundle, orbit_cameras
 
 __all__ = [
-    "ModelTensors", "render_forward", "ThermalNerfModel", "ThermalNerfModelConfig", "CameraOptimizer",
+    "ModelTensors", "render_forward", "render", "losses", "adam_step", "FusedAdam", "ThermalNerfModel", "ThermalNerfModelConfig", "CameraOptimizer",
     "FieldHeadNames", "FieldHeadNamesT", "HashMLPDensityField", "ThermalFieldHead", "ThermalNerfactoTField",
     "PinholeCameras", "RayBundle", "orbit_cameras",
 ]

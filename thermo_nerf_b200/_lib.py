@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 from typing import Optional
 
-TNF_ABI_VERSION = 1
+TNF_ABI_VERSION = 2
 TNF_MAX_LEVELS = 16
 TNF_MAX_PROP_LEVELS = 8
 TNF_MAX_SAMPLES = 256
@@ -77,6 +77,8 @@ class TnfModel(C.Structure):
         ("aabb", C.c_float * 6),
         ("appearance_mode", C.c_int32),
         ("precision", C.c_int32),
+        ("detach_thermal_geo", C.c_int32),
+        ("_pad", C.c_int32),
     ]
 
 
@@ -102,6 +104,90 @@ class TnfOutputs(C.Structure):
         ("prop_depth", _fp * TNF_NUM_PROP),
         ("weights", _fp * (TNF_NUM_PROP + 1)),
         ("sdist", _fp * (TNF_NUM_PROP + 1)),
+        ("field_features", _fp),
+        ("field_samples", _fp),
+    ]
+
+
+class TnfLinearGrad(C.Structure):
+    _fields_ = [("weight", _fp), ("bias", _fp)]
+
+
+class TnfDensityNetGrad(C.Structure):
+    _fields_ = [("table", _fp), ("l0", TnfLinearGrad), ("l1", TnfLinearGrad)]
+
+
+class TnfFieldGrad(C.Structure):
+    _fields_ = [
+        ("table", _fp),
+        ("base0", TnfLinearGrad),
+        ("base1", TnfLinearGrad),
+        ("rgb0", TnfLinearGrad),
+        ("rgb1", TnfLinearGrad),
+        ("rgb2", TnfLinearGrad),
+        ("th0", TnfLinearGrad),
+        ("th1", TnfLinearGrad),
+        ("th2", TnfLinearGrad),
+        ("appearance", _fp),
+    ]
+
+
+class TnfModelGrad(C.Structure):
+    _fields_ = [("prop", TnfDensityNetGrad * TNF_NUM_PROP), ("field", TnfFieldGrad)]
+
+
+class TnfSaved(C.Structure):
+    _fields_ = [
+        ("sdist", _fp * (TNF_NUM_PROP + 1)),
+        ("weights", _fp * (TNF_NUM_PROP + 1)),
+        ("field_features", _fp),
+        ("field_samples", _fp),
+    ]
+
+
+class TnfOutputGrads(C.Structure):
+    _fields_ = [
+        ("rgb", _fp),
+        ("thermal", _fp),
+        ("accumulation", _fp),
+        ("weights", _fp * (TNF_NUM_PROP + 1)),
+    ]
+
+
+class TnfLossArgs(C.Structure):
+    _fields_ = [
+        ("weights", _fp * (TNF_NUM_PROP + 1)),
+        ("sdist", _fp * (TNF_NUM_PROP + 1)),
+        ("rgb", _fp),
+        ("thermal", _fp),
+        ("gt_rgb", _fp),
+        ("gt_thermal", _fp),
+        ("num_rays", C.c_int64),
+        ("num_samples", C.c_int32 * (TNF_NUM_PROP + 1)),
+        ("interlevel_mult", C.c_float),
+        ("distortion_mult", C.c_float),
+        ("use_rgb_loss", C.c_int32),
+        ("use_thermal_loss", C.c_int32),
+        ("grad_scale", C.c_float),
+        ("losses", _fp),
+        ("g_rgb", _fp),
+        ("g_thermal", _fp),
+        ("g_weights", _fp * (TNF_NUM_PROP + 1)),
+    ]
+
+
+TNF_ADAM_MAX_TENSORS = 48
+
+
+class TnfAdamTensor(C.Structure):
+    _fields_ = [
+        ("param", _fp),
+        ("grad", _fp),
+        ("exp_avg", _fp),
+        ("exp_avg_sq", _fp),
+        ("numel", C.c_int64),
+        ("lr", C.c_float),
+        ("_pad", C.c_int32),
     ]
 
 
@@ -111,6 +197,10 @@ EXPORTED_SYMBOLS = (
     "tnf_last_error",
     "tnf_forward_workspace_bytes",
     "tnf_render_forward",
+    "tnf_backward_workspace_bytes",
+    "tnf_render_backward",
+    "tnf_losses",
+    "tnf_adam_step",
 )
 
 
@@ -156,6 +246,35 @@ def load() -> C.CDLL:
         C.c_int64,
         C.c_void_p,
         C.c_size_t,
+        C.c_void_p,
+    ]
+    lib.tnf_backward_workspace_bytes.restype = C.c_size_t
+    lib.tnf_backward_workspace_bytes.argtypes = [C.POINTER(TnfModel), C.c_int64]
+    lib.tnf_render_backward.restype = C.c_int
+    lib.tnf_render_backward.argtypes = [
+        C.POINTER(TnfModel),
+        C.POINTER(TnfRays),
+        C.POINTER(TnfSaved),
+        C.POINTER(TnfOutputGrads),
+        C.POINTER(TnfModelGrad),
+        C.c_void_p,
+        C.c_size_t,
+        C.c_void_p,
+    ]
+    lib.tnf_losses.restype = C.c_int
+    lib.tnf_losses.argtypes = [C.POINTER(TnfLossArgs), C.c_void_p]
+    lib.tnf_adam_step.restype = C.c_int
+    lib.tnf_adam_step.argtypes = [
+        C.POINTER(TnfAdamTensor),
+        C.c_int32,
+        C.c_float,
+        C.c_float,
+        C.c_float,
+        C.c_int64,
+        C.c_float,
+        C.c_void_p,
+        C.c_void_p,
+        C.c_int32,
         C.c_void_p,
     ]
     got = lib.tnf_version()

@@ -1,0 +1,825 @@
+// Backward of ThermalNerfModel.get_outputs (thermo_nerf/thermal_nerf/thermal_nerf_model.py:210-275)
+// as driven by get_loss_dict (:277-326), for sm_100a.
+//
+//   tnf_backward_prop_kernel   the two HashMLPDensityField proposal levels (:127-148): re-gather the
+//                              hash features, 10->16->1 MLP forward + backward in fp32, table scatter,
+//                              the 193 weight gradients accumulated in registers (lane owns a slot)
+//   tnf_backward_field_kernel  ThermalNerfactoTField (thermal_field.py:108-201): compositing backward
+//                              (suffix scans), field MLPs recomputed from the saved hash features,
+//                              dX chain, hash-grid scatter with vector reductions (REDG.F32x2), and
+//                              the per-layer (X, dY) rows staged for the weight-gradient GEMMs
+//   tnf_wgrad_kernel           dW = dY^T X, split-K over the samples (K = R*48): the one genuinely
+//                              dense contraction of the step; bf16 mma.sync with fp32 accumulate
+//                              (TC mode) or fp32 FFMA (fp32 mode)
+//
+// Sample positions are constants here: PDFSampler detaches its bins and this build does not
+// propagate into ray origins/directions (camera optimiser), see DESIGN.md.
+#include <cuda_bf16.h>
+
+#include "tnf_field.cuh"
+#include "tnf_host.h"
+
+namespace tnf {
+
+// ------------------------------------------------------------------------------------
+// staging layout of the field backward (element type T = float | __nv_bfloat16)
+// ------------------------------------------------------------------------------------
+struct BwdLayout {
+  // per sample rows [Ns, width]
+  unsigned char *XF, *XH, *XG, *XA1, *XA2, *XB1, *XB2;   // layer inputs
+  unsigned char *dH, *dG, *dGeo, *dA2, *dZ, *dB2, *dT;   // pre-activation gradients
+  // per ray rows
+  unsigned char *XRay, *dRay;                            // [R,48] sh|appearance, [R,64] sum_s dA1pre
+};
+constexpr int kWXF = 32, kWXH = 64, kWXG = 16, kWX = 64, kWdGeo = 128, kWdZ = 8, kWdT = 8, kWXRay = 48, kWdRay = 64;
+
+__host__ inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+// Carves the staging tensors out of `base` (or only sizes them when L == nullptr).
+__host__ inline size_t make_layout(BwdLayout* L, unsigned char* base, long long Ns, long long R, size_t es,
+                                   bool own_xf) {
+  size_t off = 0;
+  auto take = [&](unsigned char* BwdLayout::*field, long long rows, int width) {
+    if (L) L->*field = base + off;
+    off += align256((size_t)rows * width * es);
+  };
+  if (own_xf) take(&BwdLayout::XF, Ns, kWXF);
+  take(&BwdLayout::XH, Ns, kWXH);
+  take(&BwdLayout::XG, Ns, kWXG);
+  take(&BwdLayout::XA1, Ns, kWX);
+  take(&BwdLayout::XA2, Ns, kWX);
+  take(&BwdLayout::XB1, Ns, kWX);
+  take(&BwdLayout::XB2, Ns, kWX);
+  take(&BwdLayout::dH, Ns, kWX);
+  take(&BwdLayout::dG, Ns, kWXG);
+  take(&BwdLayout::dGeo, Ns, kWdGeo);
+  take(&BwdLayout::dA2, Ns, kWX);
+  take(&BwdLayout::dZ, Ns, kWdZ);
+  take(&BwdLayout::dB2, Ns, kWX);
+  take(&BwdLayout::dT, Ns, kWdT);
+  take(&BwdLayout::XRay, R, kWXRay);
+  take(&BwdLayout::dRay, R, kWdRay);
+  return off;
+}
+
+// ------------------------------------------------------------------------------------
+// hash-grid scatter: transpose of hash_level (same corner order / weights as hash_blend)
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void scatter_level(float2* __restrict__ gtab, float px, float py, float pz, float scale,
+                                              uint32_t mask, float gx, float gy) {
+  if (gx == 0.f && gy == 0.f) return;
+  HashCorners hc;
+  hash_corners(px, py, pz, scale, mask, hc);
+  const float ox = hc.ox, oy = hc.oy, oz = hc.oz, ix = 1.f - ox, iy = 1.f - oy, iz = 1.f - oz;
+  const float w[8] = {ox * oy * oz, ox * iy * oz, ix * iy * oz, ix * oy * oz,
+                      ox * oy * iz, ox * iy * iz, ix * iy * iz, ix * oy * iz};
+#pragma unroll
+  for (int c = 0; c < 8; ++c) atomicAdd(gtab + hc.idx[c], make_float2(w[c] * gx, w[c] * gy));
+}
+
+// reverse (suffix) exclusive scan helper over one 32-wide chunk: returns sum_{j>lane} v_j
+__device__ __forceinline__ float warp_suffix_excl(float v, int lane, float& total) {
+  const float rv = __shfl_sync(kFull, v, 31 - lane);
+  const float incl = warp_incl_scan(rv, lane);
+  total = __shfl_sync(kFull, incl, 31);
+  return __shfl_sync(kFull, incl, 31 - lane) - v;
+}
+
+// ------------------------------------------------------------------------------------
+// proposal levels
+// ------------------------------------------------------------------------------------
+constexpr int kPropRow = 51;    // dh(16) | do | feat(16) | 1 | relu(h)(16)  (+ pad to an odd stride)
+constexpr int kPropSlots = 10;  // ceil((16*16 + 33) / 32)
+
+struct PropBwdScratch {
+  float bins[kBuf];
+  float gw[kBuf];
+  float P[kBuf];  // saved weights, then suffix sums of gw*w
+  float stage[32 * kPropRow];
+};
+
+struct PropBwdSmem {
+  PropW prop[TNF_NUM_PROP];
+  PropBwdScratch ws[kWarpsPerCta];
+};
+
+struct SlotMap {
+  int ia[kPropSlots], ib[kPropSlots];
+  int nslots;
+};
+__device__ __forceinline__ void make_slots(SlotMap& sm, int K2, int lane) {
+  const int total = 16 * K2 + 33;
+  sm.nslots = (total + 31) / 32;
+#pragma unroll
+  for (int r = 0; r < kPropSlots; ++r) {
+    const int t = lane + 32 * r;
+    int ia = 50, ib = 50;  // both point at the zeroed pad column -> contributes 0
+    if (t < 16 * K2) { ia = t / K2; ib = 17 + t % K2; }
+    else if (t < 16 * K2 + 16) { ia = t - 16 * K2; ib = 33; }
+    else if (t < 16 * K2 + 32) { ia = 16; ib = 34 + (t - 16 * K2 - 16); }
+    else if (t == 16 * K2 + 32) { ia = 16; ib = 33; }
+    sm.ia[r] = ia;
+    sm.ib[r] = ib;
+  }
+}
+__device__ __forceinline__ void flush_slots(const SlotMap& sm, const float (&acc)[kPropSlots], int K2, int lane,
+                                            const TnfDensityNetGrad& g) {
+#pragma unroll
+  for (int r = 0; r < kPropSlots; ++r) {
+    const int t = lane + 32 * r;
+    if (acc[r] == 0.f) continue;
+    if (t < 16 * K2) atomicAdd(g.l0.weight + t, acc[r]);  // [16, K2] row-major: j*K2 + k == t
+    else if (t < 16 * K2 + 16) atomicAdd(g.l0.bias + (t - 16 * K2), acc[r]);
+    else if (t < 16 * K2 + 32) atomicAdd(g.l1.weight + (t - 16 * K2 - 16), acc[r]);
+    else if (t == 16 * K2 + 32) atomicAdd(g.l1.bias, acc[r]);
+  }
+}
+
+template <int LVL>
+__device__ __forceinline__ void prop_backward_level(const TnfModel& m, const PropW& W, PropBwdScratch& ws,
+                                                    const RayCtx& rc, const int S, const int lane,
+                                                    const float* __restrict__ sdist, const float* __restrict__ wsaved,
+                                                    const float* __restrict__ gw, float2* __restrict__ gtab,
+                                                    const SlotMap& sm, float (&acc)[kPropSlots]) {
+  const TnfDensityNet& net = m.prop[LVL];
+  const int L = net.grid.num_levels;
+  const uint32_t mask = (1u << net.grid.log2_size) - 1u;
+  const float2* __restrict__ tab = reinterpret_cast<const float2*>(net.grid.table);
+  for (int i = lane; i <= S; i += 32) ws.bins[i] = sdist[i];
+  for (int i = lane; i < S; i += 32) {
+    ws.gw[i] = gw[i];
+    ws.P[i] = wsaved[i];
+  }
+  __syncwarp();
+  // P_i = sum_{j>i} gw_j * w_j  (chunks visited from the far end)
+  {
+    float carry = 0.f;
+    for (int base = ((S - 1) / 32) * 32; base >= 0; base -= 32) {
+      const int i = base + lane;
+      const float v = i < S ? ws.gw[i] * ws.P[i] : 0.f;
+      float tot;
+      const float ex = warp_suffix_excl(v, lane, tot);
+      __syncwarp();
+      if (i < S) ws.P[i] = ex + carry;
+      carry += tot;
+    }
+    __syncwarp();
+  }
+  float carry = 0.f;  // sum of delta*sigma of previous chunks
+  for (int base = 0; base < S; base += 32) {
+    const int i = base + lane;
+    const bool active = i < S;
+    const int ii = active ? i : S - 1;
+    float mid, delta;
+    sample_geometry(rc, ws.bins[ii], ws.bins[ii + 1], mid, delta);
+    float px, py, pz;
+    const float sel = normalise_position(m, ray_x(rc, mid), ray_y(rc, mid), ray_z(rc, mid), px, py, pz);
+    float feat[2 * TNF_MAX_PROP_LEVELS];
+#pragma unroll
+    for (int l = 0; l < TNF_MAX_PROP_LEVELS; ++l) {
+      float2 f = make_float2(0.f, 0.f);
+      if (l < L) f = hash_level(tab + ((size_t)l << net.grid.log2_size), px, py, pz, net.grid.scalings[l], mask);
+      feat[2 * l] = f.x;
+      feat[2 * l + 1] = f.y;
+    }
+    float h[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) h[j] = W.b0[j];
+#pragma unroll
+    for (int k = 0; k < 2 * TNF_MAX_PROP_LEVELS; ++k) {
+      if (k < 2 * L) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) h[j] = fmaf(feat[k], W.w0t[k * 16 + j], h[j]);
+      }
+    }
+    float o = W.b1;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o = fmaf(fmaxf(h[j], 0.f), W.w1[j], o);
+    const float density = expf(o) * sel;
+    const float ds = active ? delta * density : 0.f;
+    const float incl = warp_incl_scan(ds, lane);
+    float excl = __shfl_up_sync(kFull, incl, 1);
+    if (lane == 0) excl = 0.f;
+    const float T = expf(-(carry + excl));
+    const float w = (1.f - expf(-ds)) * T;
+    carry += __shfl_sync(kFull, incl, 31);
+    // d loss / d (delta*sigma), then through density = trunc_exp(o) * selector
+    float d_o = 0.f;
+    if (active) {
+      const float dds = ws.gw[i] * (T - w) - ws.P[i];
+      d_o = dds * delta * expf(fminf(fmaxf(o, -15.f), 15.f)) * sel;
+    }
+    float* row = ws.stage + lane * kPropRow;
+    float dfeat[2 * TNF_MAX_PROP_LEVELS];
+#pragma unroll
+    for (int k = 0; k < 2 * TNF_MAX_PROP_LEVELS; ++k) dfeat[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float dh = h[j] > 0.f ? d_o * W.w1[j] : 0.f;
+      row[j] = dh;
+      row[34 + j] = fmaxf(h[j], 0.f);
+#pragma unroll
+      for (int k = 0; k < 2 * TNF_MAX_PROP_LEVELS; ++k)
+        if (k < 2 * L) dfeat[k] = fmaf(dh, W.w0t[k * 16 + j], dfeat[k]);
+    }
+    row[16] = d_o;
+    row[33] = 1.f;
+    row[50] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) row[17 + k] = k < 2 * TNF_MAX_PROP_LEVELS ? feat[k] : 0.f;
+    if (d_o != 0.f) {
+#pragma unroll
+      for (int l = 0; l < TNF_MAX_PROP_LEVELS; ++l)
+        if (l < L)
+          scatter_level(gtab + ((size_t)l << net.grid.log2_size), px, py, pz, net.grid.scalings[l], mask,
+                        dfeat[2 * l], dfeat[2 * l + 1]);
+    }
+    __syncwarp();
+    // weight gradients: lane owns up to kPropSlots (a,b) column pairs, summed over the 32 staged rows
+    for (int s = 0; s < 32; ++s) {
+      const float* r_ = ws.stage + s * kPropRow;
+#pragma unroll
+      for (int r = 0; r < kPropSlots; ++r)
+        if (r < sm.nslots) acc[r] = fmaf(r_[sm.ia[r]], r_[sm.ib[r]], acc[r]);
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+    tnf_backward_prop_kernel(const __grid_constant__ TnfModel m, const __grid_constant__ TnfRays rays,
+                             const __grid_constant__ TnfSaved sv, const __grid_constant__ TnfOutputGrads go,
+                             const __grid_constant__ TnfModelGrad gr) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PropBwdSmem& S = *reinterpret_cast<PropBwdSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  stage_prop(S.prop[0], m.prop[0], tid);
+  stage_prop(S.prop[1], m.prop[1], tid);
+  __syncthreads();
+  PropBwdScratch& ws = S.ws[warp];
+  const int S0 = m.num_samples[0], S1 = m.num_samples[1];
+  const bool do0 = gr.prop[0].table != nullptr && go.weights[0] != nullptr;
+  const bool do1 = gr.prop[1].table != nullptr && go.weights[1] != nullptr;
+  SlotMap sm0, sm1;
+  make_slots(sm0, 2 * m.prop[0].grid.num_levels, lane);
+  make_slots(sm1, 2 * m.prop[1].grid.num_levels, lane);
+  float acc0[kPropSlots], acc1[kPropSlots];
+#pragma unroll
+  for (int r = 0; r < kPropSlots; ++r) acc0[r] = acc1[r] = 0.f;
+  const long long R = rays.num_rays;
+  for (long long ray = (long long)blockIdx.x * kWarpsPerCta + warp; ray < R;
+       ray += (long long)gridDim.x * kWarpsPerCta) {
+    RayCtx rc;
+    rc.ox = __ldg(rays.origins + ray * 3 + 0);
+    rc.oy = __ldg(rays.origins + ray * 3 + 1);
+    rc.oz = __ldg(rays.origins + ray * 3 + 2);
+    rc.dx = __ldg(rays.directions + ray * 3 + 0);
+    rc.dy = __ldg(rays.directions + ray * 3 + 1);
+    rc.dz = __ldg(rays.directions + ray * 3 + 2);
+    rc.s_near = spacing_fn(rays.nears ? __ldg(rays.nears + ray) : m.near_plane);
+    rc.s_far = spacing_fn(rays.fars ? __ldg(rays.fars + ray) : m.far_plane);
+    if (do0)
+      prop_backward_level<0>(m, S.prop[0], ws, rc, S0, lane, sv.sdist[0] + ray * (S0 + 1), sv.weights[0] + ray * S0,
+                             go.weights[0] + ray * S0, reinterpret_cast<float2*>(gr.prop[0].table), sm0, acc0);
+    if (do1)
+      prop_backward_level<1>(m, S.prop[1], ws, rc, S1, lane, sv.sdist[1] + ray * (S1 + 1), sv.weights[1] + ray * S1,
+                             go.weights[1] + ray * S1, reinterpret_cast<float2*>(gr.prop[1].table), sm1, acc1);
+  }
+  if (do0) flush_slots(sm0, acc0, 2 * m.prop[0].grid.num_levels, lane, gr.prop[0]);
+  if (do1) flush_slots(sm1, acc1, 2 * m.prop[1].grid.num_levels, lane, gr.prop[1]);
+}
+
+// ------------------------------------------------------------------------------------
+// field level: shared per-ray prologue (compositing backward)
+// ------------------------------------------------------------------------------------
+struct FieldBwdScratch {
+  float bins[kMaxFieldS + 8];
+  float dsig[kMaxFieldS];  // dL/d sigma_i
+  float dzr[kMaxFieldS], dzg[kMaxFieldS], dzb[kMaxFieldS];  // dL/d (pre-sigmoid colour)
+  float dtau[kMaxFieldS];  // dL/d thermal_i
+  float T[kMaxFieldS], w[kMaxFieldS], gw[kMaxFieldS];
+  float rayb[64];
+};
+
+// RGBRenderer / ThermalRenderer (background "last_sample"), AccumulationRenderer and get_weights,
+// differentiated: fills dsig, dz*, dtau for the S2 samples of one ray.
+__device__ __forceinline__ void composite_backward(const TnfModel& m, FieldBwdScratch& ws, const RayCtx& rc,
+                                                   const int S2, const int lane, const float* __restrict__ fs,
+                                                   const float* __restrict__ g_w2, const float gr_, const float gg_,
+                                                   const float gb_, const float gth, const float gacc) {
+  // pass 1: weights and transmittance from the saved densities
+  float carry = 0.f, sw = 0.f;
+  for (int base = 0; base < S2; base += 32) {
+    const int i = base + lane;
+    const bool active = i < S2;
+    const int ii = active ? i : S2 - 1;
+    float mid, delta;
+    sample_geometry(rc, ws.bins[ii], ws.bins[ii + 1], mid, delta);
+    const float ds = active ? delta * fs[ii * 5] : 0.f;
+    const float incl = warp_incl_scan(ds, lane);
+    float excl = __shfl_up_sync(kFull, incl, 1);
+    if (lane == 0) excl = 0.f;
+    const float T = expf(-(carry + excl));
+    const float w = active ? (1.f - expf(-ds)) * T : 0.f;
+    carry += __shfl_sync(kFull, incl, 31);
+    if (active) { ws.T[i] = T; ws.w[i] = w; }
+    sw += w;
+  }
+  sw = warp_sum(sw);
+  const float bgw = 1.f - sw;
+  const float* fl = fs + (S2 - 1) * 5;
+  const float lr = fl[1], lg = fl[2], lb = fl[3], lt = fl[4];
+  __syncwarp();
+  // pass 2: dL/dw_i, then dL/d(delta*sigma)_i = gw_i (T_i - w_i) - sum_{j>i} gw_j w_j
+  for (int i = lane; i < S2; i += 32) {
+    const float* f = fs + i * 5;
+    float g = gr_ * (f[1] - lr) + gg_ * (f[2] - lg) + gb_ * (f[3] - lb) + gth * (f[4] - lt) + gacc;
+    if (g_w2) g += g_w2[i];
+    ws.gw[i] = g;
+    const float wc = ws.w[i] + (i == S2 - 1 ? bgw : 0.f);
+    ws.dzr[i] = gr_ * wc * f[1] * (1.f - f[1]);
+    ws.dzg[i] = gg_ * wc * f[2] * (1.f - f[2]);
+    ws.dzb[i] = gb_ * wc * f[3] * (1.f - f[3]);
+    ws.dtau[i] = gth * wc;
+  }
+  __syncwarp();
+  float scarry = 0.f;
+  for (int base = ((S2 - 1) / 32) * 32; base >= 0; base -= 32) {
+    const int i = base + lane;
+    const float v = i < S2 ? ws.gw[i] * ws.w[i] : 0.f;
+    float tot;
+    const float ex = warp_suffix_excl(v, lane, tot);
+    if (i < S2) {
+      float mid, delta;
+      sample_geometry(rc, ws.bins[i], ws.bins[i + 1], mid, delta);
+      ws.dsig[i] = (ws.gw[i] * (ws.T[i] - ws.w[i]) - (ex + scarry)) * delta;
+    }
+    scarry += tot;
+  }
+  __syncwarp();
+}
+
+// per-ray first-layer bias of the colour head, as in the forward, from global weights
+__device__ __forceinline__ void ray_bias_and_inputs(const TnfModel& m, const TnfRays& rays, const long long ray,
+                                                    const RayCtx& rc, const int lane, float* rayb, float (&sh)[16],
+                                                    float& app_lane) {
+  sh4((rc.dx + 1.f) * 0.5f, (rc.dy + 1.f) * 0.5f, (rc.dz + 1.f) * 0.5f, sh);
+  const float* W = m.field.rgb0.weight;
+  float e = 0.f;
+  if (m.appearance_mode == TNF_APPEARANCE_LOOKUP) {
+    e = __ldg(m.field.appearance + rays.camera_indices[ray] * 32 + lane);
+  } else if (m.appearance_mode == TNF_APPEARANCE_MEAN) {
+    for (int i = 0; i < m.field.num_images; ++i) e += m.field.appearance[i * 32 + lane];
+    e /= (float)m.field.num_images;
+  }
+  app_lane = e;
+#pragma unroll
+  for (int hlf = 0; hlf < 2; ++hlf) {
+    const int n = lane + 32 * hlf;
+    float b = m.field.rgb0.bias[n];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) b = fmaf(sh[k], W[n * 63 + k], b);
+    for (int j = 0; j < 32; ++j) b = fmaf(__shfl_sync(kFull, e, j), W[n * 63 + 31 + j], b);
+    rayb[n] = b;
+  }
+}
+
+// per-ray epilogue: stage [sh | appearance] and sum_s dA1pre, appearance-embedding gradient
+template <typename T>
+__device__ __forceinline__ void ray_epilogue(const TnfModel& m, const TnfRays& rays, const long long ray,
+                                             const int lane, const float (&sh)[16], const float app_lane,
+                                             const float racc0, const float racc1, const BwdLayout& L,
+                                             float* __restrict__ gapp) {
+  T* xr = reinterpret_cast<T*>(L.XRay) + ray * kWXRay;
+  T* dr = reinterpret_cast<T*>(L.dRay) + ray * kWdRay;
+  if (lane < 16) xr[lane] = T(sh[lane]);
+  xr[16 + lane] = T(app_lane);
+  dr[lane] = T(racc0);
+  dr[lane + 32] = T(racc1);
+  if (m.appearance_mode == TNF_APPEARANCE_LOOKUP && gapp) {
+    const float* W = m.field.rgb0.weight;
+    float acc = 0.f;
+    for (int n = 0; n < 64; ++n) {
+      const float v = __shfl_sync(kFull, n < 32 ? racc0 : racc1, n & 31);
+      acc = fmaf(v, W[n * 63 + 31 + lane], acc);
+    }
+    atomicAdd(gapp + rays.camera_indices[ray] * 32 + lane, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// field level, fp32: lane per sample (mirror of the fp32 forward)
+// ------------------------------------------------------------------------------------
+struct FieldBwdSmem32 {
+  FieldW32 fw;
+  FieldBwdScratch ws[kWarpsPerCta];
+  float act[kWarpsPerCta][64 * 32];
+  float geo[kWarpsPerCta][16 * 32];
+  float dgc[kWarpsPerCta][16 * 32];
+};
+
+// out[k] = sum_n dy[n] * wt[k*N + n]   (wt is the k-major image of torch weight[n][k]);
+// MASK: multiply by (col[k] > 0) where col currently holds the layer input; result replaces col[k].
+template <int N, int K, bool MASK, bool ACCUM>
+__device__ __forceinline__ void dense_row_t(const float* __restrict__ wt, const float (&dy)[N], float* col) {
+#pragma unroll 2
+  for (int k = 0; k < K; ++k) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int n = 0; n < N; n += 4) {
+      const float4 w = *reinterpret_cast<const float4*>(wt + k * N + n);
+      a0 = fmaf(dy[n], w.x, a0);
+      a1 = fmaf(dy[n + 1], w.y, a1);
+      a2 = fmaf(dy[n + 2], w.z, a2);
+      a3 = fmaf(dy[n + 3], w.w, a3);
+    }
+    float r = (a0 + a1) + (a2 + a3);
+    if (MASK) r = col[k * 32] > 0.f ? r : 0.f;
+    if (ACCUM) r += col[k * 32];
+    col[k * 32] = r;
+  }
+}
+template <int N>
+__device__ __forceinline__ void load_col(const float* col, float (&y)[N]) {
+#pragma unroll
+  for (int n = 0; n < N; ++n) y[n] = col[n * 32];
+}
+template <int N>
+__device__ __forceinline__ void stage_row(unsigned char* base, long long row, int ld, int col0, const float (&y)[N]) {
+  float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + row * ld + col0);
+#pragma unroll
+  for (int n = 0; n < N; n += 4) p[n >> 2] = make_float4(y[n], y[n + 1], y[n + 2], y[n + 3]);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+    tnf_backward_field_kernel_fp32(const __grid_constant__ TnfModel m, const __grid_constant__ TnfRays rays,
+                                   const __grid_constant__ TnfSaved sv, const __grid_constant__ TnfOutputGrads go,
+                                   const __grid_constant__ TnfModelGrad gr, const __grid_constant__ BwdLayout L) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FieldBwdSmem32& S = *reinterpret_cast<FieldBwdSmem32*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  stage_field(S.fw, m.field, tid);
+  __syncthreads();
+  const FieldW32& W = S.fw;
+  FieldBwdScratch& ws = S.ws[warp];
+  float* a = &S.act[warp][lane];
+  float* geo = &S.geo[warp][lane];
+  float* dgc = &S.dgc[warp][lane];
+  const int S2 = m.num_samples[TNF_NUM_PROP];
+  const TnfHashGrid& grid = m.field.grid;
+  const uint32_t mask = (1u << grid.log2_size) - 1u;
+  float2* __restrict__ gtab = reinterpret_cast<float2*>(gr.field.table);
+  const float* __restrict__ F = static_cast<const float*>(sv.field_features);
+  const long long R = rays.num_rays;
+
+  for (long long ray = (long long)blockIdx.x * kWarpsPerCta + warp; ray < R;
+       ray += (long long)gridDim.x * kWarpsPerCta) {
+    RayCtx rc;
+    rc.ox = __ldg(rays.origins + ray * 3 + 0);
+    rc.oy = __ldg(rays.origins + ray * 3 + 1);
+    rc.oz = __ldg(rays.origins + ray * 3 + 2);
+    rc.dx = __ldg(rays.directions + ray * 3 + 0);
+    rc.dy = __ldg(rays.directions + ray * 3 + 1);
+    rc.dz = __ldg(rays.directions + ray * 3 + 2);
+    rc.s_near = spacing_fn(rays.nears ? __ldg(rays.nears + ray) : m.near_plane);
+    rc.s_far = spacing_fn(rays.fars ? __ldg(rays.fars + ray) : m.far_plane);
+    for (int i = lane; i <= S2; i += 32) ws.bins[i] = sv.sdist[TNF_NUM_PROP][ray * (S2 + 1) + i];
+    float sh[16], app_lane;
+    ray_bias_and_inputs(m, rays, ray, rc, lane, ws.rayb, sh, app_lane);
+    __syncwarp();
+    composite_backward(m, ws, rc, S2, lane, sv.field_samples + ray * S2 * 5,
+                       go.weights[TNF_NUM_PROP] ? go.weights[TNF_NUM_PROP] + ray * S2 : nullptr,
+                       go.rgb ? go.rgb[ray * 3 + 0] : 0.f, go.rgb ? go.rgb[ray * 3 + 1] : 0.f,
+                       go.rgb ? go.rgb[ray * 3 + 2] : 0.f, go.thermal ? go.thermal[ray] : 0.f,
+                       go.accumulation ? go.accumulation[ray] : 0.f);
+    float racc0 = 0.f, racc1 = 0.f;
+    for (int base = 0; base < S2; base += 32) {
+      const int i = base + lane;
+      const bool active = i < S2;
+      const int ii = active ? i : S2 - 1;
+      const long long row = ray * S2 + ii;
+      float mid, delta;
+      sample_geometry(rc, ws.bins[ii], ws.bins[ii + 1], mid, delta);
+      float px, py, pz;
+      const float sel = normalise_position(m, ray_x(rc, mid), ray_y(rc, mid), ray_z(rc, mid), px, py, pz);
+      // upstream gradients of this sample (zero for padding lanes: every product below vanishes)
+      const float dsig = active ? ws.dsig[ii] : 0.f;
+      const float dz[3] = {active ? ws.dzr[ii] : 0.f, active ? ws.dzg[ii] : 0.f, active ? ws.dzb[ii] : 0.f};
+      const float dtau = active ? ws.dtau[ii] : 0.f;
+      // ---- forward recompute: F -> H -> G
+      {
+        const float4* fr = reinterpret_cast<const float4*>(F + row * 32);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float4 v = fr[k];
+          a[(4 * k) * 32] = v.x; a[(4 * k + 1) * 32] = v.y; a[(4 * k + 2) * 32] = v.z; a[(4 * k + 3) * 32] = v.w;
+        }
+      }
+      float h0;
+      {
+        float y[64];
+        dense_col<32, 64, ACT_RELU>(W.base0t, W.base0b, a, y);
+        store_col(a, y);
+        if (active) stage_row(L.XH, row, kWXH, 0, y);
+      }
+      {
+        float y[16];
+        dense_col<64, 16, ACT_NONE>(W.base1t, W.base1b, a, y);
+        h0 = y[0];
+        if (active) stage_row(L.XG, row, kWXG, 0, y);
+        y[0] = 0.f;
+        store_col(geo, y);
+      }
+      // ---- thermal head: forward then backward down to dB1pre and its share of dG
+      {
+        float y[64];
+        dense_col<16, 64, ACT_RELU>(W.th0t, W.th0b, geo, y);
+        store_col(a, y);
+        if (active) stage_row(L.XB1, row, kWX, 0, y);
+        dense_col<64, 64, ACT_SIGMOID>(W.th1t, W.th1b, a, y);
+        if (active) stage_row(L.XB2, row, kWX, 0, y);
+#pragma unroll
+        for (int n = 0; n < 64; ++n) y[n] = dtau * W.th2[n] * y[n] * (1.f - y[n]);
+        if (active) stage_row(L.dB2, row, kWX, 0, y);
+        dense_row_t<64, 64, true, false>(W.th1t, y, a);  // a: B1 -> dB1pre
+        load_col(a, y);
+        if (active) stage_row(L.dGeo, row, kWdGeo, 64, y);
+        if (m.detach_thermal_geo) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) dgc[k * 32] = 0.f;
+        } else {
+          dense_row_t<64, 16, false, false>(W.th0t, y, dgc);
+        }
+        float t8[8] = {dtau, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (active) stage_row(L.dT, row, kWdT, 0, t8);
+      }
+      // ---- colour head
+      {
+        float y[64];
+        dense_col<16, 64, ACT_RELU>(W.rgb0geo_t, ws.rayb, geo, y);
+        store_col(a, y);
+        if (active) stage_row(L.XA1, row, kWX, 0, y);
+        dense_col<64, 64, ACT_RELU>(W.rgb1t, W.rgb1b, a, y);
+        if (active) stage_row(L.XA2, row, kWX, 0, y);
+#pragma unroll
+        for (int n = 0; n < 64; ++n) {
+          const float4 w2 = *reinterpret_cast<const float4*>(W.rgb2t + n * 4);
+          y[n] = y[n] > 0.f ? dz[0] * w2.x + dz[1] * w2.y + dz[2] * w2.z : 0.f;
+        }
+        if (active) stage_row(L.dA2, row, kWX, 0, y);
+        float z8[8] = {dz[0], dz[1], dz[2], 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (active) stage_row(L.dZ, row, kWdZ, 0, z8);
+        dense_row_t<64, 64, true, false>(W.rgb1t, y, a);  // a: A1 -> dA1pre
+        load_col(a, y);
+        if (active) stage_row(L.dGeo, row, kWdGeo, 0, y);
+#pragma unroll
+        for (int n = 0; n < 64; ++n) {
+          const float s = warp_sum(y[n]);
+          if (lane == (n & 31)) { if (n < 32) racc0 += s; else racc1 += s; }
+        }
+        dense_row_t<64, 16, false, true>(W.rgb0geo_t, y, dgc);
+      }
+      // ---- trunk: dG -> dH -> dF
+      {
+        float y[16];
+        load_col(dgc, y);
+        y[0] = dsig * expf(fminf(fmaxf(h0, -15.f), 15.f)) * sel;  // trunc_exp backward, times selector
+        if (active) stage_row(L.dG, row, kWXG, 0, y);
+        {
+          const float4* hr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(L.XH) + row * kWXH);
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const float4 v = hr[k];
+            a[(4 * k) * 32] = v.x; a[(4 * k + 1) * 32] = v.y; a[(4 * k + 2) * 32] = v.z; a[(4 * k + 3) * 32] = v.w;
+          }
+        }
+        dense_row_t<16, 64, true, false>(W.base1t, y, a);  // a: H -> dHpre
+      }
+      {
+        float y[64];
+        load_col(a, y);
+        if (active) stage_row(L.dH, row, kWX, 0, y);
+        dense_row_t<64, 32, false, false>(W.base0t, y, a);  // a[0..31]: dF
+      }
+      if (active) {
+#pragma unroll 4
+        for (int l = 0; l < TNF_MAX_LEVELS; ++l)
+          scatter_level(gtab + ((size_t)l << grid.log2_size), px, py, pz, grid.scalings[l], mask, a[(2 * l) * 32],
+                        a[(2 * l + 1) * 32]);
+      }
+    }
+    ray_epilogue<float>(m, rays, ray, lane, sh, app_lane, racc0, racc1, L, gr.field.appearance);
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// weight-gradient GEMMs: dW[n][k] += sum_rows dY[row][n0+n] * X[row][k];  db[n] += sum_rows dY
+// ------------------------------------------------------------------------------------
+struct WgradProblem {
+  const void* dY; int ldY, n0, N, n_valid;   // N: loaded columns (multiple of 8), n_valid <= N are written
+  const void* X;  int ldX, K, k_skip;        // K: loaded columns (multiple of 8); output col = k - k_skip >= 0
+  long long rows;
+  float* W; int ldW, wcol0;
+  float* bias;                               // may be null
+};
+constexpr int kMaxWgradProblems = 12;
+struct WgradArgs {
+  WgradProblem p[kMaxWgradProblems];
+  int n;
+};
+constexpr int kWgradRows = 64;
+
+__global__ void __launch_bounds__(256) tnf_wgrad_kernel_fp32(const __grid_constant__ WgradArgs args) {
+  const WgradProblem& P = args.p[blockIdx.y];
+  __shared__ __align__(16) float sdY[kWgradRows][68];
+  __shared__ __align__(16) float sX[kWgradRows][68];
+  const int tid = threadIdx.x, tn = tid >> 4, tk = tid & 15;
+  const float* dY = static_cast<const float*>(P.dY);
+  const float* X = static_cast<const float*>(P.X);
+  float acc[4][4] = {};
+  float bacc[4] = {};
+  const long long tiles = (P.rows + kWgradRows - 1) / kWgradRows;
+  for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const long long row0 = t * kWgradRows;
+    for (int idx = tid; idx < kWgradRows * 16; idx += 256) {
+      const int r = idx >> 4, c4 = (idx & 15) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f), x = v;
+      if (row0 + r < P.rows) {
+        if (c4 < P.N) v = *reinterpret_cast<const float4*>(dY + (row0 + r) * P.ldY + P.n0 + c4);
+        if (c4 < P.K) x = *reinterpret_cast<const float4*>(X + (row0 + r) * P.ldX + c4);
+      }
+      *reinterpret_cast<float4*>(&sdY[r][c4]) = v;
+      *reinterpret_cast<float4*>(&sX[r][c4]) = x;
+    }
+    __syncthreads();
+    if (4 * tn < P.N && 4 * tk < P.K) {
+#pragma unroll 4
+      for (int r = 0; r < kWgradRows; ++r) {
+        const float4 d = *reinterpret_cast<const float4*>(&sdY[r][4 * tn]);
+        const float4 x = *reinterpret_cast<const float4*>(&sX[r][4 * tk]);
+        const float dv[4] = {d.x, d.y, d.z, d.w}, xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(dv[i], xv[j], acc[i][j]);
+          if (tk == 0) bacc[i] += dv[i];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (4 * tn < P.N && 4 * tk < P.K) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = 4 * tn + i;
+      if (n >= P.n_valid) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = 4 * tk + j - P.k_skip;
+        if (k >= 0 && 4 * tk + j < P.K && acc[i][j] != 0.f) atomicAdd(P.W + n * P.ldW + P.wcol0 + k, acc[i][j]);
+      }
+      if (tk == 0 && P.bias && bacc[i] != 0.f) atomicAdd(P.bias + n, bacc[i]);
+    }
+  }
+}
+
+}  // namespace tnf
+
+// ====================================================================================
+// C ABI
+// ====================================================================================
+namespace {
+using tnf::fail;
+
+int check_grads(const TnfModel& m, const TnfModelGrad* g) {
+  if (!g) return fail(TNF_ERR_INVALID_ARGUMENT, "grads is null");
+  for (int k = 0; k < TNF_NUM_PROP; ++k) {
+    const TnfDensityNetGrad& p = g->prop[k];
+    if (p.table && (!p.l0.weight || !p.l0.bias || !p.l1.weight || !p.l1.bias))
+      return fail(TNF_ERR_INVALID_ARGUMENT, "grads.prop[%d]: table given but a linear gradient is null", k);
+  }
+  const TnfFieldGrad& f = g->field;
+  if (!f.table) return fail(TNF_ERR_INVALID_ARGUMENT, "grads.field.table is null");
+  const TnfLinearGrad* ls[] = {&f.base0, &f.base1, &f.rgb0, &f.rgb1, &f.rgb2, &f.th0, &f.th1, &f.th2};
+  for (const TnfLinearGrad* l : ls)
+    if (!l->weight || !l->bias) return fail(TNF_ERR_INVALID_ARGUMENT, "grads.field: a linear gradient is null");
+  if (m.appearance_mode == TNF_APPEARANCE_LOOKUP && !f.appearance)
+    return fail(TNF_ERR_INVALID_ARGUMENT, "grads.field.appearance is required for TNF_APPEARANCE_LOOKUP");
+  return TNF_OK;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes, const char* name) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "cudaFuncSetAttribute(%s, smem=%zu): %s", name, bytes,
+                                    cudaGetErrorString(e));
+  return TNF_OK;
+}
+
+void add_problem(tnf::WgradArgs& a, const void* dY, int ldY, int n0, int N, int n_valid, const void* X, int ldX,
+                 int K, int k_skip, long long rows, float* W, int ldW, int wcol0, float* bias) {
+  tnf::WgradProblem& p = a.p[a.n++];
+  p.dY = dY; p.ldY = ldY; p.n0 = n0; p.N = N; p.n_valid = n_valid;
+  p.X = X; p.ldX = ldX; p.K = K; p.k_skip = k_skip;
+  p.rows = rows; p.W = W; p.ldW = ldW; p.wcol0 = wcol0; p.bias = bias;
+}
+
+// the eight field layers (+ the two per-ray blocks of mlp_head.layers.0) as GEMM problems
+void field_problems(tnf::WgradArgs& a, const tnf::BwdLayout& L, const void* XF, size_t es, const TnfFieldGrad& g,
+                    long long Ns, long long R) {
+  using namespace tnf;
+  a.n = 0;
+  auto off = [&](const unsigned char* p, int elems) { return static_cast<const void*>(p + (size_t)elems * es); };
+  add_problem(a, L.dH, kWX, 0, 64, 64, XF, kWXF, 32, 0, Ns, g.base0.weight, 32, 0, g.base0.bias);
+  add_problem(a, L.dG, kWXG, 0, 16, 16, L.XH, kWXH, 64, 0, Ns, g.base1.weight, 64, 0, g.base1.bias);
+  add_problem(a, L.dGeo, kWdGeo, 0, 64, 64, L.XG, kWXG, 16, 1, Ns, g.rgb0.weight, 63, 16, nullptr);
+  add_problem(a, L.dGeo, kWdGeo, 64, 64, 64, L.XG, kWXG, 16, 1, Ns, g.th0.weight, 15, 0, g.th0.bias);
+  add_problem(a, L.dA2, kWX, 0, 64, 64, L.XA1, kWX, 64, 0, Ns, g.rgb1.weight, 64, 0, g.rgb1.bias);
+  add_problem(a, L.dZ, kWdZ, 0, 8, 3, L.XA2, kWX, 64, 0, Ns, g.rgb2.weight, 64, 0, g.rgb2.bias);
+  add_problem(a, L.dB2, kWX, 0, 64, 64, L.XB1, kWX, 64, 0, Ns, g.th1.weight, 64, 0, g.th1.bias);
+  add_problem(a, L.dT, kWdT, 0, 8, 1, L.XB2, kWX, 64, 0, Ns, g.th2.weight, 64, 0, g.th2.bias);
+  add_problem(a, L.dRay, kWdRay, 0, 64, 64, L.XRay, kWXRay, 16, 0, R, g.rgb0.weight, 63, 0, g.rgb0.bias);
+  add_problem(a, L.dRay, kWdRay, 0, 64, 64, off(L.XRay, 16), kWXRay, 32, 0, R, g.rgb0.weight, 63, 31, nullptr);
+}
+}  // namespace
+
+extern "C" {
+
+size_t tnf_backward_workspace_bytes(const TnfModel* model, int64_t num_rays) {
+  if (!model || num_rays <= 0) return 256;
+  const long long Ns = (long long)num_rays * model->num_samples[TNF_NUM_PROP];
+  const bool tc = model->precision == TNF_PRECISION_TC_FP16;
+  return tnf::make_layout(nullptr, nullptr, Ns, num_rays, tc ? 2 : 4, tc) + 256;
+}
+
+int tnf_render_backward(const TnfModel* model, const TnfRays* rays, const TnfSaved* saved, const TnfOutputGrads* gout,
+                        const TnfModelGrad* grads, void* workspace, size_t workspace_bytes, void* stream_) {
+  tnf::g_err[0] = 0;
+  if (int e = tnf::check_model(model)) return e;
+  if (!rays || !saved || !gout) return fail(TNF_ERR_INVALID_ARGUMENT, "rays/saved/gout is null");
+  if (int e = check_grads(*model, grads)) return e;
+  if (!model->training) return fail(TNF_ERR_INVALID_ARGUMENT, "backward needs a training-mode forward (training=1)");
+  const long long R = rays->num_rays;
+  if (R < 0) return fail(TNF_ERR_INVALID_ARGUMENT, "num_rays=%lld", R);
+  if (R == 0) return TNF_OK;
+  if (!rays->origins || !rays->directions) return fail(TNF_ERR_INVALID_ARGUMENT, "origins/directions is null");
+  if (model->appearance_mode == TNF_APPEARANCE_LOOKUP && !rays->camera_indices)
+    return fail(TNF_ERR_INVALID_ARGUMENT, "camera_indices required for TNF_APPEARANCE_LOOKUP");
+  for (int k = 0; k <= TNF_NUM_PROP; ++k) {
+    const bool need = k == TNF_NUM_PROP || (grads->prop[k].table && gout->weights[k]);
+    if (need && (!saved->sdist[k] || !saved->weights[k]))
+      return fail(TNF_ERR_INVALID_ARGUMENT, "saved.sdist[%d]/weights[%d] is null", k, k);
+  }
+  if (!saved->field_features || !saved->field_samples)
+    return fail(TNF_ERR_INVALID_ARGUMENT, "saved.field_features/field_samples is null");
+  const size_t need = tnf_backward_workspace_bytes(model, R);
+  if (!workspace || workspace_bytes < need)
+    return fail(TNF_ERR_WORKSPACE_TOO_SMALL, "workspace %zu < %zu bytes", workspace_bytes, need);
+  if (!tnf::aligned16(workspace)) return fail(TNF_ERR_INVALID_ARGUMENT, "workspace must be 16-byte aligned");
+
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int sms = tnf::num_sms();
+  const long long want = (R + tnf::kWarpsPerCta - 1) / tnf::kWarpsPerCta;
+  cudaError_t e;
+
+  // ---- proposal levels
+  const bool do_prop = (grads->prop[0].table && gout->weights[0]) || (grads->prop[1].table && gout->weights[1]);
+  if (do_prop) {
+    const size_t smem = sizeof(tnf::PropBwdSmem);
+    if (int rc = set_smem(tnf::tnf_backward_prop_kernel, smem, "backward_prop")) return rc;
+    const long long cap = (long long)sms * 2;
+    tnf::tnf_backward_prop_kernel<<<(unsigned)(want < cap ? want : cap), tnf::kThreads, smem, stream>>>(
+        *model, *rays, *saved, *gout, *grads);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "backward_prop launch: %s", cudaGetErrorString(e));
+  }
+
+  // ---- field level
+  const long long Ns = R * model->num_samples[TNF_NUM_PROP];
+  const bool tc = model->precision == TNF_PRECISION_TC_FP16;
+  tnf::BwdLayout L{};
+  tnf::make_layout(&L, static_cast<unsigned char*>(workspace), Ns, R, tc ? 2 : 4, tc);
+  tnf::WgradArgs wa;
+  if (!tc) {
+    const size_t smem = sizeof(tnf::FieldBwdSmem32);
+    if (int rc = set_smem(tnf::tnf_backward_field_kernel_fp32, smem, "backward_field_fp32")) return rc;
+    const long long cap = sms;
+    tnf::tnf_backward_field_kernel_fp32<<<(unsigned)(want < cap ? want : cap), tnf::kThreads, smem, stream>>>(
+        *model, *rays, *saved, *gout, *grads, L);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "backward_field launch: %s", cudaGetErrorString(e));
+    field_problems(wa, L, saved->field_features, 4, grads->field, Ns, R);
+    const long long tiles = (Ns + tnf::kWgradRows - 1) / tnf::kWgradRows;
+    const long long capx = (long long)sms * 2 / wa.n + 1;
+    dim3 grid((unsigned)(tiles < capx ? tiles : capx), wa.n);
+    tnf::tnf_wgrad_kernel_fp32<<<grid, 256, 0, stream>>>(wa);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(e));
+  } else {
+    return fail(TNF_ERR_UNSUPPORTED_CONFIG, "tensor-core backward not built yet");
+  }
+  return TNF_OK;
+}
+
+}  // extern "C"

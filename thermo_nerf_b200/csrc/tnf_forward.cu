@@ -18,55 +18,9 @@
 #include <cstdio>
 #include <cstring>
 
-#include "tnf_device.cuh"
+#include "tnf_field.cuh"
 
 namespace tnf {
-
-// ------------------------------------------------------------------------------------
-// shared-memory images of the field MLPs
-// ------------------------------------------------------------------------------------
-struct FieldCommon {
-  float rgb0sh_t[16 * 64];   // [k][n] SH block of mlp_head.layers.0 (cols 0..15)
-  float rgb0app_t[32 * 64];  // [j][n] appearance block (cols 31..62)
-  float rgb0b[64];           // bias (+ folded constant appearance part in eval)
-  float app_const[32];
-};
-
-struct FieldW32 {
-  float base0t[32 * 64];
-  float base0b[64];
-  float base1t[64 * 16];
-  float base1b[16];
-  float rgb0geo_t[16 * 64];  // row 0 = 0 (density slot), rows 1..15 = geo block (cols 16..30)
-  float rgb1t[64 * 64];
-  float rgb1b[64];
-  float rgb2t[64 * 4];
-  float rgb2b[4];
-  float th0t[16 * 64];  // row 0 = 0
-  float th0b[64];
-  float th1t[64 * 64];
-  float th1b[64];
-  float th2[64];
-  float th2b[4];
-};
-
-// mma.m16n8k16 B fragments, [k-tile][n-tile][lane]
-struct FieldWTC {
-  uint2 base0[2][8][32];
-  uint2 base1[4][2][32];
-  uint2 geo0[1][16][32];  // n-tiles 0..7: rgb0 geo block, 8..15: mlp_thermal.layers.0
-  uint2 rgb1[4][8][32];
-  uint2 rgb2[4][1][32];
-  uint2 th1[4][8][32];
-  uint2 th2[4][1][32];
-  float base0b[64];
-  float base1b[16];
-  float rgb1b[64];
-  float rgb2b[8];
-  float th0b[64];
-  float th1b[64];
-  float th2b[8];
-};
 
 template <int PREC>
 struct Smem;
@@ -85,151 +39,6 @@ struct Smem<TNF_PRECISION_TC_FP16> {
   FieldCommon fc;
   FieldWTC fw;
   WarpScratch ws[kWarpsPerCta];
-};
-
-// ------------------------------------------------------------------------------------
-// weight staging (once per CTA; weights are tiny and L2 resident)
-// ------------------------------------------------------------------------------------
-__device__ void stage_prop(PropW& W, const TnfDensityNet& net, int tid) {
-  const int K = 2 * net.grid.num_levels;
-  for (int i = tid; i < 256; i += kThreads) {
-    const int k = i >> 4, j = i & 15;
-    W.w0t[i] = (k < K) ? net.l0.weight[j * K + k] : 0.f;
-  }
-  if (tid < 16) {
-    W.b0[tid] = net.l0.bias[tid];
-    W.w1[tid] = net.l1.weight[tid];
-  }
-  if (tid == 0) W.b1 = net.l1.bias[0];
-}
-
-// logical [K][N] views (zero padded) of the torch [out,in] matrices
-struct ViewPlain {  // W[k][n] = w[n*ld + k], k < kv, n < nv
-  const float* w;
-  int ld, kv, nv;
-  __device__ float operator()(int k, int n) const { return (k < kv && n < nv) ? w[n * ld + k] : 0.f; }
-};
-struct ViewShift {  // row 0 is the (unused) density slot: W[k][n] = w[n*ld + col0 + k-1] for 1 <= k <= kv
-  const float* w;
-  int ld, col0, kv, nv;
-  __device__ float operator()(int k, int n) const {
-    return (k >= 1 && k <= kv && n < nv) ? w[n * ld + col0 + k - 1] : 0.f;
-  }
-};
-struct ViewGeo0 {  // n < 64: rgb0 geo block, n >= 64: thermal layer 0
-  ViewShift rgb, th;
-  __device__ float operator()(int k, int n) const { return n < 64 ? rgb(k, n) : th(k, n - 64); }
-};
-
-template <typename V>
-__device__ void stage_t(float* dst, int K, int N, const V& v, int tid) {
-  for (int i = tid; i < K * N; i += kThreads) dst[i] = v(i / N, i % N);
-}
-template <typename V>
-__device__ void stage_frag(uint2* dst, int KT, int NT, const V& v, int tid) {
-  for (int i = tid; i < KT * NT * 32; i += kThreads) {
-    const int lane = i & 31, nt = (i >> 5) % NT, kt = (i >> 5) / NT;
-    const int g = lane >> 2, q = lane & 3;
-    const int n = nt * 8 + g, k = kt * 16 + 2 * q;
-    dst[i] = make_uint2(pack_half2(v(k, n), v(k + 1, n)), pack_half2(v(k + 8, n), v(k + 9, n)));
-  }
-}
-__device__ void stage_vec(float* dst, const float* src, int n, int npad, int tid) {
-  for (int i = tid; i < npad; i += kThreads) dst[i] = i < n ? src[i] : 0.f;
-}
-
-__device__ void stage_common(FieldCommon& C, const TnfField& f, bool fold_appearance, int tid) {
-  stage_t(C.rgb0sh_t, 16, 64, ViewPlain{f.rgb0.weight, 63, 16, 64}, tid);
-  stage_t(C.rgb0app_t, 32, 64, ViewPlain{f.rgb0.weight + 31, 63, 32, 64}, tid);
-  if (tid < 64) {
-    float b = f.rgb0.bias[tid];
-    if (fold_appearance) {
-      for (int j = 0; j < 32; ++j) b = fmaf(C.app_const[j], f.rgb0.weight[tid * 63 + 31 + j], b);
-    }
-    C.rgb0b[tid] = b;
-  }
-}
-
-__device__ void stage_field(FieldW32& W, const TnfField& f, int tid) {
-  stage_t(W.base0t, 32, 64, ViewPlain{f.base0.weight, 32, 32, 64}, tid);
-  stage_t(W.base1t, 64, 16, ViewPlain{f.base1.weight, 64, 64, 16}, tid);
-  stage_t(W.rgb0geo_t, 16, 64, ViewShift{f.rgb0.weight, 63, 16, 15, 64}, tid);
-  stage_t(W.rgb1t, 64, 64, ViewPlain{f.rgb1.weight, 64, 64, 64}, tid);
-  stage_t(W.rgb2t, 64, 4, ViewPlain{f.rgb2.weight, 64, 64, 3}, tid);
-  stage_t(W.th0t, 16, 64, ViewShift{f.th0.weight, 15, 0, 15, 64}, tid);
-  stage_t(W.th1t, 64, 64, ViewPlain{f.th1.weight, 64, 64, 64}, tid);
-  stage_vec(W.base0b, f.base0.bias, 64, 64, tid);
-  stage_vec(W.base1b, f.base1.bias, 16, 16, tid);
-  stage_vec(W.rgb1b, f.rgb1.bias, 64, 64, tid);
-  stage_vec(W.rgb2b, f.rgb2.bias, 3, 4, tid);
-  stage_vec(W.th0b, f.th0.bias, 64, 64, tid);
-  stage_vec(W.th1b, f.th1.bias, 64, 64, tid);
-  stage_vec(W.th2, f.th2.weight, 64, 64, tid);
-  stage_vec(W.th2b, f.th2.bias, 1, 4, tid);
-}
-
-__device__ void stage_field(FieldWTC& W, const TnfField& f, int tid) {
-  stage_frag(&W.base0[0][0][0], 2, 8, ViewPlain{f.base0.weight, 32, 32, 64}, tid);
-  stage_frag(&W.base1[0][0][0], 4, 2, ViewPlain{f.base1.weight, 64, 64, 16}, tid);
-  stage_frag(&W.geo0[0][0][0], 1, 16,
-             ViewGeo0{ViewShift{f.rgb0.weight, 63, 16, 15, 64}, ViewShift{f.th0.weight, 15, 0, 15, 64}}, tid);
-  stage_frag(&W.rgb1[0][0][0], 4, 8, ViewPlain{f.rgb1.weight, 64, 64, 64}, tid);
-  stage_frag(&W.rgb2[0][0][0], 4, 1, ViewPlain{f.rgb2.weight, 64, 64, 3}, tid);
-  stage_frag(&W.th1[0][0][0], 4, 8, ViewPlain{f.th1.weight, 64, 64, 64}, tid);
-  stage_frag(&W.th2[0][0][0], 4, 1, ViewPlain{f.th2.weight, 64, 64, 1}, tid);
-  stage_vec(W.base0b, f.base0.bias, 64, 64, tid);
-  stage_vec(W.base1b, f.base1.bias, 16, 16, tid);
-  stage_vec(W.rgb1b, f.rgb1.bias, 64, 64, tid);
-  stage_vec(W.rgb2b, f.rgb2.bias, 3, 8, tid);
-  stage_vec(W.th0b, f.th0.bias, 64, 64, tid);
-  stage_vec(W.th1b, f.th1.bias, 64, 64, tid);
-  stage_vec(W.th2b, f.th2.bias, 1, 8, tid);
-}
-
-// ------------------------------------------------------------------------------------
-// per-ray state
-// ------------------------------------------------------------------------------------
-struct RayCtx {
-  float ox, oy, oz, dx, dy, dz;
-  float s_near, s_far;
-};
-
-// frustums.get_positions(): origins + directions * (starts + ends) / 2, rounded like ATen (separate
-// multiply and add, no FMA contraction) so that the discontinuous selector sees the same point.
-__device__ __forceinline__ float ray_x(const RayCtx& rc, float mid) { return __fadd_rn(rc.ox, __fmul_rn(rc.dx, mid)); }
-__device__ __forceinline__ float ray_y(const RayCtx& rc, float mid) { return __fadd_rn(rc.oy, __fmul_rn(rc.dy, mid)); }
-__device__ __forceinline__ float ray_z(const RayCtx& rc, float mid) { return __fadd_rn(rc.oz, __fmul_rn(rc.dz, mid)); }
-
-__device__ __forceinline__ void sample_geometry(const RayCtx& rc, float s0, float s1, float& mid, float& delta) {
-  const float t0 = to_euclid(s0, rc.s_near, rc.s_far);
-  const float t1 = to_euclid(s1, rc.s_near, rc.s_far);
-  mid = (t0 + t1) * 0.5f;
-  delta = t1 - t0;
-}
-
-// Running alpha-compositing state of one level (RaySamples.get_weights + median depth).
-struct Compositor {
-  float carry = 0.f;     // sum of delta*sigma of all previous samples
-  float cw = 0.f;        // cumulative weight
-  float median = 0.f;    // DepthRenderer("median")
-  bool found = false;
-  __device__ __forceinline__ float step(float ds, float mid, bool active, int lane) {
-    const float incl = warp_incl_scan(ds, lane);
-    float excl = __shfl_up_sync(kFull, incl, 1);
-    if (lane == 0) excl = 0.f;
-    const float T = expf(-(carry + excl));
-    const float alpha = 1.f - expf(-ds);
-    const float w = active ? nan_to_num(alpha * T) : 0.f;
-    carry += __shfl_sync(kFull, incl, 31);
-    const float cwi = warp_incl_scan(w, lane) + cw;
-    const unsigned hit = __ballot_sync(kFull, active && cwi >= 0.5f);
-    if (!found && hit) {
-      median = __shfl_sync(kFull, mid, __ffs(hit) - 1);
-      found = true;
-    }
-    cw = __shfl_sync(kFull, cwi, 31);
-    return w;
-  }
 };
 
 // ------------------------------------------------------------------------------------
@@ -357,43 +166,11 @@ __device__ __forceinline__ void pdf_resample(WarpScratch& ws, const int Sprev, c
 // ------------------------------------------------------------------------------------
 // field level, fp32: lane per sample, activations in a per-lane shared-memory column
 // ------------------------------------------------------------------------------------
-enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2 };
-
-template <int K, int N, int ACT>
-__device__ __forceinline__ void dense_col(const float* __restrict__ wt, const float* __restrict__ bias,
-                                          const float* xin, float (&y)[N]) {
-#pragma unroll
-  for (int n = 0; n < N; n += 4) {
-    const float4 b = *reinterpret_cast<const float4*>(bias + n);
-    y[n] = b.x; y[n + 1] = b.y; y[n + 2] = b.z; y[n + 3] = b.w;
-  }
-#pragma unroll 2
-  for (int k = 0; k < K; ++k) {
-    const float x = xin[k * 32];
-#pragma unroll
-    for (int n = 0; n < N; n += 4) {
-      const float4 w = *reinterpret_cast<const float4*>(wt + k * N + n);
-      y[n] = fmaf(x, w.x, y[n]);
-      y[n + 1] = fmaf(x, w.y, y[n + 1]);
-      y[n + 2] = fmaf(x, w.z, y[n + 2]);
-      y[n + 3] = fmaf(x, w.w, y[n + 3]);
-    }
-  }
-#pragma unroll
-  for (int n = 0; n < N; ++n) {
-    if (ACT == ACT_RELU) y[n] = fmaxf(y[n], 0.f);
-    if (ACT == ACT_SIGMOID) y[n] = sigmoidf(y[n]);
-  }
-}
-template <int N>
-__device__ __forceinline__ void store_col(float* xout, const float (&y)[N]) {
-#pragma unroll
-  for (int n = 0; n < N; ++n) xout[n * 32] = y[n];
-}
-
 __device__ __forceinline__ void field_level(const TnfModel& m, Smem<TNF_PRECISION_FP32>& S, WarpScratch& ws,
-                                            const RayCtx& rc, const int S2, const int lane, const int warp) {
+                                            const RayCtx& rc, const int S2, const int lane, const int warp,
+                                            void* __restrict__ save_feat) {
   const FieldW32& W = S.fw;
+  float2* __restrict__ sf = reinterpret_cast<float2*>(save_feat);  // [S2][16] float2 of this ray, or null
   float* a = &S.act[warp][lane];
   float* geo = &S.geo[warp][lane];
   const TnfHashGrid& grid = m.field.grid;
@@ -412,6 +189,7 @@ __device__ __forceinline__ void field_level(const TnfModel& m, Smem<TNF_PRECISIO
       const float2 f = hash_level(tab + ((size_t)l << grid.log2_size), px, py, pz, grid.scalings[l], mask);
       a[(2 * l) * 32] = f.x;
       a[(2 * l + 1) * 32] = f.y;
+      if (sf && active) sf[i * 16 + l] = f;
     }
     {
       float y[64];
@@ -459,45 +237,11 @@ __device__ __forceinline__ void field_level(const TnfModel& m, Smem<TNF_PRECISIO
 // ------------------------------------------------------------------------------------
 // field level, tensor cores: 16-sample tiles, mma.m16n8k16, activations stay in registers
 // ------------------------------------------------------------------------------------
-template <int NT, int KT>
-__device__ __forceinline__ void mma_layer(float (&c)[NT][4], const uint32_t (&a)[KT][4], const uint2* __restrict__ w,
-                                          const int nt0, const int ntw, const int lane) {
-  // w is [KT][ntw][32]; uses n-tiles nt0 .. nt0+NT-1
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-    for (int kt = 0; kt < KT; ++kt) mma_16816(c[nt], a[kt], w[(kt * ntw + nt0 + nt) * 32 + lane]);
-}
-template <int NT>
-__device__ __forceinline__ void init_bias(float (&c)[NT][4], const float* bias, const int q) {
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    const float2 b = *reinterpret_cast<const float2*>(bias + nt * 8 + 2 * q);
-    c[nt][0] = b.x; c[nt][1] = b.y; c[nt][2] = b.x; c[nt][3] = b.y;
-  }
-}
-template <int NT, int ACT>
-__device__ __forceinline__ void act_pack(const float (&c)[NT][4], uint32_t (&a)[NT / 2][4]) {
-#pragma unroll
-  for (int kt = 0; kt < NT / 2; ++kt) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      float v[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        v[e] = c[2 * kt + h][e];
-        if (ACT == ACT_RELU) v[e] = fmaxf(v[e], 0.f);
-        if (ACT == ACT_SIGMOID) v[e] = sigmoidf(v[e]);
-      }
-      a[kt][2 * h] = pack_half2(v[0], v[1]);      // row g
-      a[kt][2 * h + 1] = pack_half2(v[2], v[3]);  // row g+8
-    }
-  }
-}
-
 __device__ __forceinline__ void field_level(const TnfModel& m, Smem<TNF_PRECISION_TC_FP16>& S, WarpScratch& ws,
-                                            const RayCtx& rc, const int S2, const int lane, const int warp) {
+                                            const RayCtx& rc, const int S2, const int lane, const int warp,
+                                            void* __restrict__ save_feat) {
   const FieldWTC& W = S.fw;
+  uint32_t* __restrict__ sf = reinterpret_cast<uint32_t*>(save_feat);  // [S2][16] half2 of this ray, or null
   const TnfHashGrid& grid = m.field.grid;
   const uint32_t mask = (1u << grid.log2_size) - 1u;
   const float2* __restrict__ tab = reinterpret_cast<const float2*>(grid.table);
@@ -525,6 +269,8 @@ __device__ __forceinline__ void field_level(const TnfModel& m, Smem<TNF_PRECISIO
         for (int h = 0; h < 2; ++h) {
           const float2 f = hash_level(lt, p[h][0], p[h][1], p[h][2], sc, mask);
           a0[kt][2 * hl + h] = pack_half2(f.x, f.y);
+          const int row = h ? r1 : r0;
+          if (sf && row < S2) sf[row * 16 + l] = a0[kt][2 * hl + h];
         }
       }
     }
@@ -683,7 +429,11 @@ __global__ void __launch_bounds__(kThreads, PREC == TNF_PRECISION_TC_FP16 ? 2 : 
                                         out.sdist[1] ? out.sdist[1] + ray * (S1 + 1) : nullptr);
     pdf_resample(ws, S1, S2, m.anneal, stratified, jit1, jit2, ws.bins, ws.w, lane);
     // ---- level 2: field; its spacing bins now live in ws.w[0..S2]
-    field_level(m, S, ws, rc, S2, lane, warp);
+    field_level(m, S, ws, rc, S2, lane, warp,
+                out.field_features
+                    ? static_cast<unsigned char*>(out.field_features) +
+                          (size_t)ray * S2 * 32 * (PREC == TNF_PRECISION_TC_FP16 ? 2 : 4)
+                    : nullptr);
 
     // ---- composite (get_weights + RGB/Thermal/Accumulation/Depth renderers)
     Compositor comp;
@@ -705,6 +455,10 @@ __global__ void __launch_bounds__(kThreads, PREC == TNF_PRECISION_TC_FP16 ? 2 : 
       sw += w;
       swt = fmaf(w, mid, swt);
       if (active && out.weights[2]) out.weights[2][ray * S2 + i] = w;
+      if (active && out.field_samples) {
+        float* fs = out.field_samples + ((size_t)ray * S2 + i) * 5;
+        fs[0] = ws.sigma[ii]; fs[1] = cr; fs[2] = cg; fs[3] = cb; fs[4] = ct;
+      }
       if (base == 0) first_mid = __shfl_sync(kFull, mid, 0);
       if (base + 32 >= S2) last_mid = __shfl_sync(kFull, mid, (S2 - 1) & 31);
     }
@@ -768,24 +522,20 @@ __global__ void tnf_clip_kernel(float* __restrict__ expected_depth, const long l
 // ====================================================================================
 // C ABI
 // ====================================================================================
+#include "tnf_host.h"
+
 namespace {
-thread_local char g_err[512] = "";
-
-int fail(int code, const char* fmt, ...) {
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(g_err, sizeof(g_err), fmt, ap);
-  va_end(ap);
-  return code;
-}
-
-bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+using tnf::fail;
+using tnf::g_err;
+using tnf::aligned16;
 
 int check_linear(const TnfLinear& l, const char* name) {
   if (!l.weight || !l.bias) return fail(TNF_ERR_INVALID_ARGUMENT, "%s: null weight/bias", name);
   return TNF_OK;
 }
+}  // namespace
 
+namespace tnf {
 int check_model(const TnfModel* m) {
   if (!m) return fail(TNF_ERR_INVALID_ARGUMENT, "model is null");
   for (int k = 0; k < TNF_NUM_PROP; ++k) {
@@ -823,6 +573,10 @@ int check_model(const TnfModel* m) {
     return fail(TNF_ERR_INVALID_ARGUMENT, "precision=%d", m->precision);
   return TNF_OK;
 }
+}  // namespace tnf
+
+namespace {
+using tnf::check_model;
 
 template <int PREC>
 int launch_forward(const TnfModel& m, const TnfRays& r, const TnfOutputs& o, long long chunk, unsigned* cmin,

@@ -126,7 +126,7 @@ class ModelTensors:
 
     def pack(self, *, num_samples: Sequence[int], training: bool, near_plane: float, far_plane: float,
              anneal: float, use_contraction: bool, aabb: Optional[Sequence[float]], appearance_mode: int,
-             precision: int) -> L.TnfModel:
+             precision: int, detach_thermal_geo: bool = False) -> L.TnfModel:
         m = L.TnfModel()
         for i in range(L.TNF_NUM_PROP):
             self._fill_grid(m.prop[i].grid, self.prop_grids[i], f"proposal_networks.{i}.encoding")
@@ -149,7 +149,61 @@ class ModelTensors:
             m.aabb[i] = float(box[i])
         m.appearance_mode = int(appearance_mode)
         m.precision = int(precision)
+        m.detach_thermal_geo = int(bool(detach_thermal_geo))
         return m
+
+    # ------------------------------------------------------------------ autograd plumbing
+    FIELD_ORDER = ("base0", "base1", "rgb0", "rgb1", "rgb2", "th0", "th1", "th2")
+
+    def param_list(self) -> List[Tensor]:
+        """Every parameter of the path in a fixed order: per proposal net (table, l0.w, l0.b, l1.w, l1.b),
+        then the field (table, 8 x (w, b) in FIELD_ORDER, appearance embedding) - 28 tensors."""
+        out: List[Tensor] = []
+        for i in range(L.TNF_NUM_PROP):
+            out += [self.prop_grids[i].table, self.prop_l0[i].weight, self.prop_l0[i].bias,
+                    self.prop_l1[i].weight, self.prop_l1[i].bias]
+        out.append(self.field_grid.table)
+        for k in self.FIELD_ORDER:
+            out += [self.field_linears[k].weight, self.field_linears[k].bias]
+        out.append(self.appearance)
+        return out
+
+    def with_params(self, params: Sequence[Tensor]) -> "ModelTensors":
+        """Same constants, tensors replaced by ``params`` (in ``param_list`` order)."""
+        it = iter(params)
+        grids, l0, l1 = [], [], []
+        for i in range(L.TNF_NUM_PROP):
+            g = self.prop_grids[i]
+            grids.append(_Grid(next(it), g.scalings, g.num_levels, g.log2_size))
+            l0.append(_Linear(next(it), next(it)))
+            l1.append(_Linear(next(it), next(it)))
+        fg = _Grid(next(it), self.field_grid.scalings, self.field_grid.num_levels, self.field_grid.log2_size)
+        lin = {k: _Linear(next(it), next(it)) for k in self.FIELD_ORDER}
+        return ModelTensors(grids, l0, l1, fg, lin, next(it), dict(self.extra))
+
+    @staticmethod
+    def pack_grads(grads: Sequence[Optional[Tensor]]) -> L.TnfModelGrad:
+        """``grads`` in ``param_list`` order (None = not wanted; a proposal net is skipped as a whole
+        when its table gradient is None)."""
+        g = L.TnfModelGrad()
+        it = iter(grads)
+
+        def ptr(t, name):
+            return 0 if t is None else _dev_f32(t, name).data_ptr()
+
+        for i in range(L.TNF_NUM_PROP):
+            five = [next(it) for _ in range(5)]
+            if five[0] is not None and any(t is None for t in five):
+                raise ValueError(f"proposal net {i}: gradients must be requested for all five tensors or none")
+            g.prop[i].table = ptr(five[0], "grad.table")
+            g.prop[i].l0.weight, g.prop[i].l0.bias = ptr(five[1], "grad"), ptr(five[2], "grad")
+            g.prop[i].l1.weight, g.prop[i].l1.bias = ptr(five[3], "grad"), ptr(five[4], "grad")
+        g.field.table = ptr(next(it), "grad.field.table")
+        for k in ModelTensors.FIELD_ORDER:
+            lg = getattr(g.field, k)
+            lg.weight, lg.bias = ptr(next(it), "grad." + k), ptr(next(it), "grad." + k)
+        g.field.appearance = ptr(next(it), "grad.appearance")
+        return g
 
 
 _OUT_KEYS = ("rgb", "thermal", "depth", "expected_depth", "accumulation", "prop_depth_0", "prop_depth_1")
@@ -176,6 +230,8 @@ def render_forward(
     depth_clip_chunk: int = 0,
     return_samples: bool = False,
     out: Optional[Dict[str, Tensor]] = None,
+    save_for_backward: bool = False,
+    detach_thermal_geo: bool = False,
 ) -> Dict[str, object]:
     """One call of ``tnf_render_forward`` over R rays (flat).  Returns the output dict of
     ThermalNerfModel.get_outputs (thermal_nerf_model.py:245-275): rgb [R,3], thermal,
@@ -214,7 +270,8 @@ def render_forward(
 
     model = tensors.pack(num_samples=num_samples, training=training, near_plane=near_plane, far_plane=far_plane,
                          anneal=anneal, use_contraction=use_contraction, aabb=aabb,
-                         appearance_mode=appearance_mode, precision=precision)
+                         appearance_mode=appearance_mode, precision=precision,
+                         detach_thermal_geo=detach_thermal_geo)
 
     res: Dict[str, object] = {}
     outs = L.TnfOutputs()
@@ -243,6 +300,16 @@ def render_forward(
             wl.append(w)
             sl.append(sd)
         res["weights_list"], res["sdist_list"] = wl, sl
+    if save_for_backward:
+        if not (return_samples and training):
+            raise ValueError("save_for_backward needs training=True and return_samples=True")
+        ns = R * int(num_samples[-1])
+        fdt = torch.float32 if precision == L.PRECISION_FP32 else torch.float16
+        res["field_features"] = torch.empty((max(ns, 1), 32), dtype=fdt, device=dev)
+        res["field_samples"] = torch.empty((max(ns, 1), 5), dtype=torch.float32, device=dev)
+        outs.field_features = res["field_features"].data_ptr()
+        outs.field_samples = res["field_samples"].data_ptr()
+        res["_model_struct"] = model
 
     chunk = int(depth_clip_chunk)
     ws_bytes = int(lib.tnf_forward_workspace_bytes(R, chunk))
@@ -254,3 +321,285 @@ def render_forward(
     L.check(rc)
     del keep  # inputs stay alive until the launch is enqueued; stream order protects them afterwards
     return res
+
+
+# ---------------------------------------------------------------------------------------------
+# training: autograd node over tnf_render_forward / tnf_render_backward
+# ---------------------------------------------------------------------------------------------
+def _ptr(t: Optional[Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def render_backward(tensors: ModelTensors, model_struct: L.TnfModel, origins: Tensor, directions: Tensor,
+                    camera_indices: Optional[Tensor], nears: Optional[Tensor], fars: Optional[Tensor],
+                    jitter: Optional[Tensor], saved: Dict[str, object], grad_outputs: Dict[str, Optional[Tensor]],
+                    grads: Sequence[Optional[Tensor]]) -> None:
+    """``tnf_render_backward``: accumulates into ``grads`` (``ModelTensors.param_list`` order)."""
+    lib = L.load()
+    R = int(origins.shape[0])
+    dev = origins.device
+    rays = L.TnfRays()
+    rays.origins, rays.directions, rays.num_rays = origins.data_ptr(), directions.data_ptr(), R
+    rays.camera_indices, rays.nears, rays.fars, rays.jitter = (_ptr(camera_indices), _ptr(nears), _ptr(fars),
+                                                               _ptr(jitter))
+    sv = L.TnfSaved()
+    for k in range(L.TNF_NUM_PROP + 1):
+        sv.sdist[k] = saved["sdist_list"][k].data_ptr()
+        sv.weights[k] = saved["weights_list"][k].data_ptr()
+    sv.field_features = saved["field_features"].data_ptr()
+    sv.field_samples = saved["field_samples"].data_ptr()
+    go = L.TnfOutputGrads()
+    keep = []
+
+    def gptr(t, n):
+        if t is None:
+            return 0
+        t = _dev_f32(t.contiguous(), n)
+        keep.append(t)
+        return t.data_ptr()
+
+    go.rgb = gptr(grad_outputs.get("rgb"), "grad rgb")
+    go.thermal = gptr(grad_outputs.get("thermal"), "grad thermal")
+    go.accumulation = gptr(grad_outputs.get("accumulation"), "grad accumulation")
+    gw = grad_outputs.get("weights_list") or [None] * (L.TNF_NUM_PROP + 1)
+    for k in range(L.TNF_NUM_PROP + 1):
+        go.weights[k] = gptr(gw[k], f"grad weights[{k}]")
+    gstruct = ModelTensors.pack_grads(grads)
+    nbytes = int(lib.tnf_backward_workspace_bytes(C.byref(model_struct), R))
+    ws = saved.get("_workspace")
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        rc = lib.tnf_render_backward(C.byref(model_struct), C.byref(rays), C.byref(sv), C.byref(go), C.byref(gstruct),
+                                     ws.data_ptr(), ws.numel(), C.c_void_p(stream))
+    L.check(rc)
+    del keep
+
+
+class _RenderFn(torch.autograd.Function):
+    """get_outputs in training mode.  Differentiable outputs: rgb, thermal, accumulation and the three
+    ``weights_list`` entries; depth-type outputs and the spacing bins are constants (as in the
+    reference: median depth is computed under no_grad, PDFSampler detaches its bins)."""
+
+    NUM_FIXED = 9  # inputs before *params
+
+    @staticmethod
+    def forward(ctx, tensors: ModelTensors, kw: dict, prop_grad: bool, origins, directions, camera_indices, nears,
+                fars, jitter, *params):
+        t = tensors.with_params([p.detach() for p in params])
+        res = render_forward(t, origins, directions, camera_indices, nears, fars, jitter, training=True,
+                             return_samples=True, save_for_backward=True, **kw)
+        ctx.tensors = t
+        ctx.model_struct = res.pop("_model_struct")
+        ctx.rays = (origins, directions, camera_indices, nears, fars, jitter)
+        ctx.saved = {k: res[k] for k in ("sdist_list", "weights_list", "field_features", "field_samples")}
+        ctx.prop_grad = bool(prop_grad)
+        ctx.params = params
+        ctx.set_materialize_grads(False)
+        w = res["weights_list"]
+        sd = res["sdist_list"]
+        nondiff = (res["depth"], res["expected_depth"], res["prop_depth_0"], res["prop_depth_1"], *sd)
+        ctx.mark_non_differentiable(*nondiff)
+        return (res["rgb"], res["thermal"], res["accumulation"], w[0], w[1], w[2], *nondiff)
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_th, g_acc, g_w0, g_w1, g_w2, *_):
+        params = ctx.params
+        need = list(ctx.needs_input_grad[_RenderFn.NUM_FIXED:])
+        # a proposal net takes part only if its upstream weights carry a gradient (the reference's
+        # no_grad steps) and its tensors want one
+        gws = [g_w0, g_w1]
+        grads: List[Optional[Tensor]] = []
+        idx = 0
+        for i in range(L.TNF_NUM_PROP):
+            on = ctx.prop_grad and gws[i] is not None and all(need[idx:idx + 5])
+            grads += [torch.zeros_like(params[idx + j]) if on else None for j in range(5)]
+            idx += 5
+        for j in range(idx, len(params)):
+            grads.append(torch.zeros_like(params[j]))
+        o, d, cam, nears, fars, jitter = ctx.rays
+
+        def flat(g):
+            return None if g is None else g.reshape(g.shape[0], -1)
+
+        render_backward(ctx.tensors, ctx.model_struct, o, d, cam, nears, fars, jitter, ctx.saved,
+                        {"rgb": g_rgb, "thermal": None if g_th is None else g_th.reshape(-1),
+                         "accumulation": None if g_acc is None else g_acc.reshape(-1),
+                         "weights_list": [flat(g_w0) if ctx.prop_grad else None,
+                                          flat(g_w1) if ctx.prop_grad else None, flat(g_w2)]},
+                        grads)
+        out = [g if n else None for g, n in zip(grads, need)]
+        return (None,) * _RenderFn.NUM_FIXED + tuple(out)
+
+
+def render(tensors: ModelTensors, origins: Tensor, directions: Tensor, camera_indices: Optional[Tensor] = None,
+           nears: Optional[Tensor] = None, fars: Optional[Tensor] = None, jitter: Optional[Tensor] = None,
+           *, prop_grad: bool = True, **kw) -> Dict[str, object]:
+    """Training-mode ``get_outputs`` with autograd: the dict of :func:`render_forward` (with
+    ``weights_list`` / ``sdist_list``), differentiable w.r.t. every parameter of ``tensors``.
+    ``prop_grad=False`` reproduces the reference's no_grad proposal steps
+    (ProposalNetworkSampler ``updated == False``)."""
+    o = _dev_f32(origins, "origins")
+    d = _dev_f32(directions, "directions")
+    R = int(o.shape[0])
+    cam = camera_indices.reshape(-1).contiguous() if camera_indices is not None else None
+    nears = _dev_f32(nears.reshape(-1), "nears") if nears is not None else None
+    fars = _dev_f32(fars.reshape(-1), "fars") if fars is not None else None
+    if jitter is not None:
+        jitter = _dev_f32(jitter.reshape(L.TNF_NUM_PROP + 1, -1), "jitter")
+    for k in ("training", "return_samples", "save_for_backward", "out"):
+        if k in kw:
+            raise TypeError(f"render() fixes {k!r}; use render_forward() for the non-differentiable call")
+    outs = _RenderFn.apply(tensors, dict(kw), bool(prop_grad), o, d, cam, nears, fars, jitter,
+                           *tensors.param_list())
+    rgb, th, acc, w0, w1, w2, depth, ed, pd0, pd1, sd0, sd1, sd2 = outs
+    if not prop_grad:
+        w0, w1 = w0.detach(), w1.detach()
+    return {"rgb": rgb, "thermal": th.view(R, 1), "accumulation": acc.view(R, 1), "depth": depth,
+            "expected_depth": ed, "prop_depth_0": pd0, "prop_depth_1": pd1,
+            "weights_list": [w0, w1, w2], "sdist_list": [sd0, sd1, sd2]}
+
+
+# ---------------------------------------------------------------------------------------------
+# losses (get_loss_dict) and Adam
+# ---------------------------------------------------------------------------------------------
+LOSS_NAMES = ("rgb_loss", "interlevel_loss", "distortion_loss", "thermal")
+
+
+def losses_forward_backward(weights_list: Sequence[Tensor], sdist_list: Sequence[Tensor], rgb: Tensor,
+                            thermal: Tensor, gt_rgb: Tensor, gt_thermal: Tensor, *, interlevel_mult: float = 1.0,
+                            distortion_mult: float = 0.002, use_rgb_loss: bool = True,
+                            use_thermal_loss: bool = True, grad_scale: float = 1.0, want_grads: bool = True,
+                            prop_grad: bool = True):
+    """``tnf_losses``: returns (losses[4] device tensor in LOSS_NAMES order, grads dict or None).
+    grads: d(loss)/d(input) * grad_scale for rgb [R,3], thermal [R], weights_list[k] [R,S_k]."""
+    lib = L.load()
+    R = int(rgb.shape[0])
+    dev = rgb.device
+    a = L.TnfLossArgs()
+    keep = []
+
+    def f32(t, n):
+        t = _dev_f32(t.detach().contiguous(), n)
+        keep.append(t)
+        return t
+
+    for k in range(L.TNF_NUM_PROP + 1):
+        w = f32(weights_list[k].reshape(R, -1), f"weights[{k}]")
+        sd = f32(sdist_list[k], f"sdist[{k}]")
+        if sd.shape != (R, w.shape[1] + 1):
+            raise ValueError(f"sdist[{k}] must be [R, S+1], got {tuple(sd.shape)} for S={w.shape[1]}")
+        a.weights[k], a.sdist[k], a.num_samples[k] = w.data_ptr(), sd.data_ptr(), int(w.shape[1])
+    a.rgb = f32(rgb.reshape(R, 3), "rgb").data_ptr()
+    a.thermal = f32(thermal.reshape(R), "thermal").data_ptr()
+    a.gt_rgb = f32(gt_rgb.reshape(R, 3), "gt_rgb").data_ptr()
+    a.gt_thermal = f32(gt_thermal.reshape(R), "gt_thermal").data_ptr()
+    a.num_rays = R
+    a.interlevel_mult, a.distortion_mult = float(interlevel_mult), float(distortion_mult)
+    a.use_rgb_loss, a.use_thermal_loss = int(bool(use_rgb_loss)), int(bool(use_thermal_loss))
+    a.grad_scale = float(grad_scale)
+    losses = torch.empty(4, dtype=torch.float32, device=dev)
+    a.losses = losses.data_ptr()
+    grads = None
+    if want_grads:
+        grads = {"rgb": torch.empty((R, 3), dtype=torch.float32, device=dev),
+                 "thermal": torch.empty((R,), dtype=torch.float32, device=dev), "weights_list": []}
+        a.g_rgb, a.g_thermal = grads["rgb"].data_ptr(), grads["thermal"].data_ptr()
+        for k in range(L.TNF_NUM_PROP + 1):
+            if k < L.TNF_NUM_PROP and not prop_grad:
+                grads["weights_list"].append(None)
+                continue
+            g = torch.empty((R, a.num_samples[k]), dtype=torch.float32, device=dev)
+            a.g_weights[k] = g.data_ptr()
+            grads["weights_list"].append(g)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        rc = lib.tnf_losses(C.byref(a), C.c_void_p(stream))
+    L.check(rc)
+    del keep
+    return losses, grads
+
+
+class _LossFn(torch.autograd.Function):
+    """The four losses as one node: forward evaluates losses and their gradients in one kernel,
+    backward scales the stashed gradients by the upstream scalars."""
+
+    @staticmethod
+    def forward(ctx, cfg: dict, rgb, thermal, w0, w1, w2, sd0, sd1, sd2, gt_rgb, gt_thermal):
+        prop_grad = bool(ctx.needs_input_grad[3] or ctx.needs_input_grad[4])
+        losses, g = losses_forward_backward([w0, w1, w2], [sd0, sd1, sd2], rgb, thermal, gt_rgb, gt_thermal,
+                                            interlevel_mult=cfg["interlevel_mult"],
+                                            distortion_mult=cfg["distortion_mult"], use_rgb_loss=cfg["use_rgb_loss"],
+                                            use_thermal_loss=cfg["use_thermal_loss"], prop_grad=prop_grad)
+        ctx.g = g
+        ctx.set_materialize_grads(False)
+        ctx.shapes = (rgb.shape, thermal.shape, w0.shape, w1.shape, w2.shape)
+        return losses[0], losses[1], losses[2], losses[3]
+
+    @staticmethod
+    def backward(ctx, u_rgb, u_inter, u_dist, u_th):
+        g = ctx.g
+        s = ctx.shapes
+        gw = g["weights_list"]
+        def sc(t, u, shape):
+            return None if (t is None or u is None) else (t * u).view(shape)
+
+        return (None, sc(g["rgb"], u_rgb, s[0]), sc(g["thermal"], u_th, s[1]), sc(gw[0], u_inter, s[2]),
+                sc(gw[1], u_inter, s[3]), sc(gw[2], u_dist, s[4]), None, None, None, None, None)
+
+
+def losses(outputs: Dict[str, object], gt_rgb: Tensor, gt_thermal: Tensor, *, interlevel_mult: float = 1.0,
+           distortion_mult: float = 0.002, use_rgb_loss: bool = True, use_thermal_loss: bool = True
+           ) -> Dict[str, Tensor]:
+    """Differentiable loss dict of get_loss_dict (thermal_nerf_model.py:277-326) from the training outputs
+    of :func:`render`."""
+    w, sd = outputs["weights_list"], outputs["sdist_list"]
+    cfg = dict(interlevel_mult=interlevel_mult, distortion_mult=distortion_mult, use_rgb_loss=use_rgb_loss,
+               use_thermal_loss=use_thermal_loss)
+    vals = _LossFn.apply(cfg, outputs["rgb"], outputs["thermal"], w[0], w[1], w[2], sd[0], sd[1], sd[2], gt_rgb,
+                         gt_thermal)
+    out = dict(zip(LOSS_NAMES, vals))
+    if not use_rgb_loss:
+        out.pop("rgb_loss")
+    if not use_thermal_loss:
+        out.pop("thermal")
+    return out
+
+
+def adam_step(params: Sequence[Tensor], grads: Sequence[Tensor], exp_avgs: Sequence[Tensor],
+              exp_avg_sqs: Sequence[Tensor], lrs: Sequence[float], *, step: int, beta1: float = 0.9,
+              beta2: float = 0.999, eps: float = 1e-8, inv_grad_scale: float = 1.0,
+              grad_scale: Optional[Tensor] = None, found_inf: Optional[Tensor] = None,
+              zero_grads: bool = False) -> None:
+    """``tnf_adam_step`` over a list of fp32 CUDA tensors (one launch per 48 tensors)."""
+    lib = L.load()
+    n = len(params)
+    if not (len(grads) == len(exp_avgs) == len(exp_avg_sqs) == len(lrs) == n):
+        raise ValueError("params/grads/exp_avgs/exp_avg_sqs/lrs must have the same length")
+    if n == 0:
+        return
+    dev = params[0].device
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    fi = gs = 0
+    if found_inf is not None:
+        fi = _dev_f32(found_inf.reshape(-1), "found_inf").data_ptr()
+    if grad_scale is not None:
+        gs = _dev_f32(grad_scale.reshape(-1), "grad_scale").data_ptr()
+    for s0 in range(0, n, L.TNF_ADAM_MAX_TENSORS):
+        m = min(L.TNF_ADAM_MAX_TENSORS, n - s0)
+        arr = (L.TnfAdamTensor * m)()
+        for j in range(m):
+            i = s0 + j
+            p, g, ea, es = params[i], grads[i], exp_avgs[i], exp_avg_sqs[i]
+            for t, nm in ((p, "param"), (g, "grad"), (ea, "exp_avg"), (es, "exp_avg_sq")):
+                _dev_f32(t, nm)
+                if t.numel() != p.numel():
+                    raise ValueError(f"{nm} numel {t.numel()} != param numel {p.numel()}")
+            arr[j].param, arr[j].grad = p.data_ptr(), g.data_ptr()
+            arr[j].exp_avg, arr[j].exp_avg_sq = ea.data_ptr(), es.data_ptr()
+            arr[j].numel, arr[j].lr = p.numel(), float(lrs[i])
+        with torch.cuda.device(dev):
+            rc = lib.tnf_adam_step(arr, m, float(beta1), float(beta2), float(eps), int(step), float(inv_grad_scale),
+                                   C.c_void_p(gs), C.c_void_p(fi), int(bool(zero_grads)), C.c_void_p(stream))
+        L.check(rc)

@@ -228,8 +228,18 @@ class ThermalNerfModel(nn.Module):
         arguments instead of [R,1] tensors (a caller-supplied nears/fars still wins)."""
         return self.get_outputs(ray_bundle)
 
+    def _render_kwargs(self) -> Dict[str, Any]:
+        cfg = self.config
+        return dict(
+            num_samples=(*cfg.num_proposal_samples_per_ray, cfg.num_nerf_samples_per_ray),
+            near_plane=self._collider_near(), far_plane=cfg.far_plane, anneal=self._anneal,
+            use_contraction=not cfg.disable_scene_contraction,
+            aabb=[float(x) for x in torch.as_tensor(self.scene_box.aabb).reshape(-1).tolist()],
+            appearance_mode=self._appearance_mode(), precision=self._precision())
+
     def get_outputs(self, ray_bundle, depth_clip_chunk: int = 0) -> Dict[str, Any]:
-        """thermal_nerf_model.py:210-275 as one fused kernel launch."""
+        """thermal_nerf_model.py:210-275 as one fused kernel launch (eval) or one autograd node over
+        tnf_render_forward / tnf_render_backward (training)."""
         cfg = self.config
         if self.training:
             self.camera_optimizer.apply_to_raybundle(ray_bundle)
@@ -240,17 +250,22 @@ class ThermalNerfModel(nn.Module):
         cam = ray_bundle.camera_indices
         if self.training and cam is None:
             raise AttributeError("Camera indices are not provided.")  # thermal_field.py:113-114
-        jitter = torch.rand((L.TNF_NUM_PROP + 1, R), device=o.device) if self.training else None
         nears = ray_bundle.nears.reshape(-1).contiguous().float() if ray_bundle.nears is not None else None
         fars = ray_bundle.fars.reshape(-1).contiguous().float() if ray_bundle.fars is not None else None
-        res = F.render_forward(
-            self.tensors(), o, d, cam.reshape(-1) if cam is not None else None, nears, fars, jitter,
-            num_samples=(*cfg.num_proposal_samples_per_ray, cfg.num_nerf_samples_per_ray),
-            training=self.training, near_plane=self._collider_near(), far_plane=cfg.far_plane, anneal=self._anneal,
-            use_contraction=not cfg.disable_scene_contraction,
-            aabb=[float(x) for x in torch.as_tensor(self.scene_box.aabb).reshape(-1).tolist()],
-            appearance_mode=self._appearance_mode(), precision=self._precision(),
-            depth_clip_chunk=depth_clip_chunk, return_samples=self.training)
+        cam_flat = cam.reshape(-1) if cam is not None else None
+        if self.training and torch.is_grad_enabled():
+            # ProposalNetworkSampler: the proposal densities only carry gradients on "updated" steps
+            updated = self._steps_since_update > self.update_schedule(self._step) or self._step < 10
+            jitter = torch.rand((L.TNF_NUM_PROP + 1, R), device=o.device)
+            res = F.render(self.tensors(), o.detach(), d.detach(), cam_flat, nears, fars, jitter, prop_grad=updated,
+                           detach_thermal_geo=not self.field.pass_thermal_gradients, **self._render_kwargs())
+            if updated:
+                self._steps_since_update = 0
+        else:
+            jitter = torch.rand((L.TNF_NUM_PROP + 1, R), device=o.device) if self.training else None
+            res = F.render_forward(self.tensors(), o, d, cam_flat, nears, fars, jitter, training=self.training,
+                                   depth_clip_chunk=depth_clip_chunk, return_samples=self.training,
+                                   **self._render_kwargs())
         outputs: Dict[str, Any] = {
             "rgb": res["rgb"].view(*shape, 3),
             "accumulation": res["accumulation"].view(*shape, 1),
@@ -291,13 +306,53 @@ class ThermalNerfModel(nn.Module):
             if not isinstance(v, Tensor):
                 continue  # nerfstudio skips non-tensor outputs (weights_list etc.)
             res[k] = v.view(*image_shape, -1).to(input_device)
+        # RenderedImageModality.RGB.value == "img" (rendered_image_modalities.py:5) while get_outputs emits
+        # "rgb": the alias lets the unchanged render_video_script.py default modalities work
+        res["img"] = res["rgb"]
         return res
 
-    # ------------------------------------------------------------------ metrics (pure torch, as in the reference)
+    # ------------------------------------------------------------------ losses / metrics
+    def _fused_losses(self, outputs, batch) -> Dict[str, Tensor]:
+        """tnf_losses over the training outputs, evaluated once per step (metrics + loss dict share it)."""
+        cache = outputs.get("_b200_losses")
+        if cache is None:
+            image = batch["image"].to(self.device)[..., :3].reshape(-1, 3).float()
+            thermal = batch["thermal"].to(self.device).reshape(-1).float()
+            w = outputs["weights_list"]
+            cache = F.losses(
+                {"rgb": outputs["rgb"].reshape(-1, 3), "thermal": outputs["thermal"].reshape(-1),
+                 "weights_list": w, "sdist_list": outputs["ray_samples_list"]},
+                image, thermal, interlevel_mult=self.config.interlevel_loss_mult,
+                distortion_mult=self.config.distortion_loss_mult, use_rgb_loss=self.field.pass_rgb_gradients,
+                use_thermal_loss=self.field.pass_thermal_gradients)
+            outputs["_b200_losses"] = cache
+        return cache
+
     def get_metrics_dict(self, outputs, batch) -> Dict[str, Tensor]:
+        """NerfactoModel.get_metrics_dict (inherited by the reference): psnr, and in training the
+        distortion metric that get_loss_dict consumes (thermal_nerf_model.py:303-305)."""
         gt_rgb = batch["image"].to(self.device)
-        mse = torch.mean((outputs["rgb"] - gt_rgb[..., :3]) ** 2)
-        return {"psnr": -10.0 * torch.log10(mse)}
+        with torch.no_grad():
+            mse = torch.mean((outputs["rgb"].detach() - gt_rgb[..., :3]) ** 2)
+        metrics = {"psnr": -10.0 * torch.log10(mse)}
+        if self.training:
+            losses = self._fused_losses(outputs, batch)
+            metrics["distortion"] = losses["distortion_loss"] / self.config.distortion_loss_mult
+        return metrics
+
+    def get_loss_dict(self, outputs, batch, metrics_dict=None) -> Dict[str, Tensor]:
+        """thermal_nerf_model.py:277-326.  background_color="last_sample" makes
+        blend_background_for_loss_computation the identity on (pred, gt)."""
+        if self.training:
+            assert metrics_dict is not None and "distortion" in metrics_dict  # thermal_nerf_model.py:302
+            return dict(self._fused_losses(outputs, batch))
+        loss_dict: Dict[str, Tensor] = {}
+        image = batch["image"].to(self.device)[..., :3]
+        if self.field.pass_rgb_gradients:
+            loss_dict["rgb_loss"] = torch.nn.functional.mse_loss(image, outputs["rgb"])
+        if self.field.pass_thermal_gradients:
+            loss_dict["thermal"] = torch.nn.functional.mse_loss(outputs["thermal"], batch["thermal"].to(self.device))
+        return loss_dict
 
     def mae_thermal(self, gt: Tensor, pred: Tensor, threshold: Optional[float] = None) -> Tensor:
         """thermal_metrics.py:5-34."""
