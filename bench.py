@@ -7,6 +7,8 @@
                                                              # on the box's host cores
 
 One "step" = one pass of the hot path over one batch of synthetic ThermoScenes-shaped rays:
+  --mode train  : (default) one full training iteration at 4096 rays/batch per GPU
+                  (BASELINE.json configs[1]; metric training rays/s = world * rays / iteration time)
   --mode render : one 800x800 frame (640 000 rays) through get_outputs_for_camera_ray_bundle
                   (BASELINE.json configs[4]; metric render Mpix/s, 1 ray = 1 pixel)
 Weights are random "trained-like" (no datasets/checkpoints offline); data is synthetic.
@@ -136,16 +138,92 @@ class L2Flusher:
         self.buf.fill_(1.0)
 
 
+# ----------------------------------------------------------------------------- synthetic training data
+def train_batches(n_batches: int, rays: int, device, rank: int, pin: bool = False):
+    """ThermoScenes-shaped random pixel batches: 100 pinhole cameras 800x800 on a sphere,
+    uniform (image, y, x) draws seeded per rank (nerfstudio DDP: every rank draws its own rays), analytic GT."""
+    from thermo_nerf_b200 import sphere_cameras
+
+    cams = sphere_cameras(NUM_IMAGES, hw=HW, focal=FOCAL)
+    out = []
+    for b in range(n_batches):
+        g = torch.Generator().manual_seed(77 + 1000 * rank + b)
+        cam = torch.randint(0, NUM_IMAGES, (rays,), generator=g)
+        ys = torch.randint(0, HW, (rays,), generator=g)
+        xs = torch.randint(0, HW, (rays,), generator=g)
+        r = cams.generate_pixel_rays(cam, ys, xs)
+        gt_rgb = (0.5 + 0.4 * torch.sin(r.directions * 7.0)).float()
+        gt_th = (0.5 + 0.4 * torch.cos(r.directions[:, :1] * 5.0 + r.directions[:, 1:2] * 3.0)).float()
+        gt_th = gt_th + 0.01 * torch.rand(gt_th.shape, generator=g)
+        t = (r.origins, r.directions, r.camera_indices.reshape(-1), gt_rgb.contiguous(), gt_th.reshape(-1).contiguous())
+        out.append(tuple(x.pin_memory() for x in t) if pin else tuple(x.to(device) for x in t))
+    return out
+
+
+TRAIN_WORKLOAD = ("thermal-nerf training iteration, ThermoScenes double_robot-shaped synthetic rays: {rays} rays/batch per "
+                  "GPU (BASELINE configs[1]), samples 256/96/48, forward + losses (rgb, thermal, interlevel, distortion) + "
+                  "backward + Adam(lr 1e-2, eps 1e-15, exp. decay) over all 19.4M parameters; each rank draws its own "
+                  "rays, gradients all-reduced (mean) over NCCL")
+
+
 # ----------------------------------------------------------------------------- reference arm
+def oracle_train_setup(rays: int):
+    from oracle import OracleConfig, OracleThermalNerf
+
+    model = OracleThermalNerf(OracleConfig(camera_optimizer_mode="off"), NUM_IMAGES, seed=0)
+    randomise_trained_like(model, 0)
+    field = [p for n, p in model.named_parameters() if n.startswith("field.")]
+    props = [p for n, p in model.named_parameters() if n.startswith("proposal_networks.")]
+    opts = [torch.optim.Adam(field, lr=1e-2, eps=1e-15), torch.optim.Adam(props, lr=1e-2, eps=1e-15)]
+    batch = train_batches(1, rays, "cpu", 0)[0]
+    return model, opts, batch
+
+
+def oracle_train_step(model, opts, batch, step: int) -> float:
+    from oracle import OracleRays
+
+    o, d, cam, gt_rgb, gt_th = batch
+    model.set_anneal_for_step(step)
+    for op in opts:
+        op.zero_grad()
+    out = model.get_outputs(OracleRays(o, d, cam.reshape(-1, 1)), training=True)
+    ld = model.get_loss_dict(out, gt_rgb, gt_th.reshape(-1, 1), training=True)
+    loss = sum(ld.values())
+    loss.backward()
+    for op in opts:
+        op.step()
+    return float(loss.detach())
+
+
 def run_reference(args, rank: int, world: int) -> None:
     """The path's own PyTorch implementation (nerfstudio torch semantics; oracle port since
     nerfstudio is not installable offline) on the host cores, bounded sample per step."""
     if rank != 0:
         return
-    from oracle import OracleConfig, OracleThermalNerf, make_synthetic_rays
-
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    if args.mode == "train":
+        sample = args.ref_rays
+        model, opts, batch = oracle_train_setup(sample)
+        for i in range(args.warmup):
+            oracle_train_step(model, opts, batch, i)
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            oracle_train_step(model, opts, batch, args.warmup + i)
+        dt = time.perf_counter() - t0
+        val = sample * args.steps / dt
+        desc = (f"{sample}-ray batch per step (full iteration: forward, 4 losses, autograd backward, torch Adam), fp32, "
+                f"torch {torch.__version__} on {cores} host threads")
+        line = {"impl": "reference", "metric": "train_rays_per_s", "value": val, "unit": "rays/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+                "config": {"workload": TRAIN_WORKLOAD.format(rays=args.rays), "sample": desc},
+                "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "sample": desc},
+                "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+    from oracle import OracleConfig, OracleThermalNerf, make_synthetic_rays
+
     sample = args.ref_rays
     model = OracleThermalNerf(OracleConfig(), NUM_IMAGES, seed=0)
     randomise_trained_like(model, 0)
@@ -171,24 +249,44 @@ def run_reference(args, rank: int, world: int) -> None:
     print(json.dumps(line), flush=True)
 
 
+def hbm_peak():
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        try:
+            return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
 # ----------------------------------------------------------------------------- our arm
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="render", choices=["render"])
+    ap.add_argument("--mode", default="train", choices=["train", "render"])
     ap.add_argument("--precision", default="tc_fp16", choices=["tc_fp16", "fp32"])
-    ap.add_argument("--ref-rays", type=int, default=4096, help="rays per step of the CPU reference sample")
+    ap.add_argument("--rays", type=int, default=4096, help="training rays per batch per GPU")
+    ap.add_argument("--ref-rays", type=int, default=None, help="rays per step of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-render", action="store_true", help="train mode: skip the short render measurement")
     ap.add_argument("--torch-cuda-baseline", action="store_true",
                     help="opt-in context number: the PyTorch restatement run eagerly on the GPU")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    ref = args.impl == "reference"
+    if args.steps is None:
+        args.steps = (3 if ref else 200) if args.mode == "train" else (3 if ref else 20)
+    if args.warmup is None:
+        args.warmup = 1 if ref else (20 if args.mode == "train" else 3)
+    if args.ref_rays is None:
+        args.ref_rays = 4096
+    if not ref:
+        args.warmup = max(args.warmup, 3)
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-    if args.impl == "reference":
+    if ref:
         run_reference(args, rank, world)
         return
 
@@ -213,6 +311,249 @@ def main() -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    ctx = dict(args=args, rank=rank, world=world, local=local, device=device, barrier=barrier,
+               max_over_ranks=max_over_ranks)
+    line = bench_train(ctx) if args.mode == "train" else bench_render(ctx)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_train(ctx) -> dict:
+    """BASELINE configs[1]: full training iterations at `--rays` rays per batch per GPU."""
+    args, rank, world, device = ctx["args"], ctx["rank"], ctx["world"], ctx["device"]
+    barrier, max_over_ranks = ctx["barrier"], ctx["max_over_ranks"]
+    from thermo_nerf_b200 import FusedAdam, RayBundle
+    from thermo_nerf_b200 import functional as F
+    from thermo_nerf_b200.engine import TrainEngine
+
+    R = args.rays
+    model = build_b200_model(device, args.precision)
+    model.config.camera_optimizer_mode = "off"
+    model.train()
+    engine = TrainEngine(model, world_size=world)
+    n_distinct = 8
+    batches = train_batches(n_distinct, R, device, rank)
+
+    # ---- device-resident throughput ("value"): inputs already in HBM
+    for i in range(args.warmup):
+        engine.step(*batches[i % n_distinct])
+    barrier()
+    sampler = ClockSampler(ctx["local"])
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        losses = engine.step(*batches[i % n_distinct])
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_per_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    value = world * R / (ms_per_step * 1e-3)
+    final_losses = [float(x) for x in losses.tolist()]
+
+    # ---- per-kernel breakdown of one iteration (CUDA events between the launches, same stream)
+    breakdown = kernel_breakdown(engine, batches, device) if rank == 0 else {}
+    roofline = None
+    if breakdown:
+        peak, peak_src = hbm_peak()
+        n_params = sum(p.numel() for p in engine.params)
+        algo = {
+            "forward": R * ALGO_BYTES_PER_RAY,
+            # fwd re-gather of the proposal levels + table scatters (read-modify-write of 8 B cells)
+            "backward": R * ((256 + 96) * 5 * 8 * 8 * 3 + 48 * 16 * 8 * 8 * 2 + 48 * (64 + 20)),
+            "wgrad": R * 48 * (688 + 32) * 2,
+            "adam": n_params * 32,
+        }
+        dom = max(("forward", "backward", "wgrad", "adam"), key=lambda k: breakdown.get(k + "_ms", 0.0))
+        ach = algo[dom] / (breakdown[dom + "_ms"] * 1e-3) / 1e9
+        traffic = None
+        tp = ROOT / "profiles" / "train_traffic.json"
+        if tp.exists():
+            try:
+                traffic = json.load(open(tp)).get(dom, {}).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                    "kernel": dom, "kernel_ms": breakdown[dom + "_ms"], "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": algo[dom],
+                    "note": "algorithmic bytes per launch as defined in DESIGN.md section 4; hash tables are "
+                            "L2-resident within a launch, so DRAM traffic sits below the algorithmic gather bytes",
+                    "all_kernels": {k: {"ms": breakdown[k + "_ms"], "algorithmic_GBps": algo[k] / (breakdown[k + "_ms"] * 1e-3) / 1e9}
+                                    for k in algo if breakdown.get(k + "_ms")}}
+
+    # ---- end to end through the plugin API with HOST buffers: model(ray_bundle) -> get_metrics_dict ->
+    #      get_loss_dict -> backward -> FusedAdam.step, pinned H2D of rays + GT and D2H of the loss every step
+    model2 = build_b200_model(device, args.precision)
+    model2.config.camera_optimizer_mode = "off"
+    model2.train()
+    groups = model2.get_param_groups()
+    opts = [FusedAdam(groups["proposal_networks"], lr=1e-2, eps=1e-15), FusedAdam(groups["fields"], lr=1e-2, eps=1e-15)]
+    cbs = model2.get_training_callbacks()
+    host = train_batches(n_distinct, R, device, rank, pin=True)
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def e2e_step(i: int) -> None:
+        for c in cbs:
+            if c.where_to_run == ["BEFORE_TRAIN_ITERATION"]:
+                c.run_callback(i)
+        ho, hd, hc, hrgb, hth = host[i % n_distinct]
+        rb = RayBundle(origins=ho.to(device, non_blocking=True), directions=hd.to(device, non_blocking=True),
+                       camera_indices=hc.to(device, non_blocking=True).view(-1, 1))
+        batch = {"image": hrgb.to(device, non_blocking=True), "thermal": hth.view(-1, 1)}  # thermal GT stays on the
+        for o in opts:                                                                       # host until the loss
+            o.zero_grad()
+        out = model2(rb)
+        metrics = model2.get_metrics_dict(out, batch)
+        ld = model2.get_loss_dict(out, batch, metrics)
+        loss = sum(ld.values())
+        loss.backward()
+        if world > 1:
+            for p in model2.parameters():
+                if p.grad is not None:
+                    dist.all_reduce(p.grad, op=dist.ReduceOp.AVG)
+        for o in opts:
+            o.step()
+        for c in cbs:
+            if c.where_to_run == ["AFTER_TRAIN_ITERATION"]:
+                c.run_callback(i)
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the trainer reads the loss on the host
+
+    n_e2e = max(args.steps // 4, 10)
+    for i in range(max(args.warmup // 2, 3)):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(n_e2e):
+        e2e_step(10 + i)
+    torch.cuda.synchronize()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_val = world * R * n_e2e / t_e2e
+
+    line = {
+        "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": ("fp32 hashing/sampling/compositing/Adam + fp16-operand forward and bf16-operand backward mma "
+                  "(fp32 accumulate) in the field MLPs" if args.precision == "tc_fp16" else "fp32"),
+        "data": "synthetic",
+        "config": {"workload": TRAIN_WORKLOAD.format(rays=R), "rays_per_batch_per_gpu": R,
+                   "l2": "working set per step (tables + gradients + Adam state = 296 MiB) exceeds the 126 MB L2; "
+                         f"{n_distinct} distinct ray batches cycle",
+                   "weights": "random trained-like init, full-size tables (field 2^19x16, proposals 2^17x5)",
+                   "final_losses": dict(zip(F.LOSS_NAMES, final_losses))},
+        "clocks": clocks,
+        "gpu_launches": None,
+        "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": n_e2e,
+                "note": "plugin API: pinned host rays+GT -> H2D -> model(ray_bundle) -> get_metrics_dict -> get_loss_dict "
+                        "-> loss.backward() -> FusedAdam.step -> D2H loss"},
+    }
+    # launches of OUR kernels per engine step: forward + clip + losses + backward_prop (on update steps) +
+    # backward_field + wgrad + adam (1 or 2 launches)
+    line["gpu_launches"] = int(args.steps * 6 + engine.prop_steps * 2)
+    if roofline:
+        line["roofline"] = roofline
+        line["breakdown_ms"] = breakdown
+    if rank == 0 and world == 1 and not args.no_render:
+        line["render"] = quick_render(model, device)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_train(min(args.ref_rays, 4096))
+    return line
+
+
+def kernel_breakdown(engine, batches, device) -> dict:
+    """Times each stage of one iteration with CUDA events on the launching stream (average of 10)."""
+    from thermo_nerf_b200 import _lib as L
+    from thermo_nerf_b200 import functional as F
+
+    names = ["forward", "losses", "backward", "wgrad", "adam"]
+    acc = {n: 0.0 for n in names}
+    lib = L.load()
+    reps = 10
+    # the stages are timed by running the C entry points individually: backward and wgrad are two
+    # launches of one entry point, so wgrad is timed as (render_backward) - (its first kernels) using
+    # a second pass with a 1-row problem is not possible -> report them together and split by ncu share
+    for rep in range(reps):
+        o, d, cam, gt_rgb, gt_th = batches[rep % len(batches)]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        R = o.shape[0]
+        cfg = engine.cfg
+        jitter = torch.rand((3, R), device=device)
+        kw = dict(num_samples=(*cfg.num_proposal_samples_per_ray, cfg.num_nerf_samples_per_ray),
+                  near_plane=cfg.near_plane, far_plane=cfg.far_plane, anneal=1.0, appearance_mode=L.APPEARANCE_LOOKUP,
+                  precision=engine.model._precision())
+        ev[0].record()
+        res = F.render_forward(engine.tensors, o, d, cam, None, None, jitter, training=True, return_samples=True,
+                               save_for_backward=True, **kw)
+        ev[1].record()
+        losses, g = F.losses_forward_backward(res["weights_list"], res["sdist_list"], res["rgb"], res["thermal"],
+                                              gt_rgb, gt_th)
+        ev[2].record()
+        res["_workspace"] = engine._ws
+        F.render_backward(engine.tensors, res["_model_struct"], o, d, cam, None, None, jitter, res,
+                          {"rgb": g["rgb"], "thermal": g["thermal"], "weights_list": g["weights_list"]},
+                          list(engine.grads))
+        ev[3].record()
+        n = len(engine.params)
+        F.adam_step(engine.params, engine.grads, engine.exp_avg, engine.exp_avg_sq, [0.0] * n, step=1000, eps=1e-15,
+                    zero_grads=True)  # lr = 0: timing only, parameters unchanged
+        ev[4].record()
+        torch.cuda.synchronize()
+        acc["forward"] += ev[0].elapsed_time(ev[1])
+        acc["losses"] += ev[1].elapsed_time(ev[2])
+        acc["backward"] += ev[2].elapsed_time(ev[3])
+        acc["adam"] += ev[3].elapsed_time(ev[4])
+    out = {k + "_ms": v / reps for k, v in acc.items() if k != "wgrad"}
+    out["note"] = "backward_ms = proposal backward + field backward + weight-gradient GEMM (one C entry point)"
+    return out
+
+
+def quick_render(model, device) -> dict:
+    """Short measurement of the second headline metric (BASELINE configs[4] shape): 800x800 frames, eval mode."""
+    model.eval()
+    bundles = frame_bundles(2, device, 0, 1)
+    flush = L2Flusher(device)
+    with torch.no_grad():
+        for i in range(2):
+            model.get_outputs_for_camera_ray_bundle(bundles[i % 2])
+        evs = []
+        for i in range(5):
+            flush()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            model.get_outputs_for_camera_ray_bundle(bundles[i % 2])
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+    model.train()
+    return {"metric": "render_mpix_per_s", "value": HW * HW / (ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_frame": ms,
+            "workload": "800x800 frame, rgb+thermal+depth+accumulation in one pass, L2 flushed between frames; "
+                        "full contract run: bench.py --mode render"}
+
+
+def cpu_baseline_train(sample: int) -> dict:
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model, opts, batch = oracle_train_setup(sample)
+    oracle_train_step(model, opts, batch, 0)
+    reps = 2
+    t0 = time.perf_counter()
+    for i in range(reps):
+        oracle_train_step(model, opts, batch, 1 + i)
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": sample / dt, "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": f"{reps} full training iterations of {sample} rays (forward, losses, autograd backward, torch "
+                      f"Adam over all parameters), fp32 oracle port on CPU"}
+
+
+def bench_render(ctx) -> dict:
+    args, rank, world, device = ctx["args"], ctx["rank"], ctx["world"], ctx["device"]
+    barrier, max_over_ranks, local = ctx["barrier"], ctx["max_over_ranks"], ctx["local"]
     from thermo_nerf_b200 import RayBundle
 
     model = build_b200_model(device, args.precision)
@@ -262,11 +603,7 @@ def main() -> None:
         b.record()
     torch.cuda.synchronize()
     k_ms = sum(a.elapsed_time(b) for a, b in kev) / len(kev)
-    peaks_path = ROOT / "MEASURED_PEAKS.json"
-    if peaks_path.exists():
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    peak, peak_src = hbm_peak()
     achieved = rays_per_step * ALGO_BYTES_PER_RAY / (k_ms * 1e-3) / 1e9
     traffic = None
     tp = ROOT / "profiles" / "forward_traffic.json"
@@ -336,10 +673,7 @@ def main() -> None:
         line["torch_cuda_baseline"] = torch_cuda_baseline(device)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.ref_rays)
-    if rank == 0:
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
 def cpu_baseline(sample: int) -> dict:

@@ -273,7 +273,7 @@ typedef struct TnfAdamTensor {
   int32_t _pad;
 } TnfAdamTensor;
 
-int tnf_adam_step(const TnfAdamTensor* tensors, int32_t num_tensors, float beta1, float beta2, float eps,
+int tnf_adam_step(const TnfAdamTensor* tensors, int32_t num_tensors, double beta1, double beta2, float eps,
                   int64_t step, float inv_grad_scale, const float* grad_scale, const float* found_inf,
                   int32_t zero_grads, void* stream);
 

@@ -11,10 +11,10 @@ from .model import ThermalNerfModel, ThermalNerfModelConfig
 from .optim import FusedAdam
 from .modules import (CameraOptimizer, FieldHeadNames, FieldHeadNamesT, HashMLPDensityField, ThermalFieldHead,
                       ThermalNerfactoTField)
-from .rays import PinholeCameras, RayBundle, orbit_cameras
+from .rays import PinholeCameras, RayBundle, orbit_cameras, sphere_cameras
 
 __all__ = [
     "ModelTensors", "render_forward", "render", "losses", "adam_step", "FusedAdam", "ThermalNerfModel", "ThermalNerfModelConfig", "CameraOptimizer",
     "FieldHeadNames", "FieldHeadNamesT", "HashMLPDensityField", "ThermalFieldHead", "ThermalNerfactoTField",
-    "PinholeCameras", "RayBundle", "orbit_cameras",
+    "PinholeCameras", "RayBundle", "orbit_cameras", "sphere_cameras",
 ]

@@ -267,8 +267,8 @@ def load() -> C.CDLL:
     lib.tnf_adam_step.argtypes = [
         C.POINTER(TnfAdamTensor),
         C.c_int32,
-        C.c_float,
-        C.c_float,
+        C.c_double,
+        C.c_double,
         C.c_float,
         C.c_int64,
         C.c_float,

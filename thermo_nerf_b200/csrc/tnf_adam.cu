@@ -16,7 +16,8 @@ struct AdamArgs {
   TnfAdamTensor t[TNF_ADAM_MAX_TENSORS];
   int chunk_start[TNF_ADAM_MAX_TENSORS + 1];  // prefix sum of ceil(numel / kAdamChunk)
   int n;
-  float beta1, beta2, eps;
+  float beta2, eps;
+  float omb1, omb2;  // 1-beta1, 1-beta2 rounded from double, as torch passes them to lerp_/addcmul_
   float inv_sqrt_bc2;
   float inv_grad_scale;
   const float* grad_scale;
@@ -27,8 +28,8 @@ struct AdamArgs {
 __device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v, const AdamArgs& a, float lr,
                                          float inv_scale) {
   const float gg = g * inv_scale;
-  m = m + (1.f - a.beta1) * (gg - m);
-  v = a.beta2 * v + (1.f - a.beta2) * gg * gg;
+  m = m + a.omb1 * (gg - m);
+  v = a.beta2 * v + a.omb2 * (gg * gg);
   const float denom = sqrtf(v) * a.inv_sqrt_bc2 + a.eps;
   p = p - lr * (m / denom);  // lr already holds step_size = lr / bias_correction1
 }
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(256) tnf_adam_kernel(const __grid_constant__ A
 
 }  // namespace tnf
 
-extern "C" int tnf_adam_step(const TnfAdamTensor* tensors, int32_t num_tensors, float beta1, float beta2, float eps,
+extern "C" int tnf_adam_step(const TnfAdamTensor* tensors, int32_t num_tensors, double beta1, double beta2, float eps,
                              int64_t step, float inv_grad_scale, const float* grad_scale, const float* found_inf,
                              int32_t zero_grads, void* stream_) {
   using tnf::fail;
@@ -102,16 +103,17 @@ extern "C" int tnf_adam_step(const TnfAdamTensor* tensors, int32_t num_tensors, 
     if (!t.param || !t.grad || !t.exp_avg || !t.exp_avg_sq || t.numel < 0)
       return fail(TNF_ERR_INVALID_ARGUMENT, "tensor %d: null pointer or negative numel", i);
     a.t[i] = t;
-    a.t[i].lr = (float)((double)t.lr / (1.0 - pow((double)beta1, (double)step)));
+    a.t[i].lr = (float)((double)t.lr / (1.0 - pow(beta1, (double)step)));
     a.chunk_start[i] = (int)chunks;
     chunks += (t.numel + tnf::kAdamChunk - 1) / tnf::kAdamChunk;
     if (chunks > 0x7fffffffLL) return fail(TNF_ERR_UNSUPPORTED_CONFIG, "too many elements for one launch");
   }
   a.chunk_start[num_tensors] = (int)chunks;
-  a.beta1 = beta1;
-  a.beta2 = beta2;
+  a.omb1 = (float)(1.0 - beta1);
+  a.omb2 = (float)(1.0 - beta2);
+  a.beta2 = (float)beta2;
   a.eps = eps;
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
   a.inv_sqrt_bc2 = 1.0f / (float)sqrt(bc2);
   a.inv_grad_scale = inv_grad_scale;
   a.grad_scale = grad_scale;

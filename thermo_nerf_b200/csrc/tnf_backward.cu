@@ -62,6 +62,21 @@ __host__ inline size_t make_layout(BwdLayout* L, unsigned char* base, long long 
   return off;
 }
 
+// weight-gradient GEMM problems: dW[n][k] += sum_rows dY[row][n0+n] * X[row][k];  db[n] += sum_rows dY
+struct WgradProblem {
+  const void* dY; int ldY, n0, N, n_valid;   // N: loaded columns (multiple of 8), n_valid <= N are written
+  const void* X;  int ldX, K, k_skip;        // K: loaded columns (multiple of 8); output col = k - k_skip >= 0
+  long long rows;
+  float* W; int ldW, wcol0;
+  float* bias;                               // may be null
+};
+constexpr int kMaxWgradProblems = 12;
+struct WgradArgs {
+  WgradProblem p[kMaxWgradProblems];
+  int n;
+};
+constexpr int kWgradRows = 64;
+
 // ------------------------------------------------------------------------------------
 // hash-grid scatter: transpose of hash_level (same corner order / weights as hash_blend)
 // ------------------------------------------------------------------------------------
@@ -614,22 +629,455 @@ __global__ void __launch_bounds__(kThreads, 1)
 }
 
 // ------------------------------------------------------------------------------------
+// field level, tensor cores: 16-sample tiles.  Forward recompute with the fp16 fragments of the
+// forward kernel (identical activations), backward products with bf16 operands (gradients span
+// far more than fp16's exponent range), fp32 accumulate; activations never leave registers
+// except as the staged (X, dY) rows the weight-gradient GEMMs read.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_bf162(float lo, float hi) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ void mma_16816_bf16(float (&c)[4], const uint32_t (&a)[4], const uint2 b) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+}
+template <int NT, int KT>
+__device__ __forceinline__ void mma_layer_bf16(float (&c)[NT][4], const uint32_t (&a)[KT][4],
+                                               const uint2* __restrict__ w, const int ntw, const int lane) {
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) mma_16816_bf16(c[nt], a[kt], w[(kt * ntw + nt) * 32 + lane]);
+}
+template <int NT>
+__device__ __forceinline__ void zero_c(float (&c)[NT][4]) {
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
+}
+// C fragments -> bf16 A fragments of the next product (same index map as act_pack)
+template <int NT>
+__device__ __forceinline__ void pack_bf16_a(const float (&c)[NT][4], uint32_t (&a)[NT / 2][4]) {
+#pragma unroll
+  for (int kt = 0; kt < NT / 2; ++kt) {
+    a[kt][0] = pack_bf162(c[2 * kt][0], c[2 * kt][1]);
+    a[kt][1] = pack_bf162(c[2 * kt][2], c[2 * kt][3]);
+    a[kt][2] = pack_bf162(c[2 * kt + 1][0], c[2 * kt + 1][1]);
+    a[kt][3] = pack_bf162(c[2 * kt + 1][2], c[2 * kt + 1][3]);
+  }
+}
+template <int NT>
+__device__ __forceinline__ uint32_t relu_mask(float (&c)[NT][4]) {  // applies ReLU in place, returns the >0 mask
+  uint32_t mk = 0;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (c[nt][e] > 0.f) mk |= 1u << (nt * 4 + e); else c[nt][e] = 0.f;
+    }
+  return mk;
+}
+template <int NT>
+__device__ __forceinline__ void apply_mask(float (&c)[NT][4], const uint32_t mk) {
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (!((mk >> (nt * 4 + e)) & 1u)) c[nt][e] = 0.f;
+}
+// C fragments -> staged bf16 rows: row0/row1 are the global row indices of fragment rows g / g+8
+template <int NT>
+__device__ __forceinline__ void stage_c(unsigned char* base, const long long row0, const long long row1,
+                                        const bool v0, const bool v1, const int ld, const int col0, const int q,
+                                        const float (&c)[NT][4]) {
+  __nv_bfloat16* b = reinterpret_cast<__nv_bfloat16*>(base);
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int col = col0 + nt * 8 + 2 * q;
+    if (v0) *reinterpret_cast<uint32_t*>(b + row0 * ld + col) = pack_bf162(c[nt][0], c[nt][1]);
+    if (v1) *reinterpret_cast<uint32_t*>(b + row1 * ld + col) = pack_bf162(c[nt][2], c[nt][3]);
+  }
+}
+
+// bf16 B fragments of the backward products: B[kk][nn] = V(kk, nn), [kt][nt][lane]
+struct FieldBwdWTC {
+  uint2 rgb1T[4][8][32];   // dA1 = dA2pre . W_rgb1
+  uint2 th1T[4][8][32];    // dB1 = dB2pre . W_th1
+  uint2 geoT[8][2][32];    // dG  = [dA1pre | dB1pre] . [W_rgb0[:,16:31] ; W_th0]   (column 0 = density slot = 0)
+  uint2 base1T[1][8][32];  // dH  = dG . W_base1
+  uint2 base0T[4][4][32];  // dF  = dHpre . W_base0
+  float rgb2w[3][64];
+  float th2w[64];
+};
+struct ViewRows {  // V(k,n) = w[k*ld + n]
+  const float* w;
+  int ld, kv, nv;
+  __device__ float operator()(int k, int n) const { return (k < kv && n < nv) ? w[k * ld + n] : 0.f; }
+};
+struct ViewGeoT {
+  const float* rgb0;
+  const float* th0;
+  bool detach;
+  __device__ float operator()(int k, int n) const {
+    if (n < 1 || n > 15) return 0.f;
+    if (k < 64) return rgb0[k * 63 + 16 + n - 1];
+    return detach ? 0.f : th0[(k - 64) * 15 + n - 1];
+  }
+};
+template <typename V>
+__device__ inline void stage_frag_bf16(uint2* dst, int KT, int NT, const V& v, int tid) {
+  for (int i = tid; i < KT * NT * 32; i += kThreads) {
+    const int lane = i & 31, nt = (i >> 5) % NT, kt = (i >> 5) / NT;
+    const int g = lane >> 2, q = lane & 3;
+    const int n = nt * 8 + g, k = kt * 16 + 2 * q;
+    dst[i] = make_uint2(pack_bf162(v(k, n), v(k + 1, n)), pack_bf162(v(k + 8, n), v(k + 9, n)));
+  }
+}
+__device__ inline void stage_field_bwd(FieldBwdWTC& W, const TnfModel& m, int tid) {
+  const TnfField& f = m.field;
+  stage_frag_bf16(&W.rgb1T[0][0][0], 4, 8, ViewRows{f.rgb1.weight, 64, 64, 64}, tid);
+  stage_frag_bf16(&W.th1T[0][0][0], 4, 8, ViewRows{f.th1.weight, 64, 64, 64}, tid);
+  stage_frag_bf16(&W.geoT[0][0][0], 8, 2, ViewGeoT{f.rgb0.weight, f.th0.weight, m.detach_thermal_geo != 0}, tid);
+  stage_frag_bf16(&W.base1T[0][0][0], 1, 8, ViewRows{f.base1.weight, 64, 16, 64}, tid);
+  stage_frag_bf16(&W.base0T[0][0][0], 4, 4, ViewRows{f.base0.weight, 32, 64, 32}, tid);
+  for (int i = tid; i < 192; i += kThreads) W.rgb2w[i / 64][i % 64] = f.rgb2.weight[i];
+  for (int i = tid; i < 64; i += kThreads) W.th2w[i] = f.th2.weight[i];
+}
+
+struct FieldBwdSmemTC {
+  FieldWTC fw;
+  FieldBwdWTC bw;
+  FieldBwdScratch ws[kWarpsPerCta];
+};
+
+__global__ void __launch_bounds__(kThreads, 2)
+    tnf_backward_field_kernel_tc(const __grid_constant__ TnfModel m, const __grid_constant__ TnfRays rays,
+                                 const __grid_constant__ TnfSaved sv, const __grid_constant__ TnfOutputGrads go,
+                                 const __grid_constant__ TnfModelGrad gr, const __grid_constant__ BwdLayout L) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FieldBwdSmemTC& S = *reinterpret_cast<FieldBwdSmemTC*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  stage_field(S.fw, m.field, tid);
+  stage_field_bwd(S.bw, m, tid);
+  __syncthreads();
+  const FieldWTC& W = S.fw;
+  const FieldBwdWTC& B = S.bw;
+  FieldBwdScratch& ws = S.ws[warp];
+  const int g = lane >> 2, q = lane & 3;
+  const int S2 = m.num_samples[TNF_NUM_PROP];
+  const TnfHashGrid& grid = m.field.grid;
+  const uint32_t mask = (1u << grid.log2_size) - 1u;
+  float2* __restrict__ gtab = reinterpret_cast<float2*>(gr.field.table);
+  const uint32_t* __restrict__ F = static_cast<const uint32_t*>(sv.field_features);  // [Ns][16] half2
+  const long long R = rays.num_rays;
+
+  for (long long ray = (long long)blockIdx.x * kWarpsPerCta + warp; ray < R;
+       ray += (long long)gridDim.x * kWarpsPerCta) {
+    RayCtx rc;
+    rc.ox = __ldg(rays.origins + ray * 3 + 0);
+    rc.oy = __ldg(rays.origins + ray * 3 + 1);
+    rc.oz = __ldg(rays.origins + ray * 3 + 2);
+    rc.dx = __ldg(rays.directions + ray * 3 + 0);
+    rc.dy = __ldg(rays.directions + ray * 3 + 1);
+    rc.dz = __ldg(rays.directions + ray * 3 + 2);
+    rc.s_near = spacing_fn(rays.nears ? __ldg(rays.nears + ray) : m.near_plane);
+    rc.s_far = spacing_fn(rays.fars ? __ldg(rays.fars + ray) : m.far_plane);
+    for (int i = lane; i <= S2; i += 32) ws.bins[i] = sv.sdist[TNF_NUM_PROP][ray * (S2 + 1) + i];
+    float sh[16], app_lane;
+    ray_bias_and_inputs(m, rays, ray, rc, lane, ws.rayb, sh, app_lane);
+    __syncwarp();
+    composite_backward(m, ws, rc, S2, lane, sv.field_samples + ray * S2 * 5,
+                       go.weights[TNF_NUM_PROP] ? go.weights[TNF_NUM_PROP] + ray * S2 : nullptr,
+                       go.rgb ? go.rgb[ray * 3 + 0] : 0.f, go.rgb ? go.rgb[ray * 3 + 1] : 0.f,
+                       go.rgb ? go.rgb[ray * 3 + 2] : 0.f, go.thermal ? go.thermal[ray] : 0.f,
+                       go.accumulation ? go.accumulation[ray] : 0.f);
+    float racc[16];  // column sums of dA1pre over the ray (meaningful on lanes with g == 0)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) racc[i] = 0.f;
+
+    for (int base = 0; base < S2; base += 16) {
+      const int r0 = base + g, r1 = base + g + 8;
+      const bool v0 = r0 < S2, v1 = r1 < S2;
+      const int i0 = min(r0, S2 - 1), i1 = min(r1, S2 - 1);
+      const long long row0 = ray * S2 + i0, row1 = ray * S2 + i1;
+      float p[2][3], sel[2];
+      {
+        float mid, delta;
+        sample_geometry(rc, ws.bins[i0], ws.bins[i0 + 1], mid, delta);
+        sel[0] = normalise_position(m, ray_x(rc, mid), ray_y(rc, mid), ray_z(rc, mid), p[0][0], p[0][1], p[0][2]);
+        sample_geometry(rc, ws.bins[i1], ws.bins[i1 + 1], mid, delta);
+        sel[1] = normalise_position(m, ray_x(rc, mid), ray_y(rc, mid), ray_z(rc, mid), p[1][0], p[1][1], p[1][2]);
+      }
+      const float dsig[2] = {v0 ? ws.dsig[i0] : 0.f, v1 ? ws.dsig[i1] : 0.f};
+      const float dtau[2] = {v0 ? ws.dtau[i0] : 0.f, v1 ? ws.dtau[i1] : 0.f};
+      const float dz[2][3] = {{v0 ? ws.dzr[i0] : 0.f, v0 ? ws.dzg[i0] : 0.f, v0 ? ws.dzb[i0] : 0.f},
+                              {v1 ? ws.dzr[i1] : 0.f, v1 ? ws.dzg[i1] : 0.f, v1 ? ws.dzb[i1] : 0.f}};
+      // ---- saved hash features -> A fragments (fp16) + bf16 copy for the base0 weight gradient
+      uint32_t a0[2][4];
+#pragma unroll
+      for (int kt = 0; kt < 2; ++kt)
+#pragma unroll
+        for (int hl = 0; hl < 2; ++hl) {
+          const int l = kt * 8 + hl * 4 + q;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const long long row = h ? row1 : row0;
+            const uint32_t v = __ldg(F + row * 16 + l);
+            a0[kt][2 * hl + h] = v;
+            if (h ? v1 : v0) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v));
+              reinterpret_cast<uint32_t*>(L.XF)[row * 16 + l] = pack_bf162(f.x, f.y);
+            }
+          }
+        }
+      // ---- trunk forward: H, G
+      uint32_t hid[4][4];
+      uint32_t mkH;
+      {
+        float c[8][4];
+        init_bias(c, W.base0b, q);
+        mma_layer<8, 2>(c, a0, &W.base0[0][0][0], 0, 8, lane);
+        mkH = relu_mask(c);
+        stage_c(L.XH, row0, row1, v0, v1, kWXH, 0, q, c);
+        act_pack<8, ACT_NONE>(c, hid);
+      }
+      float h0r0, h0r1;
+      uint32_t ga[1][4];
+      {
+        float c[2][4];
+        init_bias(c, W.base1b, q);
+        mma_layer<2, 4>(c, hid, &W.base1[0][0][0], 0, 2, lane);
+        stage_c(L.XG, row0, row1, v0, v1, kWXG, 0, q, c);
+        h0r0 = c[0][0];
+        h0r1 = c[0][2];
+        if (q == 0) { c[0][0] = 0.f; c[0][2] = 0.f; }
+        act_pack<2, ACT_NONE>(c, ga);
+      }
+      // ---- thermal head forward + backward down to dB1pre
+      uint32_t dB1A[4][4];
+      {
+        float c[8][4];
+        init_bias(c, W.th0b, q);
+        mma_layer<8, 1>(c, ga, &W.geo0[0][0][0], 8, 16, lane);
+        const uint32_t mkB1 = relu_mask(c);
+        stage_c(L.XB1, row0, row1, v0, v1, kWX, 0, q, c);
+        act_pack<8, ACT_NONE>(c, hid);
+        init_bias(c, W.th1b, q);
+        mma_layer<8, 4>(c, hid, &W.th1[0][0][0], 0, 8, lane);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) c[nt][e] = sigmoidf(c[nt][e]);
+        stage_c(L.XB2, row0, row1, v0, v1, kWX, 0, q, c);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            c[nt][e] = dtau[e >> 1] * B.th2w[nt * 8 + 2 * q + (e & 1)] * c[nt][e] * (1.f - c[nt][e]);
+        stage_c(L.dB2, row0, row1, v0, v1, kWX, 0, q, c);
+        uint32_t dy[4][4];
+        pack_bf16_a(c, dy);
+        zero_c(c);
+        mma_layer_bf16<8, 4>(c, dy, &B.th1T[0][0][0], 8, lane);
+        apply_mask(c, mkB1);
+        stage_c(L.dGeo, row0, row1, v0, v1, kWdGeo, 64, q, c);
+        pack_bf16_a(c, dB1A);
+        if (q == 0) {
+          uint4* dt = reinterpret_cast<uint4*>(L.dT);
+          if (v0) dt[row0] = make_uint4(pack_bf162(dtau[0], 0.f), 0u, 0u, 0u);
+          if (v1) dt[row1] = make_uint4(pack_bf162(dtau[1], 0.f), 0u, 0u, 0u);
+        }
+      }
+      // ---- colour head forward + backward down to dA1pre
+      uint32_t dA1A[4][4];
+      {
+        float c[8][4];
+        init_bias(c, ws.rayb, q);
+        mma_layer<8, 1>(c, ga, &W.geo0[0][0][0], 0, 16, lane);
+        const uint32_t mkA1 = relu_mask(c);
+        stage_c(L.XA1, row0, row1, v0, v1, kWX, 0, q, c);
+        act_pack<8, ACT_NONE>(c, hid);
+        init_bias(c, W.rgb1b, q);
+        mma_layer<8, 4>(c, hid, &W.rgb1[0][0][0], 0, 8, lane);
+        relu_mask(c);
+        stage_c(L.XA2, row0, row1, v0, v1, kWX, 0, q, c);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int col = nt * 8 + 2 * q + (e & 1), h = e >> 1;
+            const float v = dz[h][0] * B.rgb2w[0][col] + dz[h][1] * B.rgb2w[1][col] + dz[h][2] * B.rgb2w[2][col];
+            c[nt][e] = c[nt][e] > 0.f ? v : 0.f;
+          }
+        stage_c(L.dA2, row0, row1, v0, v1, kWX, 0, q, c);
+        uint32_t dy[4][4];
+        pack_bf16_a(c, dy);
+        zero_c(c);
+        mma_layer_bf16<8, 4>(c, dy, &B.rgb1T[0][0][0], 8, lane);
+        apply_mask(c, mkA1);
+        stage_c(L.dGeo, row0, row1, v0, v1, kWdGeo, 0, q, c);
+        pack_bf16_a(c, dA1A);
+        // column sums over the 16 rows of the tile -> per-ray sum of dA1pre
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            float sum = c[nt][b] + c[nt][b + 2];
+            sum += __shfl_xor_sync(kFull, sum, 4);
+            sum += __shfl_xor_sync(kFull, sum, 8);
+            sum += __shfl_xor_sync(kFull, sum, 16);
+            racc[nt * 2 + b] += sum;
+          }
+        if (q == 0) {
+          uint4* dzp = reinterpret_cast<uint4*>(L.dZ);
+          if (v0) dzp[row0] = make_uint4(pack_bf162(dz[0][0], dz[0][1]), pack_bf162(dz[0][2], 0.f), 0u, 0u);
+          if (v1) dzp[row1] = make_uint4(pack_bf162(dz[1][0], dz[1][1]), pack_bf162(dz[1][2], 0.f), 0u, 0u);
+        }
+      }
+      // ---- trunk backward: dG -> dH -> dF -> hash table
+      uint32_t dGA[1][4];
+      {
+        float c[2][4];
+        zero_c(c);
+        mma_layer_bf16<2, 4>(c, dA1A, &B.geoT[0][0][0], 2, lane);
+        mma_layer_bf16<2, 4>(c, dB1A, &B.geoT[4][0][0], 2, lane);
+        if (q == 0) {  // density slot: trunc_exp backward times selector
+          c[0][0] = dsig[0] * expf(fminf(fmaxf(h0r0, -15.f), 15.f)) * sel[0];
+          c[0][2] = dsig[1] * expf(fminf(fmaxf(h0r1, -15.f), 15.f)) * sel[1];
+        }
+        stage_c(L.dG, row0, row1, v0, v1, kWXG, 0, q, c);
+        pack_bf16_a(c, dGA);
+      }
+      uint32_t dHA[4][4];
+      {
+        float c[8][4];
+        zero_c(c);
+        mma_layer_bf16<8, 1>(c, dGA, &B.base1T[0][0][0], 8, lane);
+        apply_mask(c, mkH);
+        stage_c(L.dH, row0, row1, v0, v1, kWX, 0, q, c);
+        pack_bf16_a(c, dHA);
+      }
+      {
+        float c[4][4];
+        zero_c(c);
+        mma_layer_bf16<4, 4>(c, dHA, &B.base0T[0][0][0], 4, lane);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int l = nt * 4 + q;
+          float2* lt = gtab + ((size_t)l << grid.log2_size);
+          const float sc = grid.scalings[l];
+          if (v0) scatter_level(lt, p[0][0], p[0][1], p[0][2], sc, mask, c[nt][0], c[nt][1]);
+          if (v1) scatter_level(lt, p[1][0], p[1][1], p[1][2], sc, mask, c[nt][2], c[nt][3]);
+        }
+      }
+    }
+    // ---- per-ray epilogue
+    {
+      __syncwarp();
+      // gather the 64 column sums: lane q (g == 0) holds columns nt*8 + 2q + b at racc[nt*2 + b]
+      float* tmp = ws.rayb;  // the first-layer bias is no longer needed
+      if (g == 0) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          tmp[nt * 8 + 2 * q] = racc[nt * 2];
+          tmp[nt * 8 + 2 * q + 1] = racc[nt * 2 + 1];
+        }
+      }
+      __syncwarp();
+      const float r0_ = tmp[lane], r1_ = tmp[lane + 32];
+      ray_epilogue<__nv_bfloat16>(m, rays, ray, lane, sh, app_lane, r0_, r1_, L, gr.field.appearance);
+      __syncwarp();
+    }
+  }
+}
+
+// bf16 tensor-core weight-gradient GEMM: dW = dY^T X over 64-row tiles, fragments via ldmatrix.trans
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_ptr) {
+  const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(smem_ptr));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
+constexpr int kWgradLd = 72;  // padded row stride (bf16 elements): 144 B, conflict-free for ldmatrix
+
+__global__ void __launch_bounds__(128) tnf_wgrad_kernel_bf16(const __grid_constant__ WgradArgs args) {
+  const WgradProblem& P = args.p[blockIdx.y];
+  __shared__ __align__(16) __nv_bfloat16 sdY[kWgradRows * kWgradLd];
+  __shared__ __align__(16) __nv_bfloat16 sX[kWgradRows * kWgradLd];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const __nv_bfloat16* dY = static_cast<const __nv_bfloat16*>(P.dY);
+  const __nv_bfloat16* X = static_cast<const __nv_bfloat16*>(P.X);
+  const int MT = (P.N + 15) / 16;  // 16-wide blocks of output rows n; warp w owns block w
+  const int NT = P.K / 8;          // 8-wide blocks of output columns k
+  float acc[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+  float bacc = 0.f;
+  const long long tiles = (P.rows + kWgradRows - 1) / kWgradRows;
+  for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const long long row0 = t * kWgradRows;
+    // 64 rows x 8 column-vectors of 8 bf16 (16 B) each, zero padded
+    for (int idx = tid; idx < kWgradRows * 8; idx += 128) {
+      const int r = idx >> 3, c8 = (idx & 7) * 8;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u), x = v;
+      if (row0 + r < P.rows) {
+        if (c8 < P.N) v = *reinterpret_cast<const uint4*>(dY + (row0 + r) * P.ldY + P.n0 + c8);
+        if (c8 < P.K) x = *reinterpret_cast<const uint4*>(X + (row0 + r) * P.ldX + c8);
+      }
+      *reinterpret_cast<uint4*>(&sdY[r * kWgradLd + c8]) = v;
+      *reinterpret_cast<uint4*>(&sX[r * kWgradLd + c8]) = x;
+    }
+    __syncthreads();
+    if (warp < MT) {
+#pragma unroll
+      for (int ks = 0; ks < kWgradRows / 16; ++ks) {
+        const int mi = lane >> 3, r = lane & 7;
+        uint32_t a[4];
+        // A = dY^T block: matrices (rows ks*16 + {0,8}, cols warp*16 + {0,8}) in order (r0,c0),(r0,c8),(r8,c0),(r8,c8)
+        ldmatrix_x4_trans(a, &sdY[(ks * 16 + (mi >> 1) * 8 + r) * kWgradLd + warp * 16 + (mi & 1) * 8]);
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          if (2 * np < NT) {
+            uint32_t b[4];
+            // B = X block pair: (r0,k),(r8,k),(r0,k+8),(r8,k+8)
+            ldmatrix_x4_trans(b, &sX[(ks * 16 + (mi & 1) * 8 + r) * kWgradLd + (2 * np + (mi >> 1)) * 8]);
+            mma_16816_bf16(acc[2 * np], a, make_uint2(b[0], b[1]));
+            mma_16816_bf16(acc[2 * np + 1], a, make_uint2(b[2], b[3]));
+          }
+        }
+      }
+    }
+    if (P.bias && tid < P.n_valid) {
+      float sum = 0.f;
+#pragma unroll 8
+      for (int r = 0; r < kWgradRows; ++r) sum += __bfloat162float(sdY[r * kWgradLd + tid]);
+      bacc += sum;
+    }
+    __syncthreads();
+  }
+  if (warp < MT) {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      if (nt >= NT) continue;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int n = warp * 16 + g + (e >> 1) * 8;
+        const int k = nt * 8 + 2 * q + (e & 1) - P.k_skip;
+        if (n < P.n_valid && k >= 0 && acc[nt][e] != 0.f) atomicAdd(P.W + n * P.ldW + P.wcol0 + k, acc[nt][e]);
+      }
+    }
+  }
+  if (P.bias && tid < P.n_valid && bacc != 0.f) atomicAdd(P.bias + tid, bacc);
+}
+
+// ------------------------------------------------------------------------------------
 // weight-gradient GEMMs: dW[n][k] += sum_rows dY[row][n0+n] * X[row][k];  db[n] += sum_rows dY
 // ------------------------------------------------------------------------------------
-struct WgradProblem {
-  const void* dY; int ldY, n0, N, n_valid;   // N: loaded columns (multiple of 8), n_valid <= N are written
-  const void* X;  int ldX, K, k_skip;        // K: loaded columns (multiple of 8); output col = k - k_skip >= 0
-  long long rows;
-  float* W; int ldW, wcol0;
-  float* bias;                               // may be null
-};
-constexpr int kMaxWgradProblems = 12;
-struct WgradArgs {
-  WgradProblem p[kMaxWgradProblems];
-  int n;
-};
-constexpr int kWgradRows = 64;
-
 __global__ void __launch_bounds__(256) tnf_wgrad_kernel_fp32(const __grid_constant__ WgradArgs args) {
   const WgradProblem& P = args.p[blockIdx.y];
   __shared__ __align__(16) float sdY[kWgradRows][68];
@@ -817,7 +1265,20 @@ int tnf_render_backward(const TnfModel* model, const TnfRays* rays, const TnfSav
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(e));
   } else {
-    return fail(TNF_ERR_UNSUPPORTED_CONFIG, "tensor-core backward not built yet");
+    const size_t smem = sizeof(tnf::FieldBwdSmemTC);
+    if (int rc = set_smem(tnf::tnf_backward_field_kernel_tc, smem, "backward_field_tc")) return rc;
+    const long long cap = (long long)sms * 2;
+    tnf::tnf_backward_field_kernel_tc<<<(unsigned)(want < cap ? want : cap), tnf::kThreads, smem, stream>>>(
+        *model, *rays, *saved, *gout, *grads, L);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "backward_field launch: %s", cudaGetErrorString(e));
+    field_problems(wa, L, L.XF, 2, grads->field, Ns, R);
+    const long long tiles = (Ns + tnf::kWgradRows - 1) / tnf::kWgradRows;
+    const long long capx = (long long)sms * 8 / wa.n + 1;
+    dim3 grid((unsigned)(tiles < capx ? tiles : capx), wa.n);
+    tnf::tnf_wgrad_kernel_bf16<<<grid, 128, 0, stream>>>(wa);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(e));
   }
   return TNF_OK;
 }

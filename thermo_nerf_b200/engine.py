@@ -1,0 +1,145 @@
+"""One ThermoNeRF training iteration on persistent device buffers, without autograd:
+
+    forward (tnf_render_forward, training) -> losses + their gradients (tnf_losses)
+    -> backward (tnf_render_backward, into one flat gradient arena)
+    -> [NCCL all-reduce(mean) of the arena, world_size > 1] -> Adam (tnf_adam_step, zeroes the arena)
+
+It reproduces what nerfstudio's ``Trainer.train_iteration`` does around the reference model
+(SURVEY 3.1): the proposal-weight anneal and the proposal update schedule
+(thermal_nerf_model.py:152-161, ProposalNetworkSampler), single-jitter stratified sampling, the
+loss multipliers of get_loss_dict (:277-326), Adam(lr=1e-2, eps=1e-15) with exponential decay to
+1e-4 over 200k steps for the ``fields`` and ``proposal_networks`` groups
+(config_thermal_nerf.py:32-45), and DDP semantics for world_size > 1 (each rank draws its own rays;
+gradients are averaged).  The autograd route (``functional.render`` + ``FusedAdam``) computes the
+same numbers through the plugin API; this class is the launch-lean fast path the benchmark times.
+"""
+
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import _lib as L
+from . import functional as F
+
+NUM_PROP_TENSORS = 5 * L.TNF_NUM_PROP  # leading entries of ModelTensors.param_list()
+
+
+def exponential_decay_lr(step: int, lr_init: float = 1e-2, lr_final: float = 1e-4, max_steps: int = 200000) -> float:
+    """nerfstudio ExponentialDecayScheduler (no warm-up, ramp 'cosine' unused): log-linear interpolation."""
+    t = float(np.clip(step / max_steps, 0.0, 1.0))
+    return float(np.exp(np.log(lr_init) * (1 - t) + np.log(lr_final) * t))
+
+
+class TrainEngine:
+    def __init__(self, model, *, lr: float = 1e-2, lr_final: float = 1e-4, lr_max_steps: int = 200000,
+                 betas=(0.9, 0.999), eps: float = 1e-15, process_group=None, world_size: int = 1) -> None:
+        self.model = model
+        self.cfg = model.config
+        self.tensors = model.tensors()
+        self.params: List[Tensor] = self.tensors.param_list()
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("TrainEngine needs the model on a CUDA device; there is no CPU path")
+        self.device = dev
+        # flat arenas (each tensor 16-byte aligned): gradients, exp_avg, exp_avg_sq
+        offs, total = [], 0
+        for p in self.params:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        self.grad_arena = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.m_arena = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.v_arena = torch.zeros(total, dtype=torch.float32, device=dev)
+
+        def views(arena):
+            return [arena[o:o + p.numel()].view_as(p) for o, p in zip(offs, self.params)]
+
+        self.grads, self.exp_avg, self.exp_avg_sq = views(self.grad_arena), views(self.m_arena), views(self.v_arena)
+        self.lr, self.lr_final, self.lr_max_steps = lr, lr_final, lr_max_steps
+        self.betas, self.eps = betas, eps
+        self.pg, self.world_size = process_group, world_size
+        self.step_count = 0          # trainer step
+        self.field_steps = 0         # Adam step counters (a tensor without gradient does not advance)
+        self.prop_steps = 0
+        self.steps_since_update = 0
+        self._ws: Optional[Tensor] = None
+
+    # ---- reference schedules -------------------------------------------------------------
+    def anneal(self, step: int) -> float:
+        if not self.cfg.use_proposal_weight_anneal:
+            return 1.0
+        n, b = self.cfg.proposal_weights_anneal_max_num_iters, self.cfg.proposal_weights_anneal_slope
+        f = float(np.clip(step / n, 0, 1))
+        return b * f / ((b - 1) * f + 1)
+
+    def prop_updated(self, step: int) -> bool:
+        return self.steps_since_update > self.model.update_schedule(step) or step < 10
+
+    # ---- one iteration -------------------------------------------------------------------
+    def step(self, origins: Tensor, directions: Tensor, camera_indices: Tensor, gt_rgb: Tensor, gt_thermal: Tensor,
+             jitter: Optional[Tensor] = None) -> Tensor:
+        """Runs one full iteration on the current stream; returns the 4 losses (device tensor, order
+        ``functional.LOSS_NAMES``).  Nothing synchronises the host."""
+        cfg, step = self.cfg, self.step_count
+        R = int(origins.shape[0])
+        if jitter is None:
+            jitter = torch.rand((L.TNF_NUM_PROP + 1, R), device=self.device)
+        updated = self.prop_updated(step)
+        kw = dict(num_samples=(*cfg.num_proposal_samples_per_ray, cfg.num_nerf_samples_per_ray),
+                  near_plane=cfg.near_plane, far_plane=cfg.far_plane, anneal=self.anneal(step),
+                  use_contraction=not cfg.disable_scene_contraction,
+                  aabb=[float(x) for x in torch.as_tensor(self.model.scene_box.aabb).reshape(-1).tolist()],
+                  appearance_mode=L.APPEARANCE_LOOKUP, precision=self.model._precision(),
+                  detach_thermal_geo=not self.model.field.pass_thermal_gradients)
+        cam = camera_indices.reshape(-1)
+        res = F.render_forward(self.tensors, origins, directions, cam, None, None, jitter, training=True,
+                               return_samples=True, save_for_backward=True, **kw)
+        losses, g = F.losses_forward_backward(
+            res["weights_list"], res["sdist_list"], res["rgb"], res["thermal"], gt_rgb, gt_thermal,
+            interlevel_mult=cfg.interlevel_loss_mult, distortion_mult=cfg.distortion_loss_mult,
+            use_rgb_loss=self.model.field.pass_rgb_gradients, use_thermal_loss=self.model.field.pass_thermal_gradients,
+            prop_grad=updated)
+        grads = list(self.grads)
+        if not updated:
+            grads[:NUM_PROP_TENSORS] = [None] * NUM_PROP_TENSORS
+        nbytes = int(L.load().tnf_backward_workspace_bytes(res["_model_struct"], R))
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        res["_workspace"] = self._ws
+        F.render_backward(self.tensors, res["_model_struct"], origins, directions, cam, None, None, jitter, res,
+                          {"rgb": g["rgb"], "thermal": g["thermal"], "weights_list": g["weights_list"]}, grads)
+        if self.world_size > 1:
+            import torch.distributed as dist
+
+            # DDP semantics: average over ranks.  The proposal part of the arena is all zeros on
+            # non-updated steps (the schedule is identical on every rank), so one collective covers both.
+            dist.all_reduce(self.grad_arena, op=dist.ReduceOp.AVG, group=self.pg)
+        lr = exponential_decay_lr(step, self.lr, self.lr_final, self.lr_max_steps)
+        sl_f = slice(NUM_PROP_TENSORS, len(self.params))
+        self.field_steps += 1
+        self._adam(sl_f, lr, self.field_steps)
+        if updated:
+            self.prop_steps += 1
+            self._adam(slice(0, NUM_PROP_TENSORS), lr, self.prop_steps)
+            self.steps_since_update = 0
+        self.step_count += 1
+        self.steps_since_update += 1  # ProposalNetworkSampler.step_cb (AFTER_TRAIN_ITERATION)
+        return losses
+
+    def _adam(self, sl: slice, lr: float, step: int) -> None:
+        n = len(self.params[sl])
+        F.adam_step(self.params[sl], self.grads[sl], self.exp_avg[sl], self.exp_avg_sq[sl], [lr] * n, step=step,
+                    beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, zero_grads=True)
+
+    def state_dict(self) -> Dict[str, object]:
+        return {"step": self.step_count, "field_steps": self.field_steps, "prop_steps": self.prop_steps,
+                "steps_since_update": self.steps_since_update, "exp_avg": self.m_arena, "exp_avg_sq": self.v_arena}
+
+    def load_state_dict(self, sd: Dict[str, object]) -> None:
+        self.step_count, self.field_steps = int(sd["step"]), int(sd["field_steps"])
+        self.prop_steps, self.steps_since_update = int(sd["prop_steps"]), int(sd["steps_since_update"])
+        self.m_arena.copy_(sd["exp_avg"])
+        self.v_arena.copy_(sd["exp_avg_sq"])

@@ -87,6 +87,37 @@ class PinholeCameras:
                          metadata={"directions_norm": norm})
 
 
+    def generate_pixel_rays(self, camera_indices: Tensor, ys: Tensor, xs: Tensor) -> RayBundle:
+        """Rays through pixels (ys, xs) of cameras ``camera_indices`` ([R] each): the output of nerfstudio's
+        pixel sampler + ray generator (``datamanager.next_train``) for one training batch."""
+        c2w = self.camera_to_worlds[camera_indices]  # [R,3,4]
+        x = (xs.to(torch.float32) + 0.5 - self.cx) / self.fx
+        y = -(ys.to(torch.float32) + 0.5 - self.cy) / self.fy
+        dirs = torch.stack([x, y, -torch.ones_like(x)], -1)
+        d = (dirs[:, None, :] * c2w[:, :3, :3]).sum(-1)
+        norm = d.norm(dim=-1, keepdim=True)
+        d = d / norm
+        return RayBundle(origins=c2w[:, :3, 3].contiguous(), directions=d.contiguous(), pixel_area=torch.ones_like(norm),
+                         camera_indices=camera_indices.reshape(-1, 1).to(torch.int64),
+                         metadata={"directions_norm": norm})
+
+
+def sphere_cameras(n: int, radius: float = 0.8, hw: int = 800, focal: float = 1111.1, device="cpu") -> PinholeCameras:
+    """n cameras on a Fibonacci sphere looking at the origin: the shape of a ThermoScenes capture after the
+    dataparser's auto-orient / auto-scale to +-1 (thermal_dataparser.py:219-225)."""
+    k = torch.arange(n, dtype=torch.float32) + 0.5
+    phi = torch.acos(1 - 2 * k / n)
+    theta = torch.pi * (1 + 5**0.5) * k
+    pos = radius * torch.stack([torch.cos(theta) * torch.sin(phi), torch.sin(theta) * torch.sin(phi), torch.cos(phi)], -1)
+    back = pos / pos.norm(dim=-1, keepdim=True)
+    up = torch.tensor([0.0, 0.0, 1.0]).expand_as(back)
+    right = torch.linalg.cross(up, back)
+    right = right / right.norm(dim=-1, keepdim=True).clamp_min(1e-6)
+    true_up = torch.linalg.cross(back, right)
+    c2w = torch.stack([right, true_up, back, pos], dim=-1)
+    return PinholeCameras(c2w.to(device), focal, focal, hw / 2, hw / 2, hw, hw)
+
+
 def orbit_cameras(n: int, radius: float = 0.8, height: float = 0.25, hw: int = 800, focal: float = 1111.1,
                   device="cpu") -> PinholeCameras:
     """n cameras on a circle looking at the origin (synthetic ThermoScenes-shaped path)."""
