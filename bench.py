@@ -112,11 +112,13 @@ def randomise_trained_like(model, seed: int = 0) -> None:
         model.field.mlp_base.mlp.layers[1].weight[0].mul_(6.0)
 
 
-def build_b200_model(device, precision: str):
+def build_b200_model(device, precision: str, camera_optimizer_mode: str = "off"):
+    """Camera optimiser off: pose refinement stays in PyTorch upstream of the path and is not part of
+    the measured workload (the oracle arm is configured the same way, oracle_train_setup)."""
     from thermo_nerf_b200 import ThermalNerfModel, ThermalNerfModelConfig
 
     torch.manual_seed(0)
-    cfg = ThermalNerfModelConfig(precision=precision)
+    cfg = ThermalNerfModelConfig(precision=precision, camera_optimizer_mode=camera_optimizer_mode)
     model = ThermalNerfModel(cfg, {"thermal": []}, torch.tensor([[-1.0, -1, -1], [1, 1, 1]]), NUM_IMAGES)
     randomise_trained_like(model, 0)
     return model.to(device).eval()
@@ -330,7 +332,6 @@ def bench_train(ctx) -> dict:
 
     R = args.rays
     model = build_b200_model(device, args.precision)
-    model.config.camera_optimizer_mode = "off"
     model.train()
     engine = TrainEngine(model, world_size=world)
     n_distinct = 8
@@ -386,7 +387,6 @@ def bench_train(ctx) -> dict:
     # ---- end to end through the plugin API with HOST buffers: model(ray_bundle) -> get_metrics_dict ->
     #      get_loss_dict -> backward -> FusedAdam.step, pinned H2D of rays + GT and D2H of the loss every step
     model2 = build_b200_model(device, args.precision)
-    model2.config.camera_optimizer_mode = "off"
     model2.train()
     groups = model2.get_param_groups()
     opts = [FusedAdam(groups["proposal_networks"], lr=1e-2, eps=1e-15), FusedAdam(groups["fields"], lr=1e-2, eps=1e-15)]
@@ -470,10 +470,9 @@ def kernel_breakdown(engine, batches, device) -> dict:
     from thermo_nerf_b200 import _lib as L
     from thermo_nerf_b200 import functional as F
 
-    names = ["forward", "losses", "backward", "wgrad", "adam"]
-    acc = {n: 0.0 for n in names}
-    lib = L.load()
-    reps = 10
+    names = ["forward", "losses", "backward", "adam"]
+    acc = {n: [] for n in names}
+    reps = 11
     # the stages are timed by running the C entry points individually: backward and wgrad are two
     # launches of one entry point, so wgrad is timed as (render_backward) - (its first kernels) using
     # a second pass with a 1-row problem is not possible -> report them together and split by ncu share
@@ -503,11 +502,13 @@ def kernel_breakdown(engine, batches, device) -> dict:
                     zero_grads=True)  # lr = 0: timing only, parameters unchanged
         ev[4].record()
         torch.cuda.synchronize()
-        acc["forward"] += ev[0].elapsed_time(ev[1])
-        acc["losses"] += ev[1].elapsed_time(ev[2])
-        acc["backward"] += ev[2].elapsed_time(ev[3])
-        acc["adam"] += ev[3].elapsed_time(ev[4])
-    out = {k + "_ms": v / reps for k, v in acc.items() if k != "wgrad"}
+        acc["forward"].append(ev[0].elapsed_time(ev[1]))
+        acc["losses"].append(ev[1].elapsed_time(ev[2]))
+        acc["backward"].append(ev[2].elapsed_time(ev[3]))
+        acc["adam"].append(ev[3].elapsed_time(ev[4]))
+    # median: the interval between two events also contains any host stall between the launches (GC pause,
+    # allocator growth), which an average would book as kernel time
+    out = {k + "_ms": sorted(v)[len(v) // 2] for k, v in acc.items()}
     out["note"] = "backward_ms = proposal backward + field backward + weight-gradient GEMM (one C entry point)"
     return out
 

@@ -69,6 +69,8 @@ struct WgradProblem {
   long long rows;
   float* W; int ldW, wcol0;
   float* bias;                               // may be null
+  int dy_swz, x_swz;                         // bf16 kernel: 64-wide rows stored chunk-swizzled (see stage_tile)
+  int x_f16;                                 // bf16 kernel: X holds fp16 (the saved hash features), converted on load
 };
 constexpr int kMaxWgradProblems = 12;
 struct WgradArgs {
@@ -92,6 +94,60 @@ __device__ __forceinline__ void scatter_level(float2* __restrict__ gtab, float p
   for (int c = 0; c < 8; ++c) atomicAdd(gtab + hc.idx[c], make_float2(w[c] * gx, w[c] * gy));
 }
 
+// Warp-cooperative scatter.  Lanes lane, lane+STRIDE, lane+2*STRIDE, ... hold consecutive samples of one
+// ray, so at the coarser levels whole runs of them fall into the same grid cell (identical corner
+// indices).  The L2 reduction units retire about one lane-address per 1.3 cycles per SM, which is what
+// bounds the table scatter; each run is therefore summed with a segmented shuffle reduction first and only
+// its first lane issues the 8 vector reductions.  The number of shuffle rounds adapts to the longest run
+// in the warp (none at the fine levels, where every sample sits in its own cell).
+// Must be called by all 32 lanes; a lane without a contribution passes gx = gy = 0.
+template <int STRIDE>
+__device__ __forceinline__ void scatter_level_runs(float2* __restrict__ gtab, float px, float py, float pz, float scale,
+                                                   uint32_t mask, float gx, float gy, const int lane) {
+  HashCorners hc;
+  hash_corners(px, py, pz, scale, mask, hc);
+  const uint32_t p1 = __shfl_up_sync(kFull, hc.k1, STRIDE), p2 = __shfl_up_sync(kFull, hc.k2, STRIDE);
+  const bool head = lane < STRIDE || p1 != hc.k1 || p2 != hc.k2;
+  const unsigned heads = __ballot_sync(kFull, head);
+  const unsigned nzm = __ballot_sync(kFull, gx != 0.f || gy != 0.f);
+  const unsigned cls = STRIDE == 1 ? kFull : (0x11111111u << (lane & (STRIDE - 1)));
+  const unsigned later = lane + STRIDE >= 32 ? 0u : ((heads & cls) >> (lane + STRIDE));
+  const int nh = later ? lane + STRIDE + __ffs(later) - 1 : 32;  // first lane of the next run of my class (or 32)
+  const int len = (nh - lane + STRIDE - 1) / STRIDE;             // lanes of my class from me to the run's end
+  const int maxlen = __reduce_max_sync(kFull, len);
+  const float ox = hc.ox, oy = hc.oy, oz = hc.oz, ix = 1.f - ox, iy = 1.f - oy, iz = 1.f - oz;
+  const float w[8] = {ox * oy * oz, ox * iy * oz, ix * iy * oz, ix * oy * oz,
+                      ox * oy * iz, ox * iy * iz, ix * iy * iz, ix * oy * iz};
+  float vx[8], vy[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) { vx[c] = w[c] * gx; vy[c] = w[c] * gy; }
+#pragma unroll
+  for (int d = 1; d < 32 / STRIDE; d <<= 1) {
+    if (d < maxlen) {  // warp-uniform
+      const bool take = lane + d * STRIDE < nh;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float tx = __shfl_down_sync(kFull, vx[c], d * STRIDE), ty = __shfl_down_sync(kFull, vy[c], d * STRIDE);
+        if (take) { vx[c] += tx; vy[c] += ty; }
+      }
+    }
+  }
+  // does any lane of my run carry a gradient?
+  const unsigned runbits = (len >= 32 / STRIDE && STRIDE == 1 && lane == 0) ? kFull : 0u;
+  unsigned mine = 0u;
+  if (STRIDE == 1) {
+    mine = runbits ? kFull : (((1u << len) - 1u) << lane);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32 / STRIDE; ++i)
+      if (i < len) mine |= 1u << (lane + i * STRIDE);
+  }
+  if (head && (nzm & mine)) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) atomicAdd(gtab + hc.idx[c], make_float2(vx[c], vy[c]));
+  }
+}
+
 // reverse (suffix) exclusive scan helper over one 32-wide chunk: returns sum_{j>lane} v_j
 __device__ __forceinline__ float warp_suffix_excl(float v, int lane, float& total) {
   const float rv = __shfl_sync(kFull, v, 31 - lane);
@@ -102,63 +158,159 @@ __device__ __forceinline__ float warp_suffix_excl(float v, int lane, float& tota
 
 // ------------------------------------------------------------------------------------
 // proposal levels
+//
+// Work unit = (level, ray), handed out by a global counter with the 256-sample level first
+// (longest-processing-time order), so the two levels of 4096 rays balance over the 2368
+// resident warps instead of quantising into whole rays per warp.  Weight gradients of the
+// 10->16->1 MLP:
+//   TC mode    dW0^T|db0 = dH^T [X | 1] and dW1 = d_o^T relu(H) as bf16 mma.m16n8k16 over the 32
+//              samples of a chunk (rows staged in shared memory, fragments via ldmatrix.trans),
+//              accumulated in C fragments across all units a warp processes
+//   fp32 mode  lane-owned (a,b) column pairs summed over the staged fp32 rows (exact fp32)
+// and flushed warp -> CTA (shared atomics) -> global (one atomic per weight per CTA).
 // ------------------------------------------------------------------------------------
-constexpr int kPropRow = 51;    // dh(16) | do | feat(16) | 1 | relu(h)(16)  (+ pad to an odd stride)
+constexpr int kPropRow = 51;    // fp32 row: dh(16) | do | feat(16) | 1 | relu(h)(16)  (+ pad to an odd stride)
 constexpr int kPropSlots = 10;  // ceil((16*16 + 33) / 32)
+constexpr int kPropLd = 24;     // bf16 row stride of the staged tiles: 48 B, conflict-free for ldmatrix
+constexpr int kPropWacc = 16 * 16 + 33;
+
+struct alignas(16) PropStageTC {
+  __nv_bfloat16 dh[32 * kPropLd];  // [sample][j]           dL/dh_pre
+  __nv_bfloat16 x[32 * kPropLd];   // [sample][feat.. | 1 at column 2L | 0..]
+  __nv_bfloat16 rh[32 * kPropLd];  // [sample][j]           relu(h)
+  __nv_bfloat16 dout[32 * 8];      // [sample][d_o, 0 x 7]
+};
+struct alignas(16) PropStage32 {
+  float rows[32 * kPropRow];
+};
+union PropStage {
+  PropStageTC tc;
+  PropStage32 f;
+};
 
 struct PropBwdScratch {
   float bins[kBuf];
   float gw[kBuf];
   float P[kBuf];  // saved weights, then suffix sums of gw*w
-  float stage[32 * kPropRow];
+  PropStage st;
 };
 
 struct PropBwdSmem {
   PropW prop[TNF_NUM_PROP];
+  float wacc[TNF_NUM_PROP][kPropWacc + 3];  // [16*K2 l0.weight | 16 l0.bias | 16 l1.weight | l1.bias]
   PropBwdScratch ws[kWarpsPerCta];
 };
 
-struct SlotMap {
-  int ia[kPropSlots], ib[kPropSlots];
-  int nslots;
-};
-__device__ __forceinline__ void make_slots(SlotMap& sm, int K2, int lane) {
-  const int total = 16 * K2 + 33;
-  sm.nslots = (total + 31) / 32;
-#pragma unroll
-  for (int r = 0; r < kPropSlots; ++r) {
-    const int t = lane + 32 * r;
-    int ia = 50, ib = 50;  // both point at the zeroed pad column -> contributes 0
-    if (t < 16 * K2) { ia = t / K2; ib = 17 + t % K2; }
-    else if (t < 16 * K2 + 16) { ia = t - 16 * K2; ib = 33; }
-    else if (t < 16 * K2 + 32) { ia = 16; ib = 34 + (t - 16 * K2 - 16); }
-    else if (t == 16 * K2 + 32) { ia = 16; ib = 33; }
-    sm.ia[r] = ia;
-    sm.ib[r] = ib;
-  }
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_ptr) {
+  const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(smem_ptr));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
 }
-__device__ __forceinline__ void flush_slots(const SlotMap& sm, const float (&acc)[kPropSlots], int K2, int lane,
-                                            const TnfDensityNetGrad& g) {
-#pragma unroll
-  for (int r = 0; r < kPropSlots; ++r) {
-    const int t = lane + 32 * r;
-    if (acc[r] == 0.f) continue;
-    if (t < 16 * K2) atomicAdd(g.l0.weight + t, acc[r]);  // [16, K2] row-major: j*K2 + k == t
-    else if (t < 16 * K2 + 16) atomicAdd(g.l0.bias + (t - 16 * K2), acc[r]);
-    else if (t < 16 * K2 + 32) atomicAdd(g.l1.weight + (t - 16 * K2 - 16), acc[r]);
-    else if (t == 16 * K2 + 32) atomicAdd(g.l1.bias, acc[r]);
-  }
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t (&r)[2], const void* smem_ptr) {
+  const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(smem_ptr));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n"
+               : "=r"(r[0]), "=r"(r[1])
+               : "r"(addr));
+}
+__device__ __forceinline__ uint32_t pack_bf162(float lo, float hi) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ void mma_16816_bf16(float (&c)[4], const uint32_t (&a)[4], const uint2 b) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
 }
 
-template <int LVL>
-__device__ __forceinline__ void prop_backward_level(const TnfModel& m, const PropW& W, PropBwdScratch& ws,
-                                                    const RayCtx& rc, const int S, const int lane,
-                                                    const float* __restrict__ sdist, const float* __restrict__ wsaved,
-                                                    const float* __restrict__ gw, float2* __restrict__ gtab,
-                                                    const SlotMap& sm, float (&acc)[kPropSlots]) {
-  const TnfDensityNet& net = m.prop[LVL];
+// per-warp weight-gradient accumulators of the level being processed
+template <bool TC, int NLC>
+struct PropAcc;
+template <int NLC>
+struct PropAcc<true, NLC> {
+  static constexpr int NT1 = (2 * NLC + 1 + 7) / 8;  // n-tiles of [X | 1]
+  float c1[NT1][4];  // dH^T [X | 1]:  row j, column k (k == 2L: bias)
+  float c2[2][4];    // d_o^T relu(H): row 0, column j
+  float dosum;       // sum of d_o (l1.bias)
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < NT1; ++i) c1[i][0] = c1[i][1] = c1[i][2] = c1[i][3] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) c2[i][0] = c2[i][1] = c2[i][2] = c2[i][3] = 0.f;
+    dosum = 0.f;
+  }
+  // warp -> CTA accumulators (layout of PropBwdSmem::wacc)
+  __device__ __forceinline__ void flush(float* wacc, const int K2, const int lane) {
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int nt = 0; nt < NT1; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = g + (e >> 1) * 8, k = nt * 8 + 2 * q + (e & 1);
+        const float v = c1[nt][e];
+        if (v != 0.f) {
+          if (k < K2) atomicAdd(wacc + j * K2 + k, v);
+          else if (k == K2) atomicAdd(wacc + 16 * K2 + j, v);
+        }
+      }
+    if (g == 0) {
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          if (c2[nt][e] != 0.f) atomicAdd(wacc + 16 * K2 + 16 + nt * 8 + 2 * q + e, c2[nt][e]);
+    }
+    const float s = warp_sum(dosum);
+    if (lane == 0 && s != 0.f) atomicAdd(wacc + 16 * K2 + 32, s);
+  }
+};
+template <int NLC>
+struct PropAcc<false, NLC> {
+  float a[kPropSlots];
+  int ia[kPropSlots], ib[kPropSlots];  // staged-row columns multiplied by slot r of this lane
+  int nslots;
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int r = 0; r < kPropSlots; ++r) a[r] = 0.f;
+  }
+  __device__ __forceinline__ void make_slots(const int K2, const int lane) {
+    const int total = 16 * K2 + 33;
+    nslots = (total + 31) / 32;
+#pragma unroll
+    for (int r = 0; r < kPropSlots; ++r) {
+      const int t = lane + 32 * r;
+      int a_ = 50, b_ = 50;  // both point at the zeroed pad column -> contributes 0
+      if (t < 16 * K2) { a_ = t / K2; b_ = 17 + t % K2; }
+      else if (t < 16 * K2 + 16) { a_ = t - 16 * K2; b_ = 33; }
+      else if (t < 16 * K2 + 32) { a_ = 16; b_ = 34 + (t - 16 * K2 - 16); }
+      else if (t == 16 * K2 + 32) { a_ = 16; b_ = 33; }
+      ia[r] = a_;
+      ib[r] = b_;
+    }
+  }
+  __device__ __forceinline__ void flush(float* wacc, const int K2, const int lane) {
+#pragma unroll
+    for (int r = 0; r < kPropSlots; ++r) {
+      const int t = lane + 32 * r;
+      if (t < 16 * K2 + 33 && a[r] != 0.f) atomicAdd(wacc + t, a[r]);
+    }
+  }
+};
+
+// One (level, ray) unit.  NLC = compile-time bound on the number of hash levels (5 for the nerfacto
+// proposal nets, TNF_MAX_PROP_LEVELS otherwise).
+template <bool TC, int NLC>
+__device__ __forceinline__ void prop_backward_unit(const TnfModel& m, const int lvl, const PropW& W,
+                                                   PropBwdScratch& ws, const RayCtx& rc, const int S, const int lane,
+                                                   const float* __restrict__ sdist, const float* __restrict__ wsaved,
+                                                   const float* __restrict__ gw, float2* __restrict__ gtab,
+                                                   PropAcc<TC, NLC>& acc) {
+  const TnfDensityNet& net = m.prop[lvl];
   const int L = net.grid.num_levels;
-  const uint32_t mask = (1u << net.grid.log2_size) - 1u;
+  const int log2 = net.grid.log2_size;
+  const uint32_t mask = (1u << log2) - 1u;
   const float2* __restrict__ tab = reinterpret_cast<const float2*>(net.grid.table);
   for (int i = lane; i <= S; i += 32) ws.bins[i] = sdist[i];
   for (int i = lane; i < S; i += 32) {
@@ -189,22 +341,31 @@ __device__ __forceinline__ void prop_backward_level(const TnfModel& m, const Pro
     sample_geometry(rc, ws.bins[ii], ws.bins[ii + 1], mid, delta);
     float px, py, pz;
     const float sel = normalise_position(m, ray_x(rc, mid), ray_y(rc, mid), ray_z(rc, mid), px, py, pz);
-    float feat[2 * TNF_MAX_PROP_LEVELS];
+    float feat[2 * NLC];
 #pragma unroll
-    for (int l = 0; l < TNF_MAX_PROP_LEVELS; ++l) {
+    for (int l = 0; l < NLC; ++l) {
       float2 f = make_float2(0.f, 0.f);
-      if (l < L) f = hash_level(tab + ((size_t)l << net.grid.log2_size), px, py, pz, net.grid.scalings[l], mask);
+      if (l < L) f = hash_level(tab + ((size_t)l << log2), px, py, pz, net.grid.scalings[l], mask);
       feat[2 * l] = f.x;
       feat[2 * l + 1] = f.y;
     }
     float h[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) h[j] = W.b0[j];
+    for (int j = 0; j < 16; j += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(&W.b0[j]);
+      h[j] = b.x; h[j + 1] = b.y; h[j + 2] = b.z; h[j + 3] = b.w;
+    }
 #pragma unroll
-    for (int k = 0; k < 2 * TNF_MAX_PROP_LEVELS; ++k) {
+    for (int k = 0; k < 2 * NLC; ++k) {
       if (k < 2 * L) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) h[j] = fmaf(feat[k], W.w0t[k * 16 + j], h[j]);
+        for (int j = 0; j < 16; j += 4) {
+          const float4 w = *reinterpret_cast<const float4*>(&W.w0t[k * 16 + j]);
+          h[j] = fmaf(feat[k], w.x, h[j]);
+          h[j + 1] = fmaf(feat[k], w.y, h[j + 1]);
+          h[j + 2] = fmaf(feat[k], w.z, h[j + 2]);
+          h[j + 3] = fmaf(feat[k], w.w, h[j + 3]);
+        }
       }
     }
     float o = W.b1;
@@ -224,66 +385,142 @@ __device__ __forceinline__ void prop_backward_level(const TnfModel& m, const Pro
       const float dds = ws.gw[i] * (T - w) - ws.P[i];
       d_o = dds * delta * expf(fminf(fmaxf(o, -15.f), 15.f)) * sel;
     }
-    float* row = ws.stage + lane * kPropRow;
-    float dfeat[2 * TNF_MAX_PROP_LEVELS];
+    float dh[16];
 #pragma unroll
-    for (int k = 0; k < 2 * TNF_MAX_PROP_LEVELS; ++k) dfeat[k] = 0.f;
+    for (int j = 0; j < 16; ++j) dh[j] = h[j] > 0.f ? d_o * W.w1[j] : 0.f;
+
+    // ---- stage this chunk's rows for the weight gradients
+    if constexpr (TC) {
+      PropStageTC& st = ws.st.tc;
+      uint4* dhr = reinterpret_cast<uint4*>(st.dh + lane * kPropLd);
+      dhr[0] = make_uint4(pack_bf162(dh[0], dh[1]), pack_bf162(dh[2], dh[3]), pack_bf162(dh[4], dh[5]),
+                          pack_bf162(dh[6], dh[7]));
+      dhr[1] = make_uint4(pack_bf162(dh[8], dh[9]), pack_bf162(dh[10], dh[11]), pack_bf162(dh[12], dh[13]),
+                          pack_bf162(dh[14], dh[15]));
+      uint4* rhr = reinterpret_cast<uint4*>(st.rh + lane * kPropLd);
+      rhr[0] = make_uint4(pack_bf162(fmaxf(h[0], 0.f), fmaxf(h[1], 0.f)), pack_bf162(fmaxf(h[2], 0.f), fmaxf(h[3], 0.f)),
+                          pack_bf162(fmaxf(h[4], 0.f), fmaxf(h[5], 0.f)), pack_bf162(fmaxf(h[6], 0.f), fmaxf(h[7], 0.f)));
+      rhr[1] = make_uint4(pack_bf162(fmaxf(h[8], 0.f), fmaxf(h[9], 0.f)), pack_bf162(fmaxf(h[10], 0.f), fmaxf(h[11], 0.f)),
+                          pack_bf162(fmaxf(h[12], 0.f), fmaxf(h[13], 0.f)), pack_bf162(fmaxf(h[14], 0.f), fmaxf(h[15], 0.f)));
+      constexpr int NT1 = PropAcc<true, NLC>::NT1;
+      uint32_t xr[NT1 * 4];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float dh = h[j] > 0.f ? d_o * W.w1[j] : 0.f;
-      row[j] = dh;
-      row[34 + j] = fmaxf(h[j], 0.f);
+      for (int c = 0; c < NT1 * 8; c += 2) {
+        float v0 = c < 2 * NLC ? feat[c < 2 * NLC ? c : 0] : 0.f;
+        float v1 = c + 1 < 2 * NLC ? feat[c + 1 < 2 * NLC ? c + 1 : 0] : 0.f;
+        if (c == 2 * L) v0 = 1.f;
+        if (c + 1 == 2 * L) v1 = 1.f;
+        xr[c >> 1] = pack_bf162(v0, v1);
+      }
+      uint4* xrow = reinterpret_cast<uint4*>(st.x + lane * kPropLd);
 #pragma unroll
-      for (int k = 0; k < 2 * TNF_MAX_PROP_LEVELS; ++k)
-        if (k < 2 * L) dfeat[k] = fmaf(dh, W.w0t[k * 16 + j], dfeat[k]);
+      for (int c = 0; c < NT1; ++c) xrow[c] = make_uint4(xr[4 * c], xr[4 * c + 1], xr[4 * c + 2], xr[4 * c + 3]);
+      *reinterpret_cast<uint4*>(st.dout + lane * 8) = make_uint4(pack_bf162(d_o, 0.f), 0u, 0u, 0u);
+    } else {
+      float* row = ws.st.f.rows + lane * kPropRow;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        row[j] = dh[j];
+        row[34 + j] = fmaxf(h[j], 0.f);
+      }
+      row[16] = d_o;
+      row[33] = 1.f;
+      row[50] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) row[17 + k] = k < 2 * NLC ? feat[k < 2 * NLC ? k : 0] : 0.f;
     }
-    row[16] = d_o;
-    row[33] = 1.f;
-    row[50] = 0.f;
+
+    // ---- table scatter: dfeat = dh . W0 (whole chunk skipped when no sample of it carries a gradient)
+    if (__any_sync(kFull, d_o != 0.f)) {
 #pragma unroll
-    for (int k = 0; k < 16; ++k) row[17 + k] = k < 2 * TNF_MAX_PROP_LEVELS ? feat[k] : 0.f;
-    if (d_o != 0.f) {
+      for (int l = 0; l < NLC; ++l) {
+        if (l < L) {
+          float gx = 0.f, gy = 0.f;
 #pragma unroll
-      for (int l = 0; l < TNF_MAX_PROP_LEVELS; ++l)
-        if (l < L)
-          scatter_level(gtab + ((size_t)l << net.grid.log2_size), px, py, pz, net.grid.scalings[l], mask,
-                        dfeat[2 * l], dfeat[2 * l + 1]);
+          for (int j = 0; j < 16; ++j) {
+            gx = fmaf(dh[j], W.w0t[(2 * l) * 16 + j], gx);
+            gy = fmaf(dh[j], W.w0t[(2 * l + 1) * 16 + j], gy);
+          }
+          scatter_level_runs<1>(gtab + ((size_t)l << log2), px, py, pz, net.grid.scalings[l], mask, gx, gy, lane);
+        }
+      }
     }
     __syncwarp();
-    // weight gradients: lane owns up to kPropSlots (a,b) column pairs, summed over the 32 staged rows
-    for (int s = 0; s < 32; ++s) {
-      const float* r_ = ws.stage + s * kPropRow;
+
+    // ---- weight gradients of this chunk
+    if constexpr (TC) {
+      PropStageTC& st = ws.st.tc;
+      constexpr int NT1 = PropAcc<true, NLC>::NT1;
+      const int mi = lane >> 3, r = lane & 7;
 #pragma unroll
-      for (int r = 0; r < kPropSlots; ++r)
-        if (r < sm.nslots) acc[r] = fmaf(r_[sm.ia[r]], r_[sm.ib[r]], acc[r]);
+      for (int ks = 0; ks < 2; ++ks) {
+        uint32_t a[4];
+        ldmatrix_x4_trans(a, &st.dh[(ks * 16 + (mi >> 1) * 8 + r) * kPropLd + (mi & 1) * 8]);
+        {
+          uint32_t b[4];
+          ldmatrix_x4_trans(b, &st.x[(ks * 16 + (mi & 1) * 8 + r) * kPropLd + (mi >> 1) * 8]);
+          mma_16816_bf16(acc.c1[0], a, make_uint2(b[0], b[1]));
+          mma_16816_bf16(acc.c1[1], a, make_uint2(b[2], b[3]));
+        }
+        if constexpr (NT1 > 2) {
+          uint32_t b[2];
+          ldmatrix_x2_trans(b, &st.x[(ks * 16 + (mi & 1) * 8 + r) * kPropLd + 16]);
+          mma_16816_bf16(acc.c1[NT1 - 1], a, make_uint2(b[0], b[1]));
+        }
+        uint32_t a2[4], t2[2];
+        ldmatrix_x2_trans(t2, &st.dout[(ks * 16 + (mi & 1) * 8 + r) * 8]);
+        a2[0] = t2[0]; a2[1] = 0u; a2[2] = t2[1]; a2[3] = 0u;
+        uint32_t b2[4];
+        ldmatrix_x4_trans(b2, &st.rh[(ks * 16 + (mi & 1) * 8 + r) * kPropLd + (mi >> 1) * 8]);
+        mma_16816_bf16(acc.c2[0], a2, make_uint2(b2[0], b2[1]));
+        mma_16816_bf16(acc.c2[1], a2, make_uint2(b2[2], b2[3]));
+      }
+      acc.dosum += d_o;
+    } else {
+      for (int s = 0; s < 32; ++s) {
+        const float* r_ = ws.st.f.rows + s * kPropRow;
+#pragma unroll
+        for (int r = 0; r < kPropSlots; ++r)
+          if (r < acc.nslots) acc.a[r] = fmaf(r_[acc.ia[r]], r_[acc.ib[r]], acc.a[r]);
+      }
     }
     __syncwarp();
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool TC, int NLC>
+__global__ void __launch_bounds__(kThreads, 2)
     tnf_backward_prop_kernel(const __grid_constant__ TnfModel m, const __grid_constant__ TnfRays rays,
                              const __grid_constant__ TnfSaved sv, const __grid_constant__ TnfOutputGrads go,
-                             const __grid_constant__ TnfModelGrad gr) {
+                             const __grid_constant__ TnfModelGrad gr, unsigned long long* __restrict__ counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PropBwdSmem& S = *reinterpret_cast<PropBwdSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   stage_prop(S.prop[0], m.prop[0], tid);
   stage_prop(S.prop[1], m.prop[1], tid);
+  for (int i = tid; i < TNF_NUM_PROP * (kPropWacc + 3); i += kThreads) (&S.wacc[0][0])[i] = 0.f;
   __syncthreads();
   PropBwdScratch& ws = S.ws[warp];
-  const int S0 = m.num_samples[0], S1 = m.num_samples[1];
-  const bool do0 = gr.prop[0].table != nullptr && go.weights[0] != nullptr;
-  const bool do1 = gr.prop[1].table != nullptr && go.weights[1] != nullptr;
-  SlotMap sm0, sm1;
-  make_slots(sm0, 2 * m.prop[0].grid.num_levels, lane);
-  make_slots(sm1, 2 * m.prop[1].grid.num_levels, lane);
-  float acc0[kPropSlots], acc1[kPropSlots];
-#pragma unroll
-  for (int r = 0; r < kPropSlots; ++r) acc0[r] = acc1[r] = 0.f;
-  const long long R = rays.num_rays;
-  for (long long ray = (long long)blockIdx.x * kWarpsPerCta + warp; ray < R;
-       ray += (long long)gridDim.x * kWarpsPerCta) {
+  const bool on[TNF_NUM_PROP] = {gr.prop[0].table != nullptr && go.weights[0] != nullptr,
+                                 gr.prop[1].table != nullptr && go.weights[1] != nullptr};
+  const unsigned long long R = (unsigned long long)rays.num_rays;
+  const unsigned long long n0 = on[0] ? R : 0ull, ntasks = n0 + (on[1] ? R : 0ull);
+  PropAcc<TC, NLC> acc;
+  acc.zero();
+  int cur = -1;
+  for (;;) {
+    unsigned long long t = 0;
+    if (lane == 0) t = atomicAdd(counter, 1ull);
+    t = __shfl_sync(kFull, t, 0);
+    if (t >= ntasks) break;
+    const int lvl = t < n0 ? 0 : 1;
+    const long long ray = (long long)(t < n0 ? t : t - n0);
+    if (lvl != cur) {
+      if (cur >= 0) acc.flush(S.wacc[cur], 2 * m.prop[cur].grid.num_levels, lane);
+      acc.zero();
+      if constexpr (!TC) acc.make_slots(2 * m.prop[lvl].grid.num_levels, lane);
+      cur = lvl;
+    }
     RayCtx rc;
     rc.ox = __ldg(rays.origins + ray * 3 + 0);
     rc.oy = __ldg(rays.origins + ray * 3 + 1);
@@ -293,15 +530,28 @@ __global__ void __launch_bounds__(kThreads, 1)
     rc.dz = __ldg(rays.directions + ray * 3 + 2);
     rc.s_near = spacing_fn(rays.nears ? __ldg(rays.nears + ray) : m.near_plane);
     rc.s_far = spacing_fn(rays.fars ? __ldg(rays.fars + ray) : m.far_plane);
-    if (do0)
-      prop_backward_level<0>(m, S.prop[0], ws, rc, S0, lane, sv.sdist[0] + ray * (S0 + 1), sv.weights[0] + ray * S0,
-                             go.weights[0] + ray * S0, reinterpret_cast<float2*>(gr.prop[0].table), sm0, acc0);
-    if (do1)
-      prop_backward_level<1>(m, S.prop[1], ws, rc, S1, lane, sv.sdist[1] + ray * (S1 + 1), sv.weights[1] + ray * S1,
-                             go.weights[1] + ray * S1, reinterpret_cast<float2*>(gr.prop[1].table), sm1, acc1);
+    const int S_l = m.num_samples[lvl];
+    prop_backward_unit<TC, NLC>(m, lvl, S.prop[lvl], ws, rc, S_l, lane, sv.sdist[lvl] + ray * (S_l + 1),
+                                sv.weights[lvl] + ray * S_l, go.weights[lvl] + ray * S_l,
+                                reinterpret_cast<float2*>(gr.prop[lvl].table), acc);
   }
-  if (do0) flush_slots(sm0, acc0, 2 * m.prop[0].grid.num_levels, lane, gr.prop[0]);
-  if (do1) flush_slots(sm1, acc1, 2 * m.prop[1].grid.num_levels, lane, gr.prop[1]);
+  if (cur >= 0) acc.flush(S.wacc[cur], 2 * m.prop[cur].grid.num_levels, lane);
+  __syncthreads();
+  // CTA -> global
+#pragma unroll
+  for (int lvl = 0; lvl < TNF_NUM_PROP; ++lvl) {
+    if (!on[lvl]) continue;
+    const int K2 = 2 * m.prop[lvl].grid.num_levels;
+    const TnfDensityNetGrad& g = gr.prop[lvl];
+    for (int t = tid; t < 16 * K2 + 33; t += kThreads) {
+      const float v = S.wacc[lvl][t];
+      if (v == 0.f) continue;
+      if (t < 16 * K2) atomicAdd(g.l0.weight + t, v);  // [16, K2] row-major: j*K2 + k == t
+      else if (t < 16 * K2 + 16) atomicAdd(g.l0.bias + (t - 16 * K2), v);
+      else if (t < 16 * K2 + 32) atomicAdd(g.l1.weight + (t - 16 * K2 - 16), v);
+      else atomicAdd(g.l1.bias, v);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------
@@ -634,17 +884,6 @@ __global__ void __launch_bounds__(kThreads, 1)
 // far more than fp16's exponent range), fp32 accumulate; activations never leave registers
 // except as the staged (X, dY) rows the weight-gradient GEMMs read.
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t pack_bf162(float lo, float hi) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<const uint32_t*>(&h);
-}
-__device__ __forceinline__ void mma_16816_bf16(float (&c)[4], const uint32_t (&a)[4], const uint2 b) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
-      "{%0,%1,%2,%3};\n"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
-}
 template <int NT, int KT>
 __device__ __forceinline__ void mma_layer_bf16(float (&c)[NT][4], const uint32_t (&a)[KT][4],
                                                const uint2* __restrict__ w, const int ntw, const int lane) {
@@ -688,18 +927,40 @@ __device__ __forceinline__ void apply_mask(float (&c)[NT][4], const uint32_t mk)
     for (int e = 0; e < 4; ++e)
       if (!((mk >> (nt * 4 + e)) & 1u)) c[nt][e] = 0.f;
 }
-// C fragments -> staged bf16 rows: row0/row1 are the global row indices of fragment rows g / g+8
+// Staged (X, dY) tiles of the tensor-core backward.  A warp writes one 16-row tile of a staged matrix into
+// its shared-memory ring (bf16, the exact byte image of the global rows) and lane 0 hands it to the
+// bulk-copy engine (cp.async.bulk.global.shared::cta): 2 KB leave the SM as one asynchronous copy instead
+// of 16 scattered 4-byte stores per lane, and no LSU/register resource is held while it drains.
+// 64-wide rows are XOR-swizzled by 16-byte chunk (chunk ^ (global_row & 7)) so the fragment stores are
+// bank-conflict free; tnf_wgrad_kernel_bf16 undoes the swizzle when it loads the rows.
+struct alignas(128) StageRing {
+  unsigned char buf[2][2048];
+};
+__device__ __forceinline__ void bulk_store_tile(void* gdst, const void* ssrc, const unsigned bytes) {
+  const uint32_t saddr = static_cast<uint32_t>(__cvta_generic_to_shared(ssrc));
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(saddr), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
 template <int NT>
-__device__ __forceinline__ void stage_c(unsigned char* base, const long long row0, const long long row1,
-                                        const bool v0, const bool v1, const int ld, const int col0, const int q,
-                                        const float (&c)[NT][4]) {
-  __nv_bfloat16* b = reinterpret_cast<__nv_bfloat16*>(base);
+__device__ __forceinline__ void stage_tile(StageRing& ring, int& slot, unsigned char* gbase, const long long tile_row0,
+                                           const int nvalid, const int g, const int q, const int lane,
+                                           const float (&c)[NT][4]) {
+  constexpr int kRowBytes = NT * 16;  // NT*8 bf16
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");  // the slot's previous copy was read
+  __syncwarp();
+  unsigned char* b = ring.buf[slot];
+  const int key = NT == 8 ? (int)((tile_row0 + g) & 7) : 0;
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
-    const int col = col0 + nt * 8 + 2 * q;
-    if (v0) *reinterpret_cast<uint32_t*>(b + row0 * ld + col) = pack_bf162(c[nt][0], c[nt][1]);
-    if (v1) *reinterpret_cast<uint32_t*>(b + row1 * ld + col) = pack_bf162(c[nt][2], c[nt][3]);
+    const int off = ((nt ^ key) * 16) + q * 4;
+    *reinterpret_cast<uint32_t*>(b + g * kRowBytes + off) = pack_bf162(c[nt][0], c[nt][1]);
+    *reinterpret_cast<uint32_t*>(b + (g + 8) * kRowBytes + off) = pack_bf162(c[nt][2], c[nt][3]);
   }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> async-proxy read
+  __syncwarp();
+  if (lane == 0) bulk_store_tile(gbase + tile_row0 * kRowBytes, b, (unsigned)(nvalid * kRowBytes));
+  slot ^= 1;
 }
 
 // bf16 B fragments of the backward products: B[kk][nn] = V(kk, nn), [kt][nt][lane]
@@ -748,10 +1009,13 @@ __device__ inline void stage_field_bwd(FieldBwdWTC& W, const TnfModel& m, int ti
 }
 
 struct FieldBwdSmemTC {
+  StageRing ring[kWarpsPerCta];
   FieldWTC fw;
   FieldBwdWTC bw;
   FieldBwdScratch ws[kWarpsPerCta];
 };
+// two CTAs per SM: 2 x (dynamic + 1 KB system) must fit the 228 KB of an sm_100 SM
+static_assert(sizeof(FieldBwdSmemTC) <= 113 * 1024, "FieldBwdSmemTC no longer fits two CTAs per SM");
 
 __global__ void __launch_bounds__(kThreads, 2)
     tnf_backward_field_kernel_tc(const __grid_constant__ TnfModel m, const __grid_constant__ TnfRays rays,
@@ -766,6 +1030,8 @@ __global__ void __launch_bounds__(kThreads, 2)
   const FieldWTC& W = S.fw;
   const FieldBwdWTC& B = S.bw;
   FieldBwdScratch& ws = S.ws[warp];
+  StageRing& ring = S.ring[warp];
+  int slot = 0;
   const int g = lane >> 2, q = lane & 3;
   const int S2 = m.num_samples[TNF_NUM_PROP];
   const TnfHashGrid& grid = m.field.grid;
@@ -773,6 +1039,8 @@ __global__ void __launch_bounds__(kThreads, 2)
   float2* __restrict__ gtab = reinterpret_cast<float2*>(gr.field.table);
   const uint32_t* __restrict__ F = static_cast<const uint32_t*>(sv.field_features);  // [Ns][16] half2
   const long long R = rays.num_rays;
+  unsigned char* const dA1 = L.dGeo;                                  // [Ns,64] dL/d(colour layer-0 pre-activation)
+  unsigned char* const dB1 = L.dGeo + (size_t)R * S2 * kWX * 2;      // [Ns,64] dL/d(thermal layer-0 pre-activation)
 
   for (long long ray = (long long)blockIdx.x * kWarpsPerCta + warp; ray < R;
        ray += (long long)gridDim.x * kWarpsPerCta) {
@@ -803,6 +1071,8 @@ __global__ void __launch_bounds__(kThreads, 2)
       const bool v0 = r0 < S2, v1 = r1 < S2;
       const int i0 = min(r0, S2 - 1), i1 = min(r1, S2 - 1);
       const long long row0 = ray * S2 + i0, row1 = ray * S2 + i1;
+      const long long trow = ray * S2 + base;          // global row of this tile's first sample
+      const int nval = min(16, S2 - base);
       float p[2][3], sel[2];
       {
         float mid, delta;
@@ -815,23 +1085,15 @@ __global__ void __launch_bounds__(kThreads, 2)
       const float dtau[2] = {v0 ? ws.dtau[i0] : 0.f, v1 ? ws.dtau[i1] : 0.f};
       const float dz[2][3] = {{v0 ? ws.dzr[i0] : 0.f, v0 ? ws.dzg[i0] : 0.f, v0 ? ws.dzb[i0] : 0.f},
                               {v1 ? ws.dzr[i1] : 0.f, v1 ? ws.dzg[i1] : 0.f, v1 ? ws.dzb[i1] : 0.f}};
-      // ---- saved hash features -> A fragments (fp16) + bf16 copy for the base0 weight gradient
+      // ---- saved hash features -> A fragments (fp16); the base0 weight-gradient GEMM reads them in place
       uint32_t a0[2][4];
 #pragma unroll
       for (int kt = 0; kt < 2; ++kt)
 #pragma unroll
         for (int hl = 0; hl < 2; ++hl) {
           const int l = kt * 8 + hl * 4 + q;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const long long row = h ? row1 : row0;
-            const uint32_t v = __ldg(F + row * 16 + l);
-            a0[kt][2 * hl + h] = v;
-            if (h ? v1 : v0) {
-              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v));
-              reinterpret_cast<uint32_t*>(L.XF)[row * 16 + l] = pack_bf162(f.x, f.y);
-            }
-          }
+          a0[kt][2 * hl] = __ldg(F + row0 * 16 + l);
+          a0[kt][2 * hl + 1] = __ldg(F + row1 * 16 + l);
         }
       // ---- trunk forward: H, G
       uint32_t hid[4][4];
@@ -841,7 +1103,7 @@ __global__ void __launch_bounds__(kThreads, 2)
         init_bias(c, W.base0b, q);
         mma_layer<8, 2>(c, a0, &W.base0[0][0][0], 0, 8, lane);
         mkH = relu_mask(c);
-        stage_c(L.XH, row0, row1, v0, v1, kWXH, 0, q, c);
+        stage_tile<8>(ring, slot, L.XH, trow, nval, g, q, lane, c);
         act_pack<8, ACT_NONE>(c, hid);
       }
       float h0r0, h0r1;
@@ -850,7 +1112,7 @@ __global__ void __launch_bounds__(kThreads, 2)
         float c[2][4];
         init_bias(c, W.base1b, q);
         mma_layer<2, 4>(c, hid, &W.base1[0][0][0], 0, 2, lane);
-        stage_c(L.XG, row0, row1, v0, v1, kWXG, 0, q, c);
+        stage_tile<2>(ring, slot, L.XG, trow, nval, g, q, lane, c);
         h0r0 = c[0][0];
         h0r1 = c[0][2];
         if (q == 0) { c[0][0] = 0.f; c[0][2] = 0.f; }
@@ -863,27 +1125,27 @@ __global__ void __launch_bounds__(kThreads, 2)
         init_bias(c, W.th0b, q);
         mma_layer<8, 1>(c, ga, &W.geo0[0][0][0], 8, 16, lane);
         const uint32_t mkB1 = relu_mask(c);
-        stage_c(L.XB1, row0, row1, v0, v1, kWX, 0, q, c);
+        stage_tile<8>(ring, slot, L.XB1, trow, nval, g, q, lane, c);
         act_pack<8, ACT_NONE>(c, hid);
         init_bias(c, W.th1b, q);
         mma_layer<8, 4>(c, hid, &W.th1[0][0][0], 0, 8, lane);
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) c[nt][e] = sigmoidf(c[nt][e]);
-        stage_c(L.XB2, row0, row1, v0, v1, kWX, 0, q, c);
+          for (int e = 0; e < 4; ++e) c[nt][e] = sigmoid_fast(c[nt][e]);
+        stage_tile<8>(ring, slot, L.XB2, trow, nval, g, q, lane, c);
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
           for (int e = 0; e < 4; ++e)
             c[nt][e] = dtau[e >> 1] * B.th2w[nt * 8 + 2 * q + (e & 1)] * c[nt][e] * (1.f - c[nt][e]);
-        stage_c(L.dB2, row0, row1, v0, v1, kWX, 0, q, c);
+        stage_tile<8>(ring, slot, L.dB2, trow, nval, g, q, lane, c);
         uint32_t dy[4][4];
         pack_bf16_a(c, dy);
         zero_c(c);
         mma_layer_bf16<8, 4>(c, dy, &B.th1T[0][0][0], 8, lane);
         apply_mask(c, mkB1);
-        stage_c(L.dGeo, row0, row1, v0, v1, kWdGeo, 64, q, c);
+        stage_tile<8>(ring, slot, dB1, trow, nval, g, q, lane, c);
         pack_bf16_a(c, dB1A);
         if (q == 0) {
           uint4* dt = reinterpret_cast<uint4*>(L.dT);
@@ -898,12 +1160,12 @@ __global__ void __launch_bounds__(kThreads, 2)
         init_bias(c, ws.rayb, q);
         mma_layer<8, 1>(c, ga, &W.geo0[0][0][0], 0, 16, lane);
         const uint32_t mkA1 = relu_mask(c);
-        stage_c(L.XA1, row0, row1, v0, v1, kWX, 0, q, c);
+        stage_tile<8>(ring, slot, L.XA1, trow, nval, g, q, lane, c);
         act_pack<8, ACT_NONE>(c, hid);
         init_bias(c, W.rgb1b, q);
         mma_layer<8, 4>(c, hid, &W.rgb1[0][0][0], 0, 8, lane);
         relu_mask(c);
-        stage_c(L.XA2, row0, row1, v0, v1, kWX, 0, q, c);
+        stage_tile<8>(ring, slot, L.XA2, trow, nval, g, q, lane, c);
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
@@ -912,13 +1174,13 @@ __global__ void __launch_bounds__(kThreads, 2)
             const float v = dz[h][0] * B.rgb2w[0][col] + dz[h][1] * B.rgb2w[1][col] + dz[h][2] * B.rgb2w[2][col];
             c[nt][e] = c[nt][e] > 0.f ? v : 0.f;
           }
-        stage_c(L.dA2, row0, row1, v0, v1, kWX, 0, q, c);
+        stage_tile<8>(ring, slot, L.dA2, trow, nval, g, q, lane, c);
         uint32_t dy[4][4];
         pack_bf16_a(c, dy);
         zero_c(c);
         mma_layer_bf16<8, 4>(c, dy, &B.rgb1T[0][0][0], 8, lane);
         apply_mask(c, mkA1);
-        stage_c(L.dGeo, row0, row1, v0, v1, kWdGeo, 0, q, c);
+        stage_tile<8>(ring, slot, dA1, trow, nval, g, q, lane, c);
         pack_bf16_a(c, dA1A);
         // column sums over the 16 rows of the tile -> per-ray sum of dA1pre
 #pragma unroll
@@ -948,7 +1210,7 @@ __global__ void __launch_bounds__(kThreads, 2)
           c[0][0] = dsig[0] * expf(fminf(fmaxf(h0r0, -15.f), 15.f)) * sel[0];
           c[0][2] = dsig[1] * expf(fminf(fmaxf(h0r1, -15.f), 15.f)) * sel[1];
         }
-        stage_c(L.dG, row0, row1, v0, v1, kWXG, 0, q, c);
+        stage_tile<2>(ring, slot, L.dG, trow, nval, g, q, lane, c);
         pack_bf16_a(c, dGA);
       }
       uint32_t dHA[4][4];
@@ -957,7 +1219,7 @@ __global__ void __launch_bounds__(kThreads, 2)
         zero_c(c);
         mma_layer_bf16<8, 1>(c, dGA, &B.base1T[0][0][0], 8, lane);
         apply_mask(c, mkH);
-        stage_c(L.dH, row0, row1, v0, v1, kWX, 0, q, c);
+        stage_tile<8>(ring, slot, L.dH, trow, nval, g, q, lane, c);
         pack_bf16_a(c, dHA);
       }
       {
@@ -968,9 +1230,9 @@ __global__ void __launch_bounds__(kThreads, 2)
         for (int nt = 0; nt < 4; ++nt) {
           const int l = nt * 4 + q;
           float2* lt = gtab + ((size_t)l << grid.log2_size);
-          const float sc = grid.scalings[l];
-          if (v0) scatter_level(lt, p[0][0], p[0][1], p[0][2], sc, mask, c[nt][0], c[nt][1]);
-          if (v1) scatter_level(lt, p[1][0], p[1][1], p[1][2], sc, mask, c[nt][2], c[nt][3]);
+          const float sc = W.scal[l];
+          scatter_level_runs<4>(lt, p[0][0], p[0][1], p[0][2], sc, mask, v0 ? c[nt][0] : 0.f, v0 ? c[nt][1] : 0.f, lane);
+          scatter_level_runs<4>(lt, p[1][0], p[1][1], p[1][2], sc, mask, v1 ? c[nt][2] : 0.f, v1 ? c[nt][3] : 0.f, lane);
         }
       }
     }
@@ -992,16 +1254,10 @@ __global__ void __launch_bounds__(kThreads, 2)
       __syncwarp();
     }
   }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");  // staged tiles have landed
 }
 
 // bf16 tensor-core weight-gradient GEMM: dW = dY^T X over 64-row tiles, fragments via ldmatrix.trans
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_ptr) {
-  const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(smem_ptr));
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(addr));
-}
-
 constexpr int kWgradLd = 72;  // padded row stride (bf16 elements): 144 B, conflict-free for ldmatrix
 
 __global__ void __launch_bounds__(128) tnf_wgrad_kernel_bf16(const __grid_constant__ WgradArgs args) {
@@ -1025,9 +1281,20 @@ __global__ void __launch_bounds__(128) tnf_wgrad_kernel_bf16(const __grid_consta
     for (int idx = tid; idx < kWgradRows * 8; idx += 128) {
       const int r = idx >> 3, c8 = (idx & 7) * 8;
       uint4 v = make_uint4(0u, 0u, 0u, 0u), x = v;
-      if (row0 + r < P.rows) {
-        if (c8 < P.N) v = *reinterpret_cast<const uint4*>(dY + (row0 + r) * P.ldY + P.n0 + c8);
-        if (c8 < P.K) x = *reinterpret_cast<const uint4*>(X + (row0 + r) * P.ldX + c8);
+      const long long gr = row0 + r;
+      if (gr < P.rows) {
+        const int key = (int)(gr & 7) << 3;
+        if (c8 < P.N) v = *reinterpret_cast<const uint4*>(dY + gr * P.ldY + P.n0 + (P.dy_swz ? (c8 ^ key) : c8));
+        if (c8 < P.K) {
+          x = *reinterpret_cast<const uint4*>(X + gr * P.ldX + (P.x_swz ? (c8 ^ key) : c8));
+          if (P.x_f16) {
+            const __half2* h = reinterpret_cast<const __half2*>(&x);
+            const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]),
+                         f3 = __half22float2(h[3]);
+            x = make_uint4(pack_bf162(f0.x, f0.y), pack_bf162(f1.x, f1.y), pack_bf162(f2.x, f2.y),
+                           pack_bf162(f3.x, f3.y));
+          }
+        }
       }
       *reinterpret_cast<uint4*>(&sdY[r * kWgradLd + c8]) = v;
       *reinterpret_cast<uint4*>(&sX[r * kWgradLd + c8]) = x;
@@ -1166,27 +1433,40 @@ int set_smem(K kernel, size_t bytes, const char* name) {
 }
 
 void add_problem(tnf::WgradArgs& a, const void* dY, int ldY, int n0, int N, int n_valid, const void* X, int ldX,
-                 int K, int k_skip, long long rows, float* W, int ldW, int wcol0, float* bias) {
+                 int K, int k_skip, long long rows, float* W, int ldW, int wcol0, float* bias, int dy_swz = 0,
+                 int x_swz = 0, int x_f16 = 0) {
   tnf::WgradProblem& p = a.p[a.n++];
   p.dY = dY; p.ldY = ldY; p.n0 = n0; p.N = N; p.n_valid = n_valid;
   p.X = X; p.ldX = ldX; p.K = K; p.k_skip = k_skip;
   p.rows = rows; p.W = W; p.ldW = ldW; p.wcol0 = wcol0; p.bias = bias;
+  p.dy_swz = dy_swz; p.x_swz = x_swz; p.x_f16 = x_f16;
 }
 
-// the eight field layers (+ the two per-ray blocks of mlp_head.layers.0) as GEMM problems
-void field_problems(tnf::WgradArgs& a, const tnf::BwdLayout& L, const void* XF, size_t es, const TnfFieldGrad& g,
+// the eight field layers (+ the two per-ray blocks of mlp_head.layers.0) as GEMM problems.
+// fp32 mode: plain row-major fp32 staging, dGeo = [Ns,128] (colour | thermal layer-0 gradients).
+// TC mode:   bf16 staging written by stage_tile (64-wide matrices chunk-swizzled), dGeo holds two
+//            [Ns,64] matrices back to back, X of base0 = the fp16 hash features saved by the forward.
+void field_problems(tnf::WgradArgs& a, const tnf::BwdLayout& L, const void* XF, bool tc, const TnfFieldGrad& g,
                     long long Ns, long long R) {
   using namespace tnf;
   a.n = 0;
-  auto off = [&](const unsigned char* p, int elems) { return static_cast<const void*>(p + (size_t)elems * es); };
-  add_problem(a, L.dH, kWX, 0, 64, 64, XF, kWXF, 32, 0, Ns, g.base0.weight, 32, 0, g.base0.bias);
-  add_problem(a, L.dG, kWXG, 0, 16, 16, L.XH, kWXH, 64, 0, Ns, g.base1.weight, 64, 0, g.base1.bias);
-  add_problem(a, L.dGeo, kWdGeo, 0, 64, 64, L.XG, kWXG, 16, 1, Ns, g.rgb0.weight, 63, 16, nullptr);
-  add_problem(a, L.dGeo, kWdGeo, 64, 64, 64, L.XG, kWXG, 16, 1, Ns, g.th0.weight, 15, 0, g.th0.bias);
-  add_problem(a, L.dA2, kWX, 0, 64, 64, L.XA1, kWX, 64, 0, Ns, g.rgb1.weight, 64, 0, g.rgb1.bias);
-  add_problem(a, L.dZ, kWdZ, 0, 8, 3, L.XA2, kWX, 64, 0, Ns, g.rgb2.weight, 64, 0, g.rgb2.bias);
-  add_problem(a, L.dB2, kWX, 0, 64, 64, L.XB1, kWX, 64, 0, Ns, g.th1.weight, 64, 0, g.th1.bias);
-  add_problem(a, L.dT, kWdT, 0, 8, 1, L.XB2, kWX, 64, 0, Ns, g.th2.weight, 64, 0, g.th2.bias);
+  const size_t es = tc ? 2 : 4;
+  auto off = [&](const unsigned char* p, size_t elems) { return static_cast<const void*>(p + elems * es); };
+  const int z = tc ? 1 : 0;  // swizzled 64-wide staging
+  add_problem(a, L.dH, kWX, 0, 64, 64, XF, kWXF, 32, 0, Ns, g.base0.weight, 32, 0, g.base0.bias, z, 0, z);
+  add_problem(a, L.dG, kWXG, 0, 16, 16, L.XH, kWXH, 64, 0, Ns, g.base1.weight, 64, 0, g.base1.bias, 0, z);
+  if (tc) {
+    add_problem(a, L.dGeo, kWX, 0, 64, 64, L.XG, kWXG, 16, 1, Ns, g.rgb0.weight, 63, 16, nullptr, 1);
+    add_problem(a, off(L.dGeo, (size_t)Ns * kWX), kWX, 0, 64, 64, L.XG, kWXG, 16, 1, Ns, g.th0.weight, 15, 0,
+                g.th0.bias, 1);
+  } else {
+    add_problem(a, L.dGeo, kWdGeo, 0, 64, 64, L.XG, kWXG, 16, 1, Ns, g.rgb0.weight, 63, 16, nullptr);
+    add_problem(a, L.dGeo, kWdGeo, 64, 64, 64, L.XG, kWXG, 16, 1, Ns, g.th0.weight, 15, 0, g.th0.bias);
+  }
+  add_problem(a, L.dA2, kWX, 0, 64, 64, L.XA1, kWX, 64, 0, Ns, g.rgb1.weight, 64, 0, g.rgb1.bias, z, z);
+  add_problem(a, L.dZ, kWdZ, 0, 8, 3, L.XA2, kWX, 64, 0, Ns, g.rgb2.weight, 64, 0, g.rgb2.bias, 0, z);
+  add_problem(a, L.dB2, kWX, 0, 64, 64, L.XB1, kWX, 64, 0, Ns, g.th1.weight, 64, 0, g.th1.bias, z, z);
+  add_problem(a, L.dT, kWdT, 0, 8, 1, L.XB2, kWX, 64, 0, Ns, g.th2.weight, 64, 0, g.th2.bias, 0, z);
   add_problem(a, L.dRay, kWdRay, 0, 64, 64, L.XRay, kWXRay, 16, 0, R, g.rgb0.weight, 63, 0, g.rgb0.bias);
   add_problem(a, L.dRay, kWdRay, 0, 64, 64, off(L.XRay, 16), kWXRay, 32, 0, R, g.rgb0.weight, 63, 31, nullptr);
 }
@@ -1198,7 +1478,7 @@ size_t tnf_backward_workspace_bytes(const TnfModel* model, int64_t num_rays) {
   if (!model || num_rays <= 0) return 256;
   const long long Ns = (long long)num_rays * model->num_samples[TNF_NUM_PROP];
   const bool tc = model->precision == TNF_PRECISION_TC_FP16;
-  return tnf::make_layout(nullptr, nullptr, Ns, num_rays, tc ? 2 : 4, tc) + 256;
+  return tnf::make_layout(nullptr, nullptr, Ns, num_rays, tc ? 2 : 4, false) + 256;
 }
 
 int tnf_render_backward(const TnfModel* model, const TnfRays* rays, const TnfSaved* saved, const TnfOutputGrads* gout,
@@ -1231,14 +1511,33 @@ int tnf_render_backward(const TnfModel* model, const TnfRays* rays, const TnfSav
   const long long want = (R + tnf::kWarpsPerCta - 1) / tnf::kWarpsPerCta;
   cudaError_t e;
 
-  // ---- proposal levels
+  // ---- proposal levels: (level, ray) units handed out by a device counter (last 8 bytes of the workspace)
   const bool do_prop = (grads->prop[0].table && gout->weights[0]) || (grads->prop[1].table && gout->weights[1]);
   if (do_prop) {
+    unsigned long long* counter =
+        reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(workspace) + need - 16);
+    e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
     const size_t smem = sizeof(tnf::PropBwdSmem);
-    if (int rc = set_smem(tnf::tnf_backward_prop_kernel, smem, "backward_prop")) return rc;
+    const bool tc_ = model->precision == TNF_PRECISION_TC_FP16;
+    const bool five = model->prop[0].grid.num_levels <= 5 && model->prop[1].grid.num_levels <= 5;
+    long long units = 0;
+    for (int k = 0; k < TNF_NUM_PROP; ++k)
+      if (grads->prop[k].table && gout->weights[k]) units += R;
+    const long long wantu = (units + tnf::kWarpsPerCta - 1) / tnf::kWarpsPerCta;
     const long long cap = (long long)sms * 2;
-    tnf::tnf_backward_prop_kernel<<<(unsigned)(want < cap ? want : cap), tnf::kThreads, smem, stream>>>(
-        *model, *rays, *saved, *gout, *grads);
+    const unsigned grid = (unsigned)(wantu < cap ? wantu : cap);
+#define TNF_LAUNCH_PROP(TC_, NLC_)                                                                              \
+  do {                                                                                                          \
+    if (int rc = set_smem(tnf::tnf_backward_prop_kernel<TC_, NLC_>, smem, "backward_prop")) return rc;          \
+    tnf::tnf_backward_prop_kernel<TC_, NLC_><<<grid, tnf::kThreads, smem, stream>>>(*model, *rays, *saved,      \
+                                                                                   *gout, *grads, counter);     \
+  } while (0)
+    if (tc_ && five) TNF_LAUNCH_PROP(true, 5);
+    else if (tc_) TNF_LAUNCH_PROP(true, TNF_MAX_PROP_LEVELS);
+    else if (five) TNF_LAUNCH_PROP(false, 5);
+    else TNF_LAUNCH_PROP(false, TNF_MAX_PROP_LEVELS);
+#undef TNF_LAUNCH_PROP
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "backward_prop launch: %s", cudaGetErrorString(e));
   }
@@ -1247,7 +1546,7 @@ int tnf_render_backward(const TnfModel* model, const TnfRays* rays, const TnfSav
   const long long Ns = R * model->num_samples[TNF_NUM_PROP];
   const bool tc = model->precision == TNF_PRECISION_TC_FP16;
   tnf::BwdLayout L{};
-  tnf::make_layout(&L, static_cast<unsigned char*>(workspace), Ns, R, tc ? 2 : 4, tc);
+  tnf::make_layout(&L, static_cast<unsigned char*>(workspace), Ns, R, tc ? 2 : 4, false);
   tnf::WgradArgs wa;
   if (!tc) {
     const size_t smem = sizeof(tnf::FieldBwdSmem32);
@@ -1257,7 +1556,7 @@ int tnf_render_backward(const TnfModel* model, const TnfRays* rays, const TnfSav
         *model, *rays, *saved, *gout, *grads, L);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "backward_field launch: %s", cudaGetErrorString(e));
-    field_problems(wa, L, saved->field_features, 4, grads->field, Ns, R);
+    field_problems(wa, L, saved->field_features, false, grads->field, Ns, R);
     const long long tiles = (Ns + tnf::kWgradRows - 1) / tnf::kWgradRows;
     const long long capx = (long long)sms * 2 / wa.n + 1;
     dim3 grid((unsigned)(tiles < capx ? tiles : capx), wa.n);
@@ -1272,7 +1571,7 @@ int tnf_render_backward(const TnfModel* model, const TnfRays* rays, const TnfSav
         *model, *rays, *saved, *gout, *grads, L);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "backward_field launch: %s", cudaGetErrorString(e));
-    field_problems(wa, L, L.XF, 2, grads->field, Ns, R);
+    field_problems(wa, L, saved->field_features, true, grads->field, Ns, R);
     const long long tiles = (Ns + tnf::kWgradRows - 1) / tnf::kWgradRows;
     const long long capx = (long long)sms * 8 / wa.n + 1;
     dim3 grid((unsigned)(tiles < capx ? tiles : capx), wa.n);

@@ -31,6 +31,13 @@ __device__ __forceinline__ float nan_to_num(float x) {
   return x;
 }
 __device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + expf(-x)); }
+// Tensor-core mode only: sigmoid(x) = 0.5 tanh(x/2) + 0.5 on the MUFU tanh unit (one SFU op instead of
+// exp + full-precision divide; |error| <= 2.5e-4, below the fp16 rounding of the activations it feeds).
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(0.5f, t, 0.5f);
+}
 
 // UniformLinDispPiecewiseSampler spacing functions (thermal_nerf_model.py:172-179 builds the
 // ProposalNetworkSampler whose default initial sampler this is).
@@ -106,6 +113,7 @@ __device__ __forceinline__ float normalise_position(const TnfModel& m, float x, 
 struct HashCorners {
   uint32_t idx[8];
   float ox, oy, oz;
+  uint32_t k1, k2;  // exact identity of the cell (floor coordinates + which axes have ceil != floor)
 };
 
 __device__ __forceinline__ void hash_corners(float px, float py, float pz, float scale, uint32_t mask,
@@ -119,6 +127,9 @@ __device__ __forceinline__ void hash_corners(float px, float py, float pz, float
   const uint32_t fx = (uint32_t)(int)fxf, cx = (uint32_t)(int)cxf;
   const uint32_t fy = (uint32_t)(int)fyf * kPrimeY, cy = (uint32_t)(int)cyf * kPrimeY;
   const uint32_t fz = (uint32_t)(int)fzf * kPrimeZ, cz = (uint32_t)(int)czf * kPrimeZ;
+  hc.k1 = fx | ((uint32_t)(int)fyf << 11) | ((cx != fx ? 1u : 0u) << 22) | ((cyf != fyf ? 1u : 0u) << 23) |
+          ((czf != fzf ? 1u : 0u) << 24);
+  hc.k2 = (uint32_t)(int)fzf;
   hc.idx[0] = (cx ^ cy ^ cz) & mask;
   hc.idx[1] = (cx ^ fy ^ cz) & mask;
   hc.idx[2] = (fx ^ fy ^ cz) & mask;

@@ -51,6 +51,8 @@ struct FieldWTC {
   float th0b[64];
   float th1b[64];
   float th2b[8];
+  float scal[TNF_MAX_LEVELS];  // grid.scalings: lanes index it with a per-lane level, which a constant-bank
+                               // read would serialise (one pass per distinct address, long-scoreboard latency)
 };
 
 // ------------------------------------------------------------------------------------
@@ -150,6 +152,7 @@ __device__ inline void stage_field(FieldWTC& W, const TnfField& f, int tid) {
   stage_vec(W.th0b, f.th0.bias, 64, 64, tid);
   stage_vec(W.th1b, f.th1.bias, 64, 64, tid);
   stage_vec(W.th2b, f.th2.bias, 1, 8, tid);
+  if (tid < TNF_MAX_LEVELS) W.scal[tid] = f.grid.scalings[tid];
 }
 
 // ------------------------------------------------------------------------------------
@@ -260,7 +263,7 @@ __device__ __forceinline__ void act_pack(const float (&c)[NT][4], uint32_t (&a)[
       for (int e = 0; e < 4; ++e) {
         v[e] = c[2 * kt + h][e];
         if (ACT == ACT_RELU) v[e] = fmaxf(v[e], 0.f);
-        if (ACT == ACT_SIGMOID) v[e] = sigmoidf(v[e]);
+        if (ACT == ACT_SIGMOID) v[e] = sigmoid_fast(v[e]);
       }
       a[kt][2 * h] = pack_half2(v[0], v[1]);      // row g
       a[kt][2 * h + 1] = pack_half2(v[2], v[3]);  // row g+8

@@ -264,7 +264,7 @@ __device__ __forceinline__ void field_level(const TnfModel& m, Smem<TNF_PRECISIO
       for (int hl = 0; hl < 2; ++hl) {
         const int l = kt * 8 + hl * 4 + q;
         const float2* lt = tab + ((size_t)l << grid.log2_size);
-        const float sc = grid.scalings[l];
+        const float sc = W.scal[l];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const float2 f = hash_level(lt, p[h][0], p[h][1], p[h][2], sc, mask);
@@ -319,19 +319,19 @@ __device__ __forceinline__ void field_level(const TnfModel& m, Smem<TNF_PRECISIO
     if (q == 0) {
       if (r0 < S2) {
         ws.sigma[r0] = expf(dba0) * sel[0];
-        ws.r[r0] = sigmoidf(rgb[0][0]);
-        ws.g[r0] = sigmoidf(rgb[0][1]);
+        ws.r[r0] = sigmoid_fast(rgb[0][0]);
+        ws.g[r0] = sigmoid_fast(rgb[0][1]);
         ws.th[r0] = th[0][0];
       }
       if (r1 < S2) {
         ws.sigma[r1] = expf(dba1) * sel[1];
-        ws.r[r1] = sigmoidf(rgb[0][2]);
-        ws.g[r1] = sigmoidf(rgb[0][3]);
+        ws.r[r1] = sigmoid_fast(rgb[0][2]);
+        ws.g[r1] = sigmoid_fast(rgb[0][3]);
         ws.th[r1] = th[0][2];
       }
     } else if (q == 1) {
-      if (r0 < S2) ws.b[r0] = sigmoidf(rgb[0][0]);
-      if (r1 < S2) ws.b[r1] = sigmoidf(rgb[0][2]);
+      if (r0 < S2) ws.b[r0] = sigmoid_fast(rgb[0][0]);
+      if (r1 < S2) ws.b[r1] = sigmoid_fast(rgb[0][2]);
     }
   }
   __syncwarp();

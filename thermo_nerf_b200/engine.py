@@ -91,7 +91,7 @@ class TrainEngine:
         kw = dict(num_samples=(*cfg.num_proposal_samples_per_ray, cfg.num_nerf_samples_per_ray),
                   near_plane=cfg.near_plane, far_plane=cfg.far_plane, anneal=self.anneal(step),
                   use_contraction=not cfg.disable_scene_contraction,
-                  aabb=[float(x) for x in torch.as_tensor(self.model.scene_box.aabb).reshape(-1).tolist()],
+                  aabb=self.model._aabb_list(),
                   appearance_mode=L.APPEARANCE_LOOKUP, precision=self.model._precision(),
                   detach_thermal_geo=not self.model.field.pass_thermal_gradients)
         cam = camera_indices.reshape(-1)

@@ -127,16 +127,25 @@ class ModelTensors:
     def pack(self, *, num_samples: Sequence[int], training: bool, near_plane: float, far_plane: float,
              anneal: float, use_contraction: bool, aabb: Optional[Sequence[float]], appearance_mode: int,
              precision: int, detach_thermal_geo: bool = False) -> L.TnfModel:
-        m = L.TnfModel()
-        for i in range(L.TNF_NUM_PROP):
-            self._fill_grid(m.prop[i].grid, self.prop_grids[i], f"proposal_networks.{i}.encoding")
-            self._fill_lin(m.prop[i].l0, self.prop_l0[i], f"proposal_networks.{i}.mlp.0")
-            self._fill_lin(m.prop[i].l1, self.prop_l1[i], f"proposal_networks.{i}.mlp.1")
-        self._fill_grid(m.field.grid, self.field_grid, "field.mlp_base.encoder")
-        for k, l in self.field_linears.items():
-            self._fill_lin(getattr(m.field, k), l, "field." + k)
-        m.field.appearance = _dev_f32(self.appearance, "field.embedding_appearance").data_ptr()
-        m.field.num_images = int(self.appearance.shape[0])
+        """Fresh ``TnfModel`` for one call.  The pointer part is validated and filled once per set of
+        tensor addresses and memcpy'd afterwards (this runs every training step)."""
+        plist = self.param_list()
+        key = tuple(t.data_ptr() for t in plist)
+        cached = self.extra.get("_packed")
+        if cached is None or cached[0] != key:
+            base = L.TnfModel()
+            for i in range(L.TNF_NUM_PROP):
+                self._fill_grid(base.prop[i].grid, self.prop_grids[i], f"proposal_networks.{i}.encoding")
+                self._fill_lin(base.prop[i].l0, self.prop_l0[i], f"proposal_networks.{i}.mlp.0")
+                self._fill_lin(base.prop[i].l1, self.prop_l1[i], f"proposal_networks.{i}.mlp.1")
+            self._fill_grid(base.field.grid, self.field_grid, "field.mlp_base.encoder")
+            for k, l in self.field_linears.items():
+                self._fill_lin(getattr(base.field, k), l, "field." + k)
+            base.field.appearance = _dev_f32(self.appearance, "field.embedding_appearance").data_ptr()
+            base.field.num_images = int(self.appearance.shape[0])
+            cached = (key, base)
+            self.extra["_packed"] = cached
+        m = L.TnfModel.from_buffer_copy(cached[1])
         if len(num_samples) != L.TNF_NUM_PROP + 1:
             raise ValueError(f"num_samples must have {L.TNF_NUM_PROP + 1} entries")
         for i, s in enumerate(num_samples):
@@ -158,7 +167,10 @@ class ModelTensors:
     def param_list(self) -> List[Tensor]:
         """Every parameter of the path in a fixed order: per proposal net (table, l0.w, l0.b, l1.w, l1.b),
         then the field (table, 8 x (w, b) in FIELD_ORDER, appearance embedding) - 28 tensors."""
-        out: List[Tensor] = []
+        out = self.extra.get("_plist")
+        if out is not None:
+            return out
+        out = []
         for i in range(L.TNF_NUM_PROP):
             out += [self.prop_grids[i].table, self.prop_l0[i].weight, self.prop_l0[i].bias,
                     self.prop_l1[i].weight, self.prop_l1[i].bias]
@@ -166,6 +178,7 @@ class ModelTensors:
         for k in self.FIELD_ORDER:
             out += [self.field_linears[k].weight, self.field_linears[k].bias]
         out.append(self.appearance)
+        self.extra["_plist"] = out
         return out
 
     def with_params(self, params: Sequence[Tensor]) -> "ModelTensors":
@@ -179,7 +192,8 @@ class ModelTensors:
             l1.append(_Linear(next(it), next(it)))
         fg = _Grid(next(it), self.field_grid.scalings, self.field_grid.num_levels, self.field_grid.log2_size)
         lin = {k: _Linear(next(it), next(it)) for k in self.FIELD_ORDER}
-        return ModelTensors(grids, l0, l1, fg, lin, next(it), dict(self.extra))
+        extra = {k: v for k, v in self.extra.items() if not k.startswith("_")}
+        return ModelTensors(grids, l0, l1, fg, lin, next(it), extra)
 
     @staticmethod
     def pack_grads(grads: Sequence[Optional[Tensor]]) -> L.TnfModelGrad:
@@ -330,6 +344,21 @@ def _ptr(t: Optional[Tensor]) -> int:
     return 0 if t is None else t.data_ptr()
 
 
+_WORKSPACES: Dict[torch.device, Tensor] = {}
+
+
+def _workspace_for(model_struct: L.TnfModel, R: int, dev: torch.device) -> Tensor:
+    """Per-device scratch of tnf_render_backward, kept across steps (it is 66 KB per ray: allocating it per
+    call would churn the caching allocator with a quarter-gigabyte block every iteration).  Stream order
+    makes reuse safe: every user is enqueued on the current stream."""
+    nbytes = int(L.load().tnf_backward_workspace_bytes(C.byref(model_struct), R))
+    ws = _WORKSPACES.get(dev)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _WORKSPACES[dev] = ws
+    return ws
+
+
 def render_backward(tensors: ModelTensors, model_struct: L.TnfModel, origins: Tensor, directions: Tensor,
                     camera_indices: Optional[Tensor], nears: Optional[Tensor], fars: Optional[Tensor],
                     jitter: Optional[Tensor], saved: Dict[str, object], grad_outputs: Dict[str, Optional[Tensor]],
@@ -387,49 +416,61 @@ class _RenderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, tensors: ModelTensors, kw: dict, prop_grad: bool, origins, directions, camera_indices, nears,
                 fars, jitter, *params):
-        t = tensors.with_params([p.detach() for p in params])
+        own = tensors.param_list()
+        same = len(own) == len(params) and all(a is b for a, b in zip(own, params))
+        t = tensors if same else tensors.with_params([p.detach() for p in params])
         res = render_forward(t, origins, directions, camera_indices, nears, fars, jitter, training=True,
                              return_samples=True, save_for_backward=True, **kw)
         ctx.tensors = t
         ctx.model_struct = res.pop("_model_struct")
-        ctx.rays = (origins, directions, camera_indices, nears, fars, jitter)
-        ctx.saved = {k: res[k] for k in ("sdist_list", "weights_list", "field_features", "field_samples")}
         ctx.prop_grad = bool(prop_grad)
-        ctx.params = params
         ctx.set_materialize_grads(False)
         w = res["weights_list"]
         sd = res["sdist_list"]
+        # save_for_backward (not attributes): weights_list / sdist_list are OUTPUTS of this node, and an
+        # output kept on ctx directly forms a reference cycle (tensor -> grad_fn -> ctx -> tensor) that
+        # only the cyclic GC frees - i.e. every step would leak its saved activations until a GC pass.
+        ctx.save_for_backward(origins, directions, camera_indices, nears, fars, jitter, *sd, *w,
+                              res["field_features"], res["field_samples"])
         nondiff = (res["depth"], res["expected_depth"], res["prop_depth_0"], res["prop_depth_1"], *sd)
         ctx.mark_non_differentiable(*nondiff)
         return (res["rgb"], res["thermal"], res["accumulation"], w[0], w[1], w[2], *nondiff)
 
     @staticmethod
     def backward(ctx, g_rgb, g_th, g_acc, g_w0, g_w1, g_w2, *_):
-        params = ctx.params
+        params = ctx.tensors.param_list()
         need = list(ctx.needs_input_grad[_RenderFn.NUM_FIXED:])
         # a proposal net takes part only if its upstream weights carry a gradient (the reference's
         # no_grad steps) and its tensors want one
         gws = [g_w0, g_w1]
-        grads: List[Optional[Tensor]] = []
-        idx = 0
-        for i in range(L.TNF_NUM_PROP):
-            on = ctx.prop_grad and gws[i] is not None and all(need[idx:idx + 5])
-            grads += [torch.zeros_like(params[idx + j]) if on else None for j in range(5)]
-            idx += 5
-        for j in range(idx, len(params)):
-            grads.append(torch.zeros_like(params[j]))
-        o, d, cam, nears, fars, jitter = ctx.rays
+        on = [ctx.prop_grad and gws[i] is not None and all(need[5 * i:5 * i + 5]) for i in range(L.TNF_NUM_PROP)]
+        # one zero-filled arena (a single memset), carved into per-parameter gradients (16-byte aligned)
+        want = [on[j // 5] if j < 5 * L.TNF_NUM_PROP else True for j in range(len(params))]
+        offs, total = [], 0
+        for p_, w_ in zip(params, want):
+            offs.append(total)
+            if w_:
+                total += (p_.numel() + 3) // 4 * 4
+        arena = torch.zeros(total, dtype=torch.float32, device=params[-1].device)
+        grads: List[Optional[Tensor]] = [arena[o_:o_ + p_.numel()].view(p_.shape) if w_ else None
+                                         for p_, w_, o_ in zip(params, want, offs)]
+        sv = ctx.saved_tensors
+        o, d, cam, nears, fars, jitter = sv[:6]
+        n = L.TNF_NUM_PROP + 1
+        saved = {"sdist_list": list(sv[6:6 + n]), "weights_list": list(sv[6 + n:6 + 2 * n]),
+                 "field_features": sv[6 + 2 * n], "field_samples": sv[7 + 2 * n],
+                 "_workspace": _workspace_for(ctx.model_struct, int(o.shape[0]), o.device)}
 
         def flat(g):
             return None if g is None else g.reshape(g.shape[0], -1)
 
-        render_backward(ctx.tensors, ctx.model_struct, o, d, cam, nears, fars, jitter, ctx.saved,
+        render_backward(ctx.tensors, ctx.model_struct, o, d, cam, nears, fars, jitter, saved,
                         {"rgb": g_rgb, "thermal": None if g_th is None else g_th.reshape(-1),
                          "accumulation": None if g_acc is None else g_acc.reshape(-1),
                          "weights_list": [flat(g_w0) if ctx.prop_grad else None,
                                           flat(g_w1) if ctx.prop_grad else None, flat(g_w2)]},
                         grads)
-        out = [g if n else None for g, n in zip(grads, need)]
+        out = [g if n_ else None for g, n_ in zip(grads, need)]
         return (None,) * _RenderFn.NUM_FIXED + tuple(out)
 
 

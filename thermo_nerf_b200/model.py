@@ -228,14 +228,20 @@ class ThermalNerfModel(nn.Module):
         arguments instead of [R,1] tensors (a caller-supplied nears/fars still wins)."""
         return self.get_outputs(ray_bundle)
 
+    def _aabb_list(self) -> List[float]:
+        box = getattr(self, "_aabb_cache", None)
+        if box is None:  # host copy made once: a CUDA-resident aabb would otherwise cost a sync per call
+            box = [float(x) for x in torch.as_tensor(self.scene_box.aabb).reshape(-1).tolist()]
+            self._aabb_cache = box
+        return box
+
     def _render_kwargs(self) -> Dict[str, Any]:
         cfg = self.config
         return dict(
             num_samples=(*cfg.num_proposal_samples_per_ray, cfg.num_nerf_samples_per_ray),
             near_plane=self._collider_near(), far_plane=cfg.far_plane, anneal=self._anneal,
             use_contraction=not cfg.disable_scene_contraction,
-            aabb=[float(x) for x in torch.as_tensor(self.scene_box.aabb).reshape(-1).tolist()],
-            appearance_mode=self._appearance_mode(), precision=self._precision())
+            aabb=self._aabb_list(), appearance_mode=self._appearance_mode(), precision=self._precision())
 
     def get_outputs(self, ray_bundle, depth_clip_chunk: int = 0) -> Dict[str, Any]:
         """thermal_nerf_model.py:210-275 as one fused kernel launch (eval) or one autograd node over
@@ -331,13 +337,17 @@ class ThermalNerfModel(nn.Module):
     def get_metrics_dict(self, outputs, batch) -> Dict[str, Tensor]:
         """NerfactoModel.get_metrics_dict (inherited by the reference): psnr, and in training the
         distortion metric that get_loss_dict consumes (thermal_nerf_model.py:303-305)."""
-        gt_rgb = batch["image"].to(self.device)
-        with torch.no_grad():
-            mse = torch.mean((outputs["rgb"].detach() - gt_rgb[..., :3]) ** 2)
-        metrics = {"psnr": -10.0 * torch.log10(mse)}
+        metrics: Dict[str, Tensor] = {}
         if self.training:
             losses = self._fused_losses(outputs, batch)
             metrics["distortion"] = losses["distortion_loss"] / self.config.distortion_loss_mult
+        with torch.no_grad():
+            if self.training and self.field.pass_rgb_gradients:
+                mse = losses["rgb_loss"].detach()  # the fused loss kernel already reduced MSE(rgb, gt)
+            else:
+                gt_rgb = batch["image"].to(self.device)
+                mse = torch.mean((outputs["rgb"].detach() - gt_rgb[..., :3]) ** 2)
+            metrics["psnr"] = -10.0 * torch.log10(mse)
         return metrics
 
     def get_loss_dict(self, outputs, batch, metrics_dict=None) -> Dict[str, Tensor]:
