@@ -127,9 +127,10 @@ def build_b200_model(device, precision: str, camera_optimizer_mode: str = "off")
 def frame_bundles(n_frames: int, device, rank: int, world: int):
     """Distinct orbit frames; rank r renders frames r, r+world, ... (frames shard with no collective)."""
     from thermo_nerf_b200 import orbit_cameras
+    from thermo_nerf_b200.dist import shard_frames
 
     cams = orbit_cameras(max(n_frames * world, 1), hw=HW, focal=FOCAL, device=device)
-    return [cams.generate_rays(rank + i * world) for i in range(n_frames)]
+    return [cams.generate_rays(i) for i in shard_frames(n_frames * world, rank, world)]
 
 
 class L2Flusher:
@@ -145,11 +146,12 @@ def train_batches(n_batches: int, rays: int, device, rank: int, pin: bool = Fals
     """ThermoScenes-shaped random pixel batches: 100 pinhole cameras 800x800 on a sphere,
     uniform (image, y, x) draws seeded per rank (nerfstudio DDP: every rank draws its own rays), analytic GT."""
     from thermo_nerf_b200 import sphere_cameras
+    from thermo_nerf_b200.dist import rank_seed
 
     cams = sphere_cameras(NUM_IMAGES, hw=HW, focal=FOCAL)
     out = []
     for b in range(n_batches):
-        g = torch.Generator().manual_seed(77 + 1000 * rank + b)
+        g = torch.Generator().manual_seed(rank_seed(77, rank, b))
         cam = torch.randint(0, NUM_IMAGES, (rays,), generator=g)
         ys = torch.randint(0, HW, (rays,), generator=g)
         xs = torch.randint(0, HW, (rays,), generator=g)
@@ -161,6 +163,10 @@ def train_batches(n_batches: int, rays: int, device, rank: int, pin: bool = Fals
         out.append(tuple(x.pin_memory() for x in t) if pin else tuple(x.to(device) for x in t))
     return out
 
+
+KERNEL_NAMES = {"forward": "tnf_forward_kernel", "backward_prop": "tnf_backward_prop_kernel",
+                "backward_field": "tnf_backward_field_kernel_tc", "wgrad": "tnf_wgrad_kernel_bf16",
+                "adam": "tnf_adam_kernel"}
 
 TRAIN_WORKLOAD = ("thermal-nerf training iteration, ThermoScenes double_robot-shaped synthetic rays: {rays} rays/batch per "
                   "GPU (BASELINE configs[1]), samples 256/96/48, forward + losses (rgb, thermal, interlevel, distortion) + "
@@ -197,7 +203,7 @@ def oracle_train_step(model, opts, batch, step: int) -> float:
     return float(loss.detach())
 
 
-def run_reference(args, rank: int, world: int) -> None:
+def run_reference(args, rank: int, world: int, emit) -> None:
     """The path's own PyTorch implementation (nerfstudio torch semantics; oracle port since
     nerfstudio is not installable offline) on the host cores, bounded sample per step."""
     if rank != 0:
@@ -222,7 +228,7 @@ def run_reference(args, rank: int, world: int) -> None:
                 "config": {"workload": TRAIN_WORKLOAD.format(rays=args.rays), "sample": desc},
                 "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "sample": desc},
                 "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
     from oracle import OracleConfig, OracleThermalNerf, make_synthetic_rays
 
@@ -248,7 +254,7 @@ def run_reference(args, rank: int, world: int) -> None:
         "cpu_baseline": {"value": mpix, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": mpix, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def hbm_peak():
@@ -288,8 +294,17 @@ def main() -> None:
         args.warmup = max(args.warmup, 3)
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner does)
+    # is sent to stderr by pointing fd 1 at fd 2 for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: dict) -> None:
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
     if ref:
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, emit)
         return
 
     import torch.distributed as dist
@@ -317,7 +332,7 @@ def main() -> None:
                max_over_ranks=max_over_ranks)
     line = bench_train(ctx) if args.mode == "train" else bench_render(ctx)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -326,8 +341,9 @@ def bench_train(ctx) -> dict:
     """BASELINE configs[1]: full training iterations at `--rays` rays per batch per GPU."""
     args, rank, world, device = ctx["args"], ctx["rank"], ctx["world"], ctx["device"]
     barrier, max_over_ranks = ctx["barrier"], ctx["max_over_ranks"]
-    from thermo_nerf_b200 import FusedAdam, RayBundle
+    from thermo_nerf_b200 import FusedAdam, ModelTensors, RayBundle
     from thermo_nerf_b200 import functional as F
+    from thermo_nerf_b200.dist import allreduce_mean_grads_
     from thermo_nerf_b200.engine import TrainEngine
 
     R = args.rays
@@ -344,11 +360,13 @@ def bench_train(ctx) -> dict:
     sampler = ClockSampler(ctx["local"])
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prop_steps_before = engine.prop_steps
     e0.record()
     for i in range(args.steps):
         losses = engine.step(*batches[i % n_distinct])
     e1.record()
     barrier()
+    prop_steps_timed = engine.prop_steps - prop_steps_before
     clocks = sampler.stop()
     ms_per_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     value = world * R / (ms_per_step * 1e-3)
@@ -360,14 +378,17 @@ def bench_train(ctx) -> dict:
     if breakdown:
         peak, peak_src = hbm_peak()
         n_params = sum(p.numel() for p in engine.params)
+        # algorithmic bytes per launch: 8-byte table cells, 8 corners per level lookup
         algo = {
             "forward": R * ALGO_BYTES_PER_RAY,
-            # fwd re-gather of the proposal levels + table scatters (read-modify-write of 8 B cells)
-            "backward": R * ((256 + 96) * 5 * 8 * 8 * 3 + 48 * 16 * 8 * 8 * 2 + 48 * (64 + 20)),
-            "wgrad": R * 48 * (688 + 32) * 2,
-            "adam": n_params * 32,
+            # re-gather of the two proposal levels + scatter (read-modify-write) of their table gradients
+            "backward_prop": R * (256 + 96) * 5 * 8 * 8 * 3,
+            # saved features + field outputs in, table-gradient scatter (RMW), staged (X, dY) rows out
+            "backward_field": R * 48 * (64 + 20 + 16 * 8 * 8 * 2 + 1376),
+            "wgrad": R * 48 * (1376 + 64) + R * (48 + 64) * 2,
+            "adam": n_params * 28,
         }
-        dom = max(("forward", "backward", "wgrad", "adam"), key=lambda k: breakdown.get(k + "_ms", 0.0))
+        dom = max(algo, key=lambda k: breakdown.get(k + "_ms", 0.0))
         ach = algo[dom] / (breakdown[dom + "_ms"] * 1e-3) / 1e9
         traffic = None
         tp = ROOT / "profiles" / "train_traffic.json"
@@ -377,11 +398,13 @@ def bench_train(ctx) -> dict:
             except Exception:
                 traffic = None
         roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                    "kernel": dom, "kernel_ms": breakdown[dom + "_ms"], "peak_source": peak_src,
+                    "kernel": KERNEL_NAMES[dom], "kernel_ms": breakdown[dom + "_ms"], "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": algo[dom],
-                    "note": "algorithmic bytes per launch as defined in DESIGN.md section 4; hash tables are "
-                            "L2-resident within a launch, so DRAM traffic sits below the algorithmic gather bytes",
-                    "all_kernels": {k: {"ms": breakdown[k + "_ms"], "algorithmic_GBps": algo[k] / (breakdown[k + "_ms"] * 1e-3) / 1e9}
+                    "note": "algorithmic bytes per launch as defined in DESIGN.md section 4; the hash tables and "
+                            "their gradients are L2-resident within a launch, so DRAM traffic sits below the "
+                            "algorithmic gather/scatter bytes",
+                    "all_kernels": {KERNEL_NAMES[k]: {"ms": breakdown[k + "_ms"],
+                                                      "algorithmic_GBps": algo[k] / (breakdown[k + "_ms"] * 1e-3) / 1e9}
                                     for k in algo if breakdown.get(k + "_ms")}}
 
     # ---- end to end through the plugin API with HOST buffers: model(ray_bundle) -> get_metrics_dict ->
@@ -391,6 +414,7 @@ def bench_train(ctx) -> dict:
     groups = model2.get_param_groups()
     opts = [FusedAdam(groups["proposal_networks"], lr=1e-2, eps=1e-15), FusedAdam(groups["fields"], lr=1e-2, eps=1e-15)]
     cbs = model2.get_training_callbacks()
+    all_params = ModelTensors.from_module(model2).param_list()  # fixed order = the backward's gradient arena order
     host = train_batches(n_distinct, R, device, rank, pin=True)
     h2d = sum(t.numel() * t.element_size() for t in host[0])
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
@@ -411,9 +435,7 @@ def bench_train(ctx) -> dict:
         loss = sum(ld.values())
         loss.backward()
         if world > 1:
-            for p in model2.parameters():
-                if p.grad is not None:
-                    dist.all_reduce(p.grad, op=dist.ReduceOp.AVG)
+            allreduce_mean_grads_(all_params, world_size=world)
         for o in opts:
             o.step()
         for c in cbs:
@@ -454,7 +476,8 @@ def bench_train(ctx) -> dict:
     }
     # launches of OUR kernels per engine step: forward + clip + losses + backward_prop (on update steps) +
     # backward_field + wgrad + adam (1 or 2 launches)
-    line["gpu_launches"] = int(args.steps * 6 + engine.prop_steps * 2)
+    # (+ the counter memset of the proposal backward and, for world > 1, NCCL's all-reduce kernel are not ours)
+    line["gpu_launches"] = int(args.steps * 6 + (prop_steps_timed) * 2)
     if roofline:
         line["roofline"] = roofline
         line["breakdown_ms"] = breakdown
@@ -466,50 +489,59 @@ def bench_train(ctx) -> dict:
 
 
 def kernel_breakdown(engine, batches, device) -> dict:
-    """Times each stage of one iteration with CUDA events on the launching stream (average of 10)."""
+    """Times every kernel of one iteration with CUDA events on the launching stream (median of 11).  The three
+    backward kernels share one C entry point; tnf_backward_stage_mask runs them one at a time."""
     from thermo_nerf_b200 import _lib as L
     from thermo_nerf_b200 import functional as F
 
-    names = ["forward", "losses", "backward", "adam"]
+    names = ["forward", "losses", "backward_prop", "backward_field", "wgrad", "adam"]
     acc = {n: [] for n in names}
+    lib = L.load()
     reps = 11
-    # the stages are timed by running the C entry points individually: backward and wgrad are two
-    # launches of one entry point, so wgrad is timed as (render_backward) - (its first kernels) using
-    # a second pass with a 1-row problem is not possible -> report them together and split by ncu share
+
+    def timed(name, fn):
+        # a ~0.3 ms device-side spin first: the host prepares and enqueues the launch while the GPU is still
+        # busy, so the two events bracket the kernel alone and not the Python/ctypes time before the launch
+        torch.cuda._sleep(600_000)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = fn()
+        b.record()
+        acc[name].append((a, b))
+        return r
+
     for rep in range(reps):
         o, d, cam, gt_rgb, gt_th = batches[rep % len(batches)]
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         R = o.shape[0]
         cfg = engine.cfg
         jitter = torch.rand((3, R), device=device)
         kw = dict(num_samples=(*cfg.num_proposal_samples_per_ray, cfg.num_nerf_samples_per_ray),
-                  near_plane=cfg.near_plane, far_plane=cfg.far_plane, anneal=1.0, appearance_mode=L.APPEARANCE_LOOKUP,
-                  precision=engine.model._precision())
-        ev[0].record()
-        res = F.render_forward(engine.tensors, o, d, cam, None, None, jitter, training=True, return_samples=True,
-                               save_for_backward=True, **kw)
-        ev[1].record()
-        losses, g = F.losses_forward_backward(res["weights_list"], res["sdist_list"], res["rgb"], res["thermal"],
-                                              gt_rgb, gt_th)
-        ev[2].record()
+                  near_plane=cfg.near_plane, far_plane=cfg.far_plane, anneal=engine.anneal(engine.step_count),
+                  appearance_mode=L.APPEARANCE_LOOKUP, precision=engine.model._precision())
+        res = timed("forward", lambda: F.render_forward(engine.tensors, o, d, cam, None, None, jitter, training=True,
+                                                        return_samples=True, save_for_backward=True, **kw))
+        losses, g = timed("losses", lambda: F.losses_forward_backward(
+            res["weights_list"], res["sdist_list"], res["rgb"], res["thermal"], gt_rgb, gt_th))
         res["_workspace"] = engine._ws
-        F.render_backward(engine.tensors, res["_model_struct"], o, d, cam, None, None, jitter, res,
-                          {"rgb": g["rgb"], "thermal": g["thermal"], "weights_list": g["weights_list"]},
-                          list(engine.grads))
-        ev[3].record()
+        gout = {"rgb": g["rgb"], "thermal": g["thermal"], "weights_list": g["weights_list"]}
+        try:
+            for nm, mask in (("backward_prop", 1), ("backward_field", 2), ("wgrad", 4)):
+                lib.tnf_backward_stage_mask(mask)
+                timed(nm, lambda: F.render_backward(engine.tensors, res["_model_struct"], o, d, cam, None, None, jitter,
+                                                    res, gout, list(engine.grads)))
+        finally:
+            lib.tnf_backward_stage_mask(7)
         n = len(engine.params)
-        F.adam_step(engine.params, engine.grads, engine.exp_avg, engine.exp_avg_sq, [0.0] * n, step=1000, eps=1e-15,
-                    zero_grads=True)  # lr = 0: timing only, parameters unchanged
-        ev[4].record()
+        # lr = 0: timing only, parameters unchanged
+        timed("adam", lambda: F.adam_step(engine.params, engine.grads, engine.exp_avg, engine.exp_avg_sq, [0.0] * n,
+                                          step=1000, eps=1e-15, zero_grads=True))
         torch.cuda.synchronize()
-        acc["forward"].append(ev[0].elapsed_time(ev[1]))
-        acc["losses"].append(ev[1].elapsed_time(ev[2]))
-        acc["backward"].append(ev[2].elapsed_time(ev[3]))
-        acc["adam"].append(ev[3].elapsed_time(ev[4]))
+    acc = {k: [a.elapsed_time(b) for a, b in v] for k, v in acc.items()}
     # median: the interval between two events also contains any host stall between the launches (GC pause,
     # allocator growth), which an average would book as kernel time
     out = {k + "_ms": sorted(v)[len(v) // 2] for k, v in acc.items()}
-    out["note"] = "backward_ms = proposal backward + field backward + weight-gradient GEMM (one C entry point)"
+    out["note"] = ("one kernel per entry (forward includes the 3 us depth-clip pass); the proposal backward runs only "
+                   "on the sampler's update steps (every 2nd step in the first 1000 iterations, every 6th after 5000)")
     return out
 
 

@@ -226,6 +226,12 @@ int tnf_render_backward(const TnfModel* model, const TnfRays* rays, const TnfSav
                         const TnfOutputGrads* gout, const TnfModelGrad* grads, void* workspace,
                         size_t workspace_bytes, void* stream);
 
+/* Measurement hook (bench.py's per-kernel roofline): restricts tnf_render_backward on the calling thread
+ * to a subset of its three kernels so each can be bracketed with CUDA events on its own.  Bit 0:
+ * proposal levels, bit 1: field level, bit 2: weight-gradient GEMMs; the default 7 runs all of them
+ * (the only setting that produces correct gradients).  Returns the previous mask. */
+int tnf_backward_stage_mask(int mask);
+
 /* get_loss_dict (thermal_nerf_model.py:277-326) + the inherited distortion metric:
  *   losses[0] rgb_loss        = MSE(gt_rgb, rgb)                       (if use_rgb_loss)
  *   losses[1] interlevel_loss = interlevel_mult * sum_k mean(outer-measure loss of level k)

@@ -62,8 +62,11 @@ for i in range(40):
     e2e_step(50 + i)
 pr.disable()
 s = io.StringIO()
-pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(45)
-print(s.getvalue()[:9000])
+pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(40)
+print(s.getvalue()[:7000])
+s = io.StringIO()
+pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(30)
+print(s.getvalue()[:6000])
 
 engine = TrainEngine(model, world_size=1)
 dev_batches = bench.train_batches(8, R, device, 0)

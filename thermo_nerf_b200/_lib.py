@@ -199,6 +199,7 @@ EXPORTED_SYMBOLS = (
     "tnf_render_forward",
     "tnf_backward_workspace_bytes",
     "tnf_render_backward",
+    "tnf_backward_stage_mask",
     "tnf_losses",
     "tnf_adam_step",
 )
@@ -261,6 +262,8 @@ def load() -> C.CDLL:
         C.c_size_t,
         C.c_void_p,
     ]
+    lib.tnf_backward_stage_mask.restype = C.c_int
+    lib.tnf_backward_stage_mask.argtypes = [C.c_int]
     lib.tnf_losses.restype = C.c_int
     lib.tnf_losses.argtypes = [C.POINTER(TnfLossArgs), C.c_void_p]
     lib.tnf_adam_step.restype = C.c_int

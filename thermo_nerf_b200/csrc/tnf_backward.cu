@@ -1472,7 +1472,17 @@ void field_problems(tnf::WgradArgs& a, const tnf::BwdLayout& L, const void* XF, 
 }
 }  // namespace
 
+namespace {
+thread_local int g_stage_mask = 7;
+}
+
 extern "C" {
+
+int tnf_backward_stage_mask(int mask) {
+  const int prev = g_stage_mask;
+  g_stage_mask = mask & 7;
+  return prev;
+}
 
 size_t tnf_backward_workspace_bytes(const TnfModel* model, int64_t num_rays) {
   if (!model || num_rays <= 0) return 256;
@@ -1513,7 +1523,7 @@ int tnf_render_backward(const TnfModel* model, const TnfRays* rays, const TnfSav
 
   // ---- proposal levels: (level, ray) units handed out by a device counter (last 8 bytes of the workspace)
   const bool do_prop = (grads->prop[0].table && gout->weights[0]) || (grads->prop[1].table && gout->weights[1]);
-  if (do_prop) {
+  if (do_prop && (g_stage_mask & 1)) {
     unsigned long long* counter =
         reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(workspace) + need - 16);
     e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
@@ -1552,30 +1562,32 @@ int tnf_render_backward(const TnfModel* model, const TnfRays* rays, const TnfSav
     const size_t smem = sizeof(tnf::FieldBwdSmem32);
     if (int rc = set_smem(tnf::tnf_backward_field_kernel_fp32, smem, "backward_field_fp32")) return rc;
     const long long cap = sms;
-    tnf::tnf_backward_field_kernel_fp32<<<(unsigned)(want < cap ? want : cap), tnf::kThreads, smem, stream>>>(
-        *model, *rays, *saved, *gout, *grads, L);
+    if (g_stage_mask & 2)
+      tnf::tnf_backward_field_kernel_fp32<<<(unsigned)(want < cap ? want : cap), tnf::kThreads, smem, stream>>>(
+          *model, *rays, *saved, *gout, *grads, L);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "backward_field launch: %s", cudaGetErrorString(e));
     field_problems(wa, L, saved->field_features, false, grads->field, Ns, R);
     const long long tiles = (Ns + tnf::kWgradRows - 1) / tnf::kWgradRows;
     const long long capx = (long long)sms * 2 / wa.n + 1;
     dim3 grid((unsigned)(tiles < capx ? tiles : capx), wa.n);
-    tnf::tnf_wgrad_kernel_fp32<<<grid, 256, 0, stream>>>(wa);
+    if (g_stage_mask & 4) tnf::tnf_wgrad_kernel_fp32<<<grid, 256, 0, stream>>>(wa);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(e));
   } else {
     const size_t smem = sizeof(tnf::FieldBwdSmemTC);
     if (int rc = set_smem(tnf::tnf_backward_field_kernel_tc, smem, "backward_field_tc")) return rc;
     const long long cap = (long long)sms * 2;
-    tnf::tnf_backward_field_kernel_tc<<<(unsigned)(want < cap ? want : cap), tnf::kThreads, smem, stream>>>(
-        *model, *rays, *saved, *gout, *grads, L);
+    if (g_stage_mask & 2)
+      tnf::tnf_backward_field_kernel_tc<<<(unsigned)(want < cap ? want : cap), tnf::kThreads, smem, stream>>>(
+          *model, *rays, *saved, *gout, *grads, L);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "backward_field launch: %s", cudaGetErrorString(e));
     field_problems(wa, L, saved->field_features, true, grads->field, Ns, R);
     const long long tiles = (Ns + tnf::kWgradRows - 1) / tnf::kWgradRows;
     const long long capx = (long long)sms * 8 / wa.n + 1;
     dim3 grid((unsigned)(tiles < capx ? tiles : capx), wa.n);
-    tnf::tnf_wgrad_kernel_bf16<<<grid, 128, 0, stream>>>(wa);
+    if (g_stage_mask & 4) tnf::tnf_wgrad_kernel_bf16<<<grid, 128, 0, stream>>>(wa);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(e));
   }

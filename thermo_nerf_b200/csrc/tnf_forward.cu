@@ -115,13 +115,15 @@ __device__ __forceinline__ float proposal_level(const TnfModel& m, const PropW& 
 // the previous level, consumed) -> `dst` (Snew+1 spacing bins).  `exist` = previous level's
 // spacing bins, or nullptr when they are the analytic initial bins.
 // ------------------------------------------------------------------------------------
+template <bool FAST>
 __device__ __forceinline__ void pdf_resample(WarpScratch& ws, const int Sprev, const int Snew, const float anneal,
                                              const bool stratified, const float jit_prev, const float jit_new,
                                              const float* exist, float* dst, const int lane) {
   float part = 0.f;
   for (int i = lane; i < Sprev; i += 32) {
     float w = ws.w[i];
-    if (anneal != 1.f) w = powf(w, anneal);
+    // tensor-core mode: w^a = exp2(a log2 w) on the SFU (w in [0,1]; 0 -> 0 for a > 0); fp32 mode: powf
+    if (anneal != 1.f) w = FAST ? __powf(w, anneal) : powf(w, anneal);
     w += 0.01f;
     ws.w[i] = w;
     part += w;
@@ -422,12 +424,12 @@ __global__ void __launch_bounds__(kThreads, PREC == TNF_PRECISION_TC_FP16 ? 2 : 
     const float pd0 = proposal_level<0>(m, S.prop[0], ws, rc, S0, stratified, jit0, lane,
                                         out.weights[0] ? out.weights[0] + ray * S0 : nullptr,
                                         out.sdist[0] ? out.sdist[0] + ray * (S0 + 1) : nullptr);
-    pdf_resample(ws, S0, S1, m.anneal, stratified, jit0, jit1, nullptr, ws.bins, lane);
+    pdf_resample<PREC == TNF_PRECISION_TC_FP16>(ws, S0, S1, m.anneal, stratified, jit0, jit1, nullptr, ws.bins, lane);
     // ---- level 1
     const float pd1 = proposal_level<1>(m, S.prop[1], ws, rc, S1, stratified, jit1, lane,
                                         out.weights[1] ? out.weights[1] + ray * S1 : nullptr,
                                         out.sdist[1] ? out.sdist[1] + ray * (S1 + 1) : nullptr);
-    pdf_resample(ws, S1, S2, m.anneal, stratified, jit1, jit2, ws.bins, ws.w, lane);
+    pdf_resample<PREC == TNF_PRECISION_TC_FP16>(ws, S1, S2, m.anneal, stratified, jit1, jit2, ws.bins, ws.w, lane);
     // ---- level 2: field; its spacing bins now live in ws.w[0..S2]
     field_level(m, S, ws, rc, S2, lane, warp,
                 out.field_features

@@ -24,6 +24,7 @@ from torch import Tensor
 
 from . import _lib as L
 from . import functional as F
+from .dist import allreduce_mean_
 
 NUM_PROP_TENSORS = 5 * L.TNF_NUM_PROP  # leading entries of ModelTensors.param_list()
 
@@ -112,11 +113,9 @@ class TrainEngine:
         F.render_backward(self.tensors, res["_model_struct"], origins, directions, cam, None, None, jitter, res,
                           {"rgb": g["rgb"], "thermal": g["thermal"], "weights_list": g["weights_list"]}, grads)
         if self.world_size > 1:
-            import torch.distributed as dist
-
             # DDP semantics: average over ranks.  The proposal part of the arena is all zeros on
             # non-updated steps (the schedule is identical on every rank), so one collective covers both.
-            dist.all_reduce(self.grad_arena, op=dist.ReduceOp.AVG, group=self.pg)
+            allreduce_mean_(self.grad_arena, self.pg, self.world_size)
         lr = exponential_decay_lr(step, self.lr, self.lr_final, self.lr_max_steps)
         sl_f = slice(NUM_PROP_TENSORS, len(self.params))
         self.field_steps += 1

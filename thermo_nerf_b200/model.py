@@ -322,8 +322,11 @@ class ThermalNerfModel(nn.Module):
         """tnf_losses over the training outputs, evaluated once per step (metrics + loss dict share it)."""
         cache = outputs.get("_b200_losses")
         if cache is None:
-            image = batch["image"].to(self.device)[..., :3].reshape(-1, 3).float()
-            thermal = batch["thermal"].to(self.device).reshape(-1).float()
+            # the reference keeps the thermal GT on the host and moves it here (thermal_dataset.py:18-20,
+            # thermal_nerf_model.py:319); non_blocking keeps that copy from draining the stream when the
+            # host tensor is pinned (a blocking .to() waits for the forward kernel before the loss can launch)
+            image = batch["image"].to(self.device, non_blocking=True)[..., :3].reshape(-1, 3).float()
+            thermal = batch["thermal"].to(self.device, non_blocking=True).reshape(-1).float()
             w = outputs["weights_list"]
             cache = F.losses(
                 {"rgb": outputs["rgb"].reshape(-1, 3), "thermal": outputs["thermal"].reshape(-1),
