@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define TNF_ABI_VERSION 2
+#define TNF_ABI_VERSION 3
 
 #define TNF_MAX_LEVELS 16      /* hash levels of the field grid (fixed: 16)          */
 #define TNF_MAX_PROP_LEVELS 8  /* max hash levels of a proposal density grid          */
@@ -126,6 +126,14 @@ typedef struct TnfModel {
   int32_t _pad;
 } TnfModel;
 
+/* One perspective camera without distortion, as nerfstudio's Cameras holds it (the cameras the reference
+ * renders: thermo_nerf/render/renderer.py:144-157 loads them, :183 and evaluator.py:69 call generate_rays). */
+typedef struct TnfCamera {
+  float c2w[12];          /* camera_to_worlds[i], row-major [3,4]                                  */
+  float fx, fy, cx, cy;
+  int32_t width, height;
+} TnfCamera;
+
 typedef struct TnfRays {
   const float* origins;          /* [R,3]                                                     */
   const float* directions;       /* [R,3]                                                     */
@@ -134,6 +142,13 @@ typedef struct TnfRays {
   const float* fars;             /* [R] or NULL                                               */
   const float* jitter;           /* [3,R] single-jitter draws in [0,1) (training) or NULL     */
   int64_t num_rays;
+  /* from_camera != 0 (tnf_render_forward, eval only): ray r is pixel first_pixel + r (row-major) of
+   * `camera`, generated inside the kernel exactly as Cameras.generate_rays does (pixel centre +0.5,
+   * ((x-cx)/fx, -(y-cy)/fy, -1) rotated by c2w and normalised); origins/directions may then be NULL. */
+  int32_t from_camera;
+  int32_t _pad;
+  int64_t first_pixel;
+  TnfCamera camera;
 } TnfRays;
 
 typedef struct TnfOutputs {
@@ -171,6 +186,23 @@ size_t tnf_forward_workspace_bytes(int64_t num_rays, int64_t depth_clip_chunk);
 int tnf_render_forward(const TnfModel* model, const TnfRays* rays, const TnfOutputs* out,
                        int64_t depth_clip_chunk, void* workspace, size_t workspace_bytes,
                        void* stream);
+
+/* Cameras.generate_rays for `num_pixels` pixels of one camera starting at first_pixel (row-major):
+ * origins/directions [n,3], directions_norm [n] (the RayBundle metadata entry; may be NULL).
+ * Replaces cameras.generate_rays(camera_indices=i) at thermo_nerf/render/renderer.py:183 and
+ * thermo_nerf/evaluator/evaluator.py:69. */
+int tnf_generate_rays(const TnfCamera* camera, int64_t first_pixel, int64_t num_pixels, float* origins,
+                      float* directions, float* directions_norm, void* stream);
+
+/* Frame post-processing of Renderer.render (thermo_nerf/render/renderer.py:189-199) on the device:
+ *   rgb8[i,c]    = (uint8)(rgb[i,c] * 255)                    for an [n,3] float image in [0,1]
+ *   scalar8[i,:] = lut8[index(scalar[i])]                     when lut8 != NULL (matplotlib Colormap.__call__:
+ *                  index = scalar*lut_n truncated, scalar == 1 -> lut_n-1, clipped to the table; NaN -> 0,0,0)
+ *                = (uint8)(scalar[i] * 255) replicated x3     when lut8 == NULL (single-channel modalities)
+ * lut8 is the colour map already converted the reference's way, (cmap(arange(N))[:, :3] * 255).astype(uint8).
+ * Either pair (rgb, rgb8) / (scalar, scalar8) may be NULL. */
+int tnf_postprocess_frame(const float* rgb, const float* scalar, int64_t num_pixels, const uint8_t* lut8,
+                          int32_t lut_n, uint8_t* rgb8, uint8_t* scalar8, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Training: backward of tnf_render_forward, the losses of get_loss_dict, Adam.

@@ -25,3 +25,4 @@ available.
 
 from .nerfstudio_math import *  # noqa: F401,F403
 from .thermo_model import *  # noqa: F401,F403
+from .camera_post import *  # noqa: F401,F403

@@ -41,21 +41,22 @@ def test_every_declared_symbol_is_exported(lib):
 def test_abi_version_and_error_string(lib):
     from thermo_nerf_b200 import _lib
 
-    assert lib.tnf_version() == _lib.TNF_ABI_VERSION == 2
+    assert lib.tnf_version() == _lib.TNF_ABI_VERSION == 3
     assert isinstance(lib.tnf_last_error(), bytes)
 
 
 def test_ctypes_layout_matches_c_header(tmp_path):
     from thermo_nerf_b200 import _lib
 
-    names = ["TnfHashGrid", "TnfLinear", "TnfDensityNet", "TnfField", "TnfModel", "TnfRays", "TnfOutputs",
+    names = ["TnfHashGrid", "TnfLinear", "TnfDensityNet", "TnfField", "TnfModel", "TnfCamera", "TnfRays", "TnfOutputs",
              "TnfLinearGrad", "TnfDensityNetGrad", "TnfFieldGrad", "TnfModelGrad", "TnfSaved", "TnfOutputGrads",
              "TnfLossArgs", "TnfAdamTensor"]
     probes = {
         "TnfModel": ["field", "num_samples", "training", "near_plane", "anneal", "use_contraction", "aabb",
                      "appearance_mode", "precision", "detach_thermal_geo"],
         "TnfField": ["grid", "base0", "th2", "appearance", "num_images"],
-        "TnfRays": ["jitter", "num_rays"],
+        "TnfRays": ["jitter", "num_rays", "from_camera", "first_pixel", "camera"],
+        "TnfCamera": ["c2w", "fx", "cy", "width", "height"],
         "TnfOutputs": ["prop_depth", "weights", "sdist", "field_features", "field_samples"],
         "TnfModelGrad": ["field"],
         "TnfFieldGrad": ["th2", "appearance"],
@@ -140,3 +141,26 @@ def test_training_entry_points_validate_arguments(lib):
     rc = lib.tnf_render_backward(C.byref(m), C.byref(r), None, None, None, None, 0, None)
     assert rc == _lib.TNF_ERR_INVALID_ARGUMENT
     assert lib.tnf_backward_workspace_bytes(None, 10) >= 16
+
+
+def test_camera_and_postprocess_entry_points_validate_arguments(lib):
+    from thermo_nerf_b200 import _lib
+
+    rc = lib.tnf_generate_rays(None, 0, 4, None, None, None, None)
+    assert rc == _lib.TNF_ERR_INVALID_ARGUMENT and b"camera" in lib.tnf_last_error()
+    cam = _lib.TnfCamera()
+    cam.width, cam.height, cam.fx, cam.fy = 4, 3, 10.0, 10.0
+    rc = lib.tnf_generate_rays(C.byref(cam), 10, 4, None, None, None, None)  # pixels 10..13 of a 12-pixel image
+    assert rc == _lib.TNF_ERR_INVALID_ARGUMENT and b"outside" in lib.tnf_last_error()
+    assert lib.tnf_generate_rays(C.byref(cam), 0, 0, None, None, None, None) == _lib.TNF_OK  # nothing to do
+    rc = lib.tnf_generate_rays(C.byref(cam), 0, 12, None, None, None, None)
+    assert rc == _lib.TNF_ERR_INVALID_ARGUMENT and b"null" in lib.tnf_last_error()
+    # an image without its output (and vice versa) is rejected; an empty call is a no-op
+    assert lib.tnf_postprocess_frame(256, None, 16, None, 0, None, None, None) == _lib.TNF_ERR_INVALID_ARGUMENT
+    assert lib.tnf_postprocess_frame(None, None, 16, None, 0, None, None, None) == _lib.TNF_OK
+    assert lib.tnf_postprocess_frame(None, 256, 16, 256, 0, None, 256, None) == _lib.TNF_ERR_INVALID_ARGUMENT  # lut_n
+    # camera rays are an eval-mode input of the forward and never of the backward
+    m, r = _lib.TnfModel(), _lib.TnfRays()
+    r.from_camera = 1
+    rc = lib.tnf_render_backward(C.byref(m), C.byref(r), None, None, None, None, 0, None)
+    assert rc == _lib.TNF_ERR_INVALID_ARGUMENT

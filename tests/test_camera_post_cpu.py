@@ -1,0 +1,91 @@
+"""Oracle known-answer tests for the neighbours of the path: ray generation, the
+matplotlib colour-map call and Renderer.render's uint8 conversion, plus the host side of the Renderer
+mirror (camera-path loading against the reference's own fixture).  CPU only."""
+
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from thermo_nerf_b200 import PinholeCameras, RenderedImageModality, Renderer
+from thermo_nerf_b200.render import lut8_from_colormap
+
+GOLDEN = Path(__file__).parent / "golden"
+
+
+def test_generate_rays_known_answers():
+    # identity pose: the principal ray looks down -z; pixel centres sit at +0.5
+    c2w = np.concatenate([np.eye(3), np.array([[1.0], [2.0], [3.0]])], 1)
+    o, d, n = oracle.generate_rays_np(c2w, 100.0, 100.0, 4.0, 3.0, 6, 8)
+    assert o.shape == (6, 8, 3) and np.all(o == np.array([1, 2, 3], np.float32))
+    # pixel (y=2, x=3): centre (3.5, 2.5) -> camera dir (-0.005, +0.005, -1) normalised
+    v = np.array([(3.5 - 4) / 100, -(2.5 - 3) / 100, -1.0])
+    assert np.allclose(d[2, 3], v / np.linalg.norm(v), atol=1e-7)
+    assert np.allclose(n[2, 3, 0], np.linalg.norm(v), atol=1e-7)
+    assert np.allclose(np.linalg.norm(d, axis=-1), 1.0, atol=1e-6)
+    # a rotated camera rotates every direction: R maps camera -z onto world +x
+    R = np.array([[0.0, 0, -1], [0, 1, 0], [1, 0, 0]])
+    _, d2, _ = oracle.generate_rays_np(np.concatenate([R, np.zeros((3, 1))], 1), 50.0, 50.0, 2.0, 2.0, 4, 4)
+    assert np.allclose(d2, d2 @ np.eye(3)) and d2[..., 0].min() > 0.99  # all rays point along +x
+    # the torch stand-in used to build benchmark rays agrees with the oracle
+    cams = PinholeCameras(torch.tensor(c2w, dtype=torch.float32)[None], 100.0, 100.0, 4.0, 3.0, 8, 6)
+    rb = cams.generate_rays(0)
+    assert np.allclose(rb.directions.numpy(), d, atol=1e-6) and np.allclose(rb.origins.numpy(), o)
+
+
+def test_colormap_call_semantics_and_uint8_conversion():
+    rng = np.random.default_rng(0)
+    colors = rng.random((7, 3))
+    cm = oracle.ListedColormapLike(colors)
+    x = np.array([0.0, 0.1428, 0.1429, 0.5, 0.999, 1.0], dtype=np.float32)
+    idx = [0, 0, 1, 3, 6, 6]  # x*7 truncated; x == 1 -> last bin
+    assert np.allclose(cm(x)[:, :3], colors[idx])
+    lut8 = oracle.colormap_to_lut8(cm)
+    assert lut8.dtype == np.uint8 and np.array_equal(lut8, (colors * 255).astype(np.uint8))
+    assert np.array_equal(lut8_from_colormap(cm), lut8)             # product-side conversion = oracle's
+    assert np.array_equal(lut8_from_colormap(colors), lut8)         # a float table is accepted as is
+    assert np.array_equal(lut8_from_colormap(lut8), lut8)           # and a uint8 table
+    # renderer.py:189-199: single-channel images are replicated, float -> uint8 truncates
+    img = np.array([[[0.0], [0.5], [0.999], [1.0]]], dtype=np.float32)
+    assert np.array_equal(oracle.postprocess_np(img, False)[0, :, 0], [0, 127, 254, 255])
+    th = oracle.postprocess_np(img, True, cm)
+    assert th.shape == (1, 4, 3) and np.array_equal(th[0, 3], lut8[6]) and np.array_equal(th[0, 0], lut8[0])
+
+
+def test_load_cameras_reference_fixture():
+    """tests/test_renderer.py:66-69 of the reference loads camera_path_facade_2.json and expects 96 poses;
+    a copy of that fixture's header + the first/last pose is committed under tests/golden/."""
+    path = GOLDEN / "camera_path_facade_2_excerpt.json"
+    cams = Renderer.load_cameras(path)
+    meta = json.load(open(path))
+    assert cams.size == len(meta["camera_path"]) == meta["_num_poses_in_excerpt"]
+    assert (cams.width, cams.height) == (1920, 1080)
+    # three_js_perspective_camera_focal_length(fov=50, h=1080)
+    assert cams.fx == pytest.approx(0.5 * 1080 / np.tan(np.deg2rad(25.0)))
+    assert cams.cx == 960 and cams.cy == 540
+    c2w, fx, fy, cx, cy, h, w = oracle.camera_path_to_cameras(meta)
+    assert np.allclose(cams.camera_to_worlds.numpy(), c2w) and (h, w) == (1080, 1920) and fx == pytest.approx(cams.fx)
+    half = Renderer.load_cameras(path, 0.5)
+    assert (half.width, half.height) == (960, 540) and half.fx == pytest.approx(cams.fx / 2)
+
+
+def test_renderer_surface():
+    assert RenderedImageModality.RGB.value == "img" and RenderedImageModality.THERMAL.value == "thermal"
+    r = Renderer(model=object())
+    assert r.model is not None and r._rendered_images == {}
+    with pytest.raises(ImportError):
+        Renderer.from_pipeline_path(Path("."), Path("."))
+
+
+def test_save_images_and_gif(tmp_path):
+    # tests/test_renderer.py:44-64 of the reference: two frames -> two jpeg files and one gif
+    r = Renderer(model=object())
+    frame = (np.arange(64 * 48 * 3) % 255).astype(np.uint8).reshape(48, 64, 3)
+    r._rendered_images = {RenderedImageModality.RGB: [frame, frame]}
+    r.save_images([RenderedImageModality.RGB], tmp_path)
+    r.save_gif([RenderedImageModality.RGB], 1, tmp_path)
+    names = sorted(p.name for p in tmp_path.iterdir())
+    assert names == ["img_00000.jpeg", "img_00001.jpeg", "synthesized_video_img.gif"]

@@ -12,9 +12,10 @@ from .optim import FusedAdam
 from .modules import (CameraOptimizer, FieldHeadNames, FieldHeadNamesT, HashMLPDensityField, ThermalFieldHead,
                       ThermalNerfactoTField)
 from .rays import PinholeCameras, RayBundle, orbit_cameras, sphere_cameras
+from .render import RenderedImageModality, Renderer
 
 __all__ = [
     "ModelTensors", "render_forward", "render", "losses", "adam_step", "FusedAdam", "ThermalNerfModel", "ThermalNerfModelConfig", "CameraOptimizer",
     "FieldHeadNames", "FieldHeadNamesT", "HashMLPDensityField", "ThermalFieldHead", "ThermalNerfactoTField",
-    "PinholeCameras", "RayBundle", "orbit_cameras", "sphere_cameras",
+    "PinholeCameras", "RayBundle", "orbit_cameras", "sphere_cameras", "Renderer", "RenderedImageModality",
 ]

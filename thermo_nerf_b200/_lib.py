@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 from typing import Optional
 
-TNF_ABI_VERSION = 2
+TNF_ABI_VERSION = 3
 TNF_MAX_LEVELS = 16
 TNF_MAX_PROP_LEVELS = 8
 TNF_MAX_SAMPLES = 256
@@ -82,6 +82,18 @@ class TnfModel(C.Structure):
     ]
 
 
+class TnfCamera(C.Structure):
+    _fields_ = [
+        ("c2w", C.c_float * 12),
+        ("fx", C.c_float),
+        ("fy", C.c_float),
+        ("cx", C.c_float),
+        ("cy", C.c_float),
+        ("width", C.c_int32),
+        ("height", C.c_int32),
+    ]
+
+
 class TnfRays(C.Structure):
     _fields_ = [
         ("origins", _fp),
@@ -91,6 +103,10 @@ class TnfRays(C.Structure):
         ("fars", _fp),
         ("jitter", _fp),
         ("num_rays", C.c_int64),
+        ("from_camera", C.c_int32),
+        ("_pad", C.c_int32),
+        ("first_pixel", C.c_int64),
+        ("camera", TnfCamera),
     ]
 
 
@@ -197,6 +213,8 @@ EXPORTED_SYMBOLS = (
     "tnf_last_error",
     "tnf_forward_workspace_bytes",
     "tnf_render_forward",
+    "tnf_generate_rays",
+    "tnf_postprocess_frame",
     "tnf_backward_workspace_bytes",
     "tnf_render_backward",
     "tnf_backward_stage_mask",
@@ -249,6 +267,12 @@ def load() -> C.CDLL:
         C.c_size_t,
         C.c_void_p,
     ]
+    lib.tnf_generate_rays.restype = C.c_int
+    lib.tnf_generate_rays.argtypes = [C.POINTER(TnfCamera), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p]
+    lib.tnf_postprocess_frame.restype = C.c_int
+    lib.tnf_postprocess_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]
     lib.tnf_backward_workspace_bytes.restype = C.c_size_t
     lib.tnf_backward_workspace_bytes.argtypes = [C.POINTER(TnfModel), C.c_int64]
     lib.tnf_render_backward.restype = C.c_int

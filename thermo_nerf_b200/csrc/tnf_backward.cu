@@ -1501,6 +1501,7 @@ int tnf_render_backward(const TnfModel* model, const TnfRays* rays, const TnfSav
   const long long R = rays->num_rays;
   if (R < 0) return fail(TNF_ERR_INVALID_ARGUMENT, "num_rays=%lld", R);
   if (R == 0) return TNF_OK;
+  if (rays->from_camera) return fail(TNF_ERR_INVALID_ARGUMENT, "from_camera rays are an eval-mode input");
   if (!rays->origins || !rays->directions) return fail(TNF_ERR_INVALID_ARGUMENT, "origins/directions is null");
   if (model->appearance_mode == TNF_APPEARANCE_LOOKUP && !rays->camera_indices)
     return fail(TNF_ERR_INVALID_ARGUMENT, "camera_indices required for TNF_APPEARANCE_LOOKUP");

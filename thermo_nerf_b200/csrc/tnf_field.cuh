@@ -163,6 +163,27 @@ struct RayCtx {
   float s_near, s_far;
 };
 
+// Cameras.generate_rays for one pixel of a perspective camera without distortion (nerfstudio 1.1.5
+// Cameras._generate_rays_from_coords, reached from thermo_nerf/render/renderer.py:183): pixel centre
+// (x+0.5, y+0.5), camera-frame direction ((x-cx)/fx, -(y-cy)/fy, -1), rotated by c2w[:3,:3] (products
+// summed left to right as torch.sum over the last dim does for 3 elements), normalised; origin = c2w[:3,3].
+__device__ __forceinline__ void camera_ray(const TnfCamera& c, const long long pix, float& ox, float& oy, float& oz,
+                                           float& dx, float& dy, float& dz, float& norm) {
+  const long long yi = pix / c.width;
+  const float px = (float)(pix - yi * c.width) + 0.5f, py = (float)yi + 0.5f;
+  const float a = (px - c.cx) / c.fx, b = -((py - c.cy) / c.fy), w = -1.f;
+  const float x = __fadd_rn(__fadd_rn(__fmul_rn(a, c.c2w[0]), __fmul_rn(b, c.c2w[1])), __fmul_rn(w, c.c2w[2]));
+  const float y = __fadd_rn(__fadd_rn(__fmul_rn(a, c.c2w[4]), __fmul_rn(b, c.c2w[5])), __fmul_rn(w, c.c2w[6]));
+  const float z = __fadd_rn(__fadd_rn(__fmul_rn(a, c.c2w[8]), __fmul_rn(b, c.c2w[9])), __fmul_rn(w, c.c2w[10]));
+  norm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+  dx = x / norm;
+  dy = y / norm;
+  dz = z / norm;
+  ox = c.c2w[3];
+  oy = c.c2w[7];
+  oz = c.c2w[11];
+}
+
 // frustums.get_positions(): origins + directions * (starts + ends) / 2, rounded like ATen (separate
 // multiply and add, no FMA contraction) so that the discontinuous selector sees the same point.
 __device__ __forceinline__ float ray_x(const RayCtx& rc, float mid) { return __fadd_rn(rc.ox, __fmul_rn(rc.dx, mid)); }

@@ -379,12 +379,17 @@ __global__ void __launch_bounds__(kThreads, PREC == TNF_PRECISION_TC_FP16 ? 2 : 
   for (long long ray = (long long)blockIdx.x * kWarpsPerCta + warp; ray < R;
        ray += (long long)gridDim.x * kWarpsPerCta) {
     RayCtx rc;
-    rc.ox = __ldg(rays.origins + ray * 3 + 0);
-    rc.oy = __ldg(rays.origins + ray * 3 + 1);
-    rc.oz = __ldg(rays.origins + ray * 3 + 2);
-    rc.dx = __ldg(rays.directions + ray * 3 + 0);
-    rc.dy = __ldg(rays.directions + ray * 3 + 1);
-    rc.dz = __ldg(rays.directions + ray * 3 + 2);
+    if (rays.from_camera) {
+      float nrm;
+      camera_ray(rays.camera, rays.first_pixel + ray, rc.ox, rc.oy, rc.oz, rc.dx, rc.dy, rc.dz, nrm);
+    } else {
+      rc.ox = __ldg(rays.origins + ray * 3 + 0);
+      rc.oy = __ldg(rays.origins + ray * 3 + 1);
+      rc.oz = __ldg(rays.origins + ray * 3 + 2);
+      rc.dx = __ldg(rays.directions + ray * 3 + 0);
+      rc.dy = __ldg(rays.directions + ray * 3 + 1);
+      rc.dz = __ldg(rays.directions + ray * 3 + 2);
+    }
     const float near = rays.nears ? __ldg(rays.nears + ray) : m.near_plane;
     const float far = rays.fars ? __ldg(rays.fars + ray) : m.far_plane;
     rc.s_near = spacing_fn(near);
@@ -519,6 +524,58 @@ __global__ void tnf_clip_kernel(float* __restrict__ expected_depth, const long l
   if (e == e) expected_depth[r] = fminf(fmaxf(e, lo), hi);
 }
 
+// Cameras.generate_rays as a stand-alone pass (callers that want the RayBundle tensors themselves).
+__global__ void tnf_rays_kernel(const __grid_constant__ TnfCamera cam, const long long first, const long long n,
+                                float* __restrict__ origins, float* __restrict__ directions,
+                                float* __restrict__ dnorm) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float ox, oy, oz, dx, dy, dz, nrm;
+  camera_ray(cam, first + i, ox, oy, oz, dx, dy, dz, nrm);
+  origins[3 * i] = ox; origins[3 * i + 1] = oy; origins[3 * i + 2] = oz;
+  directions[3 * i] = dx; directions[3 * i + 1] = dy; directions[3 * i + 2] = dz;
+  if (dnorm) dnorm[i] = nrm;
+}
+
+// Renderer.render's per-frame conversion (thermo_nerf/render/renderer.py:189-199): float image -> uint8,
+// scalar image -> colour-mapped (or grey) uint8; the colour table sits in shared memory.
+__device__ __forceinline__ unsigned char to_u8(float v) {  // numpy (x * 255).astype(uint8) for x in [0,1]
+  return (unsigned char)(int)__fmul_rn(v, 255.f);
+}
+__global__ void tnf_post_kernel(const float* __restrict__ rgb, const float* __restrict__ scalar, const long long n,
+                                const unsigned char* __restrict__ lut8, const int lut_n,
+                                unsigned char* __restrict__ rgb8, unsigned char* __restrict__ scalar8) {
+  extern __shared__ unsigned char s_lut[];
+  if (lut8)
+    for (int i = threadIdx.x; i < 3 * lut_n; i += blockDim.x) s_lut[i] = lut8[i];
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (rgb && rgb8) {
+      rgb8[3 * i] = to_u8(rgb[3 * i]);
+      rgb8[3 * i + 1] = to_u8(rgb[3 * i + 1]);
+      rgb8[3 * i + 2] = to_u8(rgb[3 * i + 2]);
+    }
+    if (scalar && scalar8) {
+      const float v = scalar[i];
+      unsigned char r, g, b;
+      if (lut8) {
+        if (v != v) {
+          r = g = b = 0;  // matplotlib's "bad" colour is transparent black
+        } else {
+          const float xa = __fmul_rn(v, (float)lut_n);
+          int k = xa == (float)lut_n ? lut_n - 1 : (int)xa;
+          k = xa < 0.f ? 0 : min(k, lut_n - 1);  // default under / over colours are the end colours
+          r = s_lut[3 * k]; g = s_lut[3 * k + 1]; b = s_lut[3 * k + 2];
+        }
+      } else {
+        r = g = b = to_u8(v);
+      }
+      scalar8[3 * i] = r; scalar8[3 * i + 1] = g; scalar8[3 * i + 2] = b;
+    }
+  }
+}
+
 }  // namespace tnf
 
 // ====================================================================================
@@ -627,13 +684,23 @@ int tnf_render_forward(const TnfModel* model, const TnfRays* rays, const TnfOutp
   if (!rays || !out) return fail(TNF_ERR_INVALID_ARGUMENT, "rays/out is null");
   if (rays->num_rays < 0) return fail(TNF_ERR_INVALID_ARGUMENT, "num_rays=%lld", (long long)rays->num_rays);
   if (rays->num_rays == 0) return TNF_OK;
-  if (!rays->origins || !rays->directions) return fail(TNF_ERR_INVALID_ARGUMENT, "origins/directions is null");
+  if (rays->from_camera) {
+    const TnfCamera& c = rays->camera;
+    if (c.width < 1 || c.height < 1 || !(c.fx != 0.f) || !(c.fy != 0.f))
+      return fail(TNF_ERR_INVALID_ARGUMENT, "camera: width=%d height=%d fx=%g fy=%g", c.width, c.height, c.fx, c.fy);
+    if (rays->first_pixel < 0 || rays->first_pixel + rays->num_rays > (int64_t)c.width * c.height)
+      return fail(TNF_ERR_INVALID_ARGUMENT, "camera: pixels [%lld, %lld) outside the %dx%d image",
+                  (long long)rays->first_pixel, (long long)(rays->first_pixel + rays->num_rays), c.width, c.height);
+    if (model->training) return fail(TNF_ERR_INVALID_ARGUMENT, "from_camera rays are an eval-mode input");
+  } else if (!rays->origins || !rays->directions) {
+    return fail(TNF_ERR_INVALID_ARGUMENT, "origins/directions is null");
+  }
   if (model->appearance_mode == TNF_APPEARANCE_LOOKUP && !rays->camera_indices)
     return fail(TNF_ERR_INVALID_ARGUMENT, "camera_indices required for TNF_APPEARANCE_LOOKUP");
   if (!out->rgb || !out->thermal || !out->depth || !out->expected_depth || !out->accumulation ||
       !out->prop_depth[0] || !out->prop_depth[1])
     return fail(TNF_ERR_INVALID_ARGUMENT, "a required output pointer is null");
-  if (!aligned16(rays->origins) || !aligned16(rays->directions) || !aligned16(out->rgb))
+  if ((!rays->from_camera && (!aligned16(rays->origins) || !aligned16(rays->directions))) || !aligned16(out->rgb))
     return fail(TNF_ERR_INVALID_ARGUMENT, "ray/output buffers must be 16-byte aligned");
   const size_t need = tnf_forward_workspace_bytes(rays->num_rays, depth_clip_chunk);
   if (!workspace || workspace_bytes < need)
@@ -660,6 +727,45 @@ int tnf_render_forward(const TnfModel* model, const TnfRays* rays, const TnfOutp
   tnf::tnf_clip_kernel<<<(unsigned)nb, tb, 0, stream>>>(out->expected_depth, rays->num_rays, chunk, cmin, cmax);
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "clip kernel launch: %s", cudaGetErrorString(e));
+  return TNF_OK;
+}
+
+int tnf_generate_rays(const TnfCamera* camera, int64_t first_pixel, int64_t num_pixels, float* origins,
+                      float* directions, float* directions_norm, void* stream_) {
+  g_err[0] = 0;
+  if (!camera) return fail(TNF_ERR_INVALID_ARGUMENT, "camera is null");
+  if (camera->width < 1 || camera->height < 1 || !(camera->fx != 0.f) || !(camera->fy != 0.f))
+    return fail(TNF_ERR_INVALID_ARGUMENT, "camera: width=%d height=%d fx=%g fy=%g", camera->width, camera->height,
+                camera->fx, camera->fy);
+  if (num_pixels < 0 || first_pixel < 0 || first_pixel + num_pixels > (int64_t)camera->width * camera->height)
+    return fail(TNF_ERR_INVALID_ARGUMENT, "pixels [%lld, %lld) outside the %dx%d image", (long long)first_pixel,
+                (long long)(first_pixel + num_pixels), camera->width, camera->height);
+  if (num_pixels == 0) return TNF_OK;
+  if (!origins || !directions) return fail(TNF_ERR_INVALID_ARGUMENT, "origins/directions is null");
+  const int tb = 256;
+  tnf::tnf_rays_kernel<<<(unsigned)((num_pixels + tb - 1) / tb), tb, 0, static_cast<cudaStream_t>(stream_)>>>(
+      *camera, first_pixel, num_pixels, origins, directions, directions_norm);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "rays kernel launch: %s", cudaGetErrorString(e));
+  return TNF_OK;
+}
+
+int tnf_postprocess_frame(const float* rgb, const float* scalar, int64_t num_pixels, const uint8_t* lut8,
+                          int32_t lut_n, uint8_t* rgb8, uint8_t* scalar8, void* stream_) {
+  g_err[0] = 0;
+  if (num_pixels < 0) return fail(TNF_ERR_INVALID_ARGUMENT, "num_pixels=%lld", (long long)num_pixels);
+  if ((rgb == nullptr) != (rgb8 == nullptr) || (scalar == nullptr) != (scalar8 == nullptr))
+    return fail(TNF_ERR_INVALID_ARGUMENT, "an input image and its uint8 output must be given together");
+  if (lut8 && (lut_n < 1 || lut_n > 4096)) return fail(TNF_ERR_INVALID_ARGUMENT, "lut_n=%d not in [1,4096]", lut_n);
+  if (num_pixels == 0 || (!rgb && !scalar)) return TNF_OK;
+  const int tb = 256;
+  long long nb = (num_pixels + tb - 1) / tb;
+  const long long cap = (long long)tnf::num_sms() * 8;
+  if (nb > cap) nb = cap;
+  tnf::tnf_post_kernel<<<(unsigned)nb, tb, lut8 ? 3 * (size_t)lut_n : 0, static_cast<cudaStream_t>(stream_)>>>(
+      rgb, scalar, num_pixels, lut8, lut_n, rgb8, scalar8);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "post kernel launch: %s", cudaGetErrorString(e));
   return TNF_OK;
 }
 

@@ -225,8 +225,8 @@ _OUT_KEYS = ("rgb", "thermal", "depth", "expected_depth", "accumulation", "prop_
 
 def render_forward(
     tensors: ModelTensors,
-    origins: Tensor,
-    directions: Tensor,
+    origins: Optional[Tensor],
+    directions: Optional[Tensor],
     camera_indices: Optional[Tensor] = None,
     nears: Optional[Tensor] = None,
     fars: Optional[Tensor] = None,
@@ -246,21 +246,38 @@ def render_forward(
     out: Optional[Dict[str, Tensor]] = None,
     save_for_backward: bool = False,
     detach_thermal_geo: bool = False,
+    camera: Optional[L.TnfCamera] = None,
+    first_pixel: int = 0,
+    num_pixels: Optional[int] = None,
 ) -> Dict[str, object]:
     """One call of ``tnf_render_forward`` over R rays (flat).  Returns the output dict of
     ThermalNerfModel.get_outputs (thermal_nerf_model.py:245-275): rgb [R,3], thermal,
     depth, expected_depth, accumulation, prop_depth_0/1 [R,1]; with ``return_samples``
     also ``weights_list`` ([R,S_k,1]) and ``sdist_list`` ([R,S_k+1])."""
     lib = L.load()
-    o = _dev_f32(origins, "origins")
-    d = _dev_f32(directions, "directions")
-    if o.dim() != 2 or o.shape[1] != 3 or d.shape != o.shape:
-        raise ValueError(f"origins/directions must both be [R,3], got {tuple(o.shape)} / {tuple(d.shape)}")
-    R = int(o.shape[0])
-    dev = o.device
     rays = L.TnfRays()
-    rays.origins, rays.directions, rays.num_rays = o.data_ptr(), d.data_ptr(), R
-    keep = [o, d]
+    if camera is not None:
+        # rays generated inside the kernel from the camera (eval only): no [R,3] tensors cross HBM or PCIe
+        if origins is not None or directions is not None:
+            raise ValueError("pass either origins/directions or camera, not both")
+        if training:
+            raise ValueError("camera rays are an eval-mode input")
+        total = int(camera.width) * int(camera.height)
+        R = total - int(first_pixel) if num_pixels is None else int(num_pixels)
+        if first_pixel < 0 or R < 0 or first_pixel + R > total:
+            raise ValueError(f"pixels [{first_pixel}, {first_pixel + R}) outside the {camera.width}x{camera.height} image")
+        dev = tensors.field_grid.table.device
+        rays.from_camera, rays.first_pixel, rays.camera, rays.num_rays = 1, int(first_pixel), camera, R
+        keep = []
+    else:
+        o = _dev_f32(origins, "origins")
+        d = _dev_f32(directions, "directions")
+        if o.dim() != 2 or o.shape[1] != 3 or d.shape != o.shape:
+            raise ValueError(f"origins/directions must both be [R,3], got {tuple(o.shape)} / {tuple(d.shape)}")
+        R = int(o.shape[0])
+        dev = o.device
+        rays.origins, rays.directions, rays.num_rays = o.data_ptr(), d.data_ptr(), R
+        keep = [o, d]
     if camera_indices is not None:
         ci = camera_indices.reshape(-1)
         if ci.dtype != torch.int64 or not ci.is_cuda or ci.numel() != R:
@@ -644,3 +661,80 @@ def adam_step(params: Sequence[Tensor], grads: Sequence[Tensor], exp_avgs: Seque
             rc = lib.tnf_adam_step(arr, m, float(beta1), float(beta2), float(eps), int(step), float(inv_grad_scale),
                                    C.c_void_p(gs), C.c_void_p(fi), int(bool(zero_grads)), C.c_void_p(stream))
         L.check(rc)
+
+
+# ---------------------------------------------------------------------------------------------
+# either side of the path: ray generation and frame post-processing
+# ---------------------------------------------------------------------------------------------
+def pack_camera(c2w: Tensor, fx: float, fy: float, cx: float, cy: float, width: int, height: int) -> L.TnfCamera:
+    """``TnfCamera`` of one perspective camera (``c2w`` = camera_to_worlds[i], [3,4]; host values)."""
+    cam = L.TnfCamera()
+    vals = [float(x) for x in torch.as_tensor(c2w, dtype=torch.float32).reshape(-1).tolist()]
+    if len(vals) != 12:
+        raise ValueError("c2w must be [3,4]")
+    for i, v in enumerate(vals):
+        cam.c2w[i] = v
+    cam.fx, cam.fy, cam.cx, cam.cy = float(fx), float(fy), float(cx), float(cy)
+    cam.width, cam.height = int(width), int(height)
+    return cam
+
+
+def generate_rays(camera: L.TnfCamera, device, first_pixel: int = 0, num_pixels: Optional[int] = None
+                  ) -> Tuple[Tensor, Tensor, Tensor]:
+    """``tnf_generate_rays``: (origins [n,3], directions [n,3], directions_norm [n,1]) of the pixels
+    [first_pixel, first_pixel + n) of ``camera`` - Cameras.generate_rays (renderer.py:183, evaluator.py:69)."""
+    lib = L.load()
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("generate_rays runs on a CUDA device; there is no CPU path")
+    n = int(camera.width) * int(camera.height) - int(first_pixel) if num_pixels is None else int(num_pixels)
+    o = torch.empty((max(n, 0), 3), dtype=torch.float32, device=dev)
+    d = torch.empty((max(n, 0), 3), dtype=torch.float32, device=dev)
+    nrm = torch.empty((max(n, 0), 1), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        rc = lib.tnf_generate_rays(C.byref(camera), int(first_pixel), n, o.data_ptr(), d.data_ptr(), nrm.data_ptr(),
+                                   C.c_void_p(stream))
+    L.check(rc)
+    return o, d, nrm
+
+
+def postprocess_frame(rgb: Optional[Tensor] = None, scalar: Optional[Tensor] = None, lut8: Optional[Tensor] = None
+                      ) -> Tuple[Optional[Tensor], Optional[Tensor]]:
+    """``tnf_postprocess_frame``: the uint8 conversion of Renderer.render (renderer.py:189-199).
+    ``rgb`` [...,3] float in [0,1] -> uint8 [...,3]; ``scalar`` [...,1] or [...] -> uint8 [...,3], through the
+    uint8 colour table ``lut8`` [N,3] when given, else grey.  Returns (rgb8, scalar8)."""
+    lib = L.load()
+    ref = rgb if rgb is not None else scalar
+    if ref is None:
+        return None, None
+    dev = ref.device
+    rgb8 = scalar8 = None
+    n = 0
+    if rgb is not None:
+        r = _dev_f32(rgb.reshape(-1, 3), "rgb")
+        n = int(r.shape[0])
+        rgb8 = torch.empty((*rgb.shape[:-1], 3), dtype=torch.uint8, device=dev)
+    if scalar is not None:
+        sc = _dev_f32(scalar.reshape(-1), "scalar")
+        if rgb is not None and sc.numel() != n:
+            raise ValueError("rgb and scalar must cover the same pixels")
+        n = int(sc.numel())
+        shape = scalar.shape[:-1] if (scalar.dim() > 1 and scalar.shape[-1] == 1) else scalar.shape
+        scalar8 = torch.empty((*shape, 3), dtype=torch.uint8, device=dev)
+    lut_ptr, lut_n = 0, 0
+    if lut8 is not None:
+        if lut8.dtype != torch.uint8 or lut8.dim() != 2 or lut8.shape[1] != 3 or not lut8.is_cuda:
+            raise ValueError("lut8 must be a CUDA uint8 tensor [N,3]")
+        lut8 = lut8.contiguous()
+        lut_ptr, lut_n = lut8.data_ptr(), int(lut8.shape[0])
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        rc = lib.tnf_postprocess_frame(C.c_void_p(r.data_ptr() if rgb is not None else 0),
+                                       C.c_void_p(sc.data_ptr() if scalar is not None else 0), n,
+                                       C.c_void_p(lut_ptr), lut_n,
+                                       C.c_void_p(rgb8.data_ptr() if rgb8 is not None else 0),
+                                       C.c_void_p(scalar8.data_ptr() if scalar8 is not None else 0),
+                                       C.c_void_p(stream))
+    L.check(rc)
+    return rgb8, scalar8

@@ -317,6 +317,30 @@ class ThermalNerfModel(nn.Module):
         res["img"] = res["rgb"]
         return res
 
+    @torch.no_grad()
+    def get_outputs_for_camera(self, cameras, camera_idx: int) -> Dict[str, Tensor]:
+        """``get_outputs_for_camera_ray_bundle(cameras.generate_rays(camera_indices=camera_idx))``
+        (renderer.py:183-187, evaluator.py:69-79) as one launch: the rays of a perspective camera are generated
+        inside the kernel, so no [H,W,3] origin/direction tensors are built, stored or re-read.  ``cameras``
+        exposes nerfstudio's ``Cameras`` attributes (camera_to_worlds, fx, fy, cx, cy, width, height).
+        Eval mode only (training batches are random pixels, not whole frames)."""
+        if self.training:
+            raise RuntimeError("get_outputs_for_camera is an eval-mode call")
+
+        def scalar(v):
+            v = v[camera_idx] if (torch.is_tensor(v) and v.dim() > 0) else v
+            return float(v)
+
+        c2w = cameras.camera_to_worlds[camera_idx].detach().to("cpu", torch.float32)
+        H, W = int(scalar(cameras.height)), int(scalar(cameras.width))
+        cam = F.pack_camera(c2w, scalar(cameras.fx), scalar(cameras.fy), scalar(cameras.cx), scalar(cameras.cy), W, H)
+        kw = self._render_kwargs()
+        res = F.render_forward(self.tensors(), None, None, camera=cam, training=False,
+                               depth_clip_chunk=self.config.eval_num_rays_per_chunk, **kw)
+        out = {k: v.view(H, W, -1) for k, v in res.items() if isinstance(v, Tensor)}
+        out["img"] = out["rgb"]
+        return out
+
     # ------------------------------------------------------------------ losses / metrics
     def _fused_losses(self, outputs, batch) -> Dict[str, Tensor]:
         """tnf_losses over the training outputs, evaluated once per step (metrics + loss dict share it)."""
