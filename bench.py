@@ -171,7 +171,8 @@ KERNEL_NAMES = {"forward": "tnf_forward_kernel", "backward_prop": "tnf_backward_
 TRAIN_WORKLOAD = ("thermal-nerf training iteration, ThermoScenes double_robot-shaped synthetic rays: {rays} rays/batch per "
                   "GPU (BASELINE configs[1]), samples 256/96/48, forward + losses (rgb, thermal, interlevel, distortion) + "
                   "backward + Adam(lr 1e-2, eps 1e-15, exp. decay) over all 19.4M parameters; each rank draws its own "
-                  "rays, gradients all-reduced (mean) over NCCL")
+                  "rays; gradient mean over ranks fused with Adam over NVLink peer memory (--exchange nccl: NCCL "
+                  "all-reduce, then Adam)")
 
 
 # ----------------------------------------------------------------------------- reference arm
@@ -278,6 +279,9 @@ def main() -> None:
     ap.add_argument("--precision", default="tc_fp16", choices=["tc_fp16", "fp32"])
     ap.add_argument("--rays", type=int, default=4096, help="training rays per batch per GPU")
     ap.add_argument("--ref-rays", type=int, default=None, help="rays per step of the CPU reference sample")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU gradient exchange: 'peer' = reduce-scatter + Adam + all-gather fused in one "
+                         "kernel over NVLink peer memory (default), 'nccl' = NCCL all-reduce, then Adam")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-render", action="store_true", help="train mode: skip the short render measurement")
     ap.add_argument("--torch-cuda-baseline", action="store_true",
@@ -349,7 +353,7 @@ def bench_train(ctx) -> dict:
     R = args.rays
     model = build_b200_model(device, args.precision)
     model.train()
-    engine = TrainEngine(model, world_size=world)
+    engine = TrainEngine(model, world_size=world, peer_fused=(world > 1 and args.exchange == "peer"))
     n_distinct = 8
     batches = train_batches(n_distinct, R, device, rank)
 
@@ -388,6 +392,7 @@ def bench_train(ctx) -> dict:
             "wgrad": R * 48 * (1376 + 64) + R * (48 + 64) * 2,
             "adam": n_params * 28,
         }
+        algo = {k: v for k, v in algo.items() if breakdown.get(k + "_ms")}
         dom = max(algo, key=lambda k: breakdown.get(k + "_ms", 0.0))
         ach = algo[dom] / (breakdown[dom + "_ms"] * 1e-3) / 1e9
         traffic = None
@@ -469,6 +474,9 @@ def bench_train(ctx) -> dict:
                    "weights": "random trained-like init, full-size tables (field 2^19x16, proposals 2^17x5)",
                    "final_losses": dict(zip(F.LOSS_NAMES, final_losses))},
         "clocks": clocks,
+        "exchange": ("none (1 GPU)" if world == 1 else
+                     ("peer-memory fused reduce-scatter + Adam + all-gather (tnf_peer_adam_step)"
+                      if engine.arena is not None else "NCCL all-reduce (mean) + tnf_adam_step")),
         "gpu_launches": None,
         "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": n_e2e,
                 "note": "plugin API: pinned host rays+GT -> H2D -> model(ray_bundle) -> get_metrics_dict -> get_loss_dict "
@@ -477,7 +485,10 @@ def bench_train(ctx) -> dict:
     # launches of OUR kernels per engine step: forward + clip + losses + backward_prop (on update steps) +
     # backward_field + wgrad + adam (1 or 2 launches)
     # (+ the counter memset of the proposal backward and, for world > 1, NCCL's all-reduce kernel are not ours)
-    line["gpu_launches"] = int(args.steps * 6 + (prop_steps_timed) * 2)
+    if engine.arena is not None:  # peer exchange: 2 barrier kernels + 1 fused Adam instead of 1-2 Adam launches
+        line["gpu_launches"] = int(args.steps * 8 + prop_steps_timed)
+    else:
+        line["gpu_launches"] = int(args.steps * 6 + prop_steps_timed * 2)
     if roofline:
         line["roofline"] = roofline
         line["breakdown_ms"] = breakdown
@@ -533,10 +544,13 @@ def kernel_breakdown(engine, batches, device) -> dict:
             lib.tnf_backward_stage_mask(7)
         n = len(engine.params)
         # lr = 0: timing only, parameters unchanged
-        timed("adam", lambda: F.adam_step(engine.params, engine.grads, engine.exp_avg, engine.exp_avg_sq, [0.0] * n,
-                                          step=1000, eps=1e-15, zero_grads=True))
+        if engine.arena is None:
+            timed("adam", lambda: F.adam_step(engine.params, engine.grads, engine.exp_avg, engine.exp_avg_sq,
+                                              [0.0] * n, step=1000, eps=1e-15, zero_grads=True))
+        else:
+            engine.grad_arena.zero_()
         torch.cuda.synchronize()
-    acc = {k: [a.elapsed_time(b) for a, b in v] for k, v in acc.items()}
+    acc = {k: [a.elapsed_time(b) for a, b in v] for k, v in acc.items() if v}
     # median: the interval between two events also contains any host stall between the launches (GC pause,
     # allocator growth), which an average would book as kernel time
     out = {k + "_ms": sorted(v)[len(v) // 2] for k, v in acc.items()}
@@ -658,7 +672,6 @@ def bench_render(ctx) -> dict:
                         f.camera_indices.cpu().pin_memory()))
     host_out = {k: torch.empty((HW, HW, 3 if k == "rgb" else 1), dtype=torch.float32).pin_memory() for k in out_keys}
     h2d = sum(t.numel() * t.element_size() for t in host_in[0])
-    d2h = sum(t.numel() * t.element_size() for t in host_out.values())
 
     def e2e_step(i: int):
         ho, hd, hc = host_in[i % n_distinct]
@@ -670,19 +683,43 @@ def bench_render(ctx) -> dict:
             host_out[k].copy_(out[k], non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller consumes the frame on the host
 
-    for i in range(args.warmup):
-        e2e_step(i)
-    barrier()
-    t_e2e = 0.0
-    for i in range(args.steps):
-        flush()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        e2e_step(i)
-        t_e2e += time.perf_counter() - t0
-    barrier()
-    t_e2e = max_over_ranks(t_e2e)
-    e2e_val = world * rays_per_step * args.steps / t_e2e / 1e6
+    def time_e2e(fn) -> float:
+        for i in range(args.warmup):
+            fn(i)
+        barrier()
+        t = 0.0
+        for i in range(args.steps):
+            flush()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn(i)
+            t += time.perf_counter() - t0
+        barrier()
+        return world * rays_per_step * args.steps / max_over_ranks(t) / 1e6
+
+    e2e_bundle = time_e2e(e2e_step)
+
+    # ---- end to end through the reference-facing call: Renderer.render([RGB, THERMAL], cameras) - the default
+    #      modalities of render_video_script.py - one camera per step: the camera (72 B of kernel arguments) goes
+    #      in, the two uint8 frames come back to pinned host memory
+    from thermo_nerf_b200 import PinholeCameras, RenderedImageModality, Renderer, orbit_cameras
+    from thermo_nerf_b200.dist import shard_frames
+
+    all_cams = orbit_cameras(n_distinct * world, hw=HW, focal=FOCAL)
+    mine = shard_frames(n_distinct * world, rank, world)
+    one = [PinholeCameras(all_cams.camera_to_worlds[i:i + 1], all_cams.fx, all_cams.fy, all_cams.cx, all_cams.cy,
+                          all_cams.width, all_cams.height) for i in mine]
+    g = torch.Generator().manual_seed(5)
+    lut = torch.rand((256, 3), generator=g).numpy()  # stand-in colour table (matplotlib's magma is not installed)
+    renderer = Renderer(model)
+    mods = [RenderedImageModality.RGB, RenderedImageModality.THERMAL]
+
+    def renderer_step(i: int):
+        renderer.render(mods, one[i % n_distinct], thermal_color_map=lut)
+
+    e2e_val = time_e2e(renderer_step)
+    d2h = 2 * HW * HW * 3
+    h2d_cam = 72
 
     line = {
         "metric": "render_mpix_per_s", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
@@ -696,9 +733,14 @@ def bench_render(ctx) -> dict:
                                "round-robin over ranks, no collective",
                    "l2": "flushed between timed iterations (256 MiB write)", "rays_per_second": value * 1e6,
                    "weights": "random trained-like, full-size tables (field 2^19x16, proposals 2^17x5)"},
-        "clocks": clocks, "gpu_launches": 2 * args.steps,
-        "e2e": {"value": e2e_val, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "note": "pinned host rays -> H2D -> get_outputs_for_camera_ray_bundle -> D2H rgb/thermal/depth/acc"},
+        "clocks": clocks, "gpu_launches": 2 * args.steps,  # forward + depth-clip pass per frame (device-resident loop)
+        "e2e": {"value": e2e_val, "unit": "Mpix/s", "h2d_bytes_per_step": h2d_cam, "d2h_bytes_per_step": d2h,
+                "note": "Renderer.render([RGB, THERMAL], one camera): rays generated in the kernel from the camera, "
+                        "uint8 conversion + colour map on the device, two uint8 frames D2H into pinned memory"},
+        "e2e_ray_bundle": {"value": e2e_bundle, "unit": "Mpix/s", "h2d_bytes_per_step": h2d,
+                           "d2h_bytes_per_step": sum(t.numel() * t.element_size() for t in host_out.values()),
+                           "note": "pinned host rays -> H2D -> get_outputs_for_camera_ray_bundle -> D2H float "
+                                   "rgb/thermal/depth/accumulation"},
         "roofline": roofline,
     }
 

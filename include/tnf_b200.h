@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define TNF_ABI_VERSION 3
+#define TNF_ABI_VERSION 4
 
 #define TNF_MAX_LEVELS 16      /* hash levels of the field grid (fixed: 16)          */
 #define TNF_MAX_PROP_LEVELS 8  /* max hash levels of a proposal density grid          */
@@ -314,6 +314,63 @@ typedef struct TnfAdamTensor {
 int tnf_adam_step(const TnfAdamTensor* tensors, int32_t num_tensors, double beta1, double beta2, float eps,
                   int64_t step, float inv_grad_scale, const float* grad_scale, const float* found_inf,
                   int32_t zero_grads, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Multi-GPU exchange step (one process per GPU): gradient mean over ranks fused with Adam
+ * over NVLink peer memory.  Replaces the DDP gradient all-reduce of nerfstudio's trainer followed by the
+ * optimizers of config_thermal_nerf.py:32-45 (reduce-scatter -> Adam on the owned shard -> all-gather in
+ * one kernel).  All three buffers of every rank must be mapped into this process (CUDA IPC) and peer
+ * access enabled from the current device (tnf_peer_enable_access).
+ * ------------------------------------------------------------------------------------ */
+#define TNF_MAX_PEERS 16
+#define TNF_PEER_FLAG_SLOTS 2       /* independent barrier slots                                   */
+#define TNF_PEER_FLAG_TIMEOUT 32    /* word of a rank's own flag block that counts timed-out waits */
+#define TNF_PEER_FLAG_WORDS 64      /* uint32 words per flag block (zero-initialised by the owner) */
+#define TNF_MAX_ADAM_SEGMENTS 4
+
+typedef struct TnfPeerArena {
+  const float* grads[TNF_MAX_PEERS]; /* flat gradient arena of every rank, `numel` floats          */
+  float* params[TNF_MAX_PEERS];      /* flat parameter arena of every rank                          */
+  uint32_t* flags[TNF_MAX_PEERS];    /* flag block of every rank, TNF_PEER_FLAG_WORDS uint32        */
+  int32_t world_size;
+  int32_t rank;
+  int64_t numel;                     /* multiple of 4 * world_size; rank r owns [r, r+1) * numel/N  */
+} TnfPeerArena;
+
+/* A run of the arena that shares one optimizer group (learning rate, step counter); inactive segments are
+ * left untouched (a param group without gradients this step, i.e. the proposal networks on the sampler's
+ * no_grad steps).  Segments are contiguous, start at 0 and cover the arena. */
+typedef struct TnfAdamSegment {
+  int64_t begin, end;
+  int64_t step;   /* >= 1 when active */
+  float lr;
+  int32_t active;
+} TnfAdamSegment;
+
+/* cudaDeviceEnablePeerAccess(peer_device) from the current device (no-op for the device itself). */
+int tnf_peer_enable_access(int32_t peer_device);
+
+/* Map a buffer another process exported with cudaIpcGetMemHandle (64-byte handle) for the CURRENT device
+ * (cudaIpcOpenMemHandle + lazy peer access), and unmap it again.  *device_ptr is the base of the exported
+ * allocation. */
+#define TNF_IPC_HANDLE_BYTES 64
+/* A zero-filled device allocation of its own (cudaMalloc) on the current device plus the 64-byte
+ * cudaIpcMemHandle_t other processes map it with; tnf_peer_free releases it. */
+int tnf_peer_alloc(size_t bytes, void** device_ptr, void* ipc_handle);
+int tnf_peer_free(void* device_ptr);
+int tnf_peer_open_handle(const void* ipc_handle, void** device_ptr);
+int tnf_peer_close_handle(void* device_ptr);
+
+/* Flag barrier across the ranks of `arena` on `stream` (slot in [0, TNF_PEER_FLAG_SLOTS), epoch strictly
+ * increasing per slot, same value on every rank). */
+int tnf_peer_barrier(const TnfPeerArena* arena, int32_t slot, uint32_t epoch, void* stream);
+
+/* The fused reduce-scatter(mean) + Adam + all-gather described above.  exp_avg / exp_avg_sq hold the
+ * state of this rank's shard only (numel / world_size floats each).  Bracket with tnf_peer_barrier:
+ * before (every rank's gradients are complete) and after (every rank's parameters are written). */
+int tnf_peer_adam_step(const TnfPeerArena* arena, float* exp_avg_shard, float* exp_avg_sq_shard,
+                       const TnfAdamSegment* segments, int32_t num_segments, double beta1, double beta2, float eps,
+                       void* stream);
 
 #ifdef __cplusplus
 }

@@ -41,7 +41,7 @@ def test_every_declared_symbol_is_exported(lib):
 def test_abi_version_and_error_string(lib):
     from thermo_nerf_b200 import _lib
 
-    assert lib.tnf_version() == _lib.TNF_ABI_VERSION == 3
+    assert lib.tnf_version() == _lib.TNF_ABI_VERSION == 4
     assert isinstance(lib.tnf_last_error(), bytes)
 
 
@@ -50,7 +50,7 @@ def test_ctypes_layout_matches_c_header(tmp_path):
 
     names = ["TnfHashGrid", "TnfLinear", "TnfDensityNet", "TnfField", "TnfModel", "TnfCamera", "TnfRays", "TnfOutputs",
              "TnfLinearGrad", "TnfDensityNetGrad", "TnfFieldGrad", "TnfModelGrad", "TnfSaved", "TnfOutputGrads",
-             "TnfLossArgs", "TnfAdamTensor"]
+             "TnfLossArgs", "TnfAdamTensor", "TnfPeerArena", "TnfAdamSegment"]
     probes = {
         "TnfModel": ["field", "num_samples", "training", "near_plane", "anneal", "use_contraction", "aabb",
                      "appearance_mode", "precision", "detach_thermal_geo"],
@@ -64,6 +64,8 @@ def test_ctypes_layout_matches_c_header(tmp_path):
         "TnfOutputGrads": ["accumulation", "weights"],
         "TnfLossArgs": ["num_rays", "num_samples", "interlevel_mult", "grad_scale", "losses", "g_weights"],
         "TnfAdamTensor": ["numel", "lr"],
+        "TnfPeerArena": ["params", "flags", "world_size", "rank", "numel"],
+        "TnfAdamSegment": ["end", "step", "lr", "active"],
         "TnfHashGrid": ["scalings", "num_levels", "log2_size"],
     }
     src = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
@@ -164,3 +166,27 @@ def test_camera_and_postprocess_entry_points_validate_arguments(lib):
     r.from_camera = 1
     rc = lib.tnf_render_backward(C.byref(m), C.byref(r), None, None, None, None, 0, None)
     assert rc == _lib.TNF_ERR_INVALID_ARGUMENT
+
+
+def test_peer_entry_points_validate_arguments(lib):
+    from thermo_nerf_b200 import _lib
+
+    assert lib.tnf_peer_barrier(None, 0, 1, None) == _lib.TNF_ERR_INVALID_ARGUMENT
+    a = _lib.TnfPeerArena()
+    a.world_size, a.rank = 2, 5
+    assert lib.tnf_peer_barrier(C.byref(a), 0, 1, None) == _lib.TNF_ERR_INVALID_ARGUMENT  # rank outside the world
+    a.rank = 1
+    assert lib.tnf_peer_barrier(C.byref(a), 0, 1, None) == _lib.TNF_ERR_INVALID_ARGUMENT  # null flag blocks
+    for r in range(2):
+        a.flags[r] = a.grads[r] = a.params[r] = 256
+    assert lib.tnf_peer_barrier(C.byref(a), 7, 1, None) == _lib.TNF_ERR_INVALID_ARGUMENT  # slot
+    a.numel = 20  # not a multiple of 4 * world_size
+    seg = (_lib.TnfAdamSegment * 1)()
+    assert lib.tnf_peer_adam_step(C.byref(a), 256, 256, seg, 1, 0.9, 0.999, 1e-15, None) == _lib.TNF_ERR_INVALID_ARGUMENT
+    a.numel = 16
+    seg[0].begin, seg[0].end, seg[0].step, seg[0].lr, seg[0].active = 0, 8, 1, 1e-2, 1
+    rc = lib.tnf_peer_adam_step(C.byref(a), 256, 256, seg, 1, 0.9, 0.999, 1e-15, None)
+    assert rc == _lib.TNF_ERR_INVALID_ARGUMENT and b"segments cover" in lib.tnf_last_error()
+    seg[0].end, seg[0].step = 16, 0
+    rc = lib.tnf_peer_adam_step(C.byref(a), 256, 256, seg, 1, 0.9, 0.999, 1e-15, None)
+    assert rc == _lib.TNF_ERR_INVALID_ARGUMENT and b"step" in lib.tnf_last_error()

@@ -1,0 +1,156 @@
+"""The multi-GPU exchange step fused with Adam over NVLink peer memory (tnf_peer_adam_step).
+
+world_size 1 (runs on the single-GPU box): the fused kernel must equal tnf_adam_step bit for bit.
+world_size 2 (skipped without two GPUs): two processes map each other's arenas over CUDA IPC; the result
+must equal "mean of the two gradient arenas, then Adam" computed independently, be identical on both ranks,
+and the flag barriers must never time out."""
+
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_adam(p, g, m, v, lr, step):
+    from thermo_nerf_b200 import functional as F
+
+    F.adam_step([p], [g], [m], [v], [lr], step=step, eps=1e-15)
+
+
+def test_world1_fused_adam_equals_adam_kernel_bitwise():
+    from thermo_nerf_b200.dist import PeerArena
+
+    dev = torch.device("cuda:0")
+    n = 4 * 12345
+    arena = PeerArena(n, dev)
+    assert arena.world == 1 and arena.numel == n and arena.shard == n
+    gen = torch.Generator(device="cpu").manual_seed(0)
+    P = torch.randn(n, generator=gen).to(dev)
+    p_ref, m_ref, v_ref = P.clone(), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    arena.params.copy_(P)
+    for step in (1, 2, 3):
+        G = (torch.randn(n, generator=gen) * 10 ** torch.randint(-8, 1, (n,), generator=gen).float()).to(dev)
+        arena.grads.copy_(G)
+        arena.adam_step([(0, n, 1e-2, step, True)])
+        _ref_adam(p_ref, G.clone(), m_ref, v_ref, 1e-2, step)
+        torch.cuda.synchronize()
+        assert torch.equal(arena.params, p_ref)
+        assert torch.equal(arena.exp_avg, m_ref) and torch.equal(arena.exp_avg_sq, v_ref)
+        assert arena.grads.abs().max().item() == 0.0  # consumed
+    # two optimizer groups, the first one without gradients this step: it must not move
+    cut = 4 * 1000
+    before = arena.params.clone()
+    arena.grads.copy_(torch.randn(n, generator=gen).to(dev))
+    g2 = arena.grads.clone()
+    arena.adam_step([(0, cut, 1e-2, 1, False), (cut, n, 5e-3, 4, True)])
+    _ref_adam(p_ref[cut:], g2[cut:].clone(), m_ref[cut:], v_ref[cut:], 5e-3, 4)
+    torch.cuda.synchronize()
+    assert torch.equal(arena.params[:cut], before[:cut])
+    assert torch.equal(arena.params[cut:], p_ref[cut:])
+    assert arena.timeouts() == 0
+
+
+def test_engine_with_fused_exchange_trains():
+    """TrainEngine(peer_fused=True) on one GPU: parameters live in the peer arena, the fused kernel replaces the
+    two Adam launches, and a fixed batch is fitted as with the plain engine."""
+    from oracle import make_synthetic_rays
+    from tests.helpers import make_pair
+    from thermo_nerf_b200.engine import TrainEngine
+
+    losses = {}
+    for fused in (False, True):
+        _, model = make_pair(trained_like=False, precision="tc_fp16", log2_field=14, log2_prop=12)
+        model.train()
+        eng = TrainEngine(model, peer_fused=fused)
+        rays = make_synthetic_rays(1024, num_images=8, seed=5)
+        gen = torch.Generator().manual_seed(1)
+        gt_rgb = torch.rand((1024, 3), generator=gen).mul(0.2).add(0.4).cuda()
+        gt_th = torch.rand((1024,), generator=gen).mul(0.2).add(0.6).cuda()
+        jit = torch.rand((3, 1024), generator=gen).cuda()
+        o, d, c = rays.origins.cuda(), rays.directions.cuda(), rays.camera_indices.cuda().reshape(-1)
+        hist = []
+        for _ in range(30):
+            ls = eng.step(o, d, c, gt_rgb, gt_th, jitter=jit)
+            hist.append(float(ls[0] + ls[3]))
+        losses[fused] = hist
+        if fused:
+            assert eng.arena is not None and eng.arena.timeouts() == 0
+            # the module's parameters are views of the arena the kernel writes
+            p0 = model.field.mlp_base.encoder.hash_table
+            assert p0.data_ptr() == eng.arena.params[eng.offsets[10]:].data_ptr()
+    for fused in (False, True):
+        assert losses[fused][-1] < 0.5 * losses[fused][0], losses[fused]
+    assert abs(losses[True][0] - losses[False][0]) < 1e-6  # identical first forward
+    assert abs(losses[True][-1] - losses[False][-1]) < 0.2 * losses[False][-1]
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank: int, world: int, port: int, q) -> None:
+    import torch.distributed as dist
+
+    from thermo_nerf_b200.dist import PeerArena
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        n = 8 * 54321
+        arena = PeerArena(n, dev)
+        gen = torch.Generator().manual_seed(123)
+        P = torch.randn(n, generator=gen).to(dev)  # identical on every rank
+        arena.params.copy_(P)
+        p_ref, m_ref, v_ref = P.clone(), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+        ok = True
+        for step in (1, 2, 3, 4):
+            g_all = [torch.randn(n, generator=torch.Generator().manual_seed(1000 * step + r)) for r in range(world)]
+            arena.grads.copy_(g_all[rank].to(dev))
+            arena.adam_step([(0, n, 1e-2, step, True)])
+            mean = torch.zeros(n, device=dev)
+            for g in g_all:  # rank order, as the kernel sums
+                mean += g.to(dev)
+            mean *= 1.0 / world
+            from thermo_nerf_b200 import functional as F
+
+            F.adam_step([p_ref], [mean], [m_ref], [v_ref], [1e-2], step=step, eps=1e-15)
+            torch.cuda.synchronize()
+            ok = ok and bool(torch.equal(arena.params, p_ref)) and arena.grads.abs().max().item() == 0.0
+            lo, hi = arena.shard * rank, arena.shard * (rank + 1)
+            ok = ok and bool(torch.equal(arena.exp_avg, m_ref[lo:hi]))
+        # every rank holds the same parameters
+        chk = arena.params.double().sum().reshape(1)
+        both = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(both, chk)
+        same = all(float(b) == float(both[0]) for b in both)
+        q.put((rank, ok, same, arena.timeouts()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.timeout(300)
+def test_world2_fused_exchange_matches_mean_then_adam():
+    import torch.multiprocessing as mp
+
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    for rank, ok, same, timeouts in out:
+        assert ok, f"rank {rank}: fused result differs from mean-then-Adam"
+        assert same and timeouts == 0

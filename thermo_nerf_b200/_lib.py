@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 from typing import Optional
 
-TNF_ABI_VERSION = 3
+TNF_ABI_VERSION = 4
 TNF_MAX_LEVELS = 16
 TNF_MAX_PROP_LEVELS = 8
 TNF_MAX_SAMPLES = 256
@@ -207,6 +207,35 @@ class TnfAdamTensor(C.Structure):
     ]
 
 
+TNF_MAX_PEERS = 16
+TNF_PEER_FLAG_SLOTS = 2
+TNF_PEER_FLAG_TIMEOUT = 32
+TNF_PEER_FLAG_WORDS = 64
+TNF_MAX_ADAM_SEGMENTS = 4
+TNF_IPC_HANDLE_BYTES = 64
+
+
+class TnfPeerArena(C.Structure):
+    _fields_ = [
+        ("grads", _fp * TNF_MAX_PEERS),
+        ("params", _fp * TNF_MAX_PEERS),
+        ("flags", _fp * TNF_MAX_PEERS),
+        ("world_size", C.c_int32),
+        ("rank", C.c_int32),
+        ("numel", C.c_int64),
+    ]
+
+
+class TnfAdamSegment(C.Structure):
+    _fields_ = [
+        ("begin", C.c_int64),
+        ("end", C.c_int64),
+        ("step", C.c_int64),
+        ("lr", C.c_float),
+        ("active", C.c_int32),
+    ]
+
+
 # every symbol include/tnf_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = (
     "tnf_version",
@@ -220,6 +249,13 @@ EXPORTED_SYMBOLS = (
     "tnf_backward_stage_mask",
     "tnf_losses",
     "tnf_adam_step",
+    "tnf_peer_enable_access",
+    "tnf_peer_alloc",
+    "tnf_peer_free",
+    "tnf_peer_open_handle",
+    "tnf_peer_close_handle",
+    "tnf_peer_barrier",
+    "tnf_peer_adam_step",
 )
 
 
@@ -304,6 +340,21 @@ def load() -> C.CDLL:
         C.c_int32,
         C.c_void_p,
     ]
+    lib.tnf_peer_enable_access.restype = C.c_int
+    lib.tnf_peer_enable_access.argtypes = [C.c_int32]
+    lib.tnf_peer_alloc.restype = C.c_int
+    lib.tnf_peer_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]
+    lib.tnf_peer_free.restype = C.c_int
+    lib.tnf_peer_free.argtypes = [C.c_void_p]
+    lib.tnf_peer_open_handle.restype = C.c_int
+    lib.tnf_peer_open_handle.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.tnf_peer_close_handle.restype = C.c_int
+    lib.tnf_peer_close_handle.argtypes = [C.c_void_p]
+    lib.tnf_peer_barrier.restype = C.c_int
+    lib.tnf_peer_barrier.argtypes = [C.POINTER(TnfPeerArena), C.c_int32, C.c_uint32, C.c_void_p]
+    lib.tnf_peer_adam_step.restype = C.c_int
+    lib.tnf_peer_adam_step.argtypes = [C.POINTER(TnfPeerArena), C.c_void_p, C.c_void_p, C.POINTER(TnfAdamSegment),
+                                       C.c_int32, C.c_double, C.c_double, C.c_float, C.c_void_p]
     got = lib.tnf_version()
     if got != TNF_ABI_VERSION:
         raise ImportError(f"{path}: ABI version {got}, binding expects {TNF_ABI_VERSION}")

@@ -1,0 +1,267 @@
+// Multi-GPU exchange step of the training path: the gradient all-reduce that nerfstudio's DDP
+// performs between backward and optimizer.step, fused with the Adam update of
+// thermo_nerf/thermal_nerf/config_thermal_nerf.py:32-45 into ONE kernel over NVLink peer memory.
+//
+//   every rank owns 1/N of the flat parameter arena.  tnf_peer_adam_kernel on rank r
+//     - reads shard r of EVERY rank's gradient arena (its own from HBM, the others as peer loads over
+//       NVLink / NVSwitch) and averages them            -> reduce-scatter(mean)
+//     - applies Adam to shard r (exp_avg / exp_avg_sq exist only for the owned shard)
+//     - stores the updated shard into EVERY rank's parameter arena (peer stores)   -> all-gather
+//   so the gradient bytes cross the fabric once in each direction, the optimizer state is sharded N ways
+//   and no rank re-computes another rank's update.  Two flag barriers (system-scope release/acquire on
+//   peer-mapped words) order it against the backward before and the forward after.
+//
+// The sum over ranks runs in rank order on the owner only, so parameters stay bit-identical on all ranks.
+#include <cstring>
+
+#include "tnf_device.cuh"
+#include "tnf_host.h"
+
+namespace tnf {
+
+struct PeerAdamArgs {
+  TnfPeerArena a;
+  long long shard_begin, shard_end;  // float indices (multiples of 4) of the shard this rank owns
+  float* m;                          // exp_avg of the shard    [shard_end - shard_begin]
+  float* v;                          // exp_avg_sq of the shard
+  long long seg_end[TNF_MAX_ADAM_SEGMENTS];
+  float seg_step_size[TNF_MAX_ADAM_SEGMENTS];     // lr / bias_correction1
+  float seg_inv_sqrt_bc2[TNF_MAX_ADAM_SEGMENTS];
+  int seg_active[TNF_MAX_ADAM_SEGMENTS];
+  int nseg;
+  float beta2, eps, omb1, omb2, inv_world;
+};
+
+__device__ __forceinline__ void peer_adam_one(float& p, float g, float& m, float& v, const PeerAdamArgs& a,
+                                              const float step_size, const float inv_sqrt_bc2) {
+  m = m + a.omb1 * (g - m);
+  v = a.beta2 * v + a.omb2 * (g * g);
+  const float denom = sqrtf(v) * inv_sqrt_bc2 + a.eps;
+  p = p - step_size * (m / denom);
+}
+
+__global__ void __launch_bounds__(256) tnf_peer_adam_kernel(const __grid_constant__ PeerAdamArgs A) {
+  const long long n4 = (A.shard_end - A.shard_begin) >> 2;
+  const int W = A.a.world_size, me = A.a.rank;
+  float4* __restrict__ M = reinterpret_cast<float4*>(A.m);
+  float4* __restrict__ V = reinterpret_cast<float4*>(A.v);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long e = A.shard_begin + 4 * i;
+    int s = 0;
+    while (s + 1 < A.nseg && e >= A.seg_end[s]) ++s;
+    if (!A.seg_active[s]) continue;
+    // reduce-scatter: this element of every rank's gradient arena (cache-volatile: peer lines are only
+    // L1-cacheable here and must never be served stale)
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int r = 0; r < W; ++r) {
+      const float4 t = __ldcv(reinterpret_cast<const float4*>(A.a.grads[r] + e));
+      g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+    }
+    g.x *= A.inv_world; g.y *= A.inv_world; g.z *= A.inv_world; g.w *= A.inv_world;
+    float4 p = *reinterpret_cast<const float4*>(A.a.params[me] + e);
+    float4 m = M[i], v = V[i];
+    const float ss = A.seg_step_size[s], ib = A.seg_inv_sqrt_bc2[s];
+    peer_adam_one(p.x, g.x, m.x, v.x, A, ss, ib);
+    peer_adam_one(p.y, g.y, m.y, v.y, A, ss, ib);
+    peer_adam_one(p.z, g.z, m.z, v.z, A, ss, ib);
+    peer_adam_one(p.w, g.w, m.w, v.w, A, ss, ib);
+    M[i] = m;
+    V[i] = v;
+    // all-gather: the updated shard goes to every rank's parameter arena
+#pragma unroll 8
+    for (int r = 0; r < W; ++r) *reinterpret_cast<float4*>(A.a.params[r] + e) = p;
+  }
+}
+
+// Flag barrier over peer-mapped words: rank r writes `epoch` into word [slot][r] of every rank's flag block
+// (release, system scope) and waits until every word of its own block reached `epoch` (acquire).
+// The wait is bounded (~2 s of SM clocks): a missing peer raises word [TNF_PEER_FLAG_TIMEOUT] instead of
+// hanging the GPU.
+__global__ void tnf_peer_barrier_kernel(const __grid_constant__ TnfPeerArena a, const int slot, const unsigned epoch) {
+  const int t = threadIdx.x;
+  if (t >= a.world_size) return;
+  __threadfence_system();
+  unsigned* dst = a.flags[t] + slot * TNF_MAX_PEERS + a.rank;
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
+  const unsigned* src = a.flags[a.rank] + slot * TNF_MAX_PEERS + t;
+  const long long t0 = clock64();
+  unsigned seen = 0;
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(src) : "memory");
+    if ((int)(seen - epoch) >= 0) break;
+    if (clock64() - t0 > 4000000000LL) {
+      atomicAdd(a.flags[a.rank] + TNF_PEER_FLAG_TIMEOUT, 1u);
+      break;
+    }
+  }
+  __threadfence_system();
+}
+
+}  // namespace tnf
+
+extern "C" {
+
+int tnf_peer_enable_access(int32_t peer_device) {
+  using tnf::fail;
+  tnf::g_err[0] = 0;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+  if (peer_device == dev) return TNF_OK;
+  int can = 0;
+  e = cudaDeviceCanAccessPeer(&can, dev, peer_device);
+  if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "cudaDeviceCanAccessPeer: %s", cudaGetErrorString(e));
+  if (!can) return fail(TNF_ERR_UNSUPPORTED_CONFIG, "device %d cannot access device %d (no NVLink/PCIe P2P)", dev,
+                        peer_device);
+  e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();  // clear the sticky-free error
+    return TNF_OK;
+  }
+  if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", peer_device, cudaGetErrorString(e));
+  return TNF_OK;
+}
+
+int tnf_peer_alloc(size_t bytes, void** device_ptr, void* ipc_handle) {
+  using tnf::fail;
+  tnf::g_err[0] = 0;
+  if (!device_ptr || !ipc_handle || bytes == 0) return fail(TNF_ERR_INVALID_ARGUMENT, "device_ptr/ipc_handle null or bytes == 0");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);  // its own allocation: cudaIpcGetMemHandle wants the base pointer
+  if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+  e = cudaMemset(p, 0, bytes);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    cudaGetLastError();
+    return fail(TNF_ERR_CUDA, "cudaMemset/cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+  }
+  memcpy(ipc_handle, &h, sizeof(h));
+  *device_ptr = p;
+  return TNF_OK;
+}
+
+int tnf_peer_free(void* device_ptr) {
+  using tnf::fail;
+  tnf::g_err[0] = 0;
+  if (!device_ptr) return TNF_OK;
+  const cudaError_t e = cudaFree(device_ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(TNF_ERR_CUDA, "cudaFree: %s", cudaGetErrorString(e));
+  }
+  return TNF_OK;
+}
+
+int tnf_peer_open_handle(const void* ipc_handle, void** device_ptr) {
+  using tnf::fail;
+  tnf::g_err[0] = 0;
+  if (!ipc_handle || !device_ptr) return fail(TNF_ERR_INVALID_ARGUMENT, "ipc_handle/device_ptr is null");
+  cudaIpcMemHandle_t h;
+  static_assert(sizeof(h) == TNF_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+  memcpy(&h, ipc_handle, sizeof(h));
+  // opened with the CONSUMER device current: the mapping (and, for a remote GPU, peer access) is created
+  // for the device whose kernels will dereference the pointer
+  const cudaError_t e = cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(TNF_ERR_CUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+  }
+  return TNF_OK;
+}
+
+int tnf_peer_close_handle(void* device_ptr) {
+  using tnf::fail;
+  tnf::g_err[0] = 0;
+  if (!device_ptr) return TNF_OK;
+  const cudaError_t e = cudaIpcCloseMemHandle(device_ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(TNF_ERR_CUDA, "cudaIpcCloseMemHandle: %s", cudaGetErrorString(e));
+  }
+  return TNF_OK;
+}
+
+static int check_arena(const TnfPeerArena* a) {
+  using tnf::fail;
+  if (!a) return fail(TNF_ERR_INVALID_ARGUMENT, "arena is null");
+  if (a->world_size < 1 || a->world_size > TNF_MAX_PEERS || a->rank < 0 || a->rank >= a->world_size)
+    return fail(TNF_ERR_INVALID_ARGUMENT, "world_size=%d rank=%d (at most %d peers)", a->world_size, a->rank,
+                TNF_MAX_PEERS);
+  for (int r = 0; r < a->world_size; ++r)
+    if (!a->flags[r]) return fail(TNF_ERR_INVALID_ARGUMENT, "flags[%d] is null", r);
+  return TNF_OK;
+}
+
+int tnf_peer_barrier(const TnfPeerArena* arena, int32_t slot, uint32_t epoch, void* stream_) {
+  using tnf::fail;
+  tnf::g_err[0] = 0;
+  if (int rc = check_arena(arena)) return rc;
+  if (slot < 0 || slot >= TNF_PEER_FLAG_SLOTS) return fail(TNF_ERR_INVALID_ARGUMENT, "slot=%d", slot);
+  tnf::tnf_peer_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream_)>>>(*arena, slot, epoch);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "peer barrier launch: %s", cudaGetErrorString(e));
+  return TNF_OK;
+}
+
+int tnf_peer_adam_step(const TnfPeerArena* arena, float* exp_avg_shard, float* exp_avg_sq_shard,
+                       const TnfAdamSegment* segments, int32_t num_segments, double beta1, double beta2, float eps,
+                       void* stream_) {
+  using tnf::fail;
+  tnf::g_err[0] = 0;
+  if (int rc = check_arena(arena)) return rc;
+  const int W = arena->world_size;
+  if (arena->numel < 0 || arena->numel % (4LL * W) != 0)
+    return fail(TNF_ERR_INVALID_ARGUMENT, "arena numel=%lld must be a multiple of 4*world_size", (long long)arena->numel);
+  for (int r = 0; r < W; ++r)
+    if (!arena->grads[r] || !arena->params[r] || !tnf::aligned16(arena->grads[r]) || !tnf::aligned16(arena->params[r]))
+      return fail(TNF_ERR_INVALID_ARGUMENT, "grads[%d]/params[%d] null or not 16-byte aligned", r, r);
+  if (!exp_avg_shard || !exp_avg_sq_shard || !tnf::aligned16(exp_avg_shard) || !tnf::aligned16(exp_avg_sq_shard))
+    return fail(TNF_ERR_INVALID_ARGUMENT, "exp_avg/exp_avg_sq shard null or not 16-byte aligned");
+  if (!segments || num_segments < 1 || num_segments > TNF_MAX_ADAM_SEGMENTS)
+    return fail(TNF_ERR_INVALID_ARGUMENT, "num_segments=%d not in [1,%d]", num_segments, TNF_MAX_ADAM_SEGMENTS);
+  tnf::PeerAdamArgs A;
+  A.a = *arena;
+  const long long shard = arena->numel / W;
+  A.shard_begin = shard * arena->rank;
+  A.shard_end = A.shard_begin + shard;
+  A.m = exp_avg_shard;
+  A.v = exp_avg_sq_shard;
+  long long prev = 0;
+  for (int s = 0; s < num_segments; ++s) {
+    const TnfAdamSegment& g = segments[s];
+    if (g.begin != prev || g.end < g.begin || (g.end & 3))
+      return fail(TNF_ERR_INVALID_ARGUMENT, "segment %d: [%lld,%lld) must continue the previous one and end on a "
+                  "multiple of 4", s, (long long)g.begin, (long long)g.end);
+    if (g.active && g.step < 1) return fail(TNF_ERR_INVALID_ARGUMENT, "segment %d: step=%lld must be >= 1", s,
+                                           (long long)g.step);
+    prev = g.end;
+    A.seg_end[s] = g.end;
+    A.seg_active[s] = g.active != 0;
+    const double st = g.active ? (double)g.step : 1.0;
+    A.seg_step_size[s] = (float)((double)g.lr / (1.0 - pow(beta1, st)));
+    A.seg_inv_sqrt_bc2[s] = 1.0f / (float)sqrt(1.0 - pow(beta2, st));
+  }
+  if (prev != arena->numel) return fail(TNF_ERR_INVALID_ARGUMENT, "segments cover %lld of %lld elements", prev,
+                                        (long long)arena->numel);
+  A.nseg = num_segments;
+  A.omb1 = (float)(1.0 - beta1);
+  A.omb2 = (float)(1.0 - beta2);
+  A.beta2 = (float)beta2;
+  A.eps = eps;
+  A.inv_world = 1.0f / (float)W;
+  const long long n4 = shard >> 2;
+  if (n4 == 0) return TNF_OK;
+  long long blocks = (n4 + 255) / 256;
+  const long long cap = (long long)tnf::num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  tnf::tnf_peer_adam_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream_)>>>(A);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "peer adam launch: %s", cudaGetErrorString(e));
+  return TNF_OK;
+}
+
+}  // extern "C"

@@ -90,3 +90,124 @@ def gather_frames(frames: Tensor, num_frames: int, group=None) -> Optional[Tenso
         idx = shard_frames(num_frames, r, world)
         out[idx] = bufs[r][: len(idx)]
     return out
+
+
+class _DeviceMemory:
+    """``__cuda_array_interface__`` view of memory owned by a PeerArena (keeps the arena alive)."""
+
+    def __init__(self, ptr: int, shape: tuple, typestr: str, owner) -> None:
+        self.owner = owner
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2,
+                                         "strides": None}
+
+
+def _wrap_device_memory(ptr: int, shape: tuple, typestr: str, device, owner) -> Tensor:
+    return torch.as_tensor(_DeviceMemory(ptr, shape, typestr, owner), device=device)
+
+
+class PeerArena:
+    """Flat gradient + parameter arenas of every rank mapped into this process (CUDA IPC over NVLink peer
+    memory), for ``tnf_peer_adam_step``: the gradient mean over ranks fused with Adam in one kernel
+    (reduce-scatter -> Adam on the owned shard -> all-gather), bracketed by two flag barriers.
+
+    ``torch.distributed`` is only the plumbing here (it carries the IPC handles once, at construction);
+    the per-step exchange is our kernel reading and writing peer memory.  world_size 1 degenerates to a
+    local fused Adam, which is what the single-GPU tests exercise."""
+
+    def __init__(self, numel: int, device, group=None) -> None:
+        import ctypes as C
+
+        from . import _lib as L
+
+        self._L, self._C = L, C
+        self.lib = L.load()
+        self.rank, self.world = world_info(group)
+        if self.world > L.TNF_MAX_PEERS:
+            raise ValueError(f"at most {L.TNF_MAX_PEERS} ranks")
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("PeerArena needs a CUDA device; there is no CPU path")
+        pad = 4 * self.world
+        self.numel = (int(numel) + pad - 1) // pad * pad
+        self.shard = self.numel // self.world
+        self.device = dev
+        # one cudaMalloc of our own per rank: [gradients | parameters | flag block].  (Tensors of the caching
+        # allocator sit inside larger segments, and the IPC handle has to name an allocation's base.)
+        arena_bytes = self.numel * 4
+        total_bytes = 2 * arena_bytes + L.TNF_PEER_FLAG_WORDS * 4
+        handle = C.create_string_buffer(L.TNF_IPC_HANDLE_BYTES)
+        base = C.c_void_p()
+        with torch.cuda.device(dev):
+            L.check(self.lib.tnf_peer_alloc(total_bytes, C.byref(base), handle))
+        self._base = int(base.value)
+        self.grads = _wrap_device_memory(self._base, (self.numel,), "<f4", dev, self)
+        self.params = _wrap_device_memory(self._base + arena_bytes, (self.numel,), "<f4", dev, self)
+        self.flags = _wrap_device_memory(self._base + 2 * arena_bytes, (L.TNF_PEER_FLAG_WORDS,), "<i4", dev, self)
+        self._mapped: dict = {}  # rank -> base pointer of that rank's allocation mapped for this device
+        bases = [self._base] * self.world
+        if self.world > 1:
+            gathered: List[object] = [None] * self.world
+            dist.all_gather_object(gathered, (bytes(handle.raw), self.numel), group=group)
+            with torch.cuda.device(dev):  # handles are opened with the consumer device current
+                for r, (h, n) in enumerate(gathered):
+                    if n != self.numel:
+                        raise RuntimeError("ranks disagree on the arena size")
+                    if r == self.rank:
+                        continue
+                    out = C.c_void_p()
+                    L.check(self.lib.tnf_peer_open_handle(h, C.byref(out)))
+                    self._mapped[r] = int(out.value)
+                    bases[r] = int(out.value)
+            dist.barrier(group=group)
+        ptrs = [(b, b + arena_bytes, b + 2 * arena_bytes) for b in bases]
+        a = L.TnfPeerArena()
+        for r, (g, p, f) in enumerate(ptrs):
+            a.grads[r], a.params[r], a.flags[r] = g, p, f
+        a.world_size, a.rank, a.numel = self.world, self.rank, self.numel
+        self.struct = a
+        self.exp_avg = torch.zeros(self.shard, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(self.shard, dtype=torch.float32, device=dev)
+        self._epoch = [0] * L.TNF_PEER_FLAG_SLOTS
+        if self.world > 1:
+            # self-test of the mappings in both directions: one barrier round must complete without a time-out
+            self.barrier(0)
+            torch.cuda.synchronize(dev)
+            if self.timeouts() != 0:
+                raise RuntimeError("peer flag barrier timed out: the IPC mappings are not reachable")
+
+    def close(self) -> None:
+        """Unmap the peers' allocations (the own allocation lives as long as tensors view it)."""
+        for base in self._mapped.values():
+            self.lib.tnf_peer_close_handle(self._C.c_void_p(base))
+        self._mapped = {}
+
+    def barrier(self, slot: int) -> None:
+        """Stream-ordered barrier over all ranks (flag words in peer memory; no NCCL call)."""
+        self._epoch[slot] += 1
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            self._L.check(self.lib.tnf_peer_barrier(self._C.byref(self.struct), slot, self._epoch[slot],
+                                                    self._C.c_void_p(stream)))
+
+    def adam_step(self, segments: Sequence[tuple], beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-15,
+                  zero_grads: bool = True) -> None:
+        """``segments`` = [(begin, end, lr, step, active), ...] covering [0, numel).  Runs
+        barrier -> fused reduce-scatter/Adam/all-gather -> barrier (-> zero this rank's gradient arena)."""
+        L, C = self._L, self._C
+        segs = (L.TnfAdamSegment * len(segments))()
+        for i, (b, e, lr, step, active) in enumerate(segments):
+            segs[i].begin, segs[i].end, segs[i].lr = int(b), int(e), float(lr)
+            segs[i].step, segs[i].active = int(step), int(bool(active))
+        self.barrier(0)  # every rank's backward has written its gradient arena
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            L.check(self.lib.tnf_peer_adam_step(C.byref(self.struct), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                                segs, len(segments), float(beta1), float(beta2), float(eps),
+                                                C.c_void_p(stream)))
+        self.barrier(1)  # every rank's shard has landed in everybody's parameter arena
+        if zero_grads:
+            self.grads.zero_()
+
+    def timeouts(self) -> int:
+        """Number of barrier waits that gave up (a peer never arrived); 0 in a healthy run."""
+        return int(self.flags[self._L.TNF_PEER_FLAG_TIMEOUT].item())

@@ -24,7 +24,7 @@ from torch import Tensor
 
 from . import _lib as L
 from . import functional as F
-from .dist import allreduce_mean_
+from .dist import PeerArena, allreduce_mean_
 
 NUM_PROP_TENSORS = 5 * L.TNF_NUM_PROP  # leading entries of ModelTensors.param_list()
 
@@ -37,7 +37,8 @@ def exponential_decay_lr(step: int, lr_init: float = 1e-2, lr_final: float = 1e-
 
 class TrainEngine:
     def __init__(self, model, *, lr: float = 1e-2, lr_final: float = 1e-4, lr_max_steps: int = 200000,
-                 betas=(0.9, 0.999), eps: float = 1e-15, process_group=None, world_size: int = 1) -> None:
+                 betas=(0.9, 0.999), eps: float = 1e-15, process_group=None, world_size: int = 1,
+                 peer_fused: bool = False) -> None:
         self.model = model
         self.cfg = model.config
         self.tensors = model.tensors()
@@ -51,14 +52,34 @@ class TrainEngine:
         for p in self.params:
             offs.append(total)
             total += (p.numel() + 3) // 4 * 4
-        self.grad_arena = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.m_arena = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.v_arena = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.offsets, self.total = offs, total
+        self.prop_end = offs[NUM_PROP_TENSORS]  # [0, prop_end): proposal networks, [prop_end, total): field
+        self.arena: Optional[PeerArena] = None
 
         def views(arena):
             return [arena[o:o + p.numel()].view_as(p) for o, p in zip(offs, self.params)]
 
-        self.grads, self.exp_avg, self.exp_avg_sq = views(self.grad_arena), views(self.m_arena), views(self.v_arena)
+        if peer_fused:
+            # multi-GPU exchange fused with Adam over NVLink peer memory (tnf_peer_adam_step): parameters move
+            # into a peer-mapped arena (every rank writes its updated shard into everybody's copy), the gradient
+            # arena is peer-mapped too, and the Adam state exists only for the shard this rank owns
+            self.arena = PeerArena(total, dev, process_group)
+            with torch.no_grad():
+                for v, p in zip(views(self.arena.params), self.params):
+                    v.copy_(p)
+                    p.data = v
+            model._tensors = None
+            self.tensors = model.tensors()
+            self.params = self.tensors.param_list()
+            self.grad_arena = self.arena.grads
+            self.m_arena, self.v_arena = self.arena.exp_avg, self.arena.exp_avg_sq  # this rank's shard
+            self.grads = views(self.grad_arena)
+            self.exp_avg = self.exp_avg_sq = None
+        else:
+            self.grad_arena = torch.zeros(total, dtype=torch.float32, device=dev)
+            self.m_arena = torch.zeros(total, dtype=torch.float32, device=dev)
+            self.v_arena = torch.zeros(total, dtype=torch.float32, device=dev)
+            self.grads, self.exp_avg, self.exp_avg_sq = views(self.grad_arena), views(self.m_arena), views(self.v_arena)
         self.lr, self.lr_final, self.lr_max_steps = lr, lr_final, lr_max_steps
         self.betas, self.eps = betas, eps
         self.pg, self.world_size = process_group, world_size
@@ -112,18 +133,24 @@ class TrainEngine:
         res["_workspace"] = self._ws
         F.render_backward(self.tensors, res["_model_struct"], origins, directions, cam, None, None, jitter, res,
                           {"rgb": g["rgb"], "thermal": g["thermal"], "weights_list": g["weights_list"]}, grads)
-        if self.world_size > 1:
-            # DDP semantics: average over ranks.  The proposal part of the arena is all zeros on
-            # non-updated steps (the schedule is identical on every rank), so one collective covers both.
-            allreduce_mean_(self.grad_arena, self.pg, self.world_size)
         lr = exponential_decay_lr(step, self.lr, self.lr_final, self.lr_max_steps)
-        sl_f = slice(NUM_PROP_TENSORS, len(self.params))
         self.field_steps += 1
-        self._adam(sl_f, lr, self.field_steps)
         if updated:
             self.prop_steps += 1
-            self._adam(slice(0, NUM_PROP_TENSORS), lr, self.prop_steps)
             self.steps_since_update = 0
+        if self.arena is not None:
+            # one kernel: mean over ranks (peer loads) + Adam on the owned shard + parameter broadcast (peer stores)
+            self.arena.adam_step([(0, self.prop_end, lr, max(self.prop_steps, 1), updated),
+                                  (self.prop_end, self.arena.numel, lr, self.field_steps, True)],
+                                 beta1=self.betas[0], beta2=self.betas[1], eps=self.eps)
+        else:
+            if self.world_size > 1:
+                # DDP semantics: average over ranks.  The proposal part of the arena is all zeros on
+                # non-updated steps (the schedule is identical on every rank), so one collective covers both.
+                allreduce_mean_(self.grad_arena, self.pg, self.world_size)
+            self._adam(slice(NUM_PROP_TENSORS, len(self.params)), lr, self.field_steps)
+            if updated:
+                self._adam(slice(0, NUM_PROP_TENSORS), lr, self.prop_steps)
         self.step_count += 1
         self.steps_since_update += 1  # ProposalNetworkSampler.step_cb (AFTER_TRAIN_ITERATION)
         return losses
