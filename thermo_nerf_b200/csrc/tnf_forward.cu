@@ -341,31 +341,54 @@ __device__ __forceinline__ void field_level(const TnfModel& m, Smem<TNF_PRECISIO
 
 // ------------------------------------------------------------------------------------
 // the kernel
+//
+// PHASE_ALL   the whole per-ray loop in one launch (eval / render: nothing per-sample reaches HBM)
+// PHASE_PROP  the two proposal levels + both resamplings only; the 49 spacing bins of the final level go
+//             to out.sdist[2] (training writes them anyway as ray_samples_list).  No tensor-core code in
+//             this instantiation, so it compiles to half the registers and runs at twice the occupancy -
+//             what the gather-latency-bound proposal levels want.
+// PHASE_FIELD the field level + compositing, reading the bins PHASE_PROP wrote.
 // ------------------------------------------------------------------------------------
+enum { PHASE_ALL = 0, PHASE_PROP = 1, PHASE_FIELD = 2 };
+
+struct SmemProp {
+  PropW prop[TNF_NUM_PROP];
+  WarpScratch ws[kWarpsPerCta];
+};
+template <int PREC, int PHASE>
+struct SmemSel { using type = Smem<PREC>; };
 template <int PREC>
-__global__ void __launch_bounds__(kThreads, PREC == TNF_PRECISION_TC_FP16 ? 2 : 1)
+struct SmemSel<PREC, PHASE_PROP> { using type = SmemProp; };
+
+template <int PREC, int PHASE, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
     tnf_forward_kernel(const __grid_constant__ TnfModel m, const __grid_constant__ TnfRays rays,
                        const __grid_constant__ TnfOutputs out, const long long chunk,
                        unsigned* __restrict__ clip_min, unsigned* __restrict__ clip_max) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem<PREC>& S = *reinterpret_cast<Smem<PREC>*>(smem_raw);
+  using SmemT = typename SmemSel<PREC, PHASE>::type;
+  SmemT& S = *reinterpret_cast<SmemT*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   // ---- stage weights
-  if (warp == 0) {
-    float e = 0.f;
-    if (m.appearance_mode == TNF_APPEARANCE_MEAN) {
-      for (int i = 0; i < m.field.num_images; ++i) e += m.field.appearance[i * 32 + lane];
-      e /= (float)m.field.num_images;
-    }
-    S.fc.app_const[lane] = e;
-  }
-  stage_prop(S.prop[0], m.prop[0], tid);
-  stage_prop(S.prop[1], m.prop[1], tid);
-  stage_field(S.fw, m.field, tid);
-  __syncthreads();
   const bool lookup = m.appearance_mode == TNF_APPEARANCE_LOOKUP;
-  stage_common(S.fc, m.field, !lookup, tid);
+  if constexpr (PHASE != PHASE_FIELD) {
+    stage_prop(S.prop[0], m.prop[0], tid);
+    stage_prop(S.prop[1], m.prop[1], tid);
+  }
+  if constexpr (PHASE != PHASE_PROP) {
+    if (warp == 0) {
+      float e = 0.f;
+      if (m.appearance_mode == TNF_APPEARANCE_MEAN) {
+        for (int i = 0; i < m.field.num_images; ++i) e += m.field.appearance[i * 32 + lane];
+        e /= (float)m.field.num_images;
+      }
+      S.fc.app_const[lane] = e;
+    }
+    stage_field(S.fw, m.field, tid);
+    __syncthreads();
+    stage_common(S.fc, m.field, !lookup, tid);
+  }
   __syncthreads();
 
   WarpScratch& ws = S.ws[warp];
@@ -402,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, PREC == TNF_PRECISION_TC_FP16 ? 2 : 
     }
 
     // ---- per-ray first-layer bias of the colour head: bias + W_sh * SH((d+1)/2) [+ W_app * e_cam]
-    {
+    if constexpr (PHASE != PHASE_PROP) {
       float sh[16];
       sh4((rc.dx + 1.f) * 0.5f, (rc.dy + 1.f) * 0.5f, (rc.dz + 1.f) * 0.5f, sh);
       float b0 = S.fc.rgb0b[lane], b1 = S.fc.rgb0b[lane + 32];
@@ -425,16 +448,34 @@ __global__ void __launch_bounds__(kThreads, PREC == TNF_PRECISION_TC_FP16 ? 2 : 
       ws.rayb[lane + 32] = b1;
     }
 
-    // ---- level 0
-    const float pd0 = proposal_level<0>(m, S.prop[0], ws, rc, S0, stratified, jit0, lane,
-                                        out.weights[0] ? out.weights[0] + ray * S0 : nullptr,
-                                        out.sdist[0] ? out.sdist[0] + ray * (S0 + 1) : nullptr);
-    pdf_resample<PREC == TNF_PRECISION_TC_FP16>(ws, S0, S1, m.anneal, stratified, jit0, jit1, nullptr, ws.bins, lane);
-    // ---- level 1
-    const float pd1 = proposal_level<1>(m, S.prop[1], ws, rc, S1, stratified, jit1, lane,
-                                        out.weights[1] ? out.weights[1] + ray * S1 : nullptr,
-                                        out.sdist[1] ? out.sdist[1] + ray * (S1 + 1) : nullptr);
-    pdf_resample<PREC == TNF_PRECISION_TC_FP16>(ws, S1, S2, m.anneal, stratified, jit1, jit2, ws.bins, ws.w, lane);
+    float pd0 = 0.f, pd1 = 0.f;
+    if constexpr (PHASE != PHASE_FIELD) {
+      // ---- level 0
+      pd0 = proposal_level<0>(m, S.prop[0], ws, rc, S0, stratified, jit0, lane,
+                              out.weights[0] ? out.weights[0] + ray * S0 : nullptr,
+                              out.sdist[0] ? out.sdist[0] + ray * (S0 + 1) : nullptr);
+      pdf_resample<PREC == TNF_PRECISION_TC_FP16>(ws, S0, S1, m.anneal, stratified, jit0, jit1, nullptr, ws.bins, lane);
+      // ---- level 1
+      pd1 = proposal_level<1>(m, S.prop[1], ws, rc, S1, stratified, jit1, lane,
+                              out.weights[1] ? out.weights[1] + ray * S1 : nullptr,
+                              out.sdist[1] ? out.sdist[1] + ray * (S1 + 1) : nullptr);
+      pdf_resample<PREC == TNF_PRECISION_TC_FP16>(ws, S1, S2, m.anneal, stratified, jit1, jit2, ws.bins, ws.w, lane);
+    }
+    if constexpr (PHASE == PHASE_PROP) {
+      // hand the final level's spacing bins (and the two proposal depths) to the field launch
+      for (int i = lane; i <= S2; i += 32) out.sdist[2][ray * (S2 + 1) + i] = ws.w[i];
+      if (lane == 0) {
+        out.prop_depth[0][ray] = pd0;
+        out.prop_depth[1][ray] = pd1;
+      }
+      __syncwarp();
+      continue;
+    }
+    if constexpr (PHASE == PHASE_FIELD) {
+      for (int i = lane; i <= S2; i += 32) ws.w[i] = out.sdist[2][ray * (S2 + 1) + i];
+      __syncwarp();
+    }
+    if constexpr (PHASE != PHASE_PROP) {
     // ---- level 2: field; its spacing bins now live in ws.w[0..S2]
     field_level(m, S, ws, rc, S2, lane, warp,
                 out.field_features
@@ -469,7 +510,7 @@ __global__ void __launch_bounds__(kThreads, PREC == TNF_PRECISION_TC_FP16 ? 2 : 
       if (base == 0) first_mid = __shfl_sync(kFull, mid, 0);
       if (base + 32 >= S2) last_mid = __shfl_sync(kFull, mid, (S2 - 1) & 31);
     }
-    if (out.sdist[2]) {
+    if (PHASE == PHASE_ALL && out.sdist[2]) {
       for (int i = lane; i <= S2; i += 32) out.sdist[2][ray * (S2 + 1) + i] = ws.w[i];
     }
     sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb); st = warp_sum(st);
@@ -490,8 +531,10 @@ __global__ void __launch_bounds__(kThreads, PREC == TNF_PRECISION_TC_FP16 ? 2 : 
       out.accumulation[ray] = sw;
       out.depth[ray] = comp.found ? comp.median : last_mid;
       out.expected_depth[ray] = swt / (sw + 1e-10f);  // clipped by tnf_clip_kernel
-      out.prop_depth[0][ray] = pd0;
-      out.prop_depth[1][ray] = pd1;
+      if (PHASE == PHASE_ALL) {
+        out.prop_depth[0][ray] = pd0;
+        out.prop_depth[1][ray] = pd1;
+      }
     }
     // ---- per-chunk min/max of the sample mid-points (tensor-global clip of DepthRenderer("expected"))
     const long long c = chunk > 0 ? ray / chunk : 0;
@@ -507,8 +550,9 @@ __global__ void __launch_bounds__(kThreads, PREC == TNF_PRECISION_TC_FP16 ? 2 : 
     if (first_mid == first_mid) cmin = fminf(cmin, first_mid);
     if (last_mid == last_mid) cmax = fmaxf(cmax, last_mid);
     __syncwarp();
+    }  // PHASE != PHASE_PROP
   }
-  if (cur_chunk >= 0 && lane == 0) {
+  if (PHASE != PHASE_PROP && cur_chunk >= 0 && lane == 0) {
     atomicMin(clip_min + cur_chunk, __float_as_uint(cmin));
     atomicMax(clip_max + cur_chunk, __float_as_uint(cmax));
   }
@@ -637,31 +681,40 @@ int check_model(const TnfModel* m) {
 namespace {
 using tnf::check_model;
 
-template <int PREC>
+template <int PREC, int PHASE, int MINB>
 int launch_forward(const TnfModel& m, const TnfRays& r, const TnfOutputs& o, long long chunk, unsigned* cmin,
                    unsigned* cmax, cudaStream_t stream) {
   static thread_local int configured_dev = -1;
-  static thread_local int num_sms = 0;
+  const int num_sms = tnf::num_sms();
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
-  const size_t smem = sizeof(tnf::Smem<PREC>);
+  const size_t smem = sizeof(typename tnf::SmemSel<PREC, PHASE>::type);
   if (configured_dev != dev) {
-    e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
-    e = cudaFuncSetAttribute(tnf::tnf_forward_kernel<PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(tnf::tnf_forward_kernel<PREC, PHASE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem);
     if (e != cudaSuccess)
       return fail(TNF_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
     configured_dev = dev;
   }
-  const int ctas_per_sm = PREC == TNF_PRECISION_TC_FP16 ? 2 : 1;
   long long want = (r.num_rays + tnf::kWarpsPerCta - 1) / tnf::kWarpsPerCta;
-  const long long cap = (long long)num_sms * ctas_per_sm;
+  const long long cap = (long long)num_sms * MINB;
   const int grid = (int)(want < cap ? want : cap);
-  tnf::tnf_forward_kernel<PREC><<<grid, tnf::kThreads, smem, stream>>>(m, r, o, chunk, cmin, cmax);
+  tnf::tnf_forward_kernel<PREC, PHASE, MINB><<<grid, tnf::kThreads, smem, stream>>>(m, r, o, chunk, cmin, cmax);
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "forward kernel launch: %s", cudaGetErrorString(e));
   return TNF_OK;
+}
+
+// 0: one fused launch; 3 / 4: proposal launch at that many CTAs per SM + field launch (needs out.sdist[2])
+int split_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* v = getenv("TNF_FORWARD_SPLIT");
+    mode = v ? atoi(v) : 0;
+    if (mode != 0 && mode != 3 && mode != 4) mode = 0;
+  }
+  return mode;
 }
 }  // namespace
 
@@ -716,10 +769,19 @@ int tnf_render_forward(const TnfModel* model, const TnfRays* rays, const TnfOutp
   if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
 
   int rc;
-  if (model->precision == TNF_PRECISION_TC_FP16)
-    rc = launch_forward<TNF_PRECISION_TC_FP16>(*model, *rays, *out, chunk, cmin, cmax, stream);
-  else
-    rc = launch_forward<TNF_PRECISION_FP32>(*model, *rays, *out, chunk, cmin, cmax, stream);
+  using namespace tnf;
+  const int split = (out->sdist[2] && model->precision == TNF_PRECISION_TC_FP16) ? split_mode() : 0;
+  if (split == 4) {
+    rc = launch_forward<TNF_PRECISION_TC_FP16, PHASE_PROP, 4>(*model, *rays, *out, chunk, cmin, cmax, stream);
+    if (rc == TNF_OK) rc = launch_forward<TNF_PRECISION_TC_FP16, PHASE_FIELD, 2>(*model, *rays, *out, chunk, cmin, cmax, stream);
+  } else if (split == 3) {
+    rc = launch_forward<TNF_PRECISION_TC_FP16, PHASE_PROP, 3>(*model, *rays, *out, chunk, cmin, cmax, stream);
+    if (rc == TNF_OK) rc = launch_forward<TNF_PRECISION_TC_FP16, PHASE_FIELD, 2>(*model, *rays, *out, chunk, cmin, cmax, stream);
+  } else if (model->precision == TNF_PRECISION_TC_FP16) {
+    rc = launch_forward<TNF_PRECISION_TC_FP16, PHASE_ALL, 2>(*model, *rays, *out, chunk, cmin, cmax, stream);
+  } else {
+    rc = launch_forward<TNF_PRECISION_FP32, PHASE_ALL, 1>(*model, *rays, *out, chunk, cmin, cmax, stream);
+  }
   if (rc != TNF_OK) return rc;
 
   const int tb = 256;
