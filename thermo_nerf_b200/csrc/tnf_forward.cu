@@ -33,12 +33,14 @@ struct Smem<TNF_PRECISION_FP32> {
   float act[kWarpsPerCta][64 * 32];  // per-lane activation column: act[k*32 + lane]
   float geo[kWarpsPerCta][16 * 32];
 };
+constexpr int kFTileLd = 40;  // halves per row of the staged hash-feature tile: 80 B, conflict-free for ldmatrix
 template <>
 struct Smem<TNF_PRECISION_TC_FP16> {
   PropW prop[TNF_NUM_PROP];
   FieldCommon fc;
   FieldWTC fw;
   WarpScratch ws[kWarpsPerCta];
+  __align__(16) __half ftile[kWarpsPerCta][16 * kFTileLd];  // hash features of one 16-sample tile, row-major
 };
 
 // ------------------------------------------------------------------------------------
@@ -248,34 +250,45 @@ __device__ __forceinline__ void field_level(const TnfModel& m, Smem<TNF_PRECISIO
   const uint32_t mask = (1u << grid.log2_size) - 1u;
   const float2* __restrict__ tab = reinterpret_cast<const float2*>(grid.table);
   const int g = lane >> 2, q = lane & 3;
+  __half* tile = S.ftile[warp];
+  const int smp = lane & 15, par = lane >> 4;  // hash phase: this lane owns sample `smp`, levels of parity `par`
   for (int base = 0; base < S2; base += 16) {
     const int r0 = base + g, r1 = base + g + 8;
-    float p[2][3], sel[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int ii = min(h ? r1 : r0, S2 - 1);
-      float mid, delta;
+    // ---- hash encode, lanes = 16 consecutive samples x 2 level parities: one gather instruction covers two
+    //      levels of 16 neighbouring samples, which at the coarser levels share grid cells (few sectors per
+    //      request); a lane-per-(row, level-quad) mapping would touch 32 distinct lines every time.
+    float selv;
+    {
+      const int ii = min(base + smp, S2 - 1);
+      float mid, delta, px, py, pz;
       sample_geometry(rc, ws.w[ii], ws.w[ii + 1], mid, delta);
-      sel[h] = normalise_position(m, ray_x(rc, mid), ray_y(rc, mid), ray_z(rc, mid), p[h][0], p[h][1], p[h][2]);
-    }
-    // hash encode straight into A-fragment layout: this lane owns levels q, q+4, q+8, q+12
-    uint32_t a0[2][4];
+      selv = normalise_position(m, ray_x(rc, mid), ray_y(rc, mid), ray_z(rc, mid), px, py, pz);
 #pragma unroll
-    for (int kt = 0; kt < 2; ++kt) {
-#pragma unroll
-      for (int hl = 0; hl < 2; ++hl) {
-        const int l = kt * 8 + hl * 4 + q;
-        const float2* lt = tab + ((size_t)l << grid.log2_size);
-        const float sc = W.scal[l];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float2 f = hash_level(lt, p[h][0], p[h][1], p[h][2], sc, mask);
-          a0[kt][2 * hl + h] = pack_half2(f.x, f.y);
-          const int row = h ? r1 : r0;
-          if (sf && row < S2) sf[row * 16 + l] = a0[kt][2 * hl + h];
-        }
+      for (int k = 0; k < 8; ++k) {
+        const int l = 2 * k + par;
+        const float2 f = hash_level(tab + ((size_t)l << grid.log2_size), px, py, pz, W.scal[l], mask);
+        *reinterpret_cast<uint32_t*>(tile + smp * kFTileLd + 2 * l) = pack_half2(f.x, f.y);
       }
     }
+    __syncwarp();
+    // ---- the tile as mma A fragments (two k-tiles of 16 halves) + the saved copy for the backward
+    uint32_t a0[2][4];
+    {
+      const __half* src = tile + ((lane & 7) + ((lane >> 3) & 1) * 8) * kFTileLd + (lane >> 4) * 8;
+      ldmatrix_x4(a0[0], src);
+      ldmatrix_x4(a0[1], src + 16);
+    }
+    if (sf) {
+#pragma unroll
+      for (int c = lane; c < 64; c += 32) {
+        const int row = c >> 2, part = c & 3;
+        if (base + row < S2)
+          reinterpret_cast<uint4*>(sf)[(base + row) * 4 + part] =
+              *reinterpret_cast<const uint4*>(tile + row * kFTileLd + part * 8);
+      }
+    }
+    const float sel[2] = {__shfl_sync(kFull, selv, g), __shfl_sync(kFull, selv, g + 8)};
+    __syncwarp();  // every lane has read the tile before the next iteration overwrites it
     uint32_t hid[4][4];
     {
       float c[8][4];

@@ -248,6 +248,15 @@ class ThermalNerfModel(nn.Module):
         tnf_render_forward / tnf_render_backward (training)."""
         cfg = self.config
         if self.training:
+            if self.camera_optimizer.mode != "off" and not getattr(self, "_warned_pose_grad", False):
+                import warnings
+
+                # tnf_render_backward differentiates w.r.t. the parameters of the path, not w.r.t. ray origins /
+                # directions: the pose deltas are applied (forward) but receive no gradient (DESIGN.md section 7)
+                warnings.warn("thermo_nerf_b200: camera_optimizer_mode=%r applies the pose deltas but libtnf_b200 does "
+                              "not yet back-propagate into ray origins/directions, so camera_opt parameters will not "
+                              "be updated" % self.camera_optimizer.mode, RuntimeWarning, stacklevel=2)
+                self._warned_pose_grad = True
             self.camera_optimizer.apply_to_raybundle(ray_bundle)
         shape = tuple(ray_bundle.origins.shape[:-1])
         o = ray_bundle.origins.reshape(-1, 3).contiguous().float()
