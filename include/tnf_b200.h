@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define TNF_ABI_VERSION 4
+#define TNF_ABI_VERSION 5
 
 #define TNF_MAX_LEVELS 16      /* hash levels of the field grid (fixed: 16)          */
 #define TNF_MAX_PROP_LEVELS 8  /* max hash levels of a proposal density grid          */
@@ -314,6 +314,30 @@ typedef struct TnfAdamTensor {
 int tnf_adam_step(const TnfAdamTensor* tensors, int32_t num_tensors, double beta1, double beta2, float eps,
                   int64_t step, float inv_grad_scale, const float* grad_scale, const float* found_inf,
                   int32_t zero_grads, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Training batches from a device-resident dataset: nerfstudio's PixelSampler.sample_method +
+ * collate_image_dataset_batch + RayGenerator (VanillaDataManager.next_train, driven from
+ * thermo_nerf/nerfstudio_config/pipeline_tracking.py:47-59) in one launch.  The reference keeps the
+ * thermal ground truth on the host and moves a batch per step (thermal_dataset.py:18-20,
+ * thermal_nerf_model.py:319).
+ * ------------------------------------------------------------------------------------ */
+typedef struct TnfDataset {
+  const void* images;            /* [N,H,W,C] float32 in [0,1], or uint8 (converted as x / 255)        */
+  const void* thermal;           /* [N,H,W]   float32 normalised temperature, or uint8; may be NULL   */
+  const float* camera_to_worlds; /* [N,3,4]                                                            */
+  const float* intrinsics;       /* [N,4] fx, fy, cx, cy                                               */
+  int32_t num_images, height, width, channels; /* channels >= 3 (the first three are RGB)              */
+  int32_t images_uint8, thermal_uint8;
+} TnfDataset;
+
+/* indices = floor(rand * (N, H, W)) per ray; gathers the ground truth at those pixels and generates the
+ * rays through their centres.  rand [R,3] uniform [0,1) (the caller draws it, e.g. torch.rand on the device);
+ * outputs: origins / directions [R,3], camera_indices [R] int64, indices [R,3] int64 (image, y, x; may be
+ * NULL), gt_rgb [R,3] and gt_thermal [R] (each may be NULL). */
+int tnf_sample_batch(const TnfDataset* dataset, const float* rand, int64_t num_rays, float* origins,
+                     float* directions, int64_t* camera_indices, int64_t* indices, float* gt_rgb, float* gt_thermal,
+                     void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Multi-GPU exchange step (one process per GPU): gradient mean over ranks fused with Adam

@@ -94,3 +94,29 @@ def camera_path_to_cameras(camera_path: dict, scaling: float = 1.0):
     cx, cy = w / 2 * scaling, h / 2 * scaling
     # rescale_output_resolution: height/width scaled and truncated to int (scaling_factor float path)
     return np.stack(c2ws), fx, fy, cx, cy, int(h * scaling), int(w * scaling)
+
+
+def sample_batch_np(rand: np.ndarray, images: np.ndarray, thermal: Optional[np.ndarray], c2w: np.ndarray,
+                    intrinsics: np.ndarray):
+    """nerfstudio PixelSampler.sample_method (no mask) + collate_image_dataset_batch + RayGenerator for a given
+    uniform draw ``rand`` [R,3] (float32): indices = floor(rand * [N,H,W]).long(); batch[key] = value[c, y, x];
+    rays through the pixel centres (y + 0.5, x + 0.5) of camera c.  uint8 images are converted as x / 255
+    (InputDataset.get_image_float32).  Returns (origins, directions, indices, gt_rgb, gt_thermal)."""
+    n, h, w = images.shape[:3]
+    dims = np.array([n, h, w], dtype=np.float32)
+    idx = np.floor(rand.astype(np.float32) * dims).astype(np.int64)
+    c, y, x = idx[:, 0], idx[:, 1], idx[:, 2]
+    img = images[c, y, x, :3]
+    gt_rgb = img.astype(np.float32) / np.float32(255.0) if images.dtype == np.uint8 else img.astype(np.float32)
+    gt_th = None
+    if thermal is not None:
+        t = thermal.reshape(n, h, w)[c, y, x]
+        gt_th = t.astype(np.float32) / np.float32(255.0) if thermal.dtype == np.uint8 else t.astype(np.float32)
+    o = np.empty((len(c), 3), np.float32)
+    d = np.empty((len(c), 3), np.float32)
+    for cam in np.unique(c):
+        sel = np.nonzero(c == cam)[0]
+        fx, fy, cx, cy = (float(v) for v in intrinsics[cam])
+        oo, dd, _ = generate_rays_np(c2w[cam], fx, fy, cx, cy, h, w)
+        o[sel], d[sel] = oo[y[sel], x[sel]], dd[y[sel], x[sel]]
+    return o, d, idx, gt_rgb, gt_th

@@ -41,7 +41,7 @@ def test_every_declared_symbol_is_exported(lib):
 def test_abi_version_and_error_string(lib):
     from thermo_nerf_b200 import _lib
 
-    assert lib.tnf_version() == _lib.TNF_ABI_VERSION == 4
+    assert lib.tnf_version() == _lib.TNF_ABI_VERSION == 5
     assert isinstance(lib.tnf_last_error(), bytes)
 
 
@@ -50,7 +50,7 @@ def test_ctypes_layout_matches_c_header(tmp_path):
 
     names = ["TnfHashGrid", "TnfLinear", "TnfDensityNet", "TnfField", "TnfModel", "TnfCamera", "TnfRays", "TnfOutputs",
              "TnfLinearGrad", "TnfDensityNetGrad", "TnfFieldGrad", "TnfModelGrad", "TnfSaved", "TnfOutputGrads",
-             "TnfLossArgs", "TnfAdamTensor", "TnfPeerArena", "TnfAdamSegment"]
+             "TnfLossArgs", "TnfAdamTensor", "TnfPeerArena", "TnfAdamSegment", "TnfDataset"]
     probes = {
         "TnfModel": ["field", "num_samples", "training", "near_plane", "anneal", "use_contraction", "aabb",
                      "appearance_mode", "precision", "detach_thermal_geo"],
@@ -66,6 +66,7 @@ def test_ctypes_layout_matches_c_header(tmp_path):
         "TnfAdamTensor": ["numel", "lr"],
         "TnfPeerArena": ["params", "flags", "world_size", "rank", "numel"],
         "TnfAdamSegment": ["end", "step", "lr", "active"],
+        "TnfDataset": ["thermal", "intrinsics", "num_images", "channels", "thermal_uint8"],
         "TnfHashGrid": ["scalings", "num_levels", "log2_size"],
     }
     src = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
@@ -190,3 +191,17 @@ def test_peer_entry_points_validate_arguments(lib):
     seg[0].end, seg[0].step = 16, 0
     rc = lib.tnf_peer_adam_step(C.byref(a), 256, 256, seg, 1, 0.9, 0.999, 1e-15, None)
     assert rc == _lib.TNF_ERR_INVALID_ARGUMENT and b"step" in lib.tnf_last_error()
+
+
+def test_sample_batch_validates_arguments(lib):
+    from thermo_nerf_b200 import _lib
+
+    assert lib.tnf_sample_batch(None, None, 4, None, None, None, None, None, None, None) == _lib.TNF_ERR_INVALID_ARGUMENT
+    ds = _lib.TnfDataset()
+    ds.images = ds.camera_to_worlds = ds.intrinsics = 256
+    ds.num_images, ds.height, ds.width, ds.channels = 2, 4, 4, 2
+    rc = lib.tnf_sample_batch(C.byref(ds), 256, 4, 256, 256, 256, None, None, None, None)
+    assert rc == _lib.TNF_ERR_INVALID_ARGUMENT and b"channels" in lib.tnf_last_error()
+    ds.channels = 3
+    assert lib.tnf_sample_batch(C.byref(ds), None, 0, None, None, None, None, None, None, None) == _lib.TNF_OK
+    assert lib.tnf_sample_batch(C.byref(ds), None, 4, None, None, None, None, None, None, None) == _lib.TNF_ERR_INVALID_ARGUMENT

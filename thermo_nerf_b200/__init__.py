@@ -13,9 +13,10 @@ from .modules import (CameraOptimizer, FieldHeadNames, FieldHeadNamesT, HashMLPD
                       ThermalNerfactoTField)
 from .rays import PinholeCameras, RayBundle, orbit_cameras, sphere_cameras
 from .render import RenderedImageModality, Renderer
+from .data import DevicePixelSampler
 
 __all__ = [
     "ModelTensors", "render_forward", "render", "losses", "adam_step", "FusedAdam", "ThermalNerfModel", "ThermalNerfModelConfig", "CameraOptimizer",
     "FieldHeadNames", "FieldHeadNamesT", "HashMLPDensityField", "ThermalFieldHead", "ThermalNerfactoTField",
-    "PinholeCameras", "RayBundle", "orbit_cameras", "sphere_cameras", "Renderer", "RenderedImageModality",
+    "PinholeCameras", "RayBundle", "orbit_cameras", "sphere_cameras", "Renderer", "RenderedImageModality", "DevicePixelSampler",
 ]

@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 from typing import Optional
 
-TNF_ABI_VERSION = 4
+TNF_ABI_VERSION = 5
 TNF_MAX_LEVELS = 16
 TNF_MAX_PROP_LEVELS = 8
 TNF_MAX_SAMPLES = 256
@@ -91,6 +91,21 @@ class TnfCamera(C.Structure):
         ("cy", C.c_float),
         ("width", C.c_int32),
         ("height", C.c_int32),
+    ]
+
+
+class TnfDataset(C.Structure):
+    _fields_ = [
+        ("images", _fp),
+        ("thermal", _fp),
+        ("camera_to_worlds", _fp),
+        ("intrinsics", _fp),
+        ("num_images", C.c_int32),
+        ("height", C.c_int32),
+        ("width", C.c_int32),
+        ("channels", C.c_int32),
+        ("images_uint8", C.c_int32),
+        ("thermal_uint8", C.c_int32),
     ]
 
 
@@ -244,6 +259,7 @@ EXPORTED_SYMBOLS = (
     "tnf_render_forward",
     "tnf_generate_rays",
     "tnf_postprocess_frame",
+    "tnf_sample_batch",
     "tnf_backward_workspace_bytes",
     "tnf_render_backward",
     "tnf_backward_stage_mask",
@@ -309,6 +325,9 @@ def load() -> C.CDLL:
     lib.tnf_postprocess_frame.restype = C.c_int
     lib.tnf_postprocess_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p,
                                           C.c_void_p, C.c_void_p]
+    lib.tnf_sample_batch.restype = C.c_int
+    lib.tnf_sample_batch.argtypes = [C.POINTER(TnfDataset), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.tnf_backward_workspace_bytes.restype = C.c_size_t
     lib.tnf_backward_workspace_bytes.argtypes = [C.POINTER(TnfModel), C.c_int64]
     lib.tnf_render_backward.restype = C.c_int
