@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define TNF_ABI_VERSION 5
+#define TNF_ABI_VERSION 6
 
 #define TNF_MAX_LEVELS 16      /* hash levels of the field grid (fixed: 16)          */
 #define TNF_MAX_PROP_LEVELS 8  /* max hash levels of a proposal density grid          */
@@ -231,6 +231,12 @@ typedef struct TnfFieldGrad {
 typedef struct TnfModelGrad {
   TnfDensityNetGrad prop[TNF_NUM_PROP];
   TnfFieldGrad field;
+  /* optional (both or neither; NULL to skip): dLoss/d origins and dLoss/d directions [R,3], accumulated
+   * (+=).  They carry the gradient into the camera optimiser's pose deltas, which the reference applies to
+   * the ray bundle before get_outputs (thermal_nerf_model.py:218-219).  Sample distances are constants
+   * (the sampler detaches its bins), so x = o + t d gives dL/do = sum_s dL/dx_s, dL/dd = sum_s t_s dL/dx_s. */
+  float* ray_origins;
+  float* ray_directions;
 } TnfModelGrad;
 
 /* What tnf_render_forward wrote in training mode (same pointers as in TnfOutputs). */

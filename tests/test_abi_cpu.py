@@ -41,7 +41,7 @@ def test_every_declared_symbol_is_exported(lib):
 def test_abi_version_and_error_string(lib):
     from thermo_nerf_b200 import _lib
 
-    assert lib.tnf_version() == _lib.TNF_ABI_VERSION == 5
+    assert lib.tnf_version() == _lib.TNF_ABI_VERSION == 6
     assert isinstance(lib.tnf_last_error(), bytes)
 
 
@@ -58,7 +58,7 @@ def test_ctypes_layout_matches_c_header(tmp_path):
         "TnfRays": ["jitter", "num_rays", "from_camera", "first_pixel", "camera"],
         "TnfCamera": ["c2w", "fx", "cy", "width", "height"],
         "TnfOutputs": ["prop_depth", "weights", "sdist", "field_features", "field_samples"],
-        "TnfModelGrad": ["field"],
+        "TnfModelGrad": ["field", "ray_origins", "ray_directions"],
         "TnfFieldGrad": ["th2", "appearance"],
         "TnfSaved": ["weights", "field_features", "field_samples"],
         "TnfOutputGrads": ["accumulation", "weights"],

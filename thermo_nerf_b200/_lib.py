@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 from typing import Optional
 
-TNF_ABI_VERSION = 5
+TNF_ABI_VERSION = 6
 TNF_MAX_LEVELS = 16
 TNF_MAX_PROP_LEVELS = 8
 TNF_MAX_SAMPLES = 256
@@ -164,7 +164,8 @@ class TnfFieldGrad(C.Structure):
 
 
 class TnfModelGrad(C.Structure):
-    _fields_ = [("prop", TnfDensityNetGrad * TNF_NUM_PROP), ("field", TnfFieldGrad)]
+    _fields_ = [("prop", TnfDensityNetGrad * TNF_NUM_PROP), ("field", TnfFieldGrad), ("ray_origins", _fp),
+                ("ray_directions", _fp)]
 
 
 class TnfSaved(C.Structure):

@@ -148,6 +148,67 @@ __device__ __forceinline__ void scatter_level_runs(float2* __restrict__ gtab, fl
   }
 }
 
+// ------------------------------------------------------------------------------------
+// gradient w.r.t. the sample position (camera-optimiser path): d feat / d p through the trilinear weights
+// (the reference differentiates offset = scaled - floor(scaled); ceil/floor carry no gradient), then back
+// through (x + 2) / 4, the selector mask and the L-inf scene contraction.
+// ------------------------------------------------------------------------------------
+// adds scale * sum_c (g . T[idx_c]) d w_c / d offset to (dpx, dpy, dpz); corner order of hash_blend
+__device__ __forceinline__ void hash_level_pos_grad(const float2* __restrict__ level_tab, const float px, const float py,
+                                                    const float pz, const float scale, const uint32_t mask,
+                                                    const float gx, const float gy, float& dpx, float& dpy, float& dpz) {
+  HashCorners hc;
+  hash_corners(px, py, pz, scale, mask, hc);
+  float s[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float2 t = __ldg(level_tab + hc.idx[c]);
+    s[c] = gx * t.x + gy * t.y;
+  }
+  const float ox = hc.ox, oy = hc.oy, oz = hc.oz, ix = 1.f - ox, iy = 1.f - oy, iz = 1.f - oz;
+  dpx += scale * (oy * oz * (s[0] - s[3]) + iy * oz * (s[1] - s[2]) + oy * iz * (s[4] - s[7]) + iy * iz * (s[5] - s[6]));
+  dpy += scale * (ox * oz * (s[0] - s[1]) + ix * oz * (s[3] - s[2]) + ox * iz * (s[4] - s[5]) + ix * iz * (s[7] - s[6]));
+  dpz += scale * (ox * oy * (s[0] - s[4]) + ox * iy * (s[1] - s[5]) + ix * iy * (s[2] - s[6]) + ix * oy * (s[3] - s[7]));
+}
+
+// dL/d(normalised position p) -> dL/d(world position x); (x, y, z) is the un-contracted sample position
+__device__ __forceinline__ void position_grad_to_world(const TnfModel& m, const float x, const float y, const float z,
+                                                       const float sel, float& gx, float& gy, float& gz) {
+  if (sel == 0.f) { gx = gy = gz = 0.f; return; }
+  if (m.use_contraction) {
+    gx *= 0.25f; gy *= 0.25f; gz *= 0.25f;
+    const float ax = fabsf(x), ay = fabsf(y), az = fabsf(z);
+    const float mag = fmaxf(ax, fmaxf(ay, az));
+    if (!(mag < 1.f)) {
+      // x' = a(m) x, a = (2 - 1/m) / m, m = |x|_inf = |x_k|:  J^T g = a g + (g . x) a'(m) sign(x_k) e_k
+      const float a = (2.f - 1.f / mag) / mag;
+      const float dadm = 2.f * (1.f - mag) / (mag * mag * mag);
+      const float dot = gx * x + gy * y + gz * z;
+      gx *= a; gy *= a; gz *= a;
+      if (ax >= ay && ax >= az) gx += dot * dadm * (x < 0.f ? -1.f : 1.f);
+      else if (ay >= az) gy += dot * dadm * (y < 0.f ? -1.f : 1.f);
+      else gz += dot * dadm * (z < 0.f ? -1.f : 1.f);
+    }
+  } else {
+    gx /= (m.aabb[3] - m.aabb[0]);
+    gy /= (m.aabb[4] - m.aabb[1]);
+    gz /= (m.aabb[5] - m.aabb[2]);
+  }
+}
+
+// per-ray accumulation of the pose gradient: dL/do += sum_s g_s, dL/dd += sum_s mid_s g_s (warp-reduced)
+__device__ __forceinline__ void flush_ray_grad(const TnfModelGrad& gr, const long long ray, float ax, float ay, float az,
+                                               float bx, float by, float bz, const int lane) {
+  ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
+  bx = warp_sum(bx); by = warp_sum(by); bz = warp_sum(bz);
+  if (lane == 0) {
+    atomicAdd(gr.ray_origins + ray * 3 + 0, ax); atomicAdd(gr.ray_origins + ray * 3 + 1, ay);
+    atomicAdd(gr.ray_origins + ray * 3 + 2, az);
+    atomicAdd(gr.ray_directions + ray * 3 + 0, bx); atomicAdd(gr.ray_directions + ray * 3 + 1, by);
+    atomicAdd(gr.ray_directions + ray * 3 + 2, bz);
+  }
+}
+
 // reverse (suffix) exclusive scan helper over one 32-wide chunk: returns sum_{j>lane} v_j
 __device__ __forceinline__ float warp_suffix_excl(float v, int lane, float& total) {
   const float rv = __shfl_sync(kFull, v, 31 - lane);
@@ -306,7 +367,7 @@ __device__ __forceinline__ void prop_backward_unit(const TnfModel& m, const int 
                                                    PropBwdScratch& ws, const RayCtx& rc, const int S, const int lane,
                                                    const float* __restrict__ sdist, const float* __restrict__ wsaved,
                                                    const float* __restrict__ gw, float2* __restrict__ gtab,
-                                                   PropAcc<TC, NLC>& acc) {
+                                                   PropAcc<TC, NLC>& acc, const bool pose, float (&pg)[6]) {
   const TnfDensityNet& net = m.prop[lvl];
   const int L = net.grid.num_levels;
   const int log2 = net.grid.log2_size;
@@ -432,6 +493,7 @@ __device__ __forceinline__ void prop_backward_unit(const TnfModel& m, const int 
 
     // ---- table scatter: dfeat = dh . W0 (whole chunk skipped when no sample of it carries a gradient)
     if (__any_sync(kFull, d_o != 0.f)) {
+      float dpx = 0.f, dpy = 0.f, dpz = 0.f;
 #pragma unroll
       for (int l = 0; l < NLC; ++l) {
         if (l < L) {
@@ -442,7 +504,14 @@ __device__ __forceinline__ void prop_backward_unit(const TnfModel& m, const int 
             gy = fmaf(dh[j], W.w0t[(2 * l + 1) * 16 + j], gy);
           }
           scatter_level_runs<1>(gtab + ((size_t)l << log2), px, py, pz, net.grid.scalings[l], mask, gx, gy, lane);
+          if (pose && d_o != 0.f)
+            hash_level_pos_grad(tab + ((size_t)l << log2), px, py, pz, net.grid.scalings[l], mask, gx, gy, dpx, dpy, dpz);
         }
+      }
+      if (pose && d_o != 0.f) {
+        position_grad_to_world(m, ray_x(rc, mid), ray_y(rc, mid), ray_z(rc, mid), sel, dpx, dpy, dpz);
+        pg[0] += dpx; pg[1] += dpy; pg[2] += dpz;
+        pg[3] = fmaf(mid, dpx, pg[3]); pg[4] = fmaf(mid, dpy, pg[4]); pg[5] = fmaf(mid, dpz, pg[5]);
       }
     }
     __syncwarp();
@@ -531,9 +600,11 @@ __global__ void __launch_bounds__(kThreads, 2)
     rc.s_near = spacing_fn(rays.nears ? __ldg(rays.nears + ray) : m.near_plane);
     rc.s_far = spacing_fn(rays.fars ? __ldg(rays.fars + ray) : m.far_plane);
     const int S_l = m.num_samples[lvl];
+    float pg[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     prop_backward_unit<TC, NLC>(m, lvl, S.prop[lvl], ws, rc, S_l, lane, sv.sdist[lvl] + ray * (S_l + 1),
                                 sv.weights[lvl] + ray * S_l, go.weights[lvl] + ray * S_l,
-                                reinterpret_cast<float2*>(gr.prop[lvl].table), acc);
+                                reinterpret_cast<float2*>(gr.prop[lvl].table), acc, gr.ray_origins != nullptr, pg);
+    if (gr.ray_origins) flush_ray_grad(gr, ray, pg[0], pg[1], pg[2], pg[3], pg[4], pg[5], lane);
   }
   if (cur >= 0) acc.flush(S.wacc[cur], 2 * m.prop[cur].grid.num_levels, lane);
   __syncthreads();
@@ -758,6 +829,8 @@ __global__ void __launch_bounds__(kThreads, 1)
                        go.rgb ? go.rgb[ray * 3 + 2] : 0.f, go.thermal ? go.thermal[ray] : 0.f,
                        go.accumulation ? go.accumulation[ray] : 0.f);
     float racc0 = 0.f, racc1 = 0.f;
+    float pg[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const bool pose = gr.ray_origins != nullptr;
     for (int base = 0; base < S2; base += 32) {
       const int i = base + lane;
       const bool active = i < S2;
@@ -867,12 +940,23 @@ __global__ void __launch_bounds__(kThreads, 1)
         dense_row_t<64, 32, false, false>(W.base0t, y, a);  // a[0..31]: dF
       }
       if (active) {
+        float dpx = 0.f, dpy = 0.f, dpz = 0.f;
 #pragma unroll 4
-        for (int l = 0; l < TNF_MAX_LEVELS; ++l)
+        for (int l = 0; l < TNF_MAX_LEVELS; ++l) {
           scatter_level(gtab + ((size_t)l << grid.log2_size), px, py, pz, grid.scalings[l], mask, a[(2 * l) * 32],
                         a[(2 * l + 1) * 32]);
+          if (pose)
+            hash_level_pos_grad(reinterpret_cast<const float2*>(grid.table) + ((size_t)l << grid.log2_size), px, py, pz,
+                                grid.scalings[l], mask, a[(2 * l) * 32], a[(2 * l + 1) * 32], dpx, dpy, dpz);
+        }
+        if (pose) {
+          position_grad_to_world(m, ray_x(rc, mid), ray_y(rc, mid), ray_z(rc, mid), sel, dpx, dpy, dpz);
+          pg[0] += dpx; pg[1] += dpy; pg[2] += dpz;
+          pg[3] = fmaf(mid, dpx, pg[3]); pg[4] = fmaf(mid, dpy, pg[4]); pg[5] = fmaf(mid, dpz, pg[5]);
+        }
       }
     }
+    if (pose) flush_ray_grad(gr, ray, pg[0], pg[1], pg[2], pg[3], pg[4], pg[5], lane);
     ray_epilogue<float>(m, rays, ray, lane, sh, app_lane, racc0, racc1, L, gr.field.appearance);
     __syncwarp();
   }
@@ -1017,6 +1101,7 @@ struct FieldBwdSmemTC {
 // two CTAs per SM: 2 x (dynamic + 1 KB system) must fit the 228 KB of an sm_100 SM
 static_assert(sizeof(FieldBwdSmemTC) <= 113 * 1024, "FieldBwdSmemTC no longer fits two CTAs per SM");
 
+template <bool POSE>  // POSE: also produce dL/d ray origins / directions (camera-optimiser path; re-gathers the table)
 __global__ void __launch_bounds__(kThreads, 2)
     tnf_backward_field_kernel_tc(const __grid_constant__ TnfModel m, const __grid_constant__ TnfRays rays,
                                  const __grid_constant__ TnfSaved sv, const __grid_constant__ TnfOutputGrads go,
@@ -1039,6 +1124,7 @@ __global__ void __launch_bounds__(kThreads, 2)
   float2* __restrict__ gtab = reinterpret_cast<float2*>(gr.field.table);
   const uint32_t* __restrict__ F = static_cast<const uint32_t*>(sv.field_features);  // [Ns][16] half2
   const long long R = rays.num_rays;
+  constexpr bool pose = POSE;
   unsigned char* const dA1 = L.dGeo;                                  // [Ns,64] dL/d(colour layer-0 pre-activation)
   unsigned char* const dB1 = L.dGeo + (size_t)R * S2 * kWX * 2;      // [Ns,64] dL/d(thermal layer-0 pre-activation)
 
@@ -1062,6 +1148,7 @@ __global__ void __launch_bounds__(kThreads, 2)
                        go.rgb ? go.rgb[ray * 3 + 0] : 0.f, go.rgb ? go.rgb[ray * 3 + 1] : 0.f,
                        go.rgb ? go.rgb[ray * 3 + 2] : 0.f, go.thermal ? go.thermal[ray] : 0.f,
                        go.accumulation ? go.accumulation[ray] : 0.f);
+    float pg[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // pose path: sum_s dL/dx_s and sum_s t_s dL/dx_s of this ray
     float racc[16];  // column sums of dA1pre over the ray (meaningful on lanes with g == 0)
 #pragma unroll
     for (int i = 0; i < 16; ++i) racc[i] = 0.f;
@@ -1073,13 +1160,14 @@ __global__ void __launch_bounds__(kThreads, 2)
       const long long row0 = ray * S2 + i0, row1 = ray * S2 + i1;
       const long long trow = ray * S2 + base;          // global row of this tile's first sample
       const int nval = min(16, S2 - base);
-      float p[2][3], sel[2];
+      float p[2][3], sel[2], mids[2];
+      float dp[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};  // dL/d(normalised position) of rows r0 / r1 (pose path)
       {
-        float mid, delta;
-        sample_geometry(rc, ws.bins[i0], ws.bins[i0 + 1], mid, delta);
-        sel[0] = normalise_position(m, ray_x(rc, mid), ray_y(rc, mid), ray_z(rc, mid), p[0][0], p[0][1], p[0][2]);
-        sample_geometry(rc, ws.bins[i1], ws.bins[i1 + 1], mid, delta);
-        sel[1] = normalise_position(m, ray_x(rc, mid), ray_y(rc, mid), ray_z(rc, mid), p[1][0], p[1][1], p[1][2]);
+        float delta;
+        sample_geometry(rc, ws.bins[i0], ws.bins[i0 + 1], mids[0], delta);
+        sel[0] = normalise_position(m, ray_x(rc, mids[0]), ray_y(rc, mids[0]), ray_z(rc, mids[0]), p[0][0], p[0][1], p[0][2]);
+        sample_geometry(rc, ws.bins[i1], ws.bins[i1 + 1], mids[1], delta);
+        sel[1] = normalise_position(m, ray_x(rc, mids[1]), ray_y(rc, mids[1]), ray_z(rc, mids[1]), p[1][0], p[1][1], p[1][2]);
       }
       const float dsig[2] = {v0 ? ws.dsig[i0] : 0.f, v1 ? ws.dsig[i1] : 0.f};
       const float dtau[2] = {v0 ? ws.dtau[i0] : 0.f, v1 ? ws.dtau[i1] : 0.f};
@@ -1233,9 +1321,33 @@ __global__ void __launch_bounds__(kThreads, 2)
           const float sc = W.scal[l];
           scatter_level_runs<4>(lt, p[0][0], p[0][1], p[0][2], sc, mask, v0 ? c[nt][0] : 0.f, v0 ? c[nt][1] : 0.f, lane);
           scatter_level_runs<4>(lt, p[1][0], p[1][1], p[1][2], sc, mask, v1 ? c[nt][2] : 0.f, v1 ? c[nt][3] : 0.f, lane);
+          if (pose) {
+            const float2* rt = reinterpret_cast<const float2*>(grid.table) + ((size_t)l << grid.log2_size);
+            if (v0) hash_level_pos_grad(rt, p[0][0], p[0][1], p[0][2], sc, mask, c[nt][0], c[nt][1], dp[0][0], dp[0][1], dp[0][2]);
+            if (v1) hash_level_pos_grad(rt, p[1][0], p[1][1], p[1][2], sc, mask, c[nt][2], c[nt][3], dp[1][0], dp[1][1], dp[1][2]);
+          }
+        }
+      }
+      if (pose) {
+        // the four q-lanes of a row hold the contributions of their four levels each
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            dp[h][j] += __shfl_xor_sync(kFull, dp[h][j], 1);
+            dp[h][j] += __shfl_xor_sync(kFull, dp[h][j], 2);
+          }
+          if (q == 0 && (h ? v1 : v0)) {
+            position_grad_to_world(m, ray_x(rc, mids[h]), ray_y(rc, mids[h]), ray_z(rc, mids[h]), sel[h], dp[h][0],
+                                   dp[h][1], dp[h][2]);
+            pg[0] += dp[h][0]; pg[1] += dp[h][1]; pg[2] += dp[h][2];
+            pg[3] = fmaf(mids[h], dp[h][0], pg[3]); pg[4] = fmaf(mids[h], dp[h][1], pg[4]);
+            pg[5] = fmaf(mids[h], dp[h][2], pg[5]);
+          }
         }
       }
     }
+    if (pose) flush_ray_grad(gr, ray, pg[0], pg[1], pg[2], pg[3], pg[4], pg[5], lane);
     // ---- per-ray epilogue
     {
       __syncwarp();
@@ -1421,6 +1533,8 @@ int check_grads(const TnfModel& m, const TnfModelGrad* g) {
     if (!l->weight || !l->bias) return fail(TNF_ERR_INVALID_ARGUMENT, "grads.field: a linear gradient is null");
   if (m.appearance_mode == TNF_APPEARANCE_LOOKUP && !f.appearance)
     return fail(TNF_ERR_INVALID_ARGUMENT, "grads.field.appearance is required for TNF_APPEARANCE_LOOKUP");
+  if ((g->ray_origins == nullptr) != (g->ray_directions == nullptr))
+    return fail(TNF_ERR_INVALID_ARGUMENT, "grads.ray_origins and grads.ray_directions must be given together");
   return TNF_OK;
 }
 
@@ -1577,11 +1691,19 @@ int tnf_render_backward(const TnfModel* model, const TnfRays* rays, const TnfSav
     if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(e));
   } else {
     const size_t smem = sizeof(tnf::FieldBwdSmemTC);
-    if (int rc = set_smem(tnf::tnf_backward_field_kernel_tc, smem, "backward_field_tc")) return rc;
     const long long cap = (long long)sms * 2;
-    if (g_stage_mask & 2)
-      tnf::tnf_backward_field_kernel_tc<<<(unsigned)(want < cap ? want : cap), tnf::kThreads, smem, stream>>>(
-          *model, *rays, *saved, *gout, *grads, L);
+    const unsigned gridf = (unsigned)(want < cap ? want : cap);
+    if (grads->ray_origins) {
+      if (int rc = set_smem(tnf::tnf_backward_field_kernel_tc<true>, smem, "backward_field_tc")) return rc;
+      if (g_stage_mask & 2)
+        tnf::tnf_backward_field_kernel_tc<true><<<gridf, tnf::kThreads, smem, stream>>>(*model, *rays, *saved, *gout,
+                                                                                      *grads, L);
+    } else {
+      if (int rc = set_smem(tnf::tnf_backward_field_kernel_tc<false>, smem, "backward_field_tc")) return rc;
+      if (g_stage_mask & 2)
+        tnf::tnf_backward_field_kernel_tc<false><<<gridf, tnf::kThreads, smem, stream>>>(*model, *rays, *saved, *gout,
+                                                                                       *grads, L);
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "backward_field launch: %s", cudaGetErrorString(e));
     field_problems(wa, L, saved->field_features, true, grads->field, Ns, R);

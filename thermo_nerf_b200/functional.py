@@ -196,10 +196,14 @@ class ModelTensors:
         return ModelTensors(grids, l0, l1, fg, lin, next(it), extra)
 
     @staticmethod
-    def pack_grads(grads: Sequence[Optional[Tensor]]) -> L.TnfModelGrad:
+    def pack_grads(grads: Sequence[Optional[Tensor]], ray_grads: Optional[Tuple[Tensor, Tensor]] = None
+                   ) -> L.TnfModelGrad:
         """``grads`` in ``param_list`` order (None = not wanted; a proposal net is skipped as a whole
-        when its table gradient is None)."""
+        when its table gradient is None); ``ray_grads`` = (d origins, d directions) [R,3] buffers or None."""
         g = L.TnfModelGrad()
+        if ray_grads is not None:
+            g.ray_origins = _dev_f32(ray_grads[0], "grad.origins").data_ptr()
+            g.ray_directions = _dev_f32(ray_grads[1], "grad.directions").data_ptr()
         it = iter(grads)
 
         def ptr(t, name):
@@ -379,8 +383,9 @@ def _workspace_for(model_struct: L.TnfModel, R: int, dev: torch.device) -> Tenso
 def render_backward(tensors: ModelTensors, model_struct: L.TnfModel, origins: Tensor, directions: Tensor,
                     camera_indices: Optional[Tensor], nears: Optional[Tensor], fars: Optional[Tensor],
                     jitter: Optional[Tensor], saved: Dict[str, object], grad_outputs: Dict[str, Optional[Tensor]],
-                    grads: Sequence[Optional[Tensor]]) -> None:
-    """``tnf_render_backward``: accumulates into ``grads`` (``ModelTensors.param_list`` order)."""
+                    grads: Sequence[Optional[Tensor]], ray_grads: Optional[Tuple[Tensor, Tensor]] = None) -> None:
+    """``tnf_render_backward``: accumulates into ``grads`` (``ModelTensors.param_list`` order) and, when
+    ``ray_grads`` = (d origins, d directions) is given, into those [R,3] buffers (camera-optimiser path)."""
     lib = L.load()
     R = int(origins.shape[0])
     dev = origins.device
@@ -410,7 +415,7 @@ def render_backward(tensors: ModelTensors, model_struct: L.TnfModel, origins: Te
     gw = grad_outputs.get("weights_list") or [None] * (L.TNF_NUM_PROP + 1)
     for k in range(L.TNF_NUM_PROP + 1):
         go.weights[k] = gptr(gw[k], f"grad weights[{k}]")
-    gstruct = ModelTensors.pack_grads(grads)
+    gstruct = ModelTensors.pack_grads(grads, ray_grads)
     nbytes = int(lib.tnf_backward_workspace_bytes(C.byref(model_struct), R))
     ws = saved.get("_workspace")
     if ws is None or ws.numel() < nbytes:
@@ -481,14 +486,22 @@ class _RenderFn(torch.autograd.Function):
         def flat(g):
             return None if g is None else g.reshape(g.shape[0], -1)
 
+        # pose path: the camera optimiser made origins / directions part of the graph (thermal_nerf_model.py:218-219)
+        ray_grads = None
+        if ctx.needs_input_grad[3] or ctx.needs_input_grad[4]:
+            ray_grads = (torch.zeros_like(o), torch.zeros_like(d))
         render_backward(ctx.tensors, ctx.model_struct, o, d, cam, nears, fars, jitter, saved,
                         {"rgb": g_rgb, "thermal": None if g_th is None else g_th.reshape(-1),
                          "accumulation": None if g_acc is None else g_acc.reshape(-1),
                          "weights_list": [flat(g_w0) if ctx.prop_grad else None,
                                           flat(g_w1) if ctx.prop_grad else None, flat(g_w2)]},
-                        grads)
+                        grads, ray_grads)
         out = [g if n_ else None for g, n_ in zip(grads, need)]
-        return (None,) * _RenderFn.NUM_FIXED + tuple(out)
+        fixed = [None] * _RenderFn.NUM_FIXED
+        if ray_grads is not None:
+            fixed[3] = ray_grads[0] if ctx.needs_input_grad[3] else None
+            fixed[4] = ray_grads[1] if ctx.needs_input_grad[4] else None
+        return tuple(fixed) + tuple(out)
 
 
 def render(tensors: ModelTensors, origins: Tensor, directions: Tensor, camera_indices: Optional[Tensor] = None,

@@ -248,15 +248,6 @@ class ThermalNerfModel(nn.Module):
         tnf_render_forward / tnf_render_backward (training)."""
         cfg = self.config
         if self.training:
-            if self.camera_optimizer.mode != "off" and not getattr(self, "_warned_pose_grad", False):
-                import warnings
-
-                # tnf_render_backward differentiates w.r.t. the parameters of the path, not w.r.t. ray origins /
-                # directions: the pose deltas are applied (forward) but receive no gradient (DESIGN.md section 7)
-                warnings.warn("thermo_nerf_b200: camera_optimizer_mode=%r applies the pose deltas but libtnf_b200 does "
-                              "not yet back-propagate into ray origins/directions, so camera_opt parameters will not "
-                              "be updated" % self.camera_optimizer.mode, RuntimeWarning, stacklevel=2)
-                self._warned_pose_grad = True
             self.camera_optimizer.apply_to_raybundle(ray_bundle)
         shape = tuple(ray_bundle.origins.shape[:-1])
         o = ray_bundle.origins.reshape(-1, 3).contiguous().float()
@@ -272,7 +263,9 @@ class ThermalNerfModel(nn.Module):
             # ProposalNetworkSampler: the proposal densities only carry gradients on "updated" steps
             updated = self._steps_since_update > self.update_schedule(self._step) or self._step < 10
             jitter = torch.rand((L.TNF_NUM_PROP + 1, R), device=o.device)
-            res = F.render(self.tensors(), o.detach(), d.detach(), cam_flat, nears, fars, jitter, prop_grad=updated,
+            # origins / directions stay in the graph when the camera optimiser produced them: the backward then
+            # also returns dL/d origins, dL/d directions and autograd carries them into the pose deltas
+            res = F.render(self.tensors(), o, d, cam_flat, nears, fars, jitter, prop_grad=updated,
                            detach_thermal_geo=not self.field.pass_thermal_gradients, **self._render_kwargs())
             if updated:
                 self._steps_since_update = 0
