@@ -361,6 +361,8 @@ def bench_train(ctx) -> dict:
     for i in range(args.warmup):
         engine.step(*batches[i % n_distinct])
     barrier()
+    if engine.arena is not None and os.environ.get("TNF_PEER_TIMING"):
+        engine.arena.timing = []  # per-phase events of the exchange (slightly perturbs the step: diagnostic runs only)
     sampler = ClockSampler(ctx["local"])
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -478,6 +480,7 @@ def bench_train(ctx) -> dict:
                      ("peer-memory fused reduce-scatter + Adam + all-gather (tnf_peer_adam_step)"
                       if engine.arena is not None else "NCCL all-reduce (mean) + tnf_adam_step")),
         "gpu_launches": None,
+        "exchange_phases_ms": engine.arena.timing_summary() if engine.arena is not None else None,
         "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": n_e2e,
                 "note": "plugin API: pinned host rays+GT -> H2D -> model(ray_bundle) -> get_metrics_dict -> get_loss_dict "
                         "-> loss.backward() -> FusedAdam.step -> D2H loss"},

@@ -402,6 +402,16 @@ int tnf_peer_adam_step(const TnfPeerArena* arena, float* exp_avg_shard, float* e
                        const TnfAdamSegment* segments, int32_t num_segments, double beta1, double beta2, float eps,
                        void* stream);
 
+/* The same exchange with a pull-style all-gather, as two launches: tnf_peer_adam_reduce (reduce-scatter + Adam,
+ * the updated shard is stored into this rank's own parameters only), a tnf_peer_barrier, then
+ * tnf_peer_gather_params (every rank copies the other ranks' shards out of their owners' arenas with peer
+ * loads).  Same results bit for bit; which flavour is faster depends on the fabric. */
+int tnf_peer_adam_reduce(const TnfPeerArena* arena, float* exp_avg_shard, float* exp_avg_sq_shard,
+                         const TnfAdamSegment* segments, int32_t num_segments, double beta1, double beta2, float eps,
+                         void* stream);
+int tnf_peer_gather_params(const TnfPeerArena* arena, const TnfAdamSegment* segments, int32_t num_segments,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

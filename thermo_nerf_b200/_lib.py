@@ -273,6 +273,8 @@ EXPORTED_SYMBOLS = (
     "tnf_peer_close_handle",
     "tnf_peer_barrier",
     "tnf_peer_adam_step",
+    "tnf_peer_adam_reduce",
+    "tnf_peer_gather_params",
 )
 
 
@@ -375,6 +377,10 @@ def load() -> C.CDLL:
     lib.tnf_peer_adam_step.restype = C.c_int
     lib.tnf_peer_adam_step.argtypes = [C.POINTER(TnfPeerArena), C.c_void_p, C.c_void_p, C.POINTER(TnfAdamSegment),
                                        C.c_int32, C.c_double, C.c_double, C.c_float, C.c_void_p]
+    lib.tnf_peer_adam_reduce.restype = C.c_int
+    lib.tnf_peer_adam_reduce.argtypes = lib.tnf_peer_adam_step.argtypes
+    lib.tnf_peer_gather_params.restype = C.c_int
+    lib.tnf_peer_gather_params.argtypes = [C.POINTER(TnfPeerArena), C.POINTER(TnfAdamSegment), C.c_int32, C.c_void_p]
     got = lib.tnf_version()
     if got != TNF_ABI_VERSION:
         raise ImportError(f"{path}: ABI version {got}, binding expects {TNF_ABI_VERSION}")

@@ -29,6 +29,7 @@ struct PeerAdamArgs {
   float seg_inv_sqrt_bc2[TNF_MAX_ADAM_SEGMENTS];
   int seg_active[TNF_MAX_ADAM_SEGMENTS];
   int nseg;
+  int push;  // 1: store the updated shard into every rank's parameters; 0: own copy only (peers pull it)
   float beta2, eps, omb1, omb2, inv_world;
 };
 
@@ -69,9 +70,32 @@ __global__ void __launch_bounds__(256) tnf_peer_adam_kernel(const __grid_constan
     peer_adam_one(p.w, g.w, m.w, v.w, A, ss, ib);
     M[i] = m;
     V[i] = v;
-    // all-gather: the updated shard goes to every rank's parameter arena
+    // all-gather, push flavour: the updated shard goes to every rank's parameter arena
+    if (A.push) {
 #pragma unroll 8
-    for (int r = 0; r < W; ++r) *reinterpret_cast<float4*>(A.a.params[r] + e) = p;
+      for (int r = 0; r < W; ++r) *reinterpret_cast<float4*>(A.a.params[r] + e) = p;
+    } else {
+      *reinterpret_cast<float4*>(A.a.params[me] + e) = p;
+    }
+  }
+}
+
+// all-gather, pull flavour: every rank copies the other ranks' freshly updated shards out of their owners'
+// parameter arenas (peer loads run at the NVLink rate; see DESIGN.md for the measured push / pull comparison)
+__global__ void __launch_bounds__(256) tnf_peer_gather_kernel(const __grid_constant__ TnfPeerArena a,
+                                                              const __grid_constant__ PeerAdamArgs A) {
+  const int W = a.world_size, me = a.rank;
+  const long long shard4 = (a.numel / W) >> 2, total4 = shard4 * (W - 1);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
+       i += (long long)gridDim.x * blockDim.x) {
+    int owner = (int)(i / shard4);
+    const long long off4 = i - (long long)owner * shard4;
+    owner = owner >= me ? owner + 1 : owner;  // skip the own shard
+    const long long e = ((long long)owner * shard4 + off4) << 2;
+    int s = 0;
+    while (s + 1 < A.nseg && e >= A.seg_end[s]) ++s;
+    if (!A.seg_active[s]) continue;
+    *reinterpret_cast<float4*>(a.params[me] + e) = __ldcv(reinterpret_cast<const float4*>(a.params[owner] + e));
   }
 }
 
@@ -207,9 +231,31 @@ int tnf_peer_barrier(const TnfPeerArena* arena, int32_t slot, uint32_t epoch, vo
   return TNF_OK;
 }
 
+static int peer_adam_impl(const TnfPeerArena* arena, float* exp_avg_shard, float* exp_avg_sq_shard,
+                          const TnfAdamSegment* segments, int32_t num_segments, double beta1, double beta2, float eps,
+                          int phase, void* stream_);
+
 int tnf_peer_adam_step(const TnfPeerArena* arena, float* exp_avg_shard, float* exp_avg_sq_shard,
                        const TnfAdamSegment* segments, int32_t num_segments, double beta1, double beta2, float eps,
                        void* stream_) {
+  return peer_adam_impl(arena, exp_avg_shard, exp_avg_sq_shard, segments, num_segments, beta1, beta2, eps, 0, stream_);
+}
+
+int tnf_peer_adam_reduce(const TnfPeerArena* arena, float* exp_avg_shard, float* exp_avg_sq_shard,
+                         const TnfAdamSegment* segments, int32_t num_segments, double beta1, double beta2, float eps,
+                         void* stream_) {
+  return peer_adam_impl(arena, exp_avg_shard, exp_avg_sq_shard, segments, num_segments, beta1, beta2, eps, 1, stream_);
+}
+
+int tnf_peer_gather_params(const TnfPeerArena* arena, const TnfAdamSegment* segments, int32_t num_segments,
+                           void* stream_) {
+  return peer_adam_impl(arena, nullptr, nullptr, segments, num_segments, 0.9, 0.999, 0.f, 2, stream_);
+}
+
+// phase 0: reduce + Adam + push to all ranks; 1: reduce + Adam, own copy only; 2: pull the other ranks' shards
+static int peer_adam_impl(const TnfPeerArena* arena, float* exp_avg_shard, float* exp_avg_sq_shard,
+                          const TnfAdamSegment* segments, int32_t num_segments, double beta1, double beta2, float eps,
+                          int phase, void* stream_) {
   using tnf::fail;
   tnf::g_err[0] = 0;
   if (int rc = check_arena(arena)) return rc;
@@ -219,7 +265,8 @@ int tnf_peer_adam_step(const TnfPeerArena* arena, float* exp_avg_shard, float* e
   for (int r = 0; r < W; ++r)
     if (!arena->grads[r] || !arena->params[r] || !tnf::aligned16(arena->grads[r]) || !tnf::aligned16(arena->params[r]))
       return fail(TNF_ERR_INVALID_ARGUMENT, "grads[%d]/params[%d] null or not 16-byte aligned", r, r);
-  if (!exp_avg_shard || !exp_avg_sq_shard || !tnf::aligned16(exp_avg_shard) || !tnf::aligned16(exp_avg_sq_shard))
+  if (phase != 2 &&
+      (!exp_avg_shard || !exp_avg_sq_shard || !tnf::aligned16(exp_avg_shard) || !tnf::aligned16(exp_avg_sq_shard)))
     return fail(TNF_ERR_INVALID_ARGUMENT, "exp_avg/exp_avg_sq shard null or not 16-byte aligned");
   if (!segments || num_segments < 1 || num_segments > TNF_MAX_ADAM_SEGMENTS)
     return fail(TNF_ERR_INVALID_ARGUMENT, "num_segments=%d not in [1,%d]", num_segments, TNF_MAX_ADAM_SEGMENTS);
@@ -253,12 +300,16 @@ int tnf_peer_adam_step(const TnfPeerArena* arena, float* exp_avg_shard, float* e
   A.beta2 = (float)beta2;
   A.eps = eps;
   A.inv_world = 1.0f / (float)W;
-  const long long n4 = shard >> 2;
+  A.push = phase == 0;
+  const long long n4 = phase == 2 ? (shard >> 2) * (W - 1) : (shard >> 2);
   if (n4 == 0) return TNF_OK;
   long long blocks = (n4 + 255) / 256;
   const long long cap = (long long)tnf::num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  tnf::tnf_peer_adam_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream_)>>>(A);
+  if (phase == 2)
+    tnf::tnf_peer_gather_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream_)>>>(*arena, A);
+  else
+    tnf::tnf_peer_adam_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream_)>>>(A);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "peer adam launch: %s", cudaGetErrorString(e));
   return TNF_OK;

@@ -168,6 +168,12 @@ class PeerArena:
         self.exp_avg = torch.zeros(self.shard, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(self.shard, dtype=torch.float32, device=dev)
         self._epoch = [0] * L.TNF_PEER_FLAG_SLOTS
+        self.timing: Optional[list] = None
+        import os
+
+        self.gather = os.environ.get("TNF_PEER_GATHER", "push")  # all-gather flavour: "push" (one kernel) | "pull"
+        if self.gather not in ("push", "pull"):
+            raise ValueError("TNF_PEER_GATHER must be 'push' or 'pull'")
         if self.world > 1:
             # self-test of the mappings in both directions: one barrier round must complete without a time-out
             self.barrier(0)
@@ -198,15 +204,42 @@ class PeerArena:
         for i, (b, e, lr, step, active) in enumerate(segments):
             segs[i].begin, segs[i].end, segs[i].lr = int(b), int(e), float(lr)
             segs[i].step, segs[i].active = int(step), int(bool(active))
+        ev = None
+        if self.timing is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            ev[0].record()
         self.barrier(0)  # every rank's backward has written its gradient arena
+        if ev:
+            ev[1].record()
         stream = torch.cuda.current_stream(self.device).cuda_stream
+        fn = self.lib.tnf_peer_adam_step if self.gather == "push" else self.lib.tnf_peer_adam_reduce
         with torch.cuda.device(self.device):
-            L.check(self.lib.tnf_peer_adam_step(C.byref(self.struct), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
-                                                segs, len(segments), float(beta1), float(beta2), float(eps),
-                                                C.c_void_p(stream)))
-        self.barrier(1)  # every rank's shard has landed in everybody's parameter arena
+            L.check(fn(C.byref(self.struct), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), segs, len(segments),
+                       float(beta1), float(beta2), float(eps), C.c_void_p(stream)))
+        if ev:
+            ev[2].record()
+        self.barrier(1)  # push: every shard has landed everywhere; pull: every owner holds its updated shard
+        if self.gather == "pull" and self.world > 1:
+            with torch.cuda.device(self.device):
+                L.check(self.lib.tnf_peer_gather_params(C.byref(self.struct), segs, len(segments), C.c_void_p(stream)))
+            # no third barrier: a peer can only overwrite its shard (next step's Adam) after the next barrier(0),
+            # which this rank reaches after its pull has completed (stream order)
+        if ev:
+            ev[3].record()
         if zero_grads:
             self.grads.zero_()
+        if ev:
+            ev[4].record()
+            self.timing.append(ev)
+
+    def timing_summary(self) -> Optional[dict]:
+        """Median milliseconds of the four phases of adam_step (measurement aid: PeerArena.timing = [] enables it)."""
+        if not self.timing:
+            return None
+        torch.cuda.synchronize(self.device)
+        names = ("barrier_wait_for_backward", "fused_reduce_adam_gather", "barrier_params_landed", "zero_grads")
+        cols = list(zip(*[[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in self.timing]))
+        return {n: sorted(c)[len(c) // 2] for n, c in zip(names, cols)}
 
     def timeouts(self) -> int:
         """Number of barrier waits that gave up (a peer never arrived); 0 in a healthy run."""
