@@ -328,3 +328,54 @@ def test_pose_gradients_match_oracle_autograd(precision, tol, med_tol):
                            camera_indices=rays.camera_indices.cuda()))
     (outm["rgb"].sum() + outm["thermal"].sum()).backward()
     assert model.camera_optimizer.pose_adjustment.grad.abs().sum().item() > 0
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 0.02), ("tc_fp16", 0.06)])
+def test_training_trajectory_tracks_oracle(precision, tol):
+    """Whole iterations, many of them: TrainEngine (forward, fused losses, backward, fused Adam, the sampler's
+    update schedule and weight annealing) against the oracle driven the way nerfstudio's Trainer drives the reference
+    (autograd + torch.optim.Adam(lr=1e-2, eps=1e-15) per param group, proposal nets under no_grad on non-update
+    steps), same initial weights, same ray batches, same jitter draws.  The loss trajectories must stay together."""
+    from thermo_nerf_b200.engine import TrainEngine, exponential_decay_lr
+
+    oracle, model = make_pair(trained_like=False, precision=precision, log2_field=12, log2_prop=10,
+                              camera_optimizer_mode="off")
+    model.train()
+    eng = TrainEngine(model)
+    field = [p for n, p in oracle.named_parameters() if n.startswith("field.")]
+    props = [p for n, p in oracle.named_parameters() if n.startswith("proposal_networks.")]
+    opt_f, opt_p = torch.optim.Adam(field, lr=1e-2, eps=1e-15), torch.optim.Adam(props, lr=1e-2, eps=1e-15)
+    R, steps = 384, 24
+    gen = torch.Generator().manual_seed(77)
+    ours_hist, ref_hist = [], []
+    since_update = 0
+    for step in range(steps):
+        rays = make_synthetic_rays(R, num_images=8, seed=100 + step % 3)  # three batches, cycled
+        gt_rgb = (0.5 + 0.4 * torch.sin(rays.directions * 7.0)).float()
+        gt_th = (0.5 + 0.4 * torch.cos(rays.directions[:, :1] * 5.0)).float()
+        jitter = torch.rand((3, R, 1), generator=gen)
+        # ---- oracle: what Trainer.train_iteration does around the reference model
+        updated = since_update > model.update_schedule(step) or step < 10
+        oracle.set_anneal_for_step(step)
+        opt_f.zero_grad(); opt_p.zero_grad()
+        out = oracle.get_outputs(rays, training=True, jitter=jitter, prop_grad=updated)
+        ld = oracle.get_loss_dict(out, gt_rgb, gt_th, training=True)
+        sum(ld.values()).backward()
+        for opt in (opt_f, opt_p):
+            for grp in opt.param_groups:
+                grp["lr"] = exponential_decay_lr(step)
+        opt_f.step()
+        if updated:
+            opt_p.step()
+            since_update = 0
+        since_update += 1
+        ref_hist.append(float(sum(ld.values())))
+        # ---- ours
+        ls = eng.step(rays.origins.cuda(), rays.directions.cuda(), rays.camera_indices.cuda().reshape(-1), gt_rgb.cuda(),
+                      gt_th.cuda().reshape(-1), jitter=jitter.cuda().reshape(3, -1))
+        ours_hist.append(float(ls.sum()))
+    print("oracle:", ["%.5f" % v for v in ref_hist[::4]])
+    print("ours:  ", ["%.5f" % v for v in ours_hist[::4]])
+    assert ref_hist[-1] < 0.6 * ref_hist[0]
+    for a, b in zip(ours_hist, ref_hist):
+        assert abs(a - b) <= tol * abs(b) + 1e-5, (ours_hist, ref_hist)

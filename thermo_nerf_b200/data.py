@@ -27,6 +27,8 @@ class DevicePixelSampler:
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("DevicePixelSampler keeps the dataset in GPU memory; there is no CPU path")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
         if images.dim() != 4 or images.shape[-1] < 3 or images.dtype not in (torch.float32, torch.uint8):
             raise ValueError("images must be [N,H,W,C>=3] float32 or uint8")
         self.images = images.to(dev).contiguous()
