@@ -44,18 +44,19 @@ struct Smem<TNF_PRECISION_TC_FP16> {
 };
 
 // ------------------------------------------------------------------------------------
-// proposal level: HashMLPDensityField.density_fn on S samples -> weights in ws.w
+// proposal level `lvl`: HashMLPDensityField.density_fn on the S samples between the spacing bins `bins`
+// (S + 1 values in the warp's scratch) -> compositing weights in `wout`.  One instantiation serves both
+// levels (runtime `lvl`): the kernel's instruction footprint has to stay inside the instruction cache.
 // ------------------------------------------------------------------------------------
-template <int LVL>
-__device__ __forceinline__ float proposal_level(const TnfModel& m, const PropW& W, WarpScratch& ws,
-                                                const RayCtx& rc, const int S, const bool stratified,
-                                                const float jit, const int lane, float* __restrict__ out_w,
-                                                float* __restrict__ out_sdist) {
-  const TnfDensityNet& net = m.prop[LVL];
+__device__ __forceinline__ float proposal_level(const TnfModel& m, const int lvl, const PropW& W,
+                                                const float* __restrict__ bins, float* __restrict__ wout,
+                                                const RayCtx& rc, const int S, const int lane,
+                                                float* __restrict__ out_w, float* __restrict__ out_sdist) {
+  const TnfDensityNet& net = m.prop[lvl];
   const int L = net.grid.num_levels;
   const uint32_t mask = (1u << net.grid.log2_size) - 1u;
   const float2* __restrict__ tab = reinterpret_cast<const float2*>(net.grid.table);
-  auto sb = [&](int i) -> float { return LVL == 0 ? initial_sbin(i, S, stratified, jit) : ws.bins[i]; };
+  auto sb = [&](int i) -> float { return bins[i]; };
 
   Compositor comp;
   float last_mid = 0.f;
@@ -100,7 +101,7 @@ __device__ __forceinline__ float proposal_level(const TnfModel& m, const PropW& 
     const float density = expf(o) * sel;  // average_init_density == 1.0
     const float w = comp.step(active ? delta * density : 0.f, mid, active, lane);
     if (active) {
-      ws.w[i] = w;
+      wout[i] = w;
       if (out_w) out_w[i] = w;
     }
     if (base + 32 >= S) last_mid = __shfl_sync(kFull, mid, (S - 1) & 31);
@@ -113,21 +114,21 @@ __device__ __forceinline__ float proposal_level(const TnfModel& m, const PropW& 
 }
 
 // ------------------------------------------------------------------------------------
-// PDFSampler (include_original=False, histogram_padding=0.01, eps=1e-5): ws.w (weights of
-// the previous level, consumed) -> `dst` (Snew+1 spacing bins).  `exist` = previous level's
-// spacing bins, or nullptr when they are the analytic initial bins.
+// PDFSampler (include_original=False, histogram_padding=0.01, eps=1e-5): `w` (weights of the previous level,
+// consumed) + `exist` (its Sprev + 1 spacing bins) -> `dst` (Snew + 1 spacing bins).  `dst` may alias `w`: every
+// read of the weights happens before the first bin is written.
 // ------------------------------------------------------------------------------------
 template <bool FAST>
-__device__ __forceinline__ void pdf_resample(WarpScratch& ws, const int Sprev, const int Snew, const float anneal,
-                                             const bool stratified, const float jit_prev, const float jit_new,
-                                             const float* exist, float* dst, const int lane) {
+__device__ __forceinline__ void pdf_resample(float* w_, float* __restrict__ cdf, const float* __restrict__ exist,
+                                             float* dst, const int Sprev, const int Snew, const float anneal,
+                                             const bool stratified, const float jit_new, const int lane) {
   float part = 0.f;
   for (int i = lane; i < Sprev; i += 32) {
-    float w = ws.w[i];
+    float w = w_[i];
     // tensor-core mode: w^a = exp2(a log2 w) on the SFU (w in [0,1]; 0 -> 0 for a > 0); fp32 mode: powf
     if (anneal != 1.f) w = FAST ? __powf(w, anneal) : powf(w, anneal);
     w += 0.01f;
-    ws.w[i] = w;
+    w_[i] = w;
     part += w;
   }
   float sum = warp_sum(part);
@@ -135,30 +136,29 @@ __device__ __forceinline__ void pdf_resample(WarpScratch& ws, const int Sprev, c
   const float padw = padding / (float)Sprev;
   sum += padding;
   float carry = 0.f;
-  if (lane == 0) ws.cdf[0] = 0.f;
+  if (lane == 0) cdf[0] = 0.f;
   for (int base = 0; base < Sprev; base += 32) {
     const int i = base + lane;
-    const float p = (i < Sprev) ? (ws.w[i] + padw) / sum : 0.f;
+    const float p = (i < Sprev) ? (w_[i] + padw) / sum : 0.f;
     const float inc = warp_incl_scan(p, lane) + carry;
-    if (i < Sprev) ws.cdf[i + 1] = fminf(1.f, inc);
+    if (i < Sprev) cdf[i + 1] = fminf(1.f, inc);
     carry = __shfl_sync(kFull, inc, 31);
   }
   __syncwarp();
   const int nb = Snew + 1;
   const float u_end = (float)(1.0 - 1.0 / (double)nb);
   const float u_off = stratified ? jit_new / (float)nb : (float)(1.0 / (double)(2 * nb));
-  auto ex = [&](int i) -> float { return exist ? exist[i] : initial_sbin(i, Sprev, stratified, jit_prev); };
   for (int j = lane; j < nb; j += 32) {
     const float u = linspace_at(j, nb, 0.f, u_end) + u_off;
     int lo = 0, hi = Sprev + 1;  // searchsorted(cdf, u, side="right")
     while (lo < hi) {
       const int midx = (lo + hi) >> 1;
-      if (ws.cdf[midx] <= u) lo = midx + 1; else hi = midx;
+      if (cdf[midx] <= u) lo = midx + 1; else hi = midx;
     }
     const int below = min(max(lo - 1, 0), Sprev);
     const int above = min(max(lo, 0), Sprev);
-    const float c0 = ws.cdf[below], c1 = ws.cdf[above];
-    const float b0 = ex(below), b1 = ex(above);
+    const float c0 = cdf[below], c1 = cdf[above];
+    const float b0 = exist[below], b1 = exist[above];
     float t = (u - c0) / (c1 - c0);
     t = isnan(t) ? 0.f : t;
     t = fminf(fmaxf(t, 0.f), 1.f);
@@ -185,7 +185,7 @@ __device__ __forceinline__ void field_level(const TnfModel& m, Smem<TNF_PRECISIO
     const bool active = i < S2;
     const int ii = active ? i : S2 - 1;
     float mid, delta;
-    sample_geometry(rc, ws.w[ii], ws.w[ii + 1], mid, delta);
+    sample_geometry(rc, ws.bins[ii], ws.bins[ii + 1], mid, delta);
     float px, py, pz;
     const float sel = normalise_position(m, ray_x(rc, mid), ray_y(rc, mid), ray_z(rc, mid), px, py, pz);
 #pragma unroll 4
@@ -261,7 +261,7 @@ __device__ __forceinline__ void field_level(const TnfModel& m, Smem<TNF_PRECISIO
     {
       const int ii = min(base + smp, S2 - 1);
       float mid, delta, px, py, pz;
-      sample_geometry(rc, ws.w[ii], ws.w[ii + 1], mid, delta);
+      sample_geometry(rc, ws.bins[ii], ws.bins[ii + 1], mid, delta);
       selv = normalise_position(m, ray_x(rc, mid), ray_y(rc, mid), ray_z(rc, mid), px, py, pz);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -463,20 +463,27 @@ __global__ void __launch_bounds__(kThreads, MINB)
 
     float pd0 = 0.f, pd1 = 0.f;
     if constexpr (PHASE != PHASE_FIELD) {
-      // ---- level 0
-      pd0 = proposal_level<0>(m, S.prop[0], ws, rc, S0, stratified, jit0, lane,
-                              out.weights[0] ? out.weights[0] + ray * S0 : nullptr,
-                              out.sdist[0] ? out.sdist[0] + ray * (S0 + 1) : nullptr);
-      pdf_resample<PREC == TNF_PRECISION_TC_FP16>(ws, S0, S1, m.anneal, stratified, jit0, jit1, nullptr, ws.bins, lane);
-      // ---- level 1
-      pd1 = proposal_level<1>(m, S.prop[1], ws, rc, S1, stratified, jit1, lane,
-                              out.weights[1] ? out.weights[1] + ray * S1 : nullptr,
-                              out.sdist[1] ? out.sdist[1] + ray * (S1 + 1) : nullptr);
-      pdf_resample<PREC == TNF_PRECISION_TC_FP16>(ws, S1, S2, m.anneal, stratified, jit1, jit2, ws.bins, ws.w, lane);
+      // three scratch lines rotate: A = bins of the current level, B = its weights -> the next level's bins,
+      // C = cdf.  After the two levels the final level's bins sit in ws.bins again.
+      float* A = ws.bins;
+      float* B = ws.w;
+      for (int i = lane; i <= S0; i += 32) A[i] = initial_sbin(i, S0, stratified, jit0);
+      __syncwarp();
+#pragma unroll 1
+      for (int lvl = 0; lvl < TNF_NUM_PROP; ++lvl) {
+        const int Sc = m.num_samples[lvl], Sn = m.num_samples[lvl + 1];
+        const float pd = proposal_level(m, lvl, S.prop[lvl], A, B, rc, Sc, lane,
+                                        out.weights[lvl] ? out.weights[lvl] + ray * Sc : nullptr,
+                                        out.sdist[lvl] ? out.sdist[lvl] + ray * (Sc + 1) : nullptr);
+        if (lvl == 0) pd0 = pd; else pd1 = pd;
+        pdf_resample<PREC == TNF_PRECISION_TC_FP16>(B, ws.cdf, A, B, Sc, Sn, m.anneal, stratified,
+                                                    lvl == 0 ? jit1 : jit2, lane);
+        float* t = A; A = B; B = t;
+      }
     }
     if constexpr (PHASE == PHASE_PROP) {
       // hand the final level's spacing bins (and the two proposal depths) to the field launch
-      for (int i = lane; i <= S2; i += 32) out.sdist[2][ray * (S2 + 1) + i] = ws.w[i];
+      for (int i = lane; i <= S2; i += 32) out.sdist[2][ray * (S2 + 1) + i] = ws.bins[i];
       if (lane == 0) {
         out.prop_depth[0][ray] = pd0;
         out.prop_depth[1][ray] = pd1;
@@ -485,11 +492,11 @@ __global__ void __launch_bounds__(kThreads, MINB)
       continue;
     }
     if constexpr (PHASE == PHASE_FIELD) {
-      for (int i = lane; i <= S2; i += 32) ws.w[i] = out.sdist[2][ray * (S2 + 1) + i];
+      for (int i = lane; i <= S2; i += 32) ws.bins[i] = out.sdist[2][ray * (S2 + 1) + i];
       __syncwarp();
     }
     if constexpr (PHASE != PHASE_PROP) {
-    // ---- level 2: field; its spacing bins now live in ws.w[0..S2]
+    // ---- level 2: field; its spacing bins live in ws.bins[0..S2]
     field_level(m, S, ws, rc, S2, lane, warp,
                 out.field_features
                     ? static_cast<unsigned char*>(out.field_features) +
@@ -505,7 +512,7 @@ __global__ void __launch_bounds__(kThreads, MINB)
       const bool active = i < S2;
       const int ii = active ? i : S2 - 1;
       float mid, delta;
-      sample_geometry(rc, ws.w[ii], ws.w[ii + 1], mid, delta);
+      sample_geometry(rc, ws.bins[ii], ws.bins[ii + 1], mid, delta);
       const float w = comp.step(active ? delta * ws.sigma[ii] : 0.f, mid, active, lane);
       float cr = ws.r[ii], cg = ws.g[ii], cb = ws.b[ii], ct = ws.th[ii];
       if (!train) { cr = nan_to_num(cr); cg = nan_to_num(cg); cb = nan_to_num(cb); ct = nan_to_num(ct); }
@@ -524,7 +531,7 @@ __global__ void __launch_bounds__(kThreads, MINB)
       if (base + 32 >= S2) last_mid = __shfl_sync(kFull, mid, (S2 - 1) & 31);
     }
     if (PHASE == PHASE_ALL && out.sdist[2]) {
-      for (int i = lane; i <= S2; i += 32) out.sdist[2][ray * (S2 + 1) + i] = ws.w[i];
+      for (int i = lane; i <= S2; i += 32) out.sdist[2][ray * (S2 + 1) + i] = ws.bins[i];
     }
     sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb); st = warp_sum(st);
     sw = warp_sum(sw); swt = warp_sum(swt);
