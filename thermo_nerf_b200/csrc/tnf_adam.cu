@@ -54,11 +54,15 @@ __global__ void __launch_bounds__(256) tnf_adam_kernel(const __grid_constant__ A
       float4* M = reinterpret_cast<float4*>(t.exp_avg + base);
       float4* V = reinterpret_cast<float4*>(t.exp_avg_sq + base);
       float4 p[4], g[4], m[4], v[4];
+      bool untouched[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int i = u * 256 + threadIdx.x;
         if (skip) { G[i] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
         p[u] = P[i]; g[u] = __ldcs(G + i); m[u] = M[i]; v[u] = V[i];
+        untouched[u] = g[u].x == 0.f && g[u].y == 0.f && g[u].z == 0.f && g[u].w == 0.f &&
+                       m[u].x == 0.f && m[u].y == 0.f && m[u].z == 0.f && m[u].w == 0.f &&
+                       v[u].x == 0.f && v[u].y == 0.f && v[u].z == 0.f && v[u].w == 0.f;
       }
       if (skip) continue;
 #pragma unroll
@@ -68,8 +72,11 @@ __global__ void __launch_bounds__(256) tnf_adam_kernel(const __grid_constant__ A
         adam_one(p[u].y, g[u].y, m[u].y, v[u].y, a, t.lr, inv_scale);
         adam_one(p[u].z, g[u].z, m[u].z, v[u].z, a, t.lr, inv_scale);
         adam_one(p[u].w, g[u].w, m[u].w, v[u].w, a, t.lr, inv_scale);
-        P[i] = p[u]; M[i] = m[u]; V[i] = v[u];
-        if (a.zero_grads) G[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // entries no ray has ever touched (most of the coarse hash levels: (res+1)^3 cells in a 2^19 table) have
+        // g = m = v = 0 and an update of exactly zero: skip their 12 B of stores (bit-identical result)
+        const bool idle = untouched[u];
+        if (!idle) { P[i] = p[u]; M[i] = m[u]; V[i] = v[u]; }
+        if (a.zero_grads && !idle) G[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     } else {
       for (long long i = threadIdx.x; i < n; i += 256) {

@@ -75,8 +75,17 @@ struct WgradProblem {
 constexpr int kMaxWgradProblems = 12;
 struct WgradArgs {
   WgradProblem p[kMaxWgradProblems];
+  int cta_start[kMaxWgradProblems + 1];  // CTAs [cta_start[i], cta_start[i+1]) work on problem i
   int n;
 };
+// which problem this CTA belongs to, its rank inside the problem's CTA range and that range's size
+__device__ __forceinline__ int wgrad_problem_of(const WgradArgs& a, int cta, int& local, int& count) {
+  int i = 0;
+  while (i + 1 < a.n && cta >= a.cta_start[i + 1]) ++i;
+  local = cta - a.cta_start[i];
+  count = a.cta_start[i + 1] - a.cta_start[i];
+  return i;
+}
 constexpr int kWgradRows = 64;
 
 // ------------------------------------------------------------------------------------
@@ -1373,7 +1382,8 @@ __global__ void __launch_bounds__(kThreads, 2)
 constexpr int kWgradLd = 72;  // padded row stride (bf16 elements): 144 B, conflict-free for ldmatrix
 
 __global__ void __launch_bounds__(128) tnf_wgrad_kernel_bf16(const __grid_constant__ WgradArgs args) {
-  const WgradProblem& P = args.p[blockIdx.y];
+  int cta_local, cta_count;
+  const WgradProblem& P = args.p[wgrad_problem_of(args, blockIdx.x, cta_local, cta_count)];
   __shared__ __align__(16) __nv_bfloat16 sdY[kWgradRows * kWgradLd];
   __shared__ __align__(16) __nv_bfloat16 sX[kWgradRows * kWgradLd];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1385,9 +1395,12 @@ __global__ void __launch_bounds__(128) tnf_wgrad_kernel_bf16(const __grid_consta
   float acc[8][4];
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-  float bacc = 0.f;
+  // bias gradients = column sums of dY: one more n-tile against a column of ones that lives in the row padding
+  // of the X tile (columns 64..71 are never written by the loader), instead of a scalar pass over the tile
+  float accb[4] = {0.f, 0.f, 0.f, 0.f};
+  if (tid < kWgradRows) *reinterpret_cast<uint4*>(&sX[tid * kWgradLd + 64]) = make_uint4(0x00003F80u, 0u, 0u, 0u);
   const long long tiles = (P.rows + kWgradRows - 1) / kWgradRows;
-  for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+  for (long long t = cta_local; t < tiles; t += cta_count) {
     const long long row0 = t * kWgradRows;
     // 64 rows x 8 column-vectors of 8 bf16 (16 B) each, zero padded
     for (int idx = tid; idx < kWgradRows * 8; idx += 128) {
@@ -1429,13 +1442,12 @@ __global__ void __launch_bounds__(128) tnf_wgrad_kernel_bf16(const __grid_consta
             mma_16816_bf16(acc[2 * np + 1], a, make_uint2(b[2], b[3]));
           }
         }
+        if (P.bias) {
+          uint32_t bb[2];
+          ldmatrix_x2_trans(bb, &sX[(ks * 16 + (mi & 1) * 8 + r) * kWgradLd + 64]);
+          mma_16816_bf16(accb, a, make_uint2(bb[0], bb[1]));
+        }
       }
-    }
-    if (P.bias && tid < P.n_valid) {
-      float sum = 0.f;
-#pragma unroll 8
-      for (int r = 0; r < kWgradRows; ++r) sum += __bfloat162float(sdY[r * kWgradLd + tid]);
-      bacc += sum;
     }
     __syncthreads();
   }
@@ -1451,14 +1463,19 @@ __global__ void __launch_bounds__(128) tnf_wgrad_kernel_bf16(const __grid_consta
       }
     }
   }
-  if (P.bias && tid < P.n_valid && bacc != 0.f) atomicAdd(P.bias + tid, bacc);
+  if (P.bias && warp < MT && q == 0) {  // column 0 of the ones tile: rows g and g + 8 of this warp's block
+    const int n = warp * 16 + g;
+    if (n < P.n_valid && accb[0] != 0.f) atomicAdd(P.bias + n, accb[0]);
+    if (n + 8 < P.n_valid && accb[2] != 0.f) atomicAdd(P.bias + n + 8, accb[2]);
+  }
 }
 
 // ------------------------------------------------------------------------------------
 // weight-gradient GEMMs: dW[n][k] += sum_rows dY[row][n0+n] * X[row][k];  db[n] += sum_rows dY
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tnf_wgrad_kernel_fp32(const __grid_constant__ WgradArgs args) {
-  const WgradProblem& P = args.p[blockIdx.y];
+  int cta_local, cta_count;
+  const WgradProblem& P = args.p[wgrad_problem_of(args, blockIdx.x, cta_local, cta_count)];
   __shared__ __align__(16) float sdY[kWgradRows][68];
   __shared__ __align__(16) float sX[kWgradRows][68];
   const int tid = threadIdx.x, tn = tid >> 4, tk = tid & 15;
@@ -1467,7 +1484,7 @@ __global__ void __launch_bounds__(256) tnf_wgrad_kernel_fp32(const __grid_consta
   float acc[4][4] = {};
   float bacc[4] = {};
   const long long tiles = (P.rows + kWgradRows - 1) / kWgradRows;
-  for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+  for (long long t = cta_local; t < tiles; t += cta_count) {
     const long long row0 = t * kWgradRows;
     for (int idx = tid; idx < kWgradRows * 16; idx += 256) {
       const int r = idx >> 4, c4 = (idx & 15) * 4;
@@ -1554,6 +1571,27 @@ void add_problem(tnf::WgradArgs& a, const void* dY, int ldY, int n0, int N, int 
   p.X = X; p.ldX = ldX; p.K = K; p.k_skip = k_skip;
   p.rows = rows; p.W = W; p.ldW = ldW; p.wcol0 = wcol0; p.bias = bias;
   p.dy_swz = dy_swz; p.x_swz = x_swz; p.x_f16 = x_f16;
+}
+
+// CTAs per problem in proportion to the bytes it streams (rows x loaded columns): the 64x64 layers move 1.7x the
+// average, and an equal split made the whole launch wait for them.  Returns the grid size.
+int assign_wgrad_ctas(tnf::WgradArgs& a, int total_ctas) {
+  double cost[tnf::kMaxWgradProblems], sum = 0.0;
+  for (int i = 0; i < a.n; ++i) {
+    cost[i] = (double)a.p[i].rows * (a.p[i].N + a.p[i].K);
+    sum += cost[i];
+  }
+  int acc = 0;
+  for (int i = 0; i < a.n; ++i) {
+    a.cta_start[i] = acc;
+    const long long tiles = (a.p[i].rows + tnf::kWgradRows - 1) / tnf::kWgradRows;
+    long long want = (long long)(cost[i] / sum * total_ctas + 0.5);
+    if (want < 1) want = 1;
+    if (want > tiles) want = tiles > 0 ? tiles : 1;
+    acc += (int)want;
+  }
+  a.cta_start[a.n] = acc;
+  return acc;
 }
 
 // the eight field layers (+ the two per-ray blocks of mlp_head.layers.0) as GEMM problems.
@@ -1683,9 +1721,7 @@ int tnf_render_backward(const TnfModel* model, const TnfRays* rays, const TnfSav
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "backward_field launch: %s", cudaGetErrorString(e));
     field_problems(wa, L, saved->field_features, false, grads->field, Ns, R);
-    const long long tiles = (Ns + tnf::kWgradRows - 1) / tnf::kWgradRows;
-    const long long capx = (long long)sms * 2 / wa.n + 1;
-    dim3 grid((unsigned)(tiles < capx ? tiles : capx), wa.n);
+    const int grid = assign_wgrad_ctas(wa, sms * 2);
     if (g_stage_mask & 4) tnf::tnf_wgrad_kernel_fp32<<<grid, 256, 0, stream>>>(wa);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(e));
@@ -1707,9 +1743,7 @@ int tnf_render_backward(const TnfModel* model, const TnfRays* rays, const TnfSav
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "backward_field launch: %s", cudaGetErrorString(e));
     field_problems(wa, L, saved->field_features, true, grads->field, Ns, R);
-    const long long tiles = (Ns + tnf::kWgradRows - 1) / tnf::kWgradRows;
-    const long long capx = (long long)sms * 8 / wa.n + 1;
-    dim3 grid((unsigned)(tiles < capx ? tiles : capx), wa.n);
+    const int grid = assign_wgrad_ctas(wa, sms * 8);
     if (g_stage_mask & 4) tnf::tnf_wgrad_kernel_bf16<<<grid, 128, 0, stream>>>(wa);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(e));

@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(kThreads, MINB)
   WarpScratch& ws = S.ws[warp];
   const bool train = m.training != 0;
   const bool stratified = train && rays.jitter != nullptr;
-  const int S0 = m.num_samples[0], S1 = m.num_samples[1], S2 = m.num_samples[2];
+  const int S0 = m.num_samples[0], S2 = m.num_samples[2];
   const long long R = rays.num_rays;
   long long cur_chunk = -1;
   float cmin = FLT_MAX, cmax = 0.f;

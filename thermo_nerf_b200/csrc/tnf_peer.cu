@@ -63,6 +63,11 @@ __global__ void __launch_bounds__(256) tnf_peer_adam_kernel(const __grid_constan
     g.x *= A.inv_world; g.y *= A.inv_world; g.z *= A.inv_world; g.w *= A.inv_world;
     float4 p = *reinterpret_cast<const float4*>(A.a.params[me] + e);
     float4 m = M[i], v = V[i];
+    // never-touched entries (g = m = v = 0 on every rank): the update is exactly zero and every rank already holds
+    // the same value - nothing to store, nothing to send
+    if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f && m.x == 0.f && m.y == 0.f && m.z == 0.f && m.w == 0.f &&
+        v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f)
+      continue;
     const float ss = A.seg_step_size[s], ib = A.seg_inv_sqrt_bc2[s];
     peer_adam_one(p.x, g.x, m.x, v.x, A, ss, ib);
     peer_adam_one(p.y, g.y, m.y, v.y, A, ss, ib);
