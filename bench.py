@@ -165,7 +165,7 @@ def train_batches(n_batches: int, rays: int, device, rank: int, pin: bool = Fals
 
 
 KERNEL_NAMES = {"forward": "tnf_forward_kernel", "backward_prop": "tnf_backward_prop_kernel",
-                "backward_field": "tnf_backward_field_kernel_tc", "wgrad": "tnf_wgrad_kernel_bf16",
+                "backward_field": "tnf_backward_field_kernel_tc", "wgrad": "tnf_wgrad_kernel_tma",
                 "adam": "tnf_adam_kernel"}
 
 TRAIN_WORKLOAD = ("thermal-nerf training iteration, ThermoScenes double_robot-shaped synthetic rays: {rays} rays/batch per "

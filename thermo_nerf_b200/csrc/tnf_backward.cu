@@ -66,6 +66,7 @@ __host__ inline size_t make_layout(BwdLayout* L, unsigned char* base, long long 
 struct WgradProblem {
   const void* dY; int ldY, n0, N, n_valid;   // N: loaded columns (multiple of 8), n_valid <= N are written
   const void* X;  int ldX, K, k_skip;        // K: loaded columns (multiple of 8); output col = k - k_skip >= 0
+  int xcol0;                                 // first loaded column of X within its row (TC kernel; X points at column 0)
   long long rows;
   float* W; int ldW, wcol0;
   float* bias;                               // may be null
@@ -1025,7 +1026,7 @@ __device__ __forceinline__ void apply_mask(float (&c)[NT][4], const uint32_t mk)
 // bulk-copy engine (cp.async.bulk.global.shared::cta): 2 KB leave the SM as one asynchronous copy instead
 // of 16 scattered 4-byte stores per lane, and no LSU/register resource is held while it drains.
 // 64-wide rows are XOR-swizzled by 16-byte chunk (chunk ^ (global_row & 7)) so the fragment stores are
-// bank-conflict free; tnf_wgrad_kernel_bf16 undoes the swizzle when it loads the rows.
+// bank-conflict free; tnf_wgrad_kernel_tma reads the raw image back with the same XOR in its ldmatrix addresses.
 struct alignas(128) StageRing {
   unsigned char buf[2][2048];
 };
@@ -1378,78 +1379,137 @@ __global__ void __launch_bounds__(kThreads, 2)
   if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");  // staged tiles have landed
 }
 
-// bf16 tensor-core weight-gradient GEMM: dW = dY^T X over 64-row tiles, fragments via ldmatrix.trans
-constexpr int kWgradLd = 72;  // padded row stride (bf16 elements): 144 B, conflict-free for ldmatrix
+// ------------------------------------------------------------------------------------
+// bf16 tensor-core weight-gradient GEMM: dW = dY^T X (+ db = column sums of dY) over 64-row tiles, fragments via
+// ldmatrix.trans, fed by the bulk-copy engine.  A 64-row tile of a staged matrix is one contiguous block of
+// global memory (rows are 128 / 96 / 64 / 32 / 16 bytes), so a tile of dY and a tile of X arrive in shared memory
+// as two cp.async.bulk copies that complete on an mbarrier - no per-thread address arithmetic, no register
+// staging - double buffered: the copies of tile i+1 are in flight while tile i is multiplied.  The 64-wide
+// matrices keep the chunk-swizzled layout stage_tile wrote them in, so the ldmatrix reads of the raw image are
+// bank-conflict free.
+// ------------------------------------------------------------------------------------
+struct alignas(128) WgradTmaSmem {
+  unsigned char dy[2][kWgradRows * 128];
+  unsigned char x[2][kWgradRows * 128];
+  unsigned char ones[kWgradRows * 16];  // [row][8] bf16, column 0 = 1: B operand of the bias-gradient tile
+  unsigned long long bar[2];
+};
 
-__global__ void __launch_bounds__(128) tnf_wgrad_kernel_bf16(const __grid_constant__ WgradArgs args) {
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_load_tile(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+          (uint32_t)__cvta_generic_to_shared(sdst)),
+      "l"(gsrc), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+      : "memory");
+}
+
+__global__ void __launch_bounds__(128) tnf_wgrad_kernel_tma(const __grid_constant__ WgradArgs args) {
+  extern __shared__ __align__(128) unsigned char wg_raw[];
+  WgradTmaSmem& S = *reinterpret_cast<WgradTmaSmem*>(wg_raw);
   int cta_local, cta_count;
   const WgradProblem& P = args.p[wgrad_problem_of(args, blockIdx.x, cta_local, cta_count)];
-  __shared__ __align__(16) __nv_bfloat16 sdY[kWgradRows * kWgradLd];
-  __shared__ __align__(16) __nv_bfloat16 sX[kWgradRows * kWgradLd];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
-  const __nv_bfloat16* dY = static_cast<const __nv_bfloat16*>(P.dY);
-  const __nv_bfloat16* X = static_cast<const __nv_bfloat16*>(P.X);
-  const int MT = (P.N + 15) / 16;  // 16-wide blocks of output rows n; warp w owns block w
-  const int NT = P.K / 8;          // 8-wide blocks of output columns k
+  const int dyB = P.ldY * 2, xB = P.ldX * 2;  // bytes per row (bf16, or fp16 for the saved hash features)
+  const int MT = (P.N + 15) / 16;             // 16-wide blocks of output rows n; warp w owns block w
+  const int NT = P.K / 8;                     // 8-wide blocks of output columns k
+  const long long tiles = (P.rows + kWgradRows - 1) / kWgradRows;
+  const long long mine = cta_local < tiles ? (tiles - cta_local + cta_count - 1) / cta_count : 0;
+  if (tid < kWgradRows) *reinterpret_cast<uint4*>(&S.ones[tid * 16]) = make_uint4(0x00003F80u, 0u, 0u, 0u);
+  if (tid == 0) {
+    mbar_init(&S.bar[0], 1);
+    mbar_init(&S.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](long long i) {  // thread 0: both tiles of my i-th 64-row block into stage i & 1
+    const int st = (int)(i & 1);
+    const long long row0 = (cta_local + i * cta_count) * kWgradRows;
+    const long long left = P.rows - row0;
+    const unsigned nrows = (unsigned)(left < kWgradRows ? left : kWgradRows);
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    mbar_expect_tx(&S.bar[st], nrows * (unsigned)(dyB + xB));
+    bulk_load_tile(S.dy[st], static_cast<const unsigned char*>(P.dY) + row0 * dyB, nrows * dyB, &S.bar[st]);
+    bulk_load_tile(S.x[st], static_cast<const unsigned char*>(P.X) + row0 * xB, nrows * xB, &S.bar[st]);
+  };
   float acc[8][4];
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-  // bias gradients = column sums of dY: one more n-tile against a column of ones that lives in the row padding
-  // of the X tile (columns 64..71 are never written by the loader), instead of a scalar pass over the tile
   float accb[4] = {0.f, 0.f, 0.f, 0.f};
-  if (tid < kWgradRows) *reinterpret_cast<uint4*>(&sX[tid * kWgradLd + 64]) = make_uint4(0x00003F80u, 0u, 0u, 0u);
-  const long long tiles = (P.rows + kWgradRows - 1) / kWgradRows;
-  for (long long t = cta_local; t < tiles; t += cta_count) {
-    const long long row0 = t * kWgradRows;
-    // 64 rows x 8 column-vectors of 8 bf16 (16 B) each, zero padded
-    for (int idx = tid; idx < kWgradRows * 8; idx += 128) {
-      const int r = idx >> 3, c8 = (idx & 7) * 8;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u), x = v;
-      const long long gr = row0 + r;
-      if (gr < P.rows) {
-        const int key = (int)(gr & 7) << 3;
-        if (c8 < P.N) v = *reinterpret_cast<const uint4*>(dY + gr * P.ldY + P.n0 + (P.dy_swz ? (c8 ^ key) : c8));
-        if (c8 < P.K) {
-          x = *reinterpret_cast<const uint4*>(X + gr * P.ldX + (P.x_swz ? (c8 ^ key) : c8));
-          if (P.x_f16) {
-            const __half2* h = reinterpret_cast<const __half2*>(&x);
-            const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]),
-                         f3 = __half22float2(h[3]);
-            x = make_uint4(pack_bf162(f0.x, f0.y), pack_bf162(f1.x, f1.y), pack_bf162(f2.x, f2.y),
-                           pack_bf162(f3.x, f3.y));
-          }
-        }
-      }
-      *reinterpret_cast<uint4*>(&sdY[r * kWgradLd + c8]) = v;
-      *reinterpret_cast<uint4*>(&sX[r * kWgradLd + c8]) = x;
+  if (tid == 0 && mine > 0) issue(0);
+  for (long long i = 0; i < mine; ++i) {
+    const int st = (int)(i & 1);
+    if (tid == 0 && i + 1 < mine) issue(i + 1);  // stage st^1 was released by the barrier that ended iteration i-1
+    const long long row0 = (cta_local + i * cta_count) * kWgradRows;
+    const int nrows = (int)(P.rows - row0 < kWgradRows ? P.rows - row0 : kWgradRows);
+    unsigned char* sdy = S.dy[st];
+    unsigned char* sx = S.x[st];
+    if (nrows < kWgradRows) {  // ragged last block: rows the copy does not write must read as zero
+      for (int b = nrows * dyB + tid * 16; b < kWgradRows * dyB; b += 128 * 16)
+        *reinterpret_cast<uint4*>(sdy + b) = make_uint4(0u, 0u, 0u, 0u);
+      for (int b = nrows * xB + tid * 16; b < kWgradRows * xB; b += 128 * 16)
+        *reinterpret_cast<uint4*>(sx + b) = make_uint4(0u, 0u, 0u, 0u);
     }
-    __syncthreads();
+    mbar_wait(&S.bar[st], (unsigned)((i >> 1) & 1));
+    if (P.x_f16) {  // saved hash features are fp16: convert the tile in place (bf16 mma operands)
+      for (int b = tid * 16; b < nrows * xB; b += 128 * 16) {
+        uint4 x = *reinterpret_cast<const uint4*>(sx + b);
+        const __half2* h = reinterpret_cast<const __half2*>(&x);
+        const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]),
+                     f3 = __half22float2(h[3]);
+        *reinterpret_cast<uint4*>(sx + b) = make_uint4(pack_bf162(f0.x, f0.y), pack_bf162(f1.x, f1.y),
+                                                       pack_bf162(f2.x, f2.y), pack_bf162(f3.x, f3.y));
+      }
+    }
+    if (P.x_f16 || nrows < kWgradRows) __syncthreads();
     if (warp < MT) {
+      const int mi = lane >> 3, r = lane & 7;
 #pragma unroll
       for (int ks = 0; ks < kWgradRows / 16; ++ks) {
-        const int mi = lane >> 3, r = lane & 7;
         uint32_t a[4];
-        // A = dY^T block: matrices (rows ks*16 + {0,8}, cols warp*16 + {0,8}) in order (r0,c0),(r0,c8),(r8,c0),(r8,c8)
-        ldmatrix_x4_trans(a, &sdY[(ks * 16 + (mi >> 1) * 8 + r) * kWgradLd + warp * 16 + (mi & 1) * 8]);
+        {  // A = dY^T block: (rows ks*16 + {0,8}, cols n0 + warp*16 + {0,8})
+          const int row = ks * 16 + (mi >> 1) * 8 + r;
+          const int chunk = ((P.n0 >> 3) + warp * 2 + (mi & 1)) ^ (P.dy_swz ? (row & 7) : 0);
+          ldmatrix_x4_trans(a, sdy + row * dyB + chunk * 16);
+        }
+        const int rowb = ks * 16 + (mi & 1) * 8 + r;
 #pragma unroll
         for (int np = 0; np < 4; ++np) {
           if (2 * np < NT) {
             uint32_t b[4];
-            // B = X block pair: (r0,k),(r8,k),(r0,k+8),(r8,k+8)
-            ldmatrix_x4_trans(b, &sX[(ks * 16 + (mi & 1) * 8 + r) * kWgradLd + (2 * np + (mi >> 1)) * 8]);
+            const int chunk = ((P.xcol0 >> 3) + 2 * np + (mi >> 1)) ^ (P.x_swz ? (rowb & 7) : 0);
+            ldmatrix_x4_trans(b, sx + rowb * xB + chunk * 16);
             mma_16816_bf16(acc[2 * np], a, make_uint2(b[0], b[1]));
             mma_16816_bf16(acc[2 * np + 1], a, make_uint2(b[2], b[3]));
           }
         }
         if (P.bias) {
           uint32_t bb[2];
-          ldmatrix_x2_trans(bb, &sX[(ks * 16 + (mi & 1) * 8 + r) * kWgradLd + 64]);
+          ldmatrix_x2_trans(bb, &S.ones[rowb * 16]);
           mma_16816_bf16(accb, a, make_uint2(bb[0], bb[1]));
         }
       }
     }
-    __syncthreads();
+    __syncthreads();  // every warp is done with stage st before iteration i+1 refills it
   }
   if (warp < MT) {
 #pragma unroll
@@ -1462,11 +1522,11 @@ __global__ void __launch_bounds__(128) tnf_wgrad_kernel_bf16(const __grid_consta
         if (n < P.n_valid && k >= 0 && acc[nt][e] != 0.f) atomicAdd(P.W + n * P.ldW + P.wcol0 + k, acc[nt][e]);
       }
     }
-  }
-  if (P.bias && warp < MT && q == 0) {  // column 0 of the ones tile: rows g and g + 8 of this warp's block
-    const int n = warp * 16 + g;
-    if (n < P.n_valid && accb[0] != 0.f) atomicAdd(P.bias + n, accb[0]);
-    if (n + 8 < P.n_valid && accb[2] != 0.f) atomicAdd(P.bias + n + 8, accb[2]);
+    if (P.bias && q == 0) {
+      const int n = warp * 16 + g;
+      if (n < P.n_valid && accb[0] != 0.f) atomicAdd(P.bias + n, accb[0]);
+      if (n + 8 < P.n_valid && accb[2] != 0.f) atomicAdd(P.bias + n + 8, accb[2]);
+    }
   }
 }
 
@@ -1565,12 +1625,12 @@ int set_smem(K kernel, size_t bytes, const char* name) {
 
 void add_problem(tnf::WgradArgs& a, const void* dY, int ldY, int n0, int N, int n_valid, const void* X, int ldX,
                  int K, int k_skip, long long rows, float* W, int ldW, int wcol0, float* bias, int dy_swz = 0,
-                 int x_swz = 0, int x_f16 = 0) {
+                 int x_swz = 0, int x_f16 = 0, int xcol0 = 0) {
   tnf::WgradProblem& p = a.p[a.n++];
   p.dY = dY; p.ldY = ldY; p.n0 = n0; p.N = N; p.n_valid = n_valid;
   p.X = X; p.ldX = ldX; p.K = K; p.k_skip = k_skip;
   p.rows = rows; p.W = W; p.ldW = ldW; p.wcol0 = wcol0; p.bias = bias;
-  p.dy_swz = dy_swz; p.x_swz = x_swz; p.x_f16 = x_f16;
+  p.dy_swz = dy_swz; p.x_swz = x_swz; p.x_f16 = x_f16; p.xcol0 = xcol0;
 }
 
 // CTAs per problem in proportion to the bytes it streams (rows x loaded columns): the 64x64 layers move 1.7x the
@@ -1620,7 +1680,10 @@ void field_problems(tnf::WgradArgs& a, const tnf::BwdLayout& L, const void* XF, 
   add_problem(a, L.dB2, kWX, 0, 64, 64, L.XB1, kWX, 64, 0, Ns, g.th1.weight, 64, 0, g.th1.bias, z, z);
   add_problem(a, L.dT, kWdT, 0, 8, 1, L.XB2, kWX, 64, 0, Ns, g.th2.weight, 64, 0, g.th2.bias, 0, z);
   add_problem(a, L.dRay, kWdRay, 0, 64, 64, L.XRay, kWXRay, 16, 0, R, g.rgb0.weight, 63, 0, g.rgb0.bias);
-  add_problem(a, L.dRay, kWdRay, 0, 64, 64, off(L.XRay, 16), kWXRay, 32, 0, R, g.rgb0.weight, 63, 31, nullptr);
+  if (tc)  // the TC kernel copies whole rows: the appearance block is columns 16..47 of the [R,48] rows
+    add_problem(a, L.dRay, kWdRay, 0, 64, 64, L.XRay, kWXRay, 32, 0, R, g.rgb0.weight, 63, 31, nullptr, 0, 0, 0, 16);
+  else
+    add_problem(a, L.dRay, kWdRay, 0, 64, 64, off(L.XRay, 16), kWXRay, 32, 0, R, g.rgb0.weight, 63, 31, nullptr);
 }
 }  // namespace
 
@@ -1743,8 +1806,10 @@ int tnf_render_backward(const TnfModel* model, const TnfRays* rays, const TnfSav
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "backward_field launch: %s", cudaGetErrorString(e));
     field_problems(wa, L, saved->field_features, true, grads->field, Ns, R);
-    const int grid = assign_wgrad_ctas(wa, sms * 8);
-    if (g_stage_mask & 4) tnf::tnf_wgrad_kernel_bf16<<<grid, 128, 0, stream>>>(wa);
+    const size_t wsmem = sizeof(tnf::WgradTmaSmem);
+    if (int rc = set_smem(tnf::tnf_wgrad_kernel_tma, wsmem, "wgrad_tma")) return rc;
+    const int grid = assign_wgrad_ctas(wa, sms * 6);  // 33.8 KB of shared memory per CTA: six CTAs per SM
+    if (g_stage_mask & 4) tnf::tnf_wgrad_kernel_tma<<<grid, 128, wsmem, stream>>>(wa);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(e));
   }
