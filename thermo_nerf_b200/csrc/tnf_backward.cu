@@ -645,6 +645,7 @@ struct FieldBwdScratch {
   float dtau[kMaxFieldS];  // dL/d thermal_i
   float T[kMaxFieldS], w[kMaxFieldS], gw[kMaxFieldS];
   float rayb[64];
+  float racc[64];  // TC kernel: per-ray column sums of dA1pre (kept here, not in 16 registers per lane)
 };
 
 // RGBRenderer / ThermalRenderer (background "last_sample"), AccumulationRenderer and get_weights,
@@ -1044,12 +1045,19 @@ __device__ __forceinline__ void stage_tile(StageRing& ring, int& slot, unsigned 
   if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");  // the slot's previous copy was read
   __syncwarp();
   unsigned char* b = ring.buf[slot];
-  const int key = NT == 8 ? (int)((tile_row0 + g) & 7) : 0;
+  // stmatrix: one instruction stores four 8x8 b16 matrices straight from the mma C-fragment layout; lane i
+  // addresses row (i & 7) of matrix (i >> 3): matrices = (rows 0-7, nt), (rows 8-15, nt), (rows 0-7, nt+1),
+  // (rows 8-15, nt+1).  16-byte chunks are XOR-swizzled by the row (64-wide matrices only).
+  const int mrow = (lane & 7) + ((lane >> 3) & 1) * 8;
+  const int mkey = NT == 8 ? (int)((tile_row0 + mrow) & 7) : 0;
 #pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    const int off = ((nt ^ key) * 16) + q * 4;
-    *reinterpret_cast<uint32_t*>(b + g * kRowBytes + off) = pack_bf162(c[nt][0], c[nt][1]);
-    *reinterpret_cast<uint32_t*>(b + (g + 8) * kRowBytes + off) = pack_bf162(c[nt][2], c[nt][3]);
+  for (int nt = 0; nt < NT; nt += 2) {
+    const int chunk = (nt + (lane >> 4)) ^ mkey;
+    const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(b + mrow * kRowBytes + chunk * 16));
+    asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1,%2,%3,%4};\n" ::"r"(addr),
+                 "r"(pack_bf162(c[nt][0], c[nt][1])), "r"(pack_bf162(c[nt][2], c[nt][3])),
+                 "r"(pack_bf162(c[nt + 1][0], c[nt + 1][1])), "r"(pack_bf162(c[nt + 1][2], c[nt + 1][3]))
+                 : "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> async-proxy read
   __syncwarp();
@@ -1159,9 +1167,8 @@ __global__ void __launch_bounds__(kThreads, 2)
                        go.rgb ? go.rgb[ray * 3 + 2] : 0.f, go.thermal ? go.thermal[ray] : 0.f,
                        go.accumulation ? go.accumulation[ray] : 0.f);
     float pg[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // pose path: sum_s dL/dx_s and sum_s t_s dL/dx_s of this ray
-    float racc[16];  // column sums of dA1pre over the ray (meaningful on lanes with g == 0)
-#pragma unroll
-    for (int i = 0; i < 16; ++i) racc[i] = 0.f;
+    ws.racc[lane] = 0.f;  // column sums of dA1pre over the ray
+    ws.racc[lane + 32] = 0.f;
 
     for (int base = 0; base < S2; base += 16) {
       const int r0 = base + g, r1 = base + g + 8;
@@ -1289,7 +1296,7 @@ __global__ void __launch_bounds__(kThreads, 2)
             sum += __shfl_xor_sync(kFull, sum, 4);
             sum += __shfl_xor_sync(kFull, sum, 8);
             sum += __shfl_xor_sync(kFull, sum, 16);
-            racc[nt * 2 + b] += sum;
+            if (g == 0) ws.racc[nt * 8 + 2 * q + b] += sum;  // one lane per column: no conflicts, no atomics
           }
         if (q == 0) {
           uint4* dzp = reinterpret_cast<uint4*>(L.dZ);
@@ -1361,17 +1368,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     // ---- per-ray epilogue
     {
       __syncwarp();
-      // gather the 64 column sums: lane q (g == 0) holds columns nt*8 + 2q + b at racc[nt*2 + b]
-      float* tmp = ws.rayb;  // the first-layer bias is no longer needed
-      if (g == 0) {
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          tmp[nt * 8 + 2 * q] = racc[nt * 2];
-          tmp[nt * 8 + 2 * q + 1] = racc[nt * 2 + 1];
-        }
-      }
-      __syncwarp();
-      const float r0_ = tmp[lane], r1_ = tmp[lane + 32];
+      const float r0_ = ws.racc[lane], r1_ = ws.racc[lane + 32];
       ray_epilogue<__nv_bfloat16>(m, rays, ray, lane, sh, app_lane, r0_, r1_, L, gr.field.appearance);
       __syncwarp();
     }
