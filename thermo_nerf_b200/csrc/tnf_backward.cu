@@ -982,10 +982,16 @@ __global__ void __launch_bounds__(kThreads, 1)
 template <int NT, int KT>
 __device__ __forceinline__ void mma_layer_bf16(float (&c)[NT][4], const uint32_t (&a)[KT][4],
                                                const uint2* __restrict__ w, const int ntw, const int lane) {
+  static_assert((NT & 1) == 0, "backward weight images use the paired-fragment layout");
+  const uint4* __restrict__ w4 = reinterpret_cast<const uint4*>(w);
 #pragma unroll
-  for (int nt = 0; nt < NT; ++nt)
+  for (int nt = 0; nt < NT; nt += 2)
 #pragma unroll
-    for (int kt = 0; kt < KT; ++kt) mma_16816_bf16(c[nt], a[kt], w[(kt * ntw + nt) * 32 + lane]);
+    for (int kt = 0; kt < KT; ++kt) {
+      const uint4 b = w4[(kt * (ntw >> 1) + (nt >> 1)) * 32 + lane];
+      mma_16816_bf16(c[nt], a[kt], make_uint2(b.x, b.y));
+      mma_16816_bf16(c[nt + 1], a[kt], make_uint2(b.z, b.w));
+    }
 }
 template <int NT>
 __device__ __forceinline__ void zero_c(float (&c)[NT][4]) {
@@ -1096,7 +1102,8 @@ __device__ inline void stage_frag_bf16(uint2* dst, int KT, int NT, const V& v, i
     const int lane = i & 31, nt = (i >> 5) % NT, kt = (i >> 5) / NT;
     const int g = lane >> 2, q = lane & 3;
     const int n = nt * 8 + g, k = kt * 16 + 2 * q;
-    dst[i] = make_uint2(pack_bf162(v(k, n), v(k + 1, n)), pack_bf162(v(k + 8, n), v(k + 9, n)));
+    dst[frag_index(kt, nt, lane, NT)] =
+        make_uint2(pack_bf162(v(k, n), v(k + 1, n)), pack_bf162(v(k + 8, n), v(k + 9, n)));
   }
 }
 __device__ inline void stage_field_bwd(FieldBwdWTC& W, const TnfModel& m, int tid) {

@@ -93,13 +93,20 @@ template <typename V>
 __device__ inline void stage_t(float* dst, int K, int N, const V& v, int tid) {
   for (int i = tid; i < K * N; i += kThreads) dst[i] = v(i / N, i % N);
 }
+// Position of the B fragment (k-tile kt, n-tile nt, lane) in a staged weight image with NT n-tiles per k-tile.
+// For an even NT the fragments of n-tiles (2j, 2j+1) of one lane sit next to each other, so one 16-byte shared
+// load feeds two mma instructions (half the LDS count of a fragment-per-load layout).
+__device__ __forceinline__ int frag_index(int kt, int nt, int lane, int NT) {
+  return (NT & 1) ? (kt * NT + nt) * 32 + lane : ((kt * (NT >> 1) + (nt >> 1)) * 32 + lane) * 2 + (nt & 1);
+}
 template <typename V>
 __device__ inline void stage_frag(uint2* dst, int KT, int NT, const V& v, int tid) {
   for (int i = tid; i < KT * NT * 32; i += kThreads) {
     const int lane = i & 31, nt = (i >> 5) % NT, kt = (i >> 5) / NT;
     const int g = lane >> 2, q = lane & 3;
     const int n = nt * 8 + g, k = kt * 16 + 2 * q;
-    dst[i] = make_uint2(pack_half2(v(k, n), v(k + 1, n)), pack_half2(v(k + 8, n), v(k + 9, n)));
+    dst[frag_index(kt, nt, lane, NT)] =
+        make_uint2(pack_half2(v(k, n), v(k + 1, n)), pack_half2(v(k + 8, n), v(k + 9, n)));
   }
 }
 __device__ inline void stage_vec(float* dst, const float* src, int n, int npad, int tid) {
@@ -259,11 +266,23 @@ __device__ __forceinline__ void store_col(float* xout, const float (&y)[N]) {
 template <int NT, int KT>
 __device__ __forceinline__ void mma_layer(float (&c)[NT][4], const uint32_t (&a)[KT][4], const uint2* __restrict__ w,
                                           const int nt0, const int ntw, const int lane) {
-  // w is [KT][ntw][32]; uses n-tiles nt0 .. nt0+NT-1
+  // w is a frag_index image with ntw n-tiles per k-tile; uses n-tiles nt0 .. nt0+NT-1 (nt0 even)
+  if constexpr ((NT & 1) == 0) {
+    const uint4* __restrict__ w4 = reinterpret_cast<const uint4*>(w);
 #pragma unroll
-  for (int nt = 0; nt < NT; ++nt)
+    for (int nt = 0; nt < NT; nt += 2)
 #pragma unroll
-    for (int kt = 0; kt < KT; ++kt) mma_16816(c[nt], a[kt], w[(kt * ntw + nt0 + nt) * 32 + lane]);
+      for (int kt = 0; kt < KT; ++kt) {
+        const uint4 b = w4[(kt * (ntw >> 1) + ((nt0 + nt) >> 1)) * 32 + lane];
+        mma_16816(c[nt], a[kt], make_uint2(b.x, b.y));
+        mma_16816(c[nt + 1], a[kt], make_uint2(b.z, b.w));
+      }
+  } else {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int kt = 0; kt < KT; ++kt) mma_16816(c[nt], a[kt], w[frag_index(kt, nt0 + nt, lane, ntw)]);
+  }
 }
 template <int NT>
 __device__ __forceinline__ void init_bias(float (&c)[NT][4], const float* bias, const int q) {
