@@ -137,3 +137,69 @@ def test_model_tensors_validate_architecture():
     model.field.mlp_head.layers[0] = torch.nn.Linear(10, 64)
     with pytest.raises(ValueError, match="fixed architecture"):
         ModelTensors.from_module(model)
+
+
+def test_image_metrics_and_images_surface():
+    """Evaluator calls model.get_image_metrics_and_images(outputs, batch, threshold=...) (evaluator.py:79-87) and
+    save_metrics needs the thermal keys (evaluator.py:155-158).  Pure PyTorch glue: runs on CPU tensors."""
+    import math
+
+    import torch
+
+    from thermo_nerf_b200 import ThermalNerfModel, ThermalNerfModelConfig
+
+    args = [{"hidden_dim": 16, "log2_hashmap_size": 8, "num_levels": 5, "max_res": 128, "use_linear": False}] * 2
+    cfg = ThermalNerfModelConfig(log2_hashmap_size=8, proposal_net_args_list=args, max_temperature=40.0, min_temperature=10.0)
+    model = ThermalNerfModel(cfg, {"thermal": []}, torch.tensor([[-1.0, -1, -1], [1, 1, 1]]), 4)
+    g = torch.Generator().manual_seed(0)
+    H, W = 24, 32
+    gt_rgb, gt_th = torch.rand((H, W, 3), generator=g), torch.rand((H, W, 1), generator=g)
+    outputs = {"rgb": (gt_rgb + 0.05 * torch.randn((H, W, 3), generator=g)).clamp(0, 1),
+               "thermal": (gt_th + 0.02).clamp(0, 1), "accumulation": torch.rand((H, W, 1), generator=g),
+               "depth": torch.rand((H, W, 1), generator=g) * 3, "prop_depth_0": torch.rand((H, W, 1), generator=g),
+               "prop_depth_1": torch.rand((H, W, 1), generator=g)}
+    metrics, images = model.get_image_metrics_and_images(outputs, {"image": gt_rgb, "thermal": gt_th}, threshold=0.5)
+    assert set(metrics) == {"psnr", "ssim", "lpips", "psnr_thermal", "ssim_thermal", "lpips_thermal",
+                            "mae_thermal_foreground", "mae_thermal"}
+    assert set(images) >= {"img", "accumulation", "depth", "prop_depth_0", "prop_depth_1", "thermal", "thermal_combined"}
+    assert images["img"].shape == (H, 2 * W, 3) and images["thermal_combined"].shape == (H, 2 * W, 3)
+    mse = torch.mean((outputs["rgb"] - gt_rgb) ** 2)
+    assert metrics["psnr"] == pytest.approx(float(-10 * torch.log10(mse)), rel=1e-6)
+    assert 0.0 < metrics["ssim"] < 1.0 and metrics["ssim_thermal"] > 0.9
+    assert math.isnan(metrics["lpips"])  # no pretrained LPIPS network offline
+    assert metrics["mae_thermal"] == pytest.approx(0.02 * 30.0, rel=0.05)  # 0.02 of a 30 degree range (clamping aside)
+    # identical images: SSIM 1, and a plugged-in LPIPS callable is used
+    model.lpips = lambda a, b: torch.tensor(0.25)
+    m2, _ = model.get_image_metrics_and_images({**outputs, "rgb": gt_rgb, "thermal": gt_th},
+                                               {"image": gt_rgb, "thermal": gt_th})
+    assert m2["ssim"] == pytest.approx(1.0, abs=1e-5) and m2["lpips_thermal"] == 0.25 and m2["mae_thermal"] == 0.0
+
+
+def test_ssim_matches_an_independent_scipy_evaluation():
+    """SSIM (torchmetrics defaults) recomputed with scipy on the valid region: 11x11 gaussian (sigma 1.5) local
+    moments, data range from the data, mean of the map."""
+    import numpy as np
+    import torch
+    from scipy.signal import convolve2d
+
+    from thermo_nerf_b200 import ThermalNerfModel
+
+    g = torch.Generator().manual_seed(5)
+    a = torch.rand((1, 2, 40, 37), generator=g)
+    b = (a + 0.1 * torch.randn(a.shape, generator=g)).clamp(0, 1)
+    got = float(ThermalNerfModel.ssim(a, b))
+    x = np.arange(11) - 5.0
+    k1 = np.exp(-(x / 1.5) ** 2 / 2)
+    k1 /= k1.sum()
+    win = np.outer(k1, k1)
+    A, B = a.numpy().astype(np.float64), b.numpy().astype(np.float64)
+    L = max(B.max() - B.min(), A.max() - A.min())
+    c1, c2 = (0.01 * L) ** 2, (0.03 * L) ** 2
+    vals = []
+    for ch in range(2):
+        f = lambda z: convolve2d(z, win, mode="valid")
+        mp, mt = f(B[0, ch]), f(A[0, ch])
+        spp, stt, spt = f(B[0, ch] ** 2) - mp * mp, f(A[0, ch] ** 2) - mt * mt, f(A[0, ch] * B[0, ch]) - mp * mt
+        vals.append(((2 * mp * mt + c1) * (2 * spt + c2)) / ((mp * mp + mt * mt + c1) * (spp + stt + c2)))
+    want = float(np.mean(np.stack(vals)))
+    assert got == pytest.approx(want, rel=1e-4)

@@ -393,6 +393,77 @@ class ThermalNerfModel(nn.Module):
             loss_dict["thermal"] = torch.nn.functional.mse_loss(outputs["thermal"], batch["thermal"].to(self.device))
         return loss_dict
 
+    # ------------------------------------------------------------------ evaluation (Evaluator, evaluator.py:79-87)
+    lpips: Optional[Callable[[Tensor, Tensor], Tensor]] = None  # LPIPS needs pretrained weights: plug a callable in
+
+    @staticmethod
+    def psnr(gt: Tensor, pred: Tensor) -> Tensor:
+        """torchmetrics PeakSignalNoiseRatio(data_range=1.0), as NerfactoModel.psnr."""
+        return -10.0 * torch.log10(torch.mean((gt - pred) ** 2))
+
+    @staticmethod
+    def ssim(gt: Tensor, pred: Tensor) -> Tensor:
+        """torchmetrics.functional.structural_similarity_index_measure with its defaults (11x11 gaussian window,
+        sigma 1.5, k1 0.01, k2 0.03, data_range taken from the data, reflect padding cropped away), [N,C,H,W]."""
+        data_range = torch.maximum(pred.max() - pred.min(), gt.max() - gt.min())
+        c1, c2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+        k, sigma, pad = 11, 1.5, 5
+        x = torch.arange(k, dtype=gt.dtype, device=gt.device) - (k - 1) / 2
+        g1 = torch.exp(-(x / sigma) ** 2 / 2)
+        g1 = g1 / g1.sum()
+        C = gt.shape[1]
+        win = (g1[:, None] * g1[None, :]).expand(C, 1, k, k)
+        p = torch.nn.functional.pad(pred, (pad, pad, pad, pad), mode="reflect")
+        t = torch.nn.functional.pad(gt, (pad, pad, pad, pad), mode="reflect")
+        stack = torch.cat([p, t, p * p, t * t, p * t])
+        out = torch.nn.functional.conv2d(stack, win, groups=C)
+        n = pred.shape[0]
+        mu_p, mu_t, e_pp, e_tt, e_pt = (out[i * n:(i + 1) * n] for i in range(5))
+        s_pp, s_tt, s_pt = e_pp - mu_p * mu_p, e_tt - mu_t * mu_t, e_pt - mu_p * mu_t
+        ssim_map = ((2 * mu_p * mu_t + c1) * (2 * s_pt + c2)) / ((mu_p * mu_p + mu_t * mu_t + c1) * (s_pp + s_tt + c2))
+        return ssim_map[..., pad:-pad, pad:-pad].reshape(n, -1).mean(-1).mean()
+
+    def _lpips(self, gt: Tensor, pred: Tensor) -> float:
+        return float(self.lpips(gt, pred)) if self.lpips is not None else float("nan")
+
+    def get_image_metrics_and_images(self, outputs: Dict[str, Tensor], batch: Dict[str, Tensor],
+                                     threshold: Optional[float] = None) -> Tuple[Dict[str, float], Dict[str, Tensor]]:
+        """thermal_nerf_model.py:328-398 on top of NerfactoModel.get_image_metrics_and_images: psnr / ssim / lpips of
+        the RGB image, psnr_thermal / ssim_thermal / lpips_thermal, mae_thermal and mae_thermal_foreground
+        (thermal_metrics.py), plus the side-by-side images the viewer logs.  Evaluation-only glue in plain PyTorch on
+        the already rendered [H,W,C] outputs.  LPIPS needs a pretrained network that is not shipped here: assign
+        ``model.lpips`` (e.g. torchmetrics' LearnedPerceptualImagePatchSimilarity) or the two lpips entries are NaN.
+        The accumulation / depth panels are grey-scale (nerfstudio's default colour maps come from matplotlib)."""
+        dev = self.device
+        gt_rgb = batch["image"].to(dev)[..., :3]
+        rgb = outputs["rgb"]
+
+        def gray(t: Tensor) -> Tensor:  # colormaps.apply_float_colormap(colormap="gray")
+            return t.repeat(1, 1, 3) if t.shape[-1] == 1 else t
+
+        acc = outputs["accumulation"]
+        depth = outputs["depth"]
+        near, far = float(depth.min()), float(depth.max())
+        depth_n = torch.clip((depth - near) / (far - near + 1e-10), 0, 1)
+        images = {"img": torch.cat([gt_rgb, rgb], dim=1), "accumulation": gray(acc), "depth": gray(depth_n)}
+        for i in range(self.config.num_proposal_iterations):
+            pd = outputs[f"prop_depth_{i}"]
+            images[f"prop_depth_{i}"] = gray(torch.clip((pd - float(pd.min())) / (float(pd.max() - pd.min()) + 1e-10), 0, 1))
+        g4, p4 = torch.moveaxis(gt_rgb, -1, 0)[None], torch.moveaxis(rgb, -1, 0)[None]
+        metrics: Dict[str, float] = {"psnr": float(self.psnr(g4, p4)), "ssim": float(self.ssim(g4, p4)),
+                                     "lpips": self._lpips(g4, p4)}
+        gt_th = batch["thermal"].to(dev)  # thermal_nerf_model.py:347 (the reference forgets the .to() at :355)
+        th = outputs["thermal"]
+        images["thermal"] = gray(th)
+        images["thermal_combined"] = torch.cat([gray(gt_th), gray(th)], dim=1)
+        gt4, th4 = torch.moveaxis(gt_th, -1, 0)[None], torch.moveaxis(th, -1, 0)[None]
+        metrics["psnr_thermal"] = float(self.psnr(gt4, th4))
+        metrics["ssim_thermal"] = float(self.ssim(gt4, th4))
+        metrics["lpips_thermal"] = self._lpips(torch.repeat_interleave(gt4, 3, dim=1), torch.repeat_interleave(th4, 3, dim=1))
+        metrics["mae_thermal_foreground"] = float(self.mae_thermal(gt4, th4, threshold=threshold))
+        metrics["mae_thermal"] = float(self.mae_thermal(gt4, th4, threshold=None))
+        return metrics, images
+
     def mae_thermal(self, gt: Tensor, pred: Tensor, threshold: Optional[float] = None) -> Tensor:
         """thermal_metrics.py:5-34."""
         if threshold:
