@@ -124,3 +124,38 @@ def test_renderer_matches_reference_loop():
             assert np.array_equal(got, want), m
     with pytest.raises(Exception):
         r.render([M.THERMAL_COMBINED], cams, thermal_color_map=cm)
+
+
+def test_evaluator_fused_and_pose_paths_agree():
+    """Evaluator (evaluator.py:47-106) over the model: with the pose deltas at zero the path that generates the rays in
+    the kernel (camera optimiser off) and the one that builds the bundle, applies the camera optimiser in PyTorch and
+    renders it (SO3xR3) must give the same metrics; images come back as uint8 side-by-side panels."""
+    from types import SimpleNamespace
+
+    from thermo_nerf_b200 import Evaluator
+    from thermo_nerf_b200 import RenderedImageModality as M
+
+    cams = _cameras(2)
+    g = torch.Generator().manual_seed(4)
+    loader = []
+    for i in range(cams.size):
+        one = type(cams)(cams.camera_to_worlds[i:i + 1], cams.fx, cams.fy, cams.cx, cams.cy, cams.width, cams.height)
+        loader.append((one, {"image": torch.rand((cams.height, cams.width, 3), generator=g),
+                             "thermal": torch.rand((cams.height, cams.width, 1), generator=g)}))
+    cfg = SimpleNamespace(experiment_name="exp", method_name="thermal-nerf")
+    results = {}
+    for mode in ("off", "SO3xR3"):
+        _, model = make_pair(trained_like=True, precision="tc_fp16", camera_optimizer_mode=mode)
+        with torch.no_grad():
+            model.camera_optimizer.pose_adjustment.zero_()
+        dm = SimpleNamespace(setup_eval=lambda: None, fixed_indices_eval_dataloader=loader)
+        ev = Evaluator(SimpleNamespace(model=model, datamanager=dm), cfg, modalities_to_save=[M.RGB, M.THERMAL_COMBINED],
+                       threshold=0.5)
+        results[mode] = ev
+        assert len(ev._evaluation_images[M.RGB]) == 2
+        assert ev._evaluation_images[M.RGB][0].shape == (cams.height, 2 * cams.width, 3)
+        assert ev._evaluation_images[M.THERMAL_COMBINED][0].dtype == np.uint8
+    a, b = results["off"].metrics, results["SO3xR3"].metrics
+    assert set(a) == set(b) and "mae_thermal_mean" in a and "psnr_thermal_std" in a
+    for k in ("psnr", "ssim", "psnr_thermal", "mae_thermal", "mae_thermal_foreground"):
+        assert a[k] == pytest.approx(b[k], rel=1e-6, abs=1e-9), k

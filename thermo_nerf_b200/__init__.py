@@ -14,9 +14,10 @@ from .modules import (CameraOptimizer, FieldHeadNames, FieldHeadNamesT, HashMLPD
 from .rays import PinholeCameras, RayBundle, orbit_cameras, sphere_cameras
 from .render import RenderedImageModality, Renderer
 from .data import DevicePixelSampler
+from .evaluator import Evaluator
 
 __all__ = [
     "ModelTensors", "render_forward", "render", "losses", "adam_step", "FusedAdam", "ThermalNerfModel", "ThermalNerfModelConfig", "CameraOptimizer",
     "FieldHeadNames", "FieldHeadNamesT", "HashMLPDensityField", "ThermalFieldHead", "ThermalNerfactoTField",
-    "PinholeCameras", "RayBundle", "orbit_cameras", "sphere_cameras", "Renderer", "RenderedImageModality", "DevicePixelSampler",
+    "PinholeCameras", "RayBundle", "orbit_cameras", "sphere_cameras", "Renderer", "RenderedImageModality", "DevicePixelSampler", "Evaluator",
 ]
