@@ -203,3 +203,26 @@ def test_ssim_matches_an_independent_scipy_evaluation():
         vals.append(((2 * mp * mt + c1) * (2 * spt + c2)) / ((mp * mp + mt * mt + c1) * (spp + stt + c2)))
     want = float(np.mean(np.stack(vals)))
     assert got == pytest.approx(want, rel=1e-4)
+
+
+def test_nerfacto_variant_has_no_thermal_head():
+    """ThermalNerfactoModel (nerfacto_config/thermal_nerfacto.py): no thermal metadata needed, no mlp_thermal /
+    field_head_thermal entries in the state_dict or the optimiser groups, thermal-head tensors are constant zeros."""
+    import torch
+
+    from thermo_nerf_b200 import ModelTensors, ThermalNerfactoModel, ThermalNerfactoModelConfig, ThermalNerfModelConfig
+
+    args = [{"hidden_dim": 16, "log2_hashmap_size": 8, "num_levels": 5, "max_res": 128, "use_linear": False}] * 2
+    cfg = ThermalNerfactoModelConfig(log2_hashmap_size=8, proposal_net_args_list=args)
+    m = cfg.setup(scene_box=torch.tensor([[-1.0, -1, -1], [1, 1, 1]]), num_train_data=3)
+    assert isinstance(m, ThermalNerfactoModel)
+    keys = list(m.state_dict())
+    assert not any("mlp_thermal" in k or "field_head_thermal" in k for k in keys)
+    assert any(k.startswith("field.mlp_head.layers.2") for k in keys)
+    names = {n for n, _ in m.named_parameters()}
+    assert not any("thermal" in n for n in names)
+    t = ModelTensors.from_module(m)  # the kernels still get (zero) thermal-head tensors of the fixed shapes
+    assert t.field_linears["th0"].weight.shape == (64, 15) and float(t.field_linears["th2"].weight.abs().sum()) == 0.0
+    assert m.field.pass_thermal_gradients is False
+    with pytest.raises(ValueError):
+        ThermalNerfactoModel(ThermalNerfModelConfig(), torch.tensor([[-1.0, -1, -1], [1, 1, 1]]), 3)

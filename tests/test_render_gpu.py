@@ -172,3 +172,36 @@ def test_constructor_requires_thermal_metadata():
 
     with pytest.raises(ValueError):
         ThermalNerfModel(ThermalNerfModelConfig(log2_hashmap_size=10), {}, torch.tensor([[-1.0, -1, -1], [1, 1, 1]]), 4)
+
+
+def test_nerfacto_variant_matches_the_full_model_without_thermal():
+    """ThermalNerfactoModel (no thermal head): rgb / depth / accumulation are those of the full model with the same
+    weights (the thermal head never feeds them), the output dict has no "thermal", and a training step runs with
+    the rgb / interlevel / distortion losses only."""
+    from thermo_nerf_b200 import RayBundle, ThermalNerfactoModelConfig
+
+    _, full = make_pair(trained_like=True, precision="tc_fp16")
+    cfg = ThermalNerfactoModelConfig(log2_hashmap_size=15, precision="tc_fp16",
+                                     proposal_net_args_list=[dict(a) for a in full.config.proposal_net_args_list],
+                                     camera_optimizer_mode="off")
+    m = cfg.setup(scene_box=torch.tensor([[-1.0, -1, -1], [1, 1, 1]]), num_train_data=8)
+    missing, unexpected = m.load_state_dict(full.state_dict(), strict=False)
+    assert not [k for k in missing if k != "device_indicator_param"]
+    assert all("thermal" in k for k in unexpected) and len(unexpected) == 6
+    m = m.cuda().eval()
+    rays = make_synthetic_rays(777, num_images=8, seed=8)
+    with torch.no_grad():
+        a, b = full.get_outputs(_bundle(rays)), m.get_outputs(_bundle(rays))
+    assert "thermal" not in b and "thermal" in a
+    for k in ("rgb", "depth", "expected_depth", "accumulation", "prop_depth_0", "prop_depth_1"):
+        assert torch.equal(a[k], b[k]), k
+    m.train()
+    gen = torch.Generator().manual_seed(2)
+    batch = {"image": torch.rand((777, 3), generator=gen).cuda()}
+    out = m(RayBundle(origins=rays.origins.cuda(), directions=rays.directions.cuda(), camera_indices=rays.camera_indices.cuda()))
+    ld = m.get_loss_dict(out, batch, m.get_metrics_dict(out, batch))
+    assert set(ld) == {"rgb_loss", "interlevel_loss", "distortion_loss"}
+    sum(ld.values()).backward()
+    torch.cuda.synchronize()
+    assert float(m.field.mlp_head.layers[2].weight.grad.abs().sum()) > 0
+    assert float(m.field.mlp_thermal.layers[0].weight.abs().sum()) == 0.0  # still the constant zeros

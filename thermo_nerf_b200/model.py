@@ -80,6 +80,7 @@ class ThermalNerfModelConfig:
     eval_num_rays_per_chunk: int = 1 << 16  # config_thermal_nerf.py:30
     # B200 specific
     precision: Literal["fp32", "tc_fp16"] = "tc_fp16"
+    thermal_head: bool = True  # False: plain nerfacto field (ThermalNerfactoModel, nerfacto_config/thermal_nerfacto.py)
 
     def setup(self, **kwargs) -> Any:
         return self._target(self, **kwargs)
@@ -114,7 +115,7 @@ class ThermalNerfModel(nn.Module):
 
     def __init__(self, config: ThermalNerfModelConfig, metadata: dict, scene_box, num_train_data: int,
                  **kwargs) -> None:
-        if "thermal" not in metadata.keys():  # thermal_nerf_model.py:75-76
+        if config.thermal_head and "thermal" not in metadata.keys():  # thermal_nerf_model.py:75-76
             raise ValueError("Thermal images not found in metadata.")
         super().__init__()
         self.config = config
@@ -146,7 +147,8 @@ class ThermalNerfModel(nn.Module):
             log2_hashmap_size=cfg.log2_hashmap_size, hidden_dim_color=cfg.hidden_dim_color,
             hidden_dim_transient=cfg.hidden_dim_transient,
             use_average_appearance_embedding=cfg.use_average_appearance_embedding,
-            appearance_embedding_dim=cfg.appearance_embed_dim, pass_thermal_gradients=cfg.pass_thermal_gradients)
+            appearance_embedding_dim=cfg.appearance_embed_dim, pass_thermal_gradients=cfg.pass_thermal_gradients,
+            thermal_head=cfg.thermal_head)
         self.camera_optimizer = CameraOptimizer(self.num_train_data, cfg.camera_optimizer_mode)
         self.proposal_networks = nn.ModuleList()
         for i in range(cfg.num_proposal_iterations):
@@ -285,7 +287,8 @@ class ThermalNerfModel(nn.Module):
             outputs["ray_samples_list"] = res["sdist_list"]  # spacing bins [R,S+1] per level
         for i in range(cfg.num_proposal_iterations):
             outputs[f"prop_depth_{i}"] = res[f"prop_depth_{i}"].view(*shape, 1)
-        outputs["thermal"] = res["thermal"].view(*shape, 1)
+        if cfg.thermal_head:
+            outputs["thermal"] = res["thermal"].view(*shape, 1)
         return outputs
 
     @torch.no_grad()
@@ -340,6 +343,8 @@ class ThermalNerfModel(nn.Module):
         res = F.render_forward(self.tensors(), None, None, camera=cam, training=False,
                                depth_clip_chunk=self.config.eval_num_rays_per_chunk, **kw)
         out = {k: v.view(H, W, -1) for k, v in res.items() if isinstance(v, Tensor)}
+        if not self.config.thermal_head:
+            out.pop("thermal", None)
         out["img"] = out["rgb"]
         return out
 
@@ -352,10 +357,14 @@ class ThermalNerfModel(nn.Module):
             # thermal_nerf_model.py:319); non_blocking keeps that copy from draining the stream when the
             # host tensor is pinned (a blocking .to() waits for the forward kernel before the loss can launch)
             image = batch["image"].to(self.device, non_blocking=True)[..., :3].reshape(-1, 3).float()
-            thermal = batch["thermal"].to(self.device, non_blocking=True).reshape(-1).float()
+            if self.config.thermal_head:
+                thermal = batch["thermal"].to(self.device, non_blocking=True).reshape(-1).float()
+                pred_th = outputs["thermal"].reshape(-1)
+            else:  # nerfacto field: no thermal term (use_thermal_loss is False below); any [R] tensors do
+                thermal = pred_th = torch.zeros(image.shape[0], dtype=torch.float32, device=self.device)
             w = outputs["weights_list"]
             cache = F.losses(
-                {"rgb": outputs["rgb"].reshape(-1, 3), "thermal": outputs["thermal"].reshape(-1),
+                {"rgb": outputs["rgb"].reshape(-1, 3), "thermal": pred_th,
                  "weights_list": w, "sdist_list": outputs["ray_samples_list"]},
                 image, thermal, interlevel_mult=self.config.interlevel_loss_mult,
                 distortion_mult=self.config.distortion_loss_mult, use_rgb_loss=self.field.pass_rgb_gradients,
@@ -452,6 +461,12 @@ class ThermalNerfModel(nn.Module):
         g4, p4 = torch.moveaxis(gt_rgb, -1, 0)[None], torch.moveaxis(rgb, -1, 0)[None]
         metrics: Dict[str, float] = {"psnr": float(self.psnr(g4, p4)), "ssim": float(self.ssim(g4, p4)),
                                      "lpips": self._lpips(g4, p4)}
+        if not self.config.thermal_head:
+            # ThermalNerfactoModel.get_image_metrics_and_images (thermal_nerfacto.py:47-84): the "RGB" images are the
+            # thermal images, so the temperature MAE is taken on rgb
+            metrics["mae_foreground"] = float(self.mae_thermal(g4, p4, threshold=threshold))
+            metrics["mae"] = float(self.mae_thermal(g4, p4, threshold=None))
+            return metrics, images
         gt_th = batch["thermal"].to(dev)  # thermal_nerf_model.py:347 (the reference forgets the .to() at :355)
         th = outputs["thermal"]
         images["thermal"] = gray(th)
@@ -471,3 +486,24 @@ class ThermalNerfModel(nn.Module):
             gt, pred = gt[idx], pred[idx]
         span = self.max_temperature - self.min_temperature
         return torch.mean(torch.abs((gt * span + self.min_temperature) - (pred * span + self.min_temperature)))
+
+
+@dataclass
+class ThermalNerfactoModelConfig(ThermalNerfModelConfig):
+    """thermo_nerf/nerfacto_config/thermal_nerfacto.py:13-25: nerfacto on one image modality (the ``nerfacto`` and
+    ``thermal-nerfacto`` ModelTypes of train_eval_script.py:66-73) - the same sampler / field / renderers without the
+    thermal head, temperature MAE computed on the rendered rgb."""
+
+    _target: Type = field(default_factory=lambda: ThermalNerfactoModel)
+    thermal_head: bool = False
+
+
+class ThermalNerfactoModel(ThermalNerfModel):
+    """ThermalNerfactoModel (thermal_nerfacto.py:28-84) on libtnf_b200: constructor without the thermal metadata
+    requirement, no "thermal" output, rgb / interlevel / distortion losses only."""
+
+    def __init__(self, config: ThermalNerfactoModelConfig, scene_box, num_train_data: int, metadata: Optional[dict] = None,
+                 **kwargs) -> None:
+        if config.thermal_head:
+            raise ValueError("ThermalNerfactoModel is the model without a thermal head (thermal_head=False)")
+        super().__init__(config, metadata or {}, scene_box, num_train_data, **kwargs)

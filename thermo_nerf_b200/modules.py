@@ -122,6 +122,20 @@ class ThermalFieldHead(nn.Module):
         _no_torch_path("ThermalFieldHead")
 
 
+class _ZeroLinear(nn.Module):
+    """A Linear whose weight and bias are constant zeros kept as NON-persistent buffers: present for the kernels
+    (which always evaluate the thermal head) but neither a parameter nor a state_dict entry - a plain nerfacto
+    field (thermo_nerf/nerfacto_config/thermal_nerfacto.py) has no thermal head."""
+
+    def __init__(self, in_dim: int, out_dim: int) -> None:
+        super().__init__()
+        self.register_buffer("weight", torch.zeros(out_dim, in_dim), persistent=False)
+        self.register_buffer("bias", torch.zeros(out_dim), persistent=False)
+
+    def forward(self, *_):
+        _no_torch_path("_ZeroLinear")
+
+
 class _Seq(nn.Sequential):
     def forward(self, *_):  # type: ignore[override]
         _no_torch_path("mlp_base")
@@ -155,7 +169,8 @@ class ThermalNerfactoTField(nn.Module):
                  geo_feat_dim: int = 15, num_levels: int = 16, base_res: int = 16, max_res: int = 2048,
                  log2_hashmap_size: int = 19, num_layers_color: int = 3, features_per_level: int = 2,
                  hidden_dim_color: int = 64, hidden_dim_transient: int = 64, appearance_embedding_dim: int = 32,
-                 use_average_appearance_embedding: bool = False, pass_thermal_gradients: bool = False) -> None:
+                 use_average_appearance_embedding: bool = False, pass_thermal_gradients: bool = False,
+                 thermal_head: bool = True) -> None:
         super().__init__()
         fixed = dict(num_layers=(num_layers, 2), hidden_dim=(hidden_dim, 64), geo_feat_dim=(geo_feat_dim, 15),
                      num_levels=(num_levels, 16), num_layers_color=(num_layers_color, 3),
@@ -174,6 +189,11 @@ class ThermalNerfactoTField(nn.Module):
         self.mlp_head = MLP(16 + geo_feat_dim + appearance_embedding_dim, num_layers_color, hidden_dim_color, 3)
         self.mlp_thermal = MLP(geo_feat_dim, 2, 64, hidden_dim_transient)
         self.field_head_thermal = ThermalFieldHead(in_dim=self.mlp_thermal.get_out_dim())
+        self.thermal_head = bool(thermal_head)
+        if not self.thermal_head:  # nerfacto field: the head exists only as constant zeros for the kernels
+            self.mlp_thermal.layers = nn.ModuleList([_ZeroLinear(geo_feat_dim, 64), _ZeroLinear(64, hidden_dim_transient)])
+            self.field_head_thermal.net = _ZeroLinear(hidden_dim_transient, 1)
+            pass_thermal_gradients = False
         self.pass_thermal_gradients = pass_thermal_gradients  # thermal_field.py:103
         self.training_iteration = 0
         self.pass_rgb_gradients = True  # thermal_field.py:106
