@@ -353,7 +353,17 @@ def bench_train(ctx) -> dict:
     R = args.rays
     model = build_b200_model(device, args.precision)
     model.train()
-    engine = TrainEngine(model, world_size=world, peer_fused=(world > 1 and args.exchange == "peer"))
+    try:
+        engine = TrainEngine(model, world_size=world, peer_fused=(world > 1 and args.exchange == "peer"))
+    except RuntimeError as e:
+        # CUDA IPC / peer access not available between these processes (PeerArena reports it on every rank at once):
+        # run the NCCL exchange instead and say so in the output line
+        if not (world > 1 and args.exchange == "peer" and "PeerArena" in str(e)):
+            raise
+        print(f"[bench] {e}; falling back to --exchange nccl", file=sys.stderr, flush=True)
+        model = build_b200_model(device, args.precision)
+        model.train()
+        engine = TrainEngine(model, world_size=world, peer_fused=False)
     n_distinct = 8
     batches = train_batches(n_distinct, R, device, rank)
 

@@ -148,17 +148,28 @@ class PeerArena:
         if self.world > 1:
             gathered: List[object] = [None] * self.world
             dist.all_gather_object(gathered, (bytes(handle.raw), self.numel), group=group)
-            with torch.cuda.device(dev):  # handles are opened with the consumer device current
-                for r, (h, n) in enumerate(gathered):
-                    if n != self.numel:
-                        raise RuntimeError("ranks disagree on the arena size")
-                    if r == self.rank:
-                        continue
-                    out = C.c_void_p()
-                    L.check(self.lib.tnf_peer_open_handle(h, C.byref(out)))
-                    self._mapped[r] = int(out.value)
-                    bases[r] = int(out.value)
-            dist.barrier(group=group)
+            err = ""
+            try:
+                with torch.cuda.device(dev):  # handles are opened with the consumer device current
+                    for r, (h, n) in enumerate(gathered):
+                        if n != self.numel:
+                            raise RuntimeError("ranks disagree on the arena size")
+                        if r == self.rank:
+                            continue
+                        out = C.c_void_p()
+                        L.check(self.lib.tnf_peer_open_handle(h, C.byref(out)))
+                        self._mapped[r] = int(out.value)
+                        bases[r] = int(out.value)
+            except Exception as e:  # noqa: BLE001 - reported collectively below
+                err = repr(e)
+            # every rank learns whether every mapping succeeded (a rank that raised alone would leave the others
+            # waiting in the next collective)
+            ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                self.close()
+                raise RuntimeError("PeerArena: mapping the peers' memory failed on at least one rank"
+                                   + (f" (this rank: {err})" if err else ""))
         ptrs = [(b, b + arena_bytes, b + 2 * arena_bytes) for b in bases]
         a = L.TnfPeerArena()
         for r, (g, p, f) in enumerate(ptrs):
