@@ -90,12 +90,16 @@ __global__ void __launch_bounds__(256) tnf_peer_adam_kernel(const __grid_constan
 __global__ void __launch_bounds__(256) tnf_peer_gather_kernel(const __grid_constant__ TnfPeerArena a,
                                                               const __grid_constant__ PeerAdamArgs A) {
   const int W = a.world_size, me = a.rank;
-  const long long shard4 = (a.numel / W) >> 2, total4 = shard4 * (W - 1);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
-       i += (long long)gridDim.x * blockDim.x) {
-    int owner = (int)(i / shard4);
-    const long long off4 = i - (long long)owner * shard4;
-    owner = owner >= me ? owner + 1 : owner;  // skip the own shard
+  const long long shard4 = (a.numel / W) >> 2;
+  // 4 KB chunks dealt round-robin over the owners, rotated by the rank: at any moment the CTAs of one GPU pull from
+  // all owners and the GPUs pull from different owners (walking the owners one after the other makes every rank
+  // read the same GPU at the same time and divides that GPU's egress by N-1)
+  const long long chunks_per_owner = (shard4 + 255) / 256, total_chunks = chunks_per_owner * (W - 1);
+  for (long long c = blockIdx.x; c < total_chunks; c += gridDim.x) {
+    const int slot = (int)((c + me) % (W - 1));
+    const int owner = slot >= me ? slot + 1 : slot;  // skip the own shard
+    const long long off4 = (c / (W - 1)) * 256 + threadIdx.x;
+    if (off4 >= shard4) continue;
     const long long e = ((long long)owner * shard4 + off4) << 2;
     int s = 0;
     while (s + 1 < A.nseg && e >= A.seg_end[s]) ++s;
@@ -306,7 +310,7 @@ static int peer_adam_impl(const TnfPeerArena* arena, float* exp_avg_shard, float
   A.eps = eps;
   A.inv_world = 1.0f / (float)W;
   A.push = phase == 0;
-  const long long n4 = phase == 2 ? (shard >> 2) * (W - 1) : (shard >> 2);
+  const long long n4 = phase == 2 ? (((shard >> 2) + 255) / 256) * 256 * (W - 1) : (shard >> 2);
   if (n4 == 0) return TNF_OK;
   long long blocks = (n4 + 255) / 256;
   const long long cap = (long long)tnf::num_sms() * 8;

@@ -182,9 +182,13 @@ class PeerArena:
         self.timing: Optional[list] = None
         import os
 
-        self.gather = os.environ.get("TNF_PEER_GATHER", "push")  # all-gather flavour: "push" (one kernel) | "pull"
+        # all-gather flavour: "push" (everything in one kernel) or "pull" (owners keep their shard, peers copy it out).
+        # Measured (profiles/r1_peer_exchange_phases.json): push wins on 2 GPUs, the owner-balanced pull on 8.
+        self.gather = os.environ.get("TNF_PEER_GATHER", "auto")
+        if self.gather == "auto":
+            self.gather = "pull" if self.world >= 4 else "push"
         if self.gather not in ("push", "pull"):
-            raise ValueError("TNF_PEER_GATHER must be 'push' or 'pull'")
+            raise ValueError("TNF_PEER_GATHER must be 'auto', 'push' or 'pull'")
         if self.world > 1:
             # self-test of the mappings in both directions: one barrier round must complete without a time-out
             self.barrier(0)
