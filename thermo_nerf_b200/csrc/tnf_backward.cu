@@ -1,19 +1,21 @@
 // Backward of ThermalNerfModel.get_outputs (thermo_nerf/thermal_nerf/thermal_nerf_model.py:210-275)
 // as driven by get_loss_dict (:277-326), for sm_100a.
 //
-//   tnf_backward_prop_kernel   the two HashMLPDensityField proposal levels (:127-148): re-gather the
-//                              hash features, 10->16->1 MLP forward + backward in fp32, table scatter,
-//                              the 193 weight gradients accumulated in registers (lane owns a slot)
+//   tnf_backward_prop_kernel   the two HashMLPDensityField proposal levels (:127-148) as (level, ray) units from
+//                              a device counter: re-gather the hash features, 10->16->1 MLP forward +
+//                              backward in fp32, run-merged table scatter, weight gradients as bf16 mma
+//                              over the 32 samples of a chunk (TC mode) or lane-owned fp32 sums (fp32 mode)
 //   tnf_backward_field_kernel  ThermalNerfactoTField (thermal_field.py:108-201): compositing backward
 //                              (suffix scans), field MLPs recomputed from the saved hash features,
-//                              dX chain, hash-grid scatter with vector reductions (REDG.F32x2), and
-//                              the per-layer (X, dY) rows staged for the weight-gradient GEMMs
-//   tnf_wgrad_kernel           dW = dY^T X, split-K over the samples (K = R*48): the one genuinely
-//                              dense contraction of the step; bf16 mma.sync with fp32 accumulate
-//                              (TC mode) or fp32 FFMA (fp32 mode)
+//                              dX chain, run-merged hash-grid scatter (REDG.F32x2), and the per-layer
+//                              (X, dY) tiles staged for the weight-gradient GEMMs (stmatrix into a
+//                              shared-memory ring, cp.async.bulk to global)
+//   tnf_wgrad_kernel_*         dW = dY^T X, split-K over the samples (K = R*48): the one genuinely
+//                              dense contraction of the step; bf16 mma.sync fed by TMA bulk copies on
+//                              mbarriers (TC mode) or fp32 FFMA (fp32 mode)
 //
-// Sample positions are constants here: PDFSampler detaches its bins and this build does not
-// propagate into ray origins/directions (camera optimiser), see DESIGN.md.
+// Sample distances are constants here (PDFSampler detaches its bins); with TnfModelGrad.ray_origins /
+// ray_directions given, the kernels also return dL/d origins and dL/d directions (camera optimiser).
 #include <cuda_bf16.h>
 
 #include "tnf_field.cuh"

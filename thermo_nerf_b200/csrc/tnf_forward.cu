@@ -11,9 +11,14 @@
 //
 // Lanes map to consecutive samples of the ray so the 8 corner gathers of a level hit
 // neighbouring (often identical) table cells -> few L1 wavefronts per load.  Weights, CDFs
-// and bins live in a per-warp shared-memory scratch; MLP weights are staged once per CTA.
-// TNF_PRECISION_TC_FP16 runs the 64-wide field MLPs on the tensor cores with
-// register-resident activations (C fragments of one layer are the A fragments of the next).
+// and bins live in three per-warp shared-memory lines that rotate between the levels; MLP
+// weights are staged once per CTA.  TNF_PRECISION_TC_FP16 runs the 64-wide field MLPs on the
+// tensor cores with register-resident activations (C fragments of one layer are the A
+// fragments of the next); the hash features of a 16-sample tile go through a shared-memory
+// tile (sample-major gathers, ldmatrix into A fragments, coalesced copy for the backward).
+// Rays come from [R,3] tensors or are generated per pixel from a TnfCamera (Cameras.generate_rays).
+// Also here: tnf_rays_kernel (stand-alone ray generation), tnf_post_kernel (Renderer.render's
+// uint8 / colour-map conversion), tnf_clip_kernel (per-chunk expected-depth clip).
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
