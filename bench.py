@@ -487,7 +487,10 @@ def bench_train(ctx) -> dict:
                    "final_losses": dict(zip(F.LOSS_NAMES, final_losses))},
         "clocks": clocks,
         "exchange": ("none (1 GPU)" if world == 1 else
-                     ("peer-memory fused reduce-scatter + Adam + all-gather (tnf_peer_adam_step)"
+                     (("peer-memory fused reduce-scatter + Adam + all-gather (tnf_peer_adam_step)"
+                       if engine.arena.gather == "push" else
+                       "peer-memory fused reduce-scatter + Adam (tnf_peer_adam_reduce), pull all-gather "
+                       "(tnf_peer_gather_params)")
                       if engine.arena is not None else "NCCL all-reduce (mean) + tnf_adam_step")),
         "gpu_launches": None,
         "exchange_phases_ms": engine.arena.timing_summary() if engine.arena is not None else None,
@@ -498,8 +501,8 @@ def bench_train(ctx) -> dict:
     # launches of OUR kernels per engine step: forward + clip + losses + backward_prop (on update steps) +
     # backward_field + wgrad + adam (1 or 2 launches)
     # (+ the counter memset of the proposal backward and, for world > 1, NCCL's all-reduce kernel are not ours)
-    if engine.arena is not None:  # peer exchange: 2 barrier kernels + 1 fused Adam instead of 1-2 Adam launches
-        line["gpu_launches"] = int(args.steps * 8 + prop_steps_timed)
+    if engine.arena is not None:  # peer exchange: 2 barrier kernels + fused Adam (+ gather kernel when pulling)
+        line["gpu_launches"] = int(args.steps * (8 if engine.arena.gather == "push" else 9) + prop_steps_timed)
     else:
         line["gpu_launches"] = int(args.steps * 6 + prop_steps_timed * 2)
     if roofline:
