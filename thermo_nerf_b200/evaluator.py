@@ -30,23 +30,27 @@ class Evaluator:
     def __init__(self, pipeline, config, job_param_identifier: Optional[str] = None,
                  modalities_to_save: Sequence[RenderedImageModality] = (RenderedImageModality.RGB,),
                  threshold: Optional[float] = None) -> None:
+        pipeline.datamanager.setup_eval()
         self._pipeline = pipeline
-        self._pipeline.datamanager.setup_eval()
+        self._run_names = (config.experiment_name, config.method_name)
         self.identifier = job_param_identifier
-        self._evaluation_images: Dict[RenderedImageModality, List[np.ndarray]] = {}
         self.modalities_to_save = list(modalities_to_save)
+        self._evaluation_images: Dict[RenderedImageModality, List[np.ndarray]] = {m: [] for m in self.modalities_to_save}
         self._metrics = self._compute_metrics(threshold=threshold)
-        self._benchmark_info = {
-            "experiment_name": config.experiment_name,
-            "method_name": config.method_name,
-            "job_param_identifier": self.identifier,
-            "results": self._metrics,
-        }
 
+    # ------------------------------------------------------------------ results
     @property
     def metrics(self) -> dict:
         return self._metrics
 
+    @property
+    def _benchmark_info(self) -> dict:
+        """What metrics.json holds (evaluator.py:38-43)."""
+        experiment, method = self._run_names
+        return {"experiment_name": experiment, "method_name": method, "job_param_identifier": self.identifier,
+                "results": self._metrics}
+
+    # ------------------------------------------------------------------ evaluation loop
     def _outputs_for(self, model, cameras, i: int):
         """One evaluation frame of camera ``i`` of ``cameras`` (evaluator.py:66-81)."""
         pose_off = getattr(model.camera_optimizer, "mode", "off") == "off"
@@ -67,54 +71,52 @@ class Evaluator:
             model.camera_optimizer.apply_to_raybundle(flat)
         return model.get_outputs_for_camera_ray_bundle(flat.reshape(shape))
 
-    def _compute_metrics(self, threshold: Optional[float]) -> dict:
-        datamanager = self._pipeline.datamanager
-        if datamanager.fixed_indices_eval_dataloader is None:
-            raise RuntimeError("Cannot evaluate without a fixed indices eval dataloader")
-        for modality in self.modalities_to_save:
-            self._evaluation_images[modality] = []
-        model = self._pipeline.model
-        metrics_dict_list = []
-        for cameras, batch in datamanager.fixed_indices_eval_dataloader:
-            n = int(cameras.camera_to_worlds.shape[0])
-            for i in range(n):  # the reference's dataloader yields one camera at a time
-                outputs = self._outputs_for(model, cameras, i)
-                metrics_dict, images_dict = model.get_image_metrics_and_images(outputs, batch, threshold=threshold)
-                for modality in self.modalities_to_save:
-                    self._evaluation_images[modality].append((images_dict[modality.value] * 255).byte().cpu().numpy())
-                metrics_dict_list.append(metrics_dict)
-        if not metrics_dict_list:
-            raise RuntimeError("the eval dataloader is empty")
-        out: dict = {}
-        for key in metrics_dict_list[0].keys():
-            vals = [m[key] for m in metrics_dict_list]
-            key_std, key_mean = torch.std_mean(torch.tensor(vals))
-            out[f"{key}_mean"] = float(key_mean)
-            out[f"{key}_std"] = float(key_std)
-            out[key] = vals
-        return out
+    @staticmethod
+    def _aggregate(per_image: List[Dict[str, float]]) -> dict:
+        """<key>_mean, <key>_std (unbiased, torch.std_mean) and the per-image list of every metric."""
+        summary: dict = {}
+        for name in per_image[0]:
+            column = [entry[name] for entry in per_image]
+            std, mean = torch.std_mean(torch.tensor(column))
+            summary[name + "_mean"], summary[name + "_std"], summary[name] = float(mean), float(std), column
+        return summary
 
+    def _compute_metrics(self, threshold: Optional[float]) -> dict:
+        loader = self._pipeline.datamanager.fixed_indices_eval_dataloader
+        if loader is None:
+            raise RuntimeError("Cannot evaluate without a fixed indices eval dataloader")
+        model = self._pipeline.model
+        per_image: List[Dict[str, float]] = []
+        for cameras, batch in loader:
+            for i in range(int(cameras.camera_to_worlds.shape[0])):  # the reference's loader yields one camera at a time
+                outputs = self._outputs_for(model, cameras, i)
+                frame_metrics, frame_images = model.get_image_metrics_and_images(outputs, batch, threshold=threshold)
+                per_image.append(frame_metrics)
+                for modality, store in self._evaluation_images.items():
+                    store.append((frame_images[modality.value] * 255).byte().cpu().numpy())
+        if not per_image:
+            raise RuntimeError("the eval dataloader is empty")
+        return self._aggregate(per_image)
+
+    # ------------------------------------------------------------------ files
     def save_images(self, modalities: Sequence[RenderedImageModality], output_path: Path) -> None:
         from PIL import Image
 
         for modality in modalities:
-            for idx, image in enumerate(self._evaluation_images[modality]):
-                if image.shape[-1] == 4:
-                    image = image[:, :, 3]
-                Image.fromarray(image).save(Path(output_path) / f"{modality.value}_{idx:05d}.jpg")
+            for idx, frame in enumerate(self._evaluation_images[modality]):
+                plane = frame[:, :, 3] if frame.shape[-1] == 4 else frame  # RGBA panels keep their alpha plane only
+                Image.fromarray(plane).save(Path(output_path) / f"{modality.value}_{idx:05d}.jpg")
 
     def save_metrics(self, output_folder: Path) -> None:
-        output_folder = Path(output_folder)
-        output_file = output_folder / "metrics.json"
-        output_file.parent.mkdir(parents=True, exist_ok=True)
-        output_file.write_text(json.dumps(self._benchmark_info, indent=2), "utf8")
+        root = Path(output_folder)
+        root.mkdir(parents=True, exist_ok=True)
+        (root / "metrics.json").write_text(json.dumps(self._benchmark_info, indent=2), "utf8")
         if self.identifier is None:
             return
+        # per-metric folders with the per-image lists; the reference's guard for the thermal files
+        # (`if THERMAL or ...`, evaluator.py:155-158) is always true, so they are always written
         for name in ("psnr", "ssim", "lpips"):
-            folder = output_folder / name
+            folder = root / name
             folder.mkdir(parents=True, exist_ok=True)
-            (folder / (self.identifier + ".txt")).write_text(json.dumps(self._metrics[name], indent=2), "utf8")
-            # the reference's condition (`if THERMAL or ...`, evaluator.py:155-158) is always true: the thermal
-            # files are always written
-            (folder / (self.identifier + "_thermal.txt")).write_text(
-                json.dumps(self._metrics[name + "_thermal"], indent=2), "utf8")
+            for suffix in ("", "_thermal"):
+                (folder / f"{self.identifier}{suffix}.txt").write_text(json.dumps(self._metrics[name + suffix], indent=2), "utf8")
