@@ -494,6 +494,8 @@ def bench_train(ctx) -> dict:
                       if engine.arena is not None else "NCCL all-reduce (mean) + tnf_adam_step")),
         "gpu_launches": None,
         "exchange_phases_ms": engine.arena.timing_summary() if engine.arena is not None else None,
+        # barrier waits that gave up because a peer never arrived (must be 0; a non-zero count invalidates the run)
+        "exchange_barrier_timeouts": engine.arena.timeouts() if engine.arena is not None else None,
         "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": n_e2e,
                 "note": "plugin API: pinned host rays+GT -> H2D -> model(ray_bundle) -> get_metrics_dict -> get_loss_dict "
                         "-> loss.backward() -> FusedAdam.step -> D2H loss"},
