@@ -21,3 +21,13 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_sessionstart(session):
+    """A fresh checkout has no libtnf_b200.so (built artefacts are not in git): build it once.  An existing
+    library is used as it is - the product path itself never builds or falls back."""
+    lib = ROOT / "thermo_nerf_b200" / "lib" / "libtnf_b200.so"
+    if not lib.exists():
+        import __graft_entry__ as g
+
+        g.build()
