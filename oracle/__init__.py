@@ -18,6 +18,10 @@ Appendix A) and anchors on the reference's call sites:
 * ``thermo_nerf/thermal_nerf/thermal_renderer.py:26-149``    (thermal compositing)
 * ``thermo_nerf/thermal_nerf/thermal_metrics.py:5-34``       (MAE de-normalisation)
 
+The only arithmetic of the path's neighbourhood that the reference itself can run here,
+``thermal_metrics.mae_thermal``, IS pinned: tests/golden/reference_thermal_metrics.pt holds its outputs
+(tests/golden/make_reference_golden.py) and ``nerfstudio_math.mae_thermal`` reproduces them bit for bit.
+
 Every detail flagged "recalled" in SURVEY.md Appendix A is a named switch in
 ``OracleConfig`` so it can be flipped if real nerfstudio source ever becomes
 available.

@@ -225,3 +225,28 @@ def test_oracle_training_gradients_flow_to_all_parameter_groups():
     assert model.proposal_networks[0].encoding.hash_table.grad.abs().sum() > 0
     assert model.field.mlp_thermal.layers[0].weight.grad.abs().sum() > 0
     assert model.camera_optimizer.pose_adjustment.grad.abs().sum() > 0
+
+
+def test_thermal_metrics_match_vectors_generated_by_the_reference_itself():
+    """tests/golden/reference_thermal_metrics.pt was produced by running the reference's own
+    thermo_nerf/thermal_nerf/thermal_metrics.py (make_reference_golden.py): the oracle's and the product model's
+    mae_thermal must reproduce it bit for bit; the modality / model-type enums must carry the reference's values."""
+    from thermo_nerf_b200 import RenderedImageModality, ThermalNerfModel, ThermalNerfModelConfig
+
+    blob = torch.load(GOLDEN / "reference_thermal_metrics.pt", weights_only=True)
+    args = [{"hidden_dim": 16, "log2_hashmap_size": 8, "num_levels": 5, "max_res": 128, "use_linear": False}] * 2
+    checked = 0
+    for c in blob["cases"]:
+        want = c["mae"]
+        got = M.mae_thermal(c["gt"], c["pred"], c["cold"], c["tmax"], c["tmin"], threshold=c["threshold"])
+        assert torch.equal(got, want) or (torch.isnan(got) and torch.isnan(want))
+        cfg = ThermalNerfModelConfig(log2_hashmap_size=8, proposal_net_args_list=args, max_temperature=c["tmax"],
+                                     min_temperature=c["tmin"], cold=c["cold"])
+        if checked % 12 == 0:  # model construction is the slow part: every 12th case through the plugin surface
+            model = ThermalNerfModel(cfg, {"thermal": []}, torch.tensor([[-1.0, -1, -1], [1, 1, 1]]), 2)
+            got_m = model.mae_thermal(c["gt"], c["pred"], threshold=c["threshold"])
+            assert torch.equal(got_m, want) or (torch.isnan(got_m) and torch.isnan(want))
+        checked += 1
+    assert checked == len(blob["cases"]) >= 72
+    assert {m.name: m.value for m in RenderedImageModality} == blob["modalities"]
+    assert blob["model_types"] == {"THERMALNERFACTO": 1, "THERMONERF": 2, "CONCATNERF": 3, "NERFACTO": 4}
