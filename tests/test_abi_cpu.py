@@ -51,24 +51,8 @@ def test_ctypes_layout_matches_c_header(tmp_path):
     names = ["TnfHashGrid", "TnfLinear", "TnfDensityNet", "TnfField", "TnfModel", "TnfCamera", "TnfRays", "TnfOutputs",
              "TnfLinearGrad", "TnfDensityNetGrad", "TnfFieldGrad", "TnfModelGrad", "TnfSaved", "TnfOutputGrads",
              "TnfLossArgs", "TnfAdamTensor", "TnfPeerArena", "TnfAdamSegment", "TnfDataset"]
-    probes = {
-        "TnfModel": ["field", "num_samples", "training", "near_plane", "anneal", "use_contraction", "aabb",
-                     "appearance_mode", "precision", "detach_thermal_geo"],
-        "TnfField": ["grid", "base0", "th2", "appearance", "num_images"],
-        "TnfRays": ["jitter", "num_rays", "from_camera", "first_pixel", "camera"],
-        "TnfCamera": ["c2w", "fx", "cy", "width", "height"],
-        "TnfOutputs": ["prop_depth", "weights", "sdist", "field_features", "field_samples"],
-        "TnfModelGrad": ["field", "ray_origins", "ray_directions"],
-        "TnfFieldGrad": ["th2", "appearance"],
-        "TnfSaved": ["weights", "field_features", "field_samples"],
-        "TnfOutputGrads": ["accumulation", "weights"],
-        "TnfLossArgs": ["num_rays", "num_samples", "interlevel_mult", "grad_scale", "losses", "g_weights"],
-        "TnfAdamTensor": ["numel", "lr"],
-        "TnfPeerArena": ["params", "flags", "world_size", "rank", "numel"],
-        "TnfAdamSegment": ["end", "step", "lr", "active"],
-        "TnfDataset": ["thermal", "intrinsics", "num_images", "channels", "thermal_uint8"],
-        "TnfHashGrid": ["scalings", "num_levels", "log2_size"],
-    }
+    # every field of every struct, taken from the ctypes mirror (a field the header lacks fails the gcc compile)
+    probes = {n: [f[0] for f in getattr(_lib, n)._fields_] for n in names}
     src = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for n in names:
         src.append(f'printf("{n} %zu\\n", sizeof({n}));')
@@ -87,6 +71,27 @@ def test_ctypes_layout_matches_c_header(tmp_path):
             assert getattr(getattr(_lib, s), f).offset == int(val), key
         else:
             assert C.sizeof(getattr(_lib, key)) == int(val), key
+
+
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md's table maps each exported symbol to the reference interface it replaces."""
+    from thermo_nerf_b200 import _lib
+
+    doc = (ROOT / "INTEGRATION.md").read_text()
+    doc = doc.replace("tnf_peer_alloc/free/open_handle/close_handle/enable_access",
+                      "tnf_peer_alloc tnf_peer_free tnf_peer_open_handle tnf_peer_close_handle tnf_peer_enable_access")
+    doc = doc.replace("tnf_*_workspace_bytes", "tnf_forward_workspace_bytes tnf_backward_workspace_bytes")
+    missing = [n for n in _lib.EXPORTED_SYMBOLS if n not in doc]
+    assert not missing, missing
+
+
+def test_header_cites_the_reference_for_each_entry_point():
+    """Each declaration's preceding comment block cites reference file:line (or says what plumbing it is)."""
+    text = HEADER.read_text()
+    assert len(re.findall(r"[a-z_]+\.py:\d+", text)) >= 12
+    for anchor in ("thermal_nerf_model.py:210", "thermal_nerf_model.py:277", "config_thermal_nerf.py:32",
+                   "renderer.py:183", "renderer.py:189", "pipeline_tracking.py"):
+        assert anchor in text, anchor
 
 
 def test_workspace_size(lib):
