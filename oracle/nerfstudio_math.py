@@ -28,6 +28,7 @@ __all__ = [
     "pdf_resample_bins",
     "get_weights",
     "render_rgb_last_sample",
+    "render_rgbt_no_background",
     "render_accumulation",
     "render_depth_median",
     "render_depth_expected",
@@ -303,6 +304,17 @@ def render_rgb_last_sample(values: Tensor, weights: Tensor, training: bool) -> T
     comp = torch.sum(weights * values, dim=-2)
     acc = torch.sum(weights, dim=-2)
     comp = comp + values[..., -1, :] * (1.0 - acc)
+    if not training:
+        comp = torch.clamp(comp, min=0.0, max=1.0)
+    return comp
+
+
+def render_rgbt_no_background(values: Tensor, weights: Tensor, training: bool) -> Tensor:
+    """RGBTRenderer with background_color="random" (reference rgb_concat/rgbt_renderer.py:63-71 and :163-174):
+    the weighted sum is returned as is ("as if the background was black"); eval adds nan_to_num / clamp."""
+    if not training:
+        values = torch.nan_to_num(values)
+    comp = torch.sum(weights * values, dim=-2)
     if not training:
         comp = torch.clamp(comp, min=0.0, max=1.0)
     return comp

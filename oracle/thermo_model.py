@@ -63,6 +63,10 @@ class OracleConfig:
     reset_near_plane_at_eval: bool = True  # NearFarCollider: eval renders from t=0 (A.2)
     sh_on_unit_remapped_dirs: bool = True  # SH evaluated directly on (d+1)/2 (A.5)
     average_init_density: float = 1.0  # thermal_field.py:86 passes 1.0 positionally
+    # "thermal": ThermalNerfModel (RGB head + temperature head).  "concat": ConcatNerfModel
+    # (rgb_concat/concat_nerfacto_model.py:60-197): one 4-channel RGBT colour head
+    # (concat_field.py:65-75), no temperature head, RGBTRenderer() with its default "random" background.
+    head: str = "thermal"
 
 
 @dataclass
@@ -176,12 +180,15 @@ class _ThermalField(nn.Module):
             cfg.num_levels, cfg.base_res, cfg.max_res, cfg.log2_hashmap_size, 2, cfg.hidden_dim, 1 + cfg.geo_feat_dim
         )
         self.embedding_appearance = _Embedding(num_images, cfg.appearance_embed_dim)
+        assert cfg.head in ("thermal", "concat"), cfg.head
         self.mlp_head = _MLP(
-            16 + cfg.geo_feat_dim + cfg.appearance_embed_dim, 3, cfg.hidden_dim_color, 3, out_activation=torch.sigmoid
+            16 + cfg.geo_feat_dim + cfg.appearance_embed_dim, 3, cfg.hidden_dim_color,
+            4 if cfg.head == "concat" else 3, out_activation=torch.sigmoid
         )
-        self.mlp_thermal = _MLP(cfg.geo_feat_dim, 2, 64, cfg.hidden_dim_transient, out_activation=torch.sigmoid)
-        self.field_head_thermal = _ThermalHead(cfg.hidden_dim_transient)
-        self.pass_thermal_gradients = cfg.pass_thermal_gradients
+        if cfg.head == "thermal":
+            self.mlp_thermal = _MLP(cfg.geo_feat_dim, 2, 64, cfg.hidden_dim_transient, out_activation=torch.sigmoid)
+            self.field_head_thermal = _ThermalHead(cfg.hidden_dim_transient)
+        self.pass_thermal_gradients = cfg.pass_thermal_gradients and cfg.head == "thermal"
         self.pass_rgb_gradients = True
 
     def get_density(self, positions: Tensor):
@@ -206,6 +213,8 @@ class _ThermalField(nn.Module):
             app = torch.zeros((*shape, cfg.appearance_embed_dim), device=directions.device)
         h = torch.cat([d, geo.reshape(-1, cfg.geo_feat_dim), app.reshape(-1, cfg.appearance_embed_dim)], dim=-1)
         rgb = self.mlp_head(h).view(*shape, -1)
+        if cfg.head == "concat":
+            return rgb, None  # [R,S,4]: temperature is the fourth colour channel
         th_in = geo.reshape(-1, cfg.geo_feat_dim)
         if not self.pass_thermal_gradients:
             th_in = th_in.detach()
@@ -316,8 +325,11 @@ class OracleThermalNerf(nn.Module):
         sdist_list.append(sbins)
         eucl_list.append(eucl)
 
+        concat = cfg.head == "concat"
         out: Dict[str, object] = {
-            "rgb": M.render_rgb_last_sample(rgb_s, weights, training),
+            # concat: RGBTRenderer "random" background = the plain weighted sum (rgbt_renderer.py:63-71)
+            "rgb": M.render_rgbt_no_background(rgb_s, weights, training) if concat
+            else M.render_rgb_last_sample(rgb_s, weights, training),
             "accumulation": M.render_accumulation(weights),
             "expected_depth": M.render_depth_expected(weights, starts, ends),
         }
@@ -326,7 +338,8 @@ class OracleThermalNerf(nn.Module):
         for i in range(n_prop):
             e = eucl_list[i]
             out[f"prop_depth_{i}"] = M.render_depth_median(weights_list[i], e[..., :-1, None], e[..., 1:, None])
-        out["thermal"] = M.render_rgb_last_sample(thermal_s, weights, training)
+        if not concat:
+            out["thermal"] = M.render_rgb_last_sample(thermal_s, weights, training)
         # always exposed by the oracle (the reference only keeps them in training)
         out["weights_list"] = weights_list
         out["sdist_list"] = sdist_list
@@ -337,10 +350,20 @@ class OracleThermalNerf(nn.Module):
         return out
 
     # --- get_loss_dict (thermal_nerf_model.py:277-326) + inherited metrics ---
-    def get_loss_dict(self, outputs, gt_rgb: Tensor, gt_thermal: Tensor, training: bool = True) -> Dict[str, Tensor]:
+    def get_loss_dict(self, outputs, gt_rgb: Tensor, gt_thermal: Optional[Tensor] = None, training: bool = True,
+                      background_noise: Optional[Tensor] = None) -> Dict[str, Tensor]:
+        """concat head (concat_nerfacto_model.py:197-233): ``gt_rgb`` is the 4-channel RGBT image; the renderer's
+        "random" background adds ``rand_like(pred) * (1 - accumulation)`` to the *prediction only*
+        (rgbt_renderer.py:134-140) - ``background_noise`` [R,4] is that draw (drawn here when None)."""
         cfg = self.cfg
         loss: Dict[str, Tensor] = {}
-        if self.field.pass_rgb_gradients:
+        if cfg.head == "concat":
+            pred = outputs["rgb"]
+            if background_noise is None:
+                background_noise = torch.rand_like(pred)
+            pred = pred + background_noise * (1.0 - outputs["accumulation"])
+            loss["rgb_loss"] = torch.nn.functional.mse_loss(gt_rgb, pred)
+        elif self.field.pass_rgb_gradients:
             loss["rgb_loss"] = torch.nn.functional.mse_loss(gt_rgb, outputs["rgb"])
         if training:
             loss["interlevel_loss"] = cfg.interlevel_loss_mult * M.interlevel_loss(
