@@ -22,6 +22,9 @@ The only arithmetic of the path's neighbourhood that the reference itself can ru
 ``thermal_metrics.mae_thermal``, IS pinned: tests/golden/reference_thermal_metrics.pt holds its outputs
 (tests/golden/make_reference_golden.py) and ``nerfstudio_math.mae_thermal`` reproduces them bit for bit.
 
+The 8-bit thermal ground-truth convention (x / 255, then (max - min) x + min) is pinned against the reference's
+own fixture tests/data/thermal/* (tests/golden/reference_thermal_image_kat.pt, tests/test_camera_post_cpu.py).
+
 Every detail flagged "recalled" in SURVEY.md Appendix A is a named switch in
 ``OracleConfig`` so it can be flipped if real nerfstudio source ever becomes
 available.

@@ -89,3 +89,56 @@ def test_save_images_and_gif(tmp_path):
     r.save_gif([RenderedImageModality.RGB], 1, tmp_path)
     names = sorted(p.name for p in tmp_path.iterdir())
     assert names == ["img_00000.jpeg", "img_00001.jpeg", "synthesized_video_img.gif"]
+
+
+# ---- the reference's own thermal fixture (tests/data/thermal/*, its tests/test_thermal_conversion.py) ----
+def _thermal_kat():
+    from pathlib import Path
+
+    return torch.load(Path(__file__).parent / "golden" / "reference_thermal_image_kat.pt", weights_only=True)
+
+
+def test_uint8_thermal_ground_truth_denormalises_to_the_flir_temperatures():
+    """8-bit thermal PNG -> x / 255 (what the batch sampler hands to the loss) -> (max - min) x + min reproduces the
+    FLIR temperatures of the reference fixture to the reference test's own tolerance (1 decimal,
+    tests/test_thermal_conversion.py:46-52) and to within one 8-bit quantisation step."""
+    from oracle.camera_post import sample_batch_np
+
+    kat = _thermal_kat()
+    px = kat["pixels_u8"].numpy()  # [80,60]
+    temps = kat["temperature_c"].numpy()
+    tmax, tmin = kat["absolute_max_temperature"], kat["absolute_min_temperature"]
+    h, w = px.shape
+    images = np.zeros((1, h, w, 3), np.uint8)
+    c2w = np.eye(4, dtype=np.float32)[None, :3]
+    intr = np.array([[50.0, 50.0, w / 2, h / 2]], np.float32)
+    # one draw per pixel centre
+    yy, xx = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+    rand = np.stack([np.zeros(h * w), (yy.ravel() + 0.5) / h, (xx.ravel() + 0.5) / w], -1).astype(np.float32)
+    _, _, idx, _, gt_th = sample_batch_np(rand, images, px[None], c2w, intr)
+    assert np.array_equal(idx[:, 1], yy.ravel()) and np.array_equal(idx[:, 2], xx.ravel())
+    assert gt_th.dtype == np.float32 and np.array_equal(gt_th, px.ravel().astype(np.float32) / np.float32(255))
+    celsius = gt_th.astype(np.float64) * (tmax - tmin) + tmin  # ThermalVisualiser.update_temperature
+    err = np.abs(celsius - temps.ravel())
+    step = (tmax - tmin) / 255
+    assert err.max() < 0.15                      # the reference's assert_almost_equal(decimal=1)
+    assert err.max() <= step * (1 + 1e-3), (err.max(), step)
+
+
+def test_mae_thermal_on_the_reference_fixture():
+    """mae_thermal between the 8-bit image and the exact (csv) temperatures, both normalised, is the mean absolute
+    temperature error in degrees - oracle and product metric agree with the direct computation."""
+    from oracle import nerfstudio_math as M
+    from thermo_nerf_b200.model import ThermalNerfModel
+
+    kat = _thermal_kat()
+    tmax, tmin = kat["absolute_max_temperature"], kat["absolute_min_temperature"]
+    pred = kat["pixels_u8"].float() / 255
+    gt = ((kat["temperature_c"] - tmin) / (tmax - tmin)).float()
+    want = (pred.double() * (tmax - tmin) + tmin - kat["temperature_c"]).abs().mean().item()
+    got = M.mae_thermal(gt, pred, False, tmax, tmin).item()
+    assert abs(got - want) < 1e-4 and 0.02 < got < 0.06
+    from types import SimpleNamespace
+
+    m = SimpleNamespace(max_temperature=tmax, min_temperature=tmin, config=SimpleNamespace(cold=False))
+    assert abs(float(ThermalNerfModel.mae_thermal(m, gt, pred)) - want) < 1e-4
