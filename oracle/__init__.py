@@ -25,6 +25,12 @@ The only arithmetic of the path's neighbourhood that the reference itself can ru
 The 8-bit thermal ground-truth convention (x / 255, then (max - min) x + min) is pinned against the reference's
 own fixture tests/data/thermal/* (tests/golden/reference_thermal_image_kat.pt, tests/test_camera_post_cpu.py).
 
+Also pinned by executing the reference's own code in the build container (generators under tests/golden/):
+ThermalRenderer / RGBTRenderer compositing bit for bit (reference_renderers.pt), and - over stand-ins that carry
+nerfstudio's interfaces with THIS package's arithmetic - the wiring of thermal_nerf_model.py, thermal_field.py,
+thermal_field_head.py, thermal_nerfacto.py, evaluator.py and renderer.py's render loop (reference_model_wiring.pt,
+reference_evaluator.pt, reference_render_frames.pt).  nerfstudio's arithmetic itself stays a restatement.
+
 Every detail flagged "recalled" in SURVEY.md Appendix A is a named switch in
 ``OracleConfig`` so it can be flipped if real nerfstudio source ever becomes
 available.

@@ -142,3 +142,29 @@ def test_mae_thermal_on_the_reference_fixture():
 
     m = SimpleNamespace(max_temperature=tmax, min_temperature=tmin, config=SimpleNamespace(cold=False))
     assert abs(float(ThermalNerfModel.mae_thermal(m, gt, pred)) - want) < 1e-4
+
+
+def test_frame_conversion_matches_the_reference_render_loop():
+    """Renderer.render (renderer.py:160-201) executed from the reference (tests/golden/make_reference_render_frames_golden.py):
+    the oracle's per-frame conversion reproduces its uint8 frames bit for bit, for the colour-mapped thermal modality and
+    the replicated single-channel ones; the loop renders every frame once per modality and rejects the RGB modality."""
+    from oracle.camera_post import ListedColormapLike, colormap_to_lut8, postprocess_np
+
+    gold = torch.load(GOLDEN / "reference_render_frames.pt", weights_only=True)
+    cmap = ListedColormapLike(gold["lut"].numpy())
+    keys = {"THERMAL": "thermal", "DEPTH": "depth", "ACCUMULATION": "accumulation"}
+    assert gold["modalities"] == list(keys)
+    for name, key in keys.items():
+        assert len(gold["rendered"][name]) == len(gold["frames"]) == 2
+        for frame, ref in zip(gold["frames"], gold["rendered"][name]):
+            ours = postprocess_np(frame[key].numpy(), name == "THERMAL", cmap)
+            assert ours.dtype == np.uint8 and ours.shape == tuple(ref.shape) == (*gold["hw"], 3)
+            assert np.array_equal(ours, ref.numpy()), name
+    # the uint8 table the CUDA post-processing kernel indexes gives the same thermal pixels (x in [0,1])
+    lut8 = colormap_to_lut8(cmap)
+    x = gold["frames"][0]["thermal"].numpy()[..., 0].astype(np.float64)
+    idx = np.minimum((x * 256).astype(np.int64), 255)
+    assert np.array_equal(lut8[idx], gold["rendered"]["THERMAL"][0].numpy())
+    # modality-outer / camera-inner: 3 modalities x 2 cameras, then the RGB attempt fails on its first frame
+    assert gold["model_calls"] == [0, 1, 0, 1, 0, 1, 0]
+    assert gold["rgb_modality_error"] == "img modality does not exist"  # RGB.value == "img", the model emits "rgb"

@@ -159,8 +159,11 @@ def test_image_metrics_and_images_surface():
                "depth": torch.rand((H, W, 1), generator=g) * 3, "prop_depth_0": torch.rand((H, W, 1), generator=g),
                "prop_depth_1": torch.rand((H, W, 1), generator=g)}
     metrics, images = model.get_image_metrics_and_images(outputs, {"image": gt_rgb, "thermal": gt_th}, threshold=0.5)
+    # incl. the two colour-image MAE entries ThermalNerfactoModel's method adds on the way (thermal_nerf_model.py:339;
+    # key set pinned by executing the reference's method, tests/test_reference_wiring_cpu.py)
     assert set(metrics) == {"psnr", "ssim", "lpips", "psnr_thermal", "ssim_thermal", "lpips_thermal",
-                            "mae_thermal_foreground", "mae_thermal"}
+                            "mae_thermal_foreground", "mae_thermal", "mae_foreground", "mae"}
+    assert metrics["mae_foreground"] == metrics["mae"]
     assert set(images) >= {"img", "accumulation", "depth", "prop_depth_0", "prop_depth_1", "thermal", "thermal_combined"}
     assert images["img"].shape == (H, 2 * W, 3) and images["thermal_combined"].shape == (H, 2 * W, 3)
     mse = torch.mean((outputs["rgb"] - gt_rgb) ** 2)

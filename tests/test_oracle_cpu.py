@@ -250,3 +250,41 @@ def test_thermal_metrics_match_vectors_generated_by_the_reference_itself():
     assert checked == len(blob["cases"]) >= 72
     assert {m.name: m.value for m in RenderedImageModality} == blob["modalities"]
     assert blob["model_types"] == {"THERMALNERFACTO": 1, "THERMONERF": 2, "CONCATNERF": 3, "NERFACTO": 4}
+
+
+# ---- compositing pinned by the reference's own renderer code (tests/golden/make_reference_renderer_golden.py) ----
+def _reference_renderers():
+    from pathlib import Path
+
+    return torch.load(Path(__file__).parent / "golden" / "reference_renderers.pt", weights_only=True)
+
+
+def test_thermal_compositing_matches_the_reference_renderer_bitwise():
+    """ThermalRenderer.forward (thermal_renderer.py:113-149) executed from the reference: train and eval mode,
+    out-of-range and non-finite samples, near-empty and opaque rays."""
+    blob = _reference_renderers()
+    assert len(blob["thermal"]) == 6
+    for case in blob["thermal"]:
+        got = M.render_rgb_last_sample(case["thermal"].clone(), case["weights"], case["training"])
+        assert got.shape == case["out"].shape
+        assert torch.equal(got, case["out"]), (case["training"], (got - case["out"]).abs().max())
+    # eval output is clamped to [0,1]; training output is not
+    assert all(((c["out"] >= 0) & (c["out"] <= 1)).all() for c in blob["thermal"] if not c["training"])
+    assert any(((c["out"] < 0) | (c["out"] > 1)).any() for c in blob["thermal"] if c["training"])
+    # the background argument is overridden to "last_sample" inside combine_thermal (thermal_renderer.py:49)
+    f = blob["thermal_forced_background"]
+    assert torch.equal(M.render_rgb_last_sample(f["thermal"], f["weights"], True), f["out"])
+
+
+def test_concat_compositing_and_loss_blend_match_the_reference_renderer_bitwise():
+    """RGBTRenderer.forward with its default "random" background (rgbt_renderer.py:63-71,163-174) and the loss-time
+    blend of rgbt_renderer.py:134-140, executed from the reference."""
+    blob = _reference_renderers()
+    for case in blob["rgbt"]:
+        got = M.render_rgbt_no_background(case["rgbt"].clone(), case["weights"], case["training"])
+        assert torch.equal(got, case["out"]), (case["training"], (got - case["out"]).abs().max())
+    for case in blob["blend"]:
+        torch.manual_seed(case["seed"])
+        noise = torch.rand_like(case["pred"])
+        assert torch.equal(case["pred"] + noise * (1.0 - case["acc"]), case["pred_out"])
+        assert torch.equal(case["gt"], case["gt_out"])  # the ground truth is left alone

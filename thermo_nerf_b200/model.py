@@ -467,6 +467,9 @@ class ThermalNerfModel(nn.Module):
             metrics["mae_foreground"] = float(self.mae_thermal(g4, p4, threshold=threshold))
             metrics["mae"] = float(self.mae_thermal(g4, p4, threshold=None))
             return metrics, images
+        # ThermalNerfModel reaches the method above through super() *without* its threshold
+        # (thermal_nerf_model.py:339), so both entries are the unthresholded MAE of the colour image
+        metrics["mae_foreground"] = metrics["mae"] = float(self.mae_thermal(g4, p4, threshold=None))
         gt_th = batch["thermal"].to(dev)  # thermal_nerf_model.py:347 (the reference forgets the .to() at :355)
         th = outputs["thermal"]
         images["thermal"] = gray(th)
