@@ -354,6 +354,10 @@ class SceneBox:
 @dataclass
 class CameraOptimizerConfig:
     mode: str = "off"
+    trans_l2_penalty: float = 1e-2
+    rot_l2_penalty: float = 1e-3
+    optimizer: object = None
+    scheduler: object = None
 
     def setup(self, num_cameras: int, device="cpu"):
         return CameraOptimizer(self, num_cameras, device)
@@ -539,6 +543,7 @@ def install() -> None:
 
     def mod(name: str, **attrs):
         m = types.ModuleType(name)
+        m.__path__ = []  # a package: lets other generators hang further stand-in sub-modules below it
         m.__dict__.update(attrs)
         sys.modules[name] = m
         parent, _, leaf = name.rpartition(".")
