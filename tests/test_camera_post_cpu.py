@@ -168,3 +168,15 @@ def test_frame_conversion_matches_the_reference_render_loop():
     # modality-outer / camera-inner: 3 modalities x 2 cameras, then the RGB attempt fails on its first frame
     assert gold["model_calls"] == [0, 1, 0, 1, 0, 1, 0]
     assert gold["rgb_modality_error"] == "img modality does not exist"  # RGB.value == "img", the model emits "rgb"
+
+
+def test_uint8_ground_truth_conversion_conventions_agree_on_every_byte():
+    """The reference converts thermal images as float64 `image / 255.0` then `.astype(float32)`
+    (thermal_dataset.py:64-65) and colour images as `image.astype("float32") / 255.0` (nerfstudio InputDataset); the
+    oracle's and the batch-sampling kernel's float32 `x / 255` give the same float32 for all 256 byte values."""
+    x = np.arange(256, dtype=np.uint8)
+    thermal_ref = (x / 255.0).astype(np.float32)
+    colour_ref = x.astype("float32") / 255.0
+    ours = x.astype(np.float32) / np.float32(255.0)
+    assert colour_ref.dtype == np.float32
+    assert np.array_equal(thermal_ref, ours) and np.array_equal(colour_ref, ours)
