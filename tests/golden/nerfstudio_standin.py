@@ -226,6 +226,30 @@ class NerfactoField(nn.Module):
         density = self.average_init_density * M.trunc_exp(dba.to(p))
         return density * selector[..., None], geo
 
+    def get_outputs(self, ray_samples: RaySamples, density_embedding: Optional[Tensor] = None):
+        """nerfstudio NerfactoField.get_outputs without transients / semantics / normals (what the reference's
+        ConcatNerfactoTField inherits, rgb_concat/concat_field.py:9-75): SH of the remapped directions, appearance
+        embedding (lookup in training, mean or zeros otherwise), colour MLP on [sh | geo features | appearance]."""
+        assert density_embedding is not None
+        camera_indices = ray_samples.camera_indices.squeeze()
+        directions = get_normalized_directions(ray_samples.frustums.directions)
+        d = self.direction_encoding(directions.view(-1, 3))
+        shape = ray_samples.frustums.directions.shape[:-1]
+        if self.training:
+            app = self.embedding_appearance(camera_indices)
+        elif self.use_average_appearance_embedding:
+            app = torch.ones((*shape, self.appearance_embedding_dim), device=directions.device) * self.embedding_appearance.mean(dim=0)
+        else:
+            app = torch.zeros((*shape, self.appearance_embedding_dim), device=directions.device)
+        h = torch.cat([d, density_embedding.view(-1, self.geo_feat_dim), app.view(-1, self.appearance_embedding_dim)], dim=-1)
+        return {FieldHeadNames.RGB: self.mlp_head(h).view(*shape, -1).to(directions)}
+
+    def forward(self, ray_samples: RaySamples, compute_normals: bool = False):
+        density, density_embedding = self.get_density(ray_samples)
+        outputs = self.get_outputs(ray_samples, density_embedding=density_embedding)
+        outputs[FieldHeadNames.DENSITY] = density
+        return outputs
+
 
 # ---------------------------------------------------------------- model components
 class NearFarCollider(nn.Module):
@@ -351,7 +375,7 @@ class SceneBox:
     aabb: Tensor
 
 
-@dataclass
+@dataclass(unsafe_hash=True)
 class CameraOptimizerConfig:
     mode: str = "off"
     trans_l2_penalty: float = 1e-2
@@ -447,6 +471,29 @@ class NerfactoModel(nn.Module):
         if self.collider is not None:
             ray_bundle = self.collider(ray_bundle)
         return self.get_outputs(ray_bundle)
+
+    def get_outputs(self, ray_bundle: RayBundle):
+        """nerfstudio NerfactoModel.get_outputs (no normals, no gradient scaling) - inherited by the reference's
+        ConcatNerfModel, whose renderer_rgb is its own RGBTRenderer."""
+        if self.training:
+            self.camera_optimizer.apply_to_raybundle(ray_bundle)
+        ray_samples, weights_list, ray_samples_list = self.proposal_sampler(ray_bundle, density_fns=self.density_fns)
+        field_outputs = self.field.forward(ray_samples, compute_normals=self.config.predict_normals)
+        weights = ray_samples.get_weights(field_outputs[FieldHeadNames.DENSITY])
+        weights_list.append(weights)
+        ray_samples_list.append(ray_samples)
+        rgb = self.renderer_rgb(rgb=field_outputs[FieldHeadNames.RGB], weights=weights)
+        with torch.no_grad():
+            depth = self.renderer_depth(weights=weights, ray_samples=ray_samples)
+        expected_depth = self.renderer_expected_depth(weights=weights, ray_samples=ray_samples)
+        accumulation = self.renderer_accumulation(weights=weights)
+        outputs = {"rgb": rgb, "accumulation": accumulation, "depth": depth, "expected_depth": expected_depth}
+        if self.training:
+            outputs["weights_list"] = weights_list
+            outputs["ray_samples_list"] = ray_samples_list
+        for i in range(self.config.num_proposal_iterations):
+            outputs[f"prop_depth_{i}"] = self.renderer_depth(weights=weights_list[i], ray_samples=ray_samples_list[i])
+        return outputs
 
     @torch.no_grad()
     def get_outputs_for_camera_ray_bundle(self, camera_ray_bundle: RayBundle):
