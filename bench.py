@@ -512,9 +512,40 @@ def bench_train(ctx) -> dict:
         line["breakdown_ms"] = breakdown
     if rank == 0 and world == 1 and not args.no_render:
         line["render"] = quick_render(model, device)
+    if rank == 0 and world == 1 and args.torch_cuda_baseline:
+        line["torch_cuda_baseline"] = torch_cuda_train_baseline(device, args.rays)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_train(min(args.ref_rays, 4096))
     return line
+
+
+def torch_cuda_train_baseline(device, rays: int) -> dict:
+    """Context only (opt-in, not the reference arm): the PyTorch restatement's full training iteration run eagerly in
+    fp32 on the GPU - what a stock install of the reference executes on CUDA (tinycudann absent from uv.lock) - for
+    north_star's ">= 10x the reference PyTorch-CUDA path" target."""
+    try:
+        model, _, batch = oracle_train_setup(rays)
+        model = model.to(device)
+        field = [p for n, p in model.named_parameters() if n.startswith("field.")]
+        props = [p for n, p in model.named_parameters() if n.startswith("proposal_networks.")]
+        opts = [torch.optim.Adam(field, lr=1e-2, eps=1e-15), torch.optim.Adam(props, lr=1e-2, eps=1e-15)]
+        batch = tuple(t.to(device) for t in batch)
+        for i in range(3):
+            oracle_train_step(model, opts, batch, i)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        a.record()
+        for i in range(reps):
+            oracle_train_step(model, opts, batch, 3 + i)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        return {"value": rays / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms,
+                "kind": "oracle port, eager PyTorch on cuda, fp32, torch Adam",
+                "sample": f"{reps} full iterations of {rays} rays (each reads the loss back, as the trainer's logging does)"}
+    except Exception as e:  # context only: never fail the bench on it
+        return {"error": repr(e)[:200]}
 
 
 def kernel_breakdown(engine, batches, device) -> dict:
