@@ -60,6 +60,11 @@ def main() -> None:
                                                 for a in Wg.MINI["proposal_net_args_list"]])
     oracle = OracleThermalNerf(ocfg, Wg.NUM_IMAGES, seed=21)
     make_trained_like(oracle, 21)
+    with torch.no_grad():  # a freshly initialised temperature head is almost constant: give the frames some contrast
+        oracle.field.mlp_thermal.layers[0].weight.mul_(6.0)
+        oracle.field.mlp_thermal.layers[1].weight.mul_(4.0)
+        oracle.field.field_head_thermal.net.weight.mul_(4.0)
+        oracle.field.field_head_thermal.net.bias.fill_(0.45)
     model.load_state_dict(oracle.state_dict(), strict=False)
     model.eval()
 

@@ -2,7 +2,7 @@
 build container on the reference's ThermalNerfModel over the nerfstudio stand-ins (tests/golden/nerfstudio_standin.py).
 matplotlib and imageio are absent here: `plt.colormaps["magma"]` is replaced by the oracle's restatement of matplotlib's
 Colormap.__call__ over a synthetic 256-entry table (so the colour map's arithmetic is NOT pinned by this file, the
-reference's conversion flow around it is), imageio by an empty module (render() does not write files).
+reference's conversion flow around it is), imageio by a recorder of the file names save_images / save_gif ask it to write.
 
     python tests/golden/make_reference_render_frames_golden.py        # needs /root/reference
 
@@ -59,7 +59,15 @@ def main() -> None:
     from thermo_nerf_b200 import sphere_cameras
 
     cmap = ListedColormapLike(synthetic_lut())
-    for name, attrs in (("imageio", {}), ("matplotlib", {}), ("matplotlib.pyplot", {"colormaps": {"magma": cmap}}),
+    written = []  # what save_images / save_gif hand to imageio: (function, file name, frames, duration)
+
+    def imwrite(path, image):
+        written.append(("imwrite", Path(path).name, 1, None))
+
+    def mimsave(path, frames, duration=None):
+        written.append(("mimsave", Path(path).name, len(frames), duration))
+
+    for name, attrs in (("imageio", {"imwrite": imwrite, "mimsave": mimsave}), ("matplotlib", {}), ("matplotlib.pyplot", {"colormaps": {"magma": cmap}}),
                         ("matplotlib.colors", {"Colormap": ListedColormapLike}),
                         ("nerfstudio.cameras.camera_paths", {"get_path_from_json": None}),
                         ("nerfstudio.cameras.cameras", {"Cameras": PathCameras}),
@@ -81,6 +89,11 @@ def main() -> None:
                                                 for a in Wg.MINI["proposal_net_args_list"]])
     oracle = OracleThermalNerf(ocfg, Wg.NUM_IMAGES, seed=31)
     make_trained_like(oracle, 31)
+    with torch.no_grad():  # a freshly initialised temperature head is almost constant: give the frames some contrast
+        oracle.field.mlp_thermal.layers[0].weight.mul_(6.0)
+        oracle.field.mlp_thermal.layers[1].weight.mul_(4.0)
+        oracle.field.field_head_thermal.net.weight.mul_(4.0)
+        oracle.field.field_head_thermal.net.bias.fill_(0.45)
     model.load_state_dict(oracle.state_dict(), strict=False)
     model.eval()
     cams = PathCameras(sphere_cameras(FRAMES, hw=H, focal=FOCAL).camera_to_worlds.clone())
@@ -100,6 +113,8 @@ def main() -> None:
     mods = [Mod.THERMAL, Mod.DEPTH, Mod.ACCUMULATION]
     r.render(mods, cams)  # default thermal_color_map = plt.colormaps["magma"] (bound at import: the stand-in map)
     rendered = {m.name: [torch.from_numpy(np.ascontiguousarray(a)) for a in r._rendered_images[m]] for m in mods}
+    r.save_images(mods, Path("/nonexistent"))          # renderer.py:202-213 (the recorder does not touch the disk)
+    r.save_gif(mods, 2.5, Path("/nonexistent"))        # renderer.py:215-228
     # the RGB modality is named "img" but the model emits "rgb" (renderer.py:186-187): the stock loop raises
     try:
         r.render([Mod.RGB], cams)
@@ -108,7 +123,7 @@ def main() -> None:
         rgb_error = str(e)
     torch.save({"frames": [frames[i] for i in range(FRAMES)], "camera_to_worlds": cams.camera_to_worlds, "hw": [H, W],
                 "focal": FOCAL, "lut": torch.from_numpy(synthetic_lut()), "modalities": [m.name for m in mods],
-                "rendered": rendered, "model_calls": calls, "rgb_modality_error": rgb_error,
+                "rendered": rendered, "model_calls": calls, "written": [list(w) for w in written], "rgb_modality_error": rgb_error,
                 "source": "thermo_nerf/render/renderer.py:160-201 executed from /root/reference over tests/golden/nerfstudio_standin.py",
                 "torch": str(torch.__version__)}, OUT)
     print(f"wrote {OUT} ({OUT.stat().st_size / 1024:.0f} KiB); model calls {calls}; RGB error: {rgb_error!r}")

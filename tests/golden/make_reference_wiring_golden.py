@@ -64,7 +64,9 @@ def main() -> None:
                       "nerfacto_config/thermal_nerfacto.py executed from /root/reference over tests/golden/nerfstudio_standin.py",
             "torch": str(torch.__version__), "mini": {k: (list(v) if isinstance(v, tuple) else v) for k, v in MINI.items()},
             "num_images": NUM_IMAGES}
-    for pass_thermal in (True, False):
+    # the third case gives the temperature head some contrast (a freshly initialised one is almost constant, and in eval
+    # mode its slightly negative output clamps to 0); cases 0 and 1 are the ones the GPU test consumes
+    for pass_thermal, contrast in ((True, False), (False, False), (True, True)):
         ref = build_reference_model(pass_thermal)
         # trained-like weights come from an oracle instance; loading them by name also checks the module tree
         ocfg = OracleConfig(log2_hashmap_size=MINI["log2_hashmap_size"],
@@ -75,6 +77,12 @@ def main() -> None:
                             pass_thermal_gradients=pass_thermal)
         oracle = OracleThermalNerf(ocfg, NUM_IMAGES, seed=11)
         make_trained_like(oracle, 11)
+        if contrast:
+            with torch.no_grad():
+                oracle.field.mlp_thermal.layers[0].weight.mul_(6.0)
+                oracle.field.mlp_thermal.layers[1].weight.mul_(4.0)
+                oracle.field.field_head_thermal.net.weight.mul_(4.0)
+                oracle.field.field_head_thermal.net.bias.fill_(0.45)
         ref_keys = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
         missing, unexpected = ref.load_state_dict(oracle.state_dict(), strict=False)
         state = {k: v.clone() for k, v in oracle.state_dict().items()}
@@ -88,7 +96,7 @@ def main() -> None:
             return S.RayBundle(origins=rays.origins.clone(), directions=rays.directions.clone(),
                                camera_indices=rays.camera_indices.clone())
 
-        case = {"pass_thermal_gradients": pass_thermal, "state_dict": state, "reference_state_dict_keys": ref_keys,
+        case = {"pass_thermal_gradients": pass_thermal, "thermal_contrast": contrast, "state_dict": state, "reference_state_dict_keys": ref_keys,
                 "load_missing": list(missing), "load_unexpected": list(unexpected),
                 "origins": rays.origins, "directions": rays.directions, "camera_indices": rays.camera_indices,
                 "jitter": jitter, "batch": batch}

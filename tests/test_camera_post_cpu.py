@@ -180,3 +180,26 @@ def test_uint8_ground_truth_conversion_conventions_agree_on_every_byte():
     ours = x.astype(np.float32) / np.float32(255.0)
     assert colour_ref.dtype == np.float32
     assert np.array_equal(thermal_ref, ours) and np.array_equal(colour_ref, ours)
+
+
+def test_saved_file_names_match_the_reference_renderer(tmp_path):
+    """Renderer.save_images / save_gif of the reference (renderer.py:202-228) were executed with a recording imageio:
+    the mirror writes the same files (names, one gif per modality over all frames) from the same frames."""
+    from PIL import Image
+
+    gold = torch.load(GOLDEN / "reference_render_frames.pt", weights_only=True)
+    mods = [RenderedImageModality[n] for n in gold["modalities"]]
+    r = Renderer(model=object())
+    r._rendered_images = {m: [f.numpy() for f in gold["rendered"][m.name]] for m in mods}
+    r.save_images(mods, tmp_path)
+    r.save_gif(mods, 2.5, tmp_path)
+    want = sorted(name for _, name, _, _ in gold["written"])
+    assert sorted(p.name for p in tmp_path.iterdir()) == want
+    for fn, name, frames, duration in gold["written"]:
+        if fn == "mimsave":
+            assert frames == 2 and duration == 2.5
+            with Image.open(tmp_path / name) as gif:
+                assert getattr(gif, "n_frames", 1) == frames
+        else:
+            with Image.open(tmp_path / name) as im:
+                assert im.size == (gold["hw"][1], gold["hw"][0])

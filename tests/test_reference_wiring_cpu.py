@@ -69,7 +69,7 @@ def test_product_model_has_the_reference_state_dict_names(blob):
         ThermalNerfModel(cfg, {}, torch.tensor([[-1.0, -1, -1], [1, 1, 1]]), 1)
 
 
-@pytest.mark.parametrize("idx", [0, 1])
+@pytest.mark.parametrize("idx", [0, 1, 2])
 def test_training_outputs_losses_and_gradients(blob, idx):
     case = blob["cases"][idx]
     o = build_oracle(blob, case)
@@ -109,7 +109,7 @@ def test_training_outputs_losses_and_gradients(blob, idx):
         assert any("field_head_thermal" in k for k in tr["params_without_grad"])
 
 
-@pytest.mark.parametrize("idx", [0, 1])
+@pytest.mark.parametrize("idx", [0, 1, 2])
 def test_eval_outputs(blob, idx):
     case = blob["cases"][idx]
     o = build_oracle(blob, case)
@@ -120,6 +120,9 @@ def test_eval_outputs(blob, idx):
     assert ev["output_keys"] == ["accumulation", "depth", "expected_depth", "prop_depth_0", "prop_depth_1", "rgb", "thermal"]
     for k, v in ev["outputs"].items():
         assert torch.allclose(out[k], v, atol=1e-6, rtol=1e-6), (k, (out[k] - v).abs().max())
+    if case["thermal_contrast"]:  # a temperature image with real structure, strictly inside the eval clamp
+        t = ev["outputs"]["thermal"]
+        assert 0.3 < float(t.min()) < float(t.max()) < 0.8 and float(t.max() - t.min()) > 0.1
     assert set(loss) == set(ev["loss"])
     for k, v in ev["loss"].items():
         assert torch.allclose(loss[k], v, atol=1e-7, rtol=1e-5), k
