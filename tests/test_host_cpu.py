@@ -229,3 +229,40 @@ def test_nerfacto_variant_has_no_thermal_head():
     assert m.field.pass_thermal_gradients is False
     with pytest.raises(ValueError):
         ThermalNerfactoModel(ThermalNerfModelConfig(), torch.tensor([[-1.0, -1, -1], [1, 1, 1]]), 3)
+
+
+def test_product_package_never_touches_the_oracle_or_the_reference():
+    """The oracle is test infrastructure: nothing under thermo_nerf_b200/ (Python or CUDA/C++) imports, includes or
+    names it, nor reads /root/reference; bench.py only reaches it from its CPU-baseline / reference-arm / opt-in
+    context-number functions."""
+    import ast
+    import re
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    for path in sorted((root / "thermo_nerf_b200").rglob("*")):
+        if path.suffix not in {".py", ".cu", ".cuh", ".h", ".cpp"}:
+            continue
+        text = path.read_text()
+        assert "/root/reference" not in text, path
+        if path.suffix == ".py":
+            for node in ast.walk(ast.parse(text)):
+                names = []
+                if isinstance(node, ast.Import):
+                    names = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom):
+                    names = [node.module or ""]
+                assert not any(n == "oracle" or n.startswith("oracle.") or n.startswith("tests") for n in names), path
+        else:
+            assert not re.search(r'#include\s+"[^"]*oracle', text), path
+    # bench.py: every oracle import sits inside one of the baseline functions
+    tree = ast.parse((root / "bench.py").read_text())
+    allowed = {"oracle_train_setup", "oracle_train_step", "run_reference", "cpu_baseline", "cpu_baseline_train",
+               "torch_cuda_baseline", "torch_cuda_train_baseline"}
+    for fn in [n for n in ast.walk(tree) if isinstance(n, (ast.FunctionDef, ast.AsyncFunctionDef))]:
+        uses = any(isinstance(n, ast.ImportFrom) and (n.module or "").split(".")[0] == "oracle" for n in ast.walk(fn))
+        assert not uses or fn.name in allowed, fn.name
+    top = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
+    assert not any(isinstance(n, ast.ImportFrom) and (n.module or "").startswith("oracle") for n in top)
+    assert "/root/reference" not in (root / "bench.py").read_text()
+    assert "/root/reference" not in (root / "__graft_entry__.py").read_text()
