@@ -9,7 +9,7 @@ from hypothesis import strategies as st
 
 from oracle import nerfstudio_math as M
 
-SETTINGS = dict(max_examples=40, deadline=None)
+SETTINGS = dict(max_examples=40, deadline=None, derandomize=True)  # the same examples on every run
 
 
 def _rand(seed, *shape):
