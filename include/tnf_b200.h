@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define TNF_ABI_VERSION 6
+#define TNF_ABI_VERSION 7
 
 #define TNF_MAX_LEVELS 16      /* hash levels of the field grid (fixed: 16)          */
 #define TNF_MAX_PROP_LEVELS 8  /* max hash levels of a proposal density grid          */
@@ -264,10 +264,35 @@ int tnf_render_backward(const TnfModel* model, const TnfRays* rays, const TnfSav
                         const TnfOutputGrads* gout, const TnfModelGrad* grads, void* workspace,
                         size_t workspace_bytes, void* stream);
 
+/* ---- Field / Renderer plugin surface: the per-module entry points of the reference's
+ * ThermalNerfactoTField and ThermalRenderer for callers that compose the modules by hand (viewer density
+ * queries, user code).  fp32, inference only; training and rendering go through tnf_render_forward. */
+
+/* NerfactoField.get_density as reached from ThermalNerfactoTField.forward (thermal_field.py:183-201)
+ * for which = -1 (density [N] and, if `geo` is given, the 15 geo features [N,15]); or
+ * HashMLPDensityField.density_fn of proposal network which = 0 / 1 (thermal_nerf_model.py:127-148).
+ * positions [N,3] are world-space points (contraction + selector applied inside, as in the field). */
+int tnf_field_density(const TnfModel* model, int32_t which, const float* positions, int64_t n, float* density,
+                      float* geo, void* stream);
+
+/* ThermalNerfactoTField.get_outputs (thermal_field.py:108-181): directions [N,3], camera_indices [N]
+ * (TNF_APPEARANCE_LOOKUP only), density_embedding geo [N,15] -> rgb [N,3] (FieldHeadNames.RGB) and
+ * thermal [N] (FieldHeadNamesT.THERMAL); either output may be NULL. */
+int tnf_field_heads(const TnfModel* model, const float* directions, const int64_t* camera_indices, const float* geo,
+                    int64_t n, float* rgb, float* thermal, void* stream);
+
+/* ThermalRenderer.forward (thermal_renderer.py:113-149; last-sample background, :49,68-70) for
+ * last_sample_background = 1, RGBTRenderer.forward of the concat baseline (rgb_concat/rgbt_renderer.py:134-140)
+ * for 0: values [R,S,C], weights [R,S] -> out [R,C]; eval_mode applies nan_to_num to the samples and
+ * clamps the result to [0,1] (thermal_renderer.py:136-137,146-147). */
+int tnf_composite(const float* values, const float* weights, int64_t num_rays, int32_t num_samples,
+                  int32_t channels, int32_t last_sample_background, int32_t eval_mode, float* out, void* stream);
+
 /* Measurement hook (bench.py's per-kernel roofline): restricts tnf_render_backward on the calling thread
- * to a subset of its three kernels so each can be bracketed with CUDA events on its own.  Bit 0:
- * proposal levels, bit 1: field level, bit 2: weight-gradient GEMMs; the default 7 runs all of them
- * (the only setting that produces correct gradients).  Returns the previous mask. */
+ * to a subset of its kernels so each can be bracketed with CUDA events on its own.  Bit 0: proposal
+ * levels, bit 1: field level, bit 2: the fp32 mode's weight-gradient pass (tensor-core mode accumulates
+ * the weight gradients inside the field kernel); the default 7 runs all of them (the only setting that
+ * produces correct gradients).  Returns the previous mask. */
 int tnf_backward_stage_mask(int mask);
 
 /* get_loss_dict (thermal_nerf_model.py:277-326) + the inherited distortion metric:

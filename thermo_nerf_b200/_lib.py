@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 from typing import Optional
 
-TNF_ABI_VERSION = 6
+TNF_ABI_VERSION = 7
 TNF_MAX_LEVELS = 16
 TNF_MAX_PROP_LEVELS = 8
 TNF_MAX_SAMPLES = 256
@@ -264,6 +264,9 @@ EXPORTED_SYMBOLS = (
     "tnf_backward_workspace_bytes",
     "tnf_render_backward",
     "tnf_backward_stage_mask",
+    "tnf_field_density",
+    "tnf_field_heads",
+    "tnf_composite",
     "tnf_losses",
     "tnf_adam_step",
     "tnf_peer_enable_access",
@@ -346,6 +349,15 @@ def load() -> C.CDLL:
     ]
     lib.tnf_backward_stage_mask.restype = C.c_int
     lib.tnf_backward_stage_mask.argtypes = [C.c_int]
+    lib.tnf_field_density.restype = C.c_int
+    lib.tnf_field_density.argtypes = [C.POINTER(TnfModel), C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                      C.c_void_p]
+    lib.tnf_field_heads.restype = C.c_int
+    lib.tnf_field_heads.argtypes = [C.POINTER(TnfModel), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]
+    lib.tnf_composite.restype = C.c_int
+    lib.tnf_composite.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_void_p, C.c_void_p]
     lib.tnf_losses.restype = C.c_int
     lib.tnf_losses.argtypes = [C.POINTER(TnfLossArgs), C.c_void_p]
     lib.tnf_adam_step.restype = C.c_int

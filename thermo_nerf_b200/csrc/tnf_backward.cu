@@ -5,20 +5,16 @@
 //                              a device counter: re-gather the hash features, 10->16->1 MLP forward +
 //                              backward in fp32, run-merged table scatter, weight gradients as bf16 mma
 //                              over the 32 samples of a chunk (TC mode) or lane-owned fp32 sums (fp32 mode)
-//   tnf_backward_field_kernel  ThermalNerfactoTField (thermal_field.py:108-201): compositing backward
-//                              (suffix scans), field MLPs recomputed from the saved hash features,
-//                              dX chain, run-merged hash-grid scatter (REDG.F32x2), and the per-layer
-//                              (X, dY) tiles staged for the weight-gradient GEMMs (stmatrix into a
-//                              shared-memory ring, cp.async.bulk to global)
-//   tnf_wgrad_kernel_*         dW = dY^T X, split-K over the samples (K = R*48): the one genuinely
-//                              dense contraction of the step; bf16 mma.sync fed by TMA bulk copies on
-//                              mbarriers (TC mode) or fp32 FFMA (fp32 mode)
+//   tnf_backward_field_kernel_fp32 + tnf_wgrad_kernel_fp32
+//                              the exact-arithmetic mode of ThermalNerfactoTField's backward
+//                              (thermal_field.py:108-201): lane per sample, fp32 FFMA, (X, dY) rows staged in
+//                              global memory for a split-K fp32 weight-gradient pass
+//   tensor-core mode           tnf_backward_tc.cu: one kernel, weight gradients accumulated in tensor memory
+//                              (tcgen05.mma), nothing per-sample written to HBM
 //
 // Sample distances are constants here (PDFSampler detaches its bins); with TnfModelGrad.ray_origins /
 // ray_directions given, the kernels also return dL/d origins and dL/d directions (camera optimiser).
-#include <cuda_bf16.h>
-
-#include "tnf_field.cuh"
+#include "tnf_backward.cuh"
 #include "tnf_host.h"
 
 namespace tnf {
@@ -68,12 +64,9 @@ __host__ inline size_t make_layout(BwdLayout* L, unsigned char* base, long long 
 struct WgradProblem {
   const void* dY; int ldY, n0, N, n_valid;   // N: loaded columns (multiple of 8), n_valid <= N are written
   const void* X;  int ldX, K, k_skip;        // K: loaded columns (multiple of 8); output col = k - k_skip >= 0
-  int xcol0;                                 // first loaded column of X within its row (TC kernel; X points at column 0)
   long long rows;
   float* W; int ldW, wcol0;
   float* bias;                               // may be null
-  int dy_swz, x_swz;                         // bf16 kernel: 64-wide rows stored chunk-swizzled (see stage_tile)
-  int x_f16;                                 // bf16 kernel: X holds fp16 (the saved hash features), converted on load
 };
 constexpr int kMaxWgradProblems = 12;
 struct WgradArgs {
@@ -90,144 +83,6 @@ __device__ __forceinline__ int wgrad_problem_of(const WgradArgs& a, int cta, int
   return i;
 }
 constexpr int kWgradRows = 64;
-
-// ------------------------------------------------------------------------------------
-// hash-grid scatter: transpose of hash_level (same corner order / weights as hash_blend)
-// ------------------------------------------------------------------------------------
-__device__ __forceinline__ void scatter_level(float2* __restrict__ gtab, float px, float py, float pz, float scale,
-                                              uint32_t mask, float gx, float gy) {
-  if (gx == 0.f && gy == 0.f) return;
-  HashCorners hc;
-  hash_corners(px, py, pz, scale, mask, hc);
-  const float ox = hc.ox, oy = hc.oy, oz = hc.oz, ix = 1.f - ox, iy = 1.f - oy, iz = 1.f - oz;
-  const float w[8] = {ox * oy * oz, ox * iy * oz, ix * iy * oz, ix * oy * oz,
-                      ox * oy * iz, ox * iy * iz, ix * iy * iz, ix * oy * iz};
-#pragma unroll
-  for (int c = 0; c < 8; ++c) atomicAdd(gtab + hc.idx[c], make_float2(w[c] * gx, w[c] * gy));
-}
-
-// Warp-cooperative scatter.  Lanes lane, lane+STRIDE, lane+2*STRIDE, ... hold consecutive samples of one
-// ray, so at the coarser levels whole runs of them fall into the same grid cell (identical corner
-// indices).  The L2 reduction units retire about one lane-address per 1.3 cycles per SM, which is what
-// bounds the table scatter; each run is therefore summed with a segmented shuffle reduction first and only
-// its first lane issues the 8 vector reductions.  The number of shuffle rounds adapts to the longest run
-// in the warp (none at the fine levels, where every sample sits in its own cell).
-// Must be called by all 32 lanes; a lane without a contribution passes gx = gy = 0.
-template <int STRIDE>
-__device__ __forceinline__ void scatter_level_runs(float2* __restrict__ gtab, float px, float py, float pz, float scale,
-                                                   uint32_t mask, float gx, float gy, const int lane) {
-  HashCorners hc;
-  hash_corners(px, py, pz, scale, mask, hc);
-  const uint32_t p1 = __shfl_up_sync(kFull, hc.k1, STRIDE), p2 = __shfl_up_sync(kFull, hc.k2, STRIDE);
-  const bool head = lane < STRIDE || p1 != hc.k1 || p2 != hc.k2;
-  const unsigned heads = __ballot_sync(kFull, head);
-  const unsigned nzm = __ballot_sync(kFull, gx != 0.f || gy != 0.f);
-  const unsigned cls = STRIDE == 1 ? kFull : (0x11111111u << (lane & (STRIDE - 1)));
-  const unsigned later = lane + STRIDE >= 32 ? 0u : ((heads & cls) >> (lane + STRIDE));
-  const int nh = later ? lane + STRIDE + __ffs(later) - 1 : 32;  // first lane of the next run of my class (or 32)
-  const int len = (nh - lane + STRIDE - 1) / STRIDE;             // lanes of my class from me to the run's end
-  const int maxlen = __reduce_max_sync(kFull, len);
-  const float ox = hc.ox, oy = hc.oy, oz = hc.oz, ix = 1.f - ox, iy = 1.f - oy, iz = 1.f - oz;
-  const float w[8] = {ox * oy * oz, ox * iy * oz, ix * iy * oz, ix * oy * oz,
-                      ox * oy * iz, ox * iy * iz, ix * iy * iz, ix * oy * iz};
-  float vx[8], vy[8];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) { vx[c] = w[c] * gx; vy[c] = w[c] * gy; }
-#pragma unroll
-  for (int d = 1; d < 32 / STRIDE; d <<= 1) {
-    if (d < maxlen) {  // warp-uniform
-      const bool take = lane + d * STRIDE < nh;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float tx = __shfl_down_sync(kFull, vx[c], d * STRIDE), ty = __shfl_down_sync(kFull, vy[c], d * STRIDE);
-        if (take) { vx[c] += tx; vy[c] += ty; }
-      }
-    }
-  }
-  // does any lane of my run carry a gradient?
-  const unsigned runbits = (len >= 32 / STRIDE && STRIDE == 1 && lane == 0) ? kFull : 0u;
-  unsigned mine = 0u;
-  if (STRIDE == 1) {
-    mine = runbits ? kFull : (((1u << len) - 1u) << lane);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32 / STRIDE; ++i)
-      if (i < len) mine |= 1u << (lane + i * STRIDE);
-  }
-  if (head && (nzm & mine)) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) atomicAdd(gtab + hc.idx[c], make_float2(vx[c], vy[c]));
-  }
-}
-
-// ------------------------------------------------------------------------------------
-// gradient w.r.t. the sample position (camera-optimiser path): d feat / d p through the trilinear weights
-// (the reference differentiates offset = scaled - floor(scaled); ceil/floor carry no gradient), then back
-// through (x + 2) / 4, the selector mask and the L-inf scene contraction.
-// ------------------------------------------------------------------------------------
-// adds scale * sum_c (g . T[idx_c]) d w_c / d offset to (dpx, dpy, dpz); corner order of hash_blend
-__device__ __forceinline__ void hash_level_pos_grad(const float2* __restrict__ level_tab, const float px, const float py,
-                                                    const float pz, const float scale, const uint32_t mask,
-                                                    const float gx, const float gy, float& dpx, float& dpy, float& dpz) {
-  HashCorners hc;
-  hash_corners(px, py, pz, scale, mask, hc);
-  float s[8];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const float2 t = __ldg(level_tab + hc.idx[c]);
-    s[c] = gx * t.x + gy * t.y;
-  }
-  const float ox = hc.ox, oy = hc.oy, oz = hc.oz, ix = 1.f - ox, iy = 1.f - oy, iz = 1.f - oz;
-  dpx += scale * (oy * oz * (s[0] - s[3]) + iy * oz * (s[1] - s[2]) + oy * iz * (s[4] - s[7]) + iy * iz * (s[5] - s[6]));
-  dpy += scale * (ox * oz * (s[0] - s[1]) + ix * oz * (s[3] - s[2]) + ox * iz * (s[4] - s[5]) + ix * iz * (s[7] - s[6]));
-  dpz += scale * (ox * oy * (s[0] - s[4]) + ox * iy * (s[1] - s[5]) + ix * iy * (s[2] - s[6]) + ix * oy * (s[3] - s[7]));
-}
-
-// dL/d(normalised position p) -> dL/d(world position x); (x, y, z) is the un-contracted sample position
-__device__ __forceinline__ void position_grad_to_world(const TnfModel& m, const float x, const float y, const float z,
-                                                       const float sel, float& gx, float& gy, float& gz) {
-  if (sel == 0.f) { gx = gy = gz = 0.f; return; }
-  if (m.use_contraction) {
-    gx *= 0.25f; gy *= 0.25f; gz *= 0.25f;
-    const float ax = fabsf(x), ay = fabsf(y), az = fabsf(z);
-    const float mag = fmaxf(ax, fmaxf(ay, az));
-    if (!(mag < 1.f)) {
-      // x' = a(m) x, a = (2 - 1/m) / m, m = |x|_inf = |x_k|:  J^T g = a g + (g . x) a'(m) sign(x_k) e_k
-      const float a = (2.f - 1.f / mag) / mag;
-      const float dadm = 2.f * (1.f - mag) / (mag * mag * mag);
-      const float dot = gx * x + gy * y + gz * z;
-      gx *= a; gy *= a; gz *= a;
-      if (ax >= ay && ax >= az) gx += dot * dadm * (x < 0.f ? -1.f : 1.f);
-      else if (ay >= az) gy += dot * dadm * (y < 0.f ? -1.f : 1.f);
-      else gz += dot * dadm * (z < 0.f ? -1.f : 1.f);
-    }
-  } else {
-    gx /= (m.aabb[3] - m.aabb[0]);
-    gy /= (m.aabb[4] - m.aabb[1]);
-    gz /= (m.aabb[5] - m.aabb[2]);
-  }
-}
-
-// per-ray accumulation of the pose gradient: dL/do += sum_s g_s, dL/dd += sum_s mid_s g_s (warp-reduced)
-__device__ __forceinline__ void flush_ray_grad(const TnfModelGrad& gr, const long long ray, float ax, float ay, float az,
-                                               float bx, float by, float bz, const int lane) {
-  ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
-  bx = warp_sum(bx); by = warp_sum(by); bz = warp_sum(bz);
-  if (lane == 0) {
-    atomicAdd(gr.ray_origins + ray * 3 + 0, ax); atomicAdd(gr.ray_origins + ray * 3 + 1, ay);
-    atomicAdd(gr.ray_origins + ray * 3 + 2, az);
-    atomicAdd(gr.ray_directions + ray * 3 + 0, bx); atomicAdd(gr.ray_directions + ray * 3 + 1, by);
-    atomicAdd(gr.ray_directions + ray * 3 + 2, bz);
-  }
-}
-
-// reverse (suffix) exclusive scan helper over one 32-wide chunk: returns sum_{j>lane} v_j
-__device__ __forceinline__ float warp_suffix_excl(float v, int lane, float& total) {
-  const float rv = __shfl_sync(kFull, v, 31 - lane);
-  const float incl = warp_incl_scan(rv, lane);
-  total = __shfl_sync(kFull, incl, 31);
-  return __shfl_sync(kFull, incl, 31 - lane) - v;
-}
 
 // ------------------------------------------------------------------------------------
 // proposal levels
@@ -273,30 +128,6 @@ struct PropBwdSmem {
   float wacc[TNF_NUM_PROP][kPropWacc + 3];  // [16*K2 l0.weight | 16 l0.bias | 16 l1.weight | l1.bias]
   PropBwdScratch ws[kWarpsPerCta];
 };
-
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_ptr) {
-  const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(smem_ptr));
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(addr));
-}
-__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t (&r)[2], const void* smem_ptr) {
-  const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(smem_ptr));
-  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n"
-               : "=r"(r[0]), "=r"(r[1])
-               : "r"(addr));
-}
-__device__ __forceinline__ uint32_t pack_bf162(float lo, float hi) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<const uint32_t*>(&h);
-}
-__device__ __forceinline__ void mma_16816_bf16(float (&c)[4], const uint32_t (&a)[4], const uint2 b) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
-      "{%0,%1,%2,%3};\n"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
-}
 
 // per-warp weight-gradient accumulators of the level being processed
 template <bool TC, int NLC>
@@ -637,102 +468,6 @@ __global__ void __launch_bounds__(kThreads, 2)
   }
 }
 
-// ------------------------------------------------------------------------------------
-// field level: shared per-ray prologue (compositing backward)
-// ------------------------------------------------------------------------------------
-struct FieldBwdScratch {
-  float bins[kMaxFieldS + 8];
-  float dsig[kMaxFieldS];  // dL/d sigma_i
-  float dzr[kMaxFieldS], dzg[kMaxFieldS], dzb[kMaxFieldS];  // dL/d (pre-sigmoid colour)
-  float dtau[kMaxFieldS];  // dL/d thermal_i
-  float T[kMaxFieldS], w[kMaxFieldS], gw[kMaxFieldS];
-  float rayb[64];
-  float racc[64];  // TC kernel: per-ray column sums of dA1pre (kept here, not in 16 registers per lane)
-};
-
-// RGBRenderer / ThermalRenderer (background "last_sample"), AccumulationRenderer and get_weights,
-// differentiated: fills dsig, dz*, dtau for the S2 samples of one ray.
-__device__ __forceinline__ void composite_backward(const TnfModel& m, FieldBwdScratch& ws, const RayCtx& rc,
-                                                   const int S2, const int lane, const float* __restrict__ fs,
-                                                   const float* __restrict__ g_w2, const float gr_, const float gg_,
-                                                   const float gb_, const float gth, const float gacc) {
-  // pass 1: weights and transmittance from the saved densities
-  float carry = 0.f, sw = 0.f;
-  for (int base = 0; base < S2; base += 32) {
-    const int i = base + lane;
-    const bool active = i < S2;
-    const int ii = active ? i : S2 - 1;
-    float mid, delta;
-    sample_geometry(rc, ws.bins[ii], ws.bins[ii + 1], mid, delta);
-    const float ds = active ? delta * fs[ii * 5] : 0.f;
-    const float incl = warp_incl_scan(ds, lane);
-    float excl = __shfl_up_sync(kFull, incl, 1);
-    if (lane == 0) excl = 0.f;
-    const float T = expf(-(carry + excl));
-    const float w = active ? (1.f - expf(-ds)) * T : 0.f;
-    carry += __shfl_sync(kFull, incl, 31);
-    if (active) { ws.T[i] = T; ws.w[i] = w; }
-    sw += w;
-  }
-  sw = warp_sum(sw);
-  const float bgw = 1.f - sw;
-  const float* fl = fs + (S2 - 1) * 5;
-  const float lr = fl[1], lg = fl[2], lb = fl[3], lt = fl[4];
-  __syncwarp();
-  // pass 2: dL/dw_i, then dL/d(delta*sigma)_i = gw_i (T_i - w_i) - sum_{j>i} gw_j w_j
-  for (int i = lane; i < S2; i += 32) {
-    const float* f = fs + i * 5;
-    float g = gr_ * (f[1] - lr) + gg_ * (f[2] - lg) + gb_ * (f[3] - lb) + gth * (f[4] - lt) + gacc;
-    if (g_w2) g += g_w2[i];
-    ws.gw[i] = g;
-    const float wc = ws.w[i] + (i == S2 - 1 ? bgw : 0.f);
-    ws.dzr[i] = gr_ * wc * f[1] * (1.f - f[1]);
-    ws.dzg[i] = gg_ * wc * f[2] * (1.f - f[2]);
-    ws.dzb[i] = gb_ * wc * f[3] * (1.f - f[3]);
-    ws.dtau[i] = gth * wc;
-  }
-  __syncwarp();
-  float scarry = 0.f;
-  for (int base = ((S2 - 1) / 32) * 32; base >= 0; base -= 32) {
-    const int i = base + lane;
-    const float v = i < S2 ? ws.gw[i] * ws.w[i] : 0.f;
-    float tot;
-    const float ex = warp_suffix_excl(v, lane, tot);
-    if (i < S2) {
-      float mid, delta;
-      sample_geometry(rc, ws.bins[i], ws.bins[i + 1], mid, delta);
-      ws.dsig[i] = (ws.gw[i] * (ws.T[i] - ws.w[i]) - (ex + scarry)) * delta;
-    }
-    scarry += tot;
-  }
-  __syncwarp();
-}
-
-// per-ray first-layer bias of the colour head, as in the forward, from global weights
-__device__ __forceinline__ void ray_bias_and_inputs(const TnfModel& m, const TnfRays& rays, const long long ray,
-                                                    const RayCtx& rc, const int lane, float* rayb, float (&sh)[16],
-                                                    float& app_lane) {
-  sh4((rc.dx + 1.f) * 0.5f, (rc.dy + 1.f) * 0.5f, (rc.dz + 1.f) * 0.5f, sh);
-  const float* W = m.field.rgb0.weight;
-  float e = 0.f;
-  if (m.appearance_mode == TNF_APPEARANCE_LOOKUP) {
-    e = __ldg(m.field.appearance + rays.camera_indices[ray] * 32 + lane);
-  } else if (m.appearance_mode == TNF_APPEARANCE_MEAN) {
-    for (int i = 0; i < m.field.num_images; ++i) e += m.field.appearance[i * 32 + lane];
-    e /= (float)m.field.num_images;
-  }
-  app_lane = e;
-#pragma unroll
-  for (int hlf = 0; hlf < 2; ++hlf) {
-    const int n = lane + 32 * hlf;
-    float b = m.field.rgb0.bias[n];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) b = fmaf(sh[k], W[n * 63 + k], b);
-    for (int j = 0; j < 32; ++j) b = fmaf(__shfl_sync(kFull, e, j), W[n * 63 + 31 + j], b);
-    rayb[n] = b;
-  }
-}
-
 // per-ray epilogue: stage [sh | appearance] and sum_s dA1pre, appearance-embedding gradient
 template <typename T>
 __device__ __forceinline__ void ray_epilogue(const TnfModel& m, const TnfRays& rays, const long long ray,
@@ -976,567 +711,6 @@ __global__ void __launch_bounds__(kThreads, 1)
 }
 
 // ------------------------------------------------------------------------------------
-// field level, tensor cores: 16-sample tiles.  Forward recompute with the fp16 fragments of the
-// forward kernel (identical activations), backward products with bf16 operands (gradients span
-// far more than fp16's exponent range), fp32 accumulate; activations never leave registers
-// except as the staged (X, dY) rows the weight-gradient GEMMs read.
-// ------------------------------------------------------------------------------------
-template <int NT, int KT>
-__device__ __forceinline__ void mma_layer_bf16(float (&c)[NT][4], const uint32_t (&a)[KT][4],
-                                               const uint2* __restrict__ w, const int ntw, const int lane) {
-  static_assert((NT & 1) == 0, "backward weight images use the paired-fragment layout");
-  const uint4* __restrict__ w4 = reinterpret_cast<const uint4*>(w);
-#pragma unroll
-  for (int nt = 0; nt < NT; nt += 2)
-#pragma unroll
-    for (int kt = 0; kt < KT; ++kt) {
-      const uint4 b = w4[(kt * (ntw >> 1) + (nt >> 1)) * 32 + lane];
-      mma_16816_bf16(c[nt], a[kt], make_uint2(b.x, b.y));
-      mma_16816_bf16(c[nt + 1], a[kt], make_uint2(b.z, b.w));
-    }
-}
-template <int NT>
-__device__ __forceinline__ void zero_c(float (&c)[NT][4]) {
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt) c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
-}
-// C fragments -> bf16 A fragments of the next product (same index map as act_pack)
-template <int NT>
-__device__ __forceinline__ void pack_bf16_a(const float (&c)[NT][4], uint32_t (&a)[NT / 2][4]) {
-#pragma unroll
-  for (int kt = 0; kt < NT / 2; ++kt) {
-    a[kt][0] = pack_bf162(c[2 * kt][0], c[2 * kt][1]);
-    a[kt][1] = pack_bf162(c[2 * kt][2], c[2 * kt][3]);
-    a[kt][2] = pack_bf162(c[2 * kt + 1][0], c[2 * kt + 1][1]);
-    a[kt][3] = pack_bf162(c[2 * kt + 1][2], c[2 * kt + 1][3]);
-  }
-}
-template <int NT>
-__device__ __forceinline__ uint32_t relu_mask(float (&c)[NT][4]) {  // applies ReLU in place, returns the >0 mask
-  uint32_t mk = 0;
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      if (c[nt][e] > 0.f) mk |= 1u << (nt * 4 + e); else c[nt][e] = 0.f;
-    }
-  return mk;
-}
-template <int NT>
-__device__ __forceinline__ void apply_mask(float (&c)[NT][4], const uint32_t mk) {
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-      if (!((mk >> (nt * 4 + e)) & 1u)) c[nt][e] = 0.f;
-}
-// Staged (X, dY) tiles of the tensor-core backward.  A warp writes one 16-row tile of a staged matrix into
-// its shared-memory ring (bf16, the exact byte image of the global rows) and lane 0 hands it to the
-// bulk-copy engine (cp.async.bulk.global.shared::cta): 2 KB leave the SM as one asynchronous copy instead
-// of 16 scattered 4-byte stores per lane, and no LSU/register resource is held while it drains.
-// 64-wide rows are XOR-swizzled by 16-byte chunk (chunk ^ (global_row & 7)) so the fragment stores are
-// bank-conflict free; tnf_wgrad_kernel_tma reads the raw image back with the same XOR in its ldmatrix addresses.
-struct alignas(128) StageRing {
-  unsigned char buf[2][2048];
-};
-__device__ __forceinline__ void bulk_store_tile(void* gdst, const void* ssrc, const unsigned bytes) {
-  const uint32_t saddr = static_cast<uint32_t>(__cvta_generic_to_shared(ssrc));
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(saddr), "r"(bytes)
-               : "memory");
-  asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-}
-template <int NT>
-__device__ __forceinline__ void stage_tile(StageRing& ring, int& slot, unsigned char* gbase, const long long tile_row0,
-                                           const int nvalid, const int g, const int q, const int lane,
-                                           const float (&c)[NT][4]) {
-  constexpr int kRowBytes = NT * 16;  // NT*8 bf16
-  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");  // the slot's previous copy was read
-  __syncwarp();
-  unsigned char* b = ring.buf[slot];
-  // stmatrix: one instruction stores four 8x8 b16 matrices straight from the mma C-fragment layout; lane i
-  // addresses row (i & 7) of matrix (i >> 3): matrices = (rows 0-7, nt), (rows 8-15, nt), (rows 0-7, nt+1),
-  // (rows 8-15, nt+1).  16-byte chunks are XOR-swizzled by the row (64-wide matrices only).
-  const int mrow = (lane & 7) + ((lane >> 3) & 1) * 8;
-  const int mkey = NT == 8 ? (int)((tile_row0 + mrow) & 7) : 0;
-#pragma unroll
-  for (int nt = 0; nt < NT; nt += 2) {
-    const int chunk = (nt + (lane >> 4)) ^ mkey;
-    const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(b + mrow * kRowBytes + chunk * 16));
-    asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1,%2,%3,%4};\n" ::"r"(addr),
-                 "r"(pack_bf162(c[nt][0], c[nt][1])), "r"(pack_bf162(c[nt][2], c[nt][3])),
-                 "r"(pack_bf162(c[nt + 1][0], c[nt + 1][1])), "r"(pack_bf162(c[nt + 1][2], c[nt + 1][3]))
-                 : "memory");
-  }
-  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> async-proxy read
-  __syncwarp();
-  if (lane == 0) bulk_store_tile(gbase + tile_row0 * kRowBytes, b, (unsigned)(nvalid * kRowBytes));
-  slot ^= 1;
-}
-
-// bf16 B fragments of the backward products: B[kk][nn] = V(kk, nn), [kt][nt][lane]
-struct FieldBwdWTC {
-  uint2 rgb1T[4][8][32];   // dA1 = dA2pre . W_rgb1
-  uint2 th1T[4][8][32];    // dB1 = dB2pre . W_th1
-  uint2 geoT[8][2][32];    // dG  = [dA1pre | dB1pre] . [W_rgb0[:,16:31] ; W_th0]   (column 0 = density slot = 0)
-  uint2 base1T[1][8][32];  // dH  = dG . W_base1
-  uint2 base0T[4][4][32];  // dF  = dHpre . W_base0
-  float rgb2w[3][64];
-  float th2w[64];
-};
-struct ViewRows {  // V(k,n) = w[k*ld + n]
-  const float* w;
-  int ld, kv, nv;
-  __device__ float operator()(int k, int n) const { return (k < kv && n < nv) ? w[k * ld + n] : 0.f; }
-};
-struct ViewGeoT {
-  const float* rgb0;
-  const float* th0;
-  bool detach;
-  __device__ float operator()(int k, int n) const {
-    if (n < 1 || n > 15) return 0.f;
-    if (k < 64) return rgb0[k * 63 + 16 + n - 1];
-    return detach ? 0.f : th0[(k - 64) * 15 + n - 1];
-  }
-};
-template <typename V>
-__device__ inline void stage_frag_bf16(uint2* dst, int KT, int NT, const V& v, int tid) {
-  for (int i = tid; i < KT * NT * 32; i += kThreads) {
-    const int lane = i & 31, nt = (i >> 5) % NT, kt = (i >> 5) / NT;
-    const int g = lane >> 2, q = lane & 3;
-    const int n = nt * 8 + g, k = kt * 16 + 2 * q;
-    dst[frag_index(kt, nt, lane, NT)] =
-        make_uint2(pack_bf162(v(k, n), v(k + 1, n)), pack_bf162(v(k + 8, n), v(k + 9, n)));
-  }
-}
-__device__ inline void stage_field_bwd(FieldBwdWTC& W, const TnfModel& m, int tid) {
-  const TnfField& f = m.field;
-  stage_frag_bf16(&W.rgb1T[0][0][0], 4, 8, ViewRows{f.rgb1.weight, 64, 64, 64}, tid);
-  stage_frag_bf16(&W.th1T[0][0][0], 4, 8, ViewRows{f.th1.weight, 64, 64, 64}, tid);
-  stage_frag_bf16(&W.geoT[0][0][0], 8, 2, ViewGeoT{f.rgb0.weight, f.th0.weight, m.detach_thermal_geo != 0}, tid);
-  stage_frag_bf16(&W.base1T[0][0][0], 1, 8, ViewRows{f.base1.weight, 64, 16, 64}, tid);
-  stage_frag_bf16(&W.base0T[0][0][0], 4, 4, ViewRows{f.base0.weight, 32, 64, 32}, tid);
-  for (int i = tid; i < 192; i += kThreads) W.rgb2w[i / 64][i % 64] = f.rgb2.weight[i];
-  for (int i = tid; i < 64; i += kThreads) W.th2w[i] = f.th2.weight[i];
-}
-
-struct FieldBwdSmemTC {
-  StageRing ring[kWarpsPerCta];
-  FieldWTC fw;
-  FieldBwdWTC bw;
-  FieldBwdScratch ws[kWarpsPerCta];
-};
-// two CTAs per SM: 2 x (dynamic + 1 KB system) must fit the 228 KB of an sm_100 SM
-static_assert(sizeof(FieldBwdSmemTC) <= 113 * 1024, "FieldBwdSmemTC no longer fits two CTAs per SM");
-
-template <bool POSE>  // POSE: also produce dL/d ray origins / directions (camera-optimiser path; re-gathers the table)
-__global__ void __launch_bounds__(kThreads, 2)
-    tnf_backward_field_kernel_tc(const __grid_constant__ TnfModel m, const __grid_constant__ TnfRays rays,
-                                 const __grid_constant__ TnfSaved sv, const __grid_constant__ TnfOutputGrads go,
-                                 const __grid_constant__ TnfModelGrad gr, const __grid_constant__ BwdLayout L) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  FieldBwdSmemTC& S = *reinterpret_cast<FieldBwdSmemTC*>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  stage_field(S.fw, m.field, tid);
-  stage_field_bwd(S.bw, m, tid);
-  __syncthreads();
-  const FieldWTC& W = S.fw;
-  const FieldBwdWTC& B = S.bw;
-  FieldBwdScratch& ws = S.ws[warp];
-  StageRing& ring = S.ring[warp];
-  int slot = 0;
-  const int g = lane >> 2, q = lane & 3;
-  const int S2 = m.num_samples[TNF_NUM_PROP];
-  const TnfHashGrid& grid = m.field.grid;
-  const uint32_t mask = (1u << grid.log2_size) - 1u;
-  float2* __restrict__ gtab = reinterpret_cast<float2*>(gr.field.table);
-  const uint32_t* __restrict__ F = static_cast<const uint32_t*>(sv.field_features);  // [Ns][16] half2
-  const long long R = rays.num_rays;
-  constexpr bool pose = POSE;
-  unsigned char* const dA1 = L.dGeo;                                  // [Ns,64] dL/d(colour layer-0 pre-activation)
-  unsigned char* const dB1 = L.dGeo + (size_t)R * S2 * kWX * 2;      // [Ns,64] dL/d(thermal layer-0 pre-activation)
-
-  for (long long ray = (long long)blockIdx.x * kWarpsPerCta + warp; ray < R;
-       ray += (long long)gridDim.x * kWarpsPerCta) {
-    RayCtx rc;
-    rc.ox = __ldg(rays.origins + ray * 3 + 0);
-    rc.oy = __ldg(rays.origins + ray * 3 + 1);
-    rc.oz = __ldg(rays.origins + ray * 3 + 2);
-    rc.dx = __ldg(rays.directions + ray * 3 + 0);
-    rc.dy = __ldg(rays.directions + ray * 3 + 1);
-    rc.dz = __ldg(rays.directions + ray * 3 + 2);
-    rc.s_near = spacing_fn(rays.nears ? __ldg(rays.nears + ray) : m.near_plane);
-    rc.s_far = spacing_fn(rays.fars ? __ldg(rays.fars + ray) : m.far_plane);
-    for (int i = lane; i <= S2; i += 32) ws.bins[i] = sv.sdist[TNF_NUM_PROP][ray * (S2 + 1) + i];
-    float sh[16], app_lane;
-    ray_bias_and_inputs(m, rays, ray, rc, lane, ws.rayb, sh, app_lane);
-    __syncwarp();
-    composite_backward(m, ws, rc, S2, lane, sv.field_samples + ray * S2 * 5,
-                       go.weights[TNF_NUM_PROP] ? go.weights[TNF_NUM_PROP] + ray * S2 : nullptr,
-                       go.rgb ? go.rgb[ray * 3 + 0] : 0.f, go.rgb ? go.rgb[ray * 3 + 1] : 0.f,
-                       go.rgb ? go.rgb[ray * 3 + 2] : 0.f, go.thermal ? go.thermal[ray] : 0.f,
-                       go.accumulation ? go.accumulation[ray] : 0.f);
-    float pg[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // pose path: sum_s dL/dx_s and sum_s t_s dL/dx_s of this ray
-    ws.racc[lane] = 0.f;  // column sums of dA1pre over the ray
-    ws.racc[lane + 32] = 0.f;
-
-    for (int base = 0; base < S2; base += 16) {
-      const int r0 = base + g, r1 = base + g + 8;
-      const bool v0 = r0 < S2, v1 = r1 < S2;
-      const int i0 = min(r0, S2 - 1), i1 = min(r1, S2 - 1);
-      const long long row0 = ray * S2 + i0, row1 = ray * S2 + i1;
-      const long long trow = ray * S2 + base;          // global row of this tile's first sample
-      const int nval = min(16, S2 - base);
-      float p[2][3], sel[2], mids[2];
-      float dp[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};  // dL/d(normalised position) of rows r0 / r1 (pose path)
-      {
-        float delta;
-        sample_geometry(rc, ws.bins[i0], ws.bins[i0 + 1], mids[0], delta);
-        sel[0] = normalise_position(m, ray_x(rc, mids[0]), ray_y(rc, mids[0]), ray_z(rc, mids[0]), p[0][0], p[0][1], p[0][2]);
-        sample_geometry(rc, ws.bins[i1], ws.bins[i1 + 1], mids[1], delta);
-        sel[1] = normalise_position(m, ray_x(rc, mids[1]), ray_y(rc, mids[1]), ray_z(rc, mids[1]), p[1][0], p[1][1], p[1][2]);
-      }
-      const float dsig[2] = {v0 ? ws.dsig[i0] : 0.f, v1 ? ws.dsig[i1] : 0.f};
-      const float dtau[2] = {v0 ? ws.dtau[i0] : 0.f, v1 ? ws.dtau[i1] : 0.f};
-      const float dz[2][3] = {{v0 ? ws.dzr[i0] : 0.f, v0 ? ws.dzg[i0] : 0.f, v0 ? ws.dzb[i0] : 0.f},
-                              {v1 ? ws.dzr[i1] : 0.f, v1 ? ws.dzg[i1] : 0.f, v1 ? ws.dzb[i1] : 0.f}};
-      // ---- saved hash features -> A fragments (fp16); the base0 weight-gradient GEMM reads them in place
-      uint32_t a0[2][4];
-#pragma unroll
-      for (int kt = 0; kt < 2; ++kt)
-#pragma unroll
-        for (int hl = 0; hl < 2; ++hl) {
-          const int l = kt * 8 + hl * 4 + q;
-          a0[kt][2 * hl] = __ldg(F + row0 * 16 + l);
-          a0[kt][2 * hl + 1] = __ldg(F + row1 * 16 + l);
-        }
-      // ---- trunk forward: H, G
-      uint32_t hid[4][4];
-      uint32_t mkH;
-      {
-        float c[8][4];
-        init_bias(c, W.base0b, q);
-        mma_layer<8, 2>(c, a0, &W.base0[0][0][0], 0, 8, lane);
-        mkH = relu_mask(c);
-        stage_tile<8>(ring, slot, L.XH, trow, nval, g, q, lane, c);
-        act_pack<8, ACT_NONE>(c, hid);
-      }
-      float h0r0, h0r1;
-      uint32_t ga[1][4];
-      {
-        float c[2][4];
-        init_bias(c, W.base1b, q);
-        mma_layer<2, 4>(c, hid, &W.base1[0][0][0], 0, 2, lane);
-        stage_tile<2>(ring, slot, L.XG, trow, nval, g, q, lane, c);
-        h0r0 = c[0][0];
-        h0r1 = c[0][2];
-        if (q == 0) { c[0][0] = 0.f; c[0][2] = 0.f; }
-        act_pack<2, ACT_NONE>(c, ga);
-      }
-      // ---- thermal head forward + backward down to dB1pre
-      uint32_t dB1A[4][4];
-      {
-        float c[8][4];
-        init_bias(c, W.th0b, q);
-        mma_layer<8, 1>(c, ga, &W.geo0[0][0][0], 8, 16, lane);
-        const uint32_t mkB1 = relu_mask(c);
-        stage_tile<8>(ring, slot, L.XB1, trow, nval, g, q, lane, c);
-        act_pack<8, ACT_NONE>(c, hid);
-        init_bias(c, W.th1b, q);
-        mma_layer<8, 4>(c, hid, &W.th1[0][0][0], 0, 8, lane);
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) c[nt][e] = sigmoid_fast(c[nt][e]);
-        stage_tile<8>(ring, slot, L.XB2, trow, nval, g, q, lane, c);
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            c[nt][e] = dtau[e >> 1] * B.th2w[nt * 8 + 2 * q + (e & 1)] * c[nt][e] * (1.f - c[nt][e]);
-        stage_tile<8>(ring, slot, L.dB2, trow, nval, g, q, lane, c);
-        uint32_t dy[4][4];
-        pack_bf16_a(c, dy);
-        zero_c(c);
-        mma_layer_bf16<8, 4>(c, dy, &B.th1T[0][0][0], 8, lane);
-        apply_mask(c, mkB1);
-        stage_tile<8>(ring, slot, dB1, trow, nval, g, q, lane, c);
-        pack_bf16_a(c, dB1A);
-        if (q == 0) {
-          uint4* dt = reinterpret_cast<uint4*>(L.dT);
-          if (v0) dt[row0] = make_uint4(pack_bf162(dtau[0], 0.f), 0u, 0u, 0u);
-          if (v1) dt[row1] = make_uint4(pack_bf162(dtau[1], 0.f), 0u, 0u, 0u);
-        }
-      }
-      // ---- colour head forward + backward down to dA1pre
-      uint32_t dA1A[4][4];
-      {
-        float c[8][4];
-        init_bias(c, ws.rayb, q);
-        mma_layer<8, 1>(c, ga, &W.geo0[0][0][0], 0, 16, lane);
-        const uint32_t mkA1 = relu_mask(c);
-        stage_tile<8>(ring, slot, L.XA1, trow, nval, g, q, lane, c);
-        act_pack<8, ACT_NONE>(c, hid);
-        init_bias(c, W.rgb1b, q);
-        mma_layer<8, 4>(c, hid, &W.rgb1[0][0][0], 0, 8, lane);
-        relu_mask(c);
-        stage_tile<8>(ring, slot, L.XA2, trow, nval, g, q, lane, c);
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int col = nt * 8 + 2 * q + (e & 1), h = e >> 1;
-            const float v = dz[h][0] * B.rgb2w[0][col] + dz[h][1] * B.rgb2w[1][col] + dz[h][2] * B.rgb2w[2][col];
-            c[nt][e] = c[nt][e] > 0.f ? v : 0.f;
-          }
-        stage_tile<8>(ring, slot, L.dA2, trow, nval, g, q, lane, c);
-        uint32_t dy[4][4];
-        pack_bf16_a(c, dy);
-        zero_c(c);
-        mma_layer_bf16<8, 4>(c, dy, &B.rgb1T[0][0][0], 8, lane);
-        apply_mask(c, mkA1);
-        stage_tile<8>(ring, slot, dA1, trow, nval, g, q, lane, c);
-        pack_bf16_a(c, dA1A);
-        // column sums over the 16 rows of the tile -> per-ray sum of dA1pre
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-          for (int b = 0; b < 2; ++b) {
-            float sum = c[nt][b] + c[nt][b + 2];
-            sum += __shfl_xor_sync(kFull, sum, 4);
-            sum += __shfl_xor_sync(kFull, sum, 8);
-            sum += __shfl_xor_sync(kFull, sum, 16);
-            if (g == 0) ws.racc[nt * 8 + 2 * q + b] += sum;  // one lane per column: no conflicts, no atomics
-          }
-        if (q == 0) {
-          uint4* dzp = reinterpret_cast<uint4*>(L.dZ);
-          if (v0) dzp[row0] = make_uint4(pack_bf162(dz[0][0], dz[0][1]), pack_bf162(dz[0][2], 0.f), 0u, 0u);
-          if (v1) dzp[row1] = make_uint4(pack_bf162(dz[1][0], dz[1][1]), pack_bf162(dz[1][2], 0.f), 0u, 0u);
-        }
-      }
-      // ---- trunk backward: dG -> dH -> dF -> hash table
-      uint32_t dGA[1][4];
-      {
-        float c[2][4];
-        zero_c(c);
-        mma_layer_bf16<2, 4>(c, dA1A, &B.geoT[0][0][0], 2, lane);
-        mma_layer_bf16<2, 4>(c, dB1A, &B.geoT[4][0][0], 2, lane);
-        if (q == 0) {  // density slot: trunc_exp backward times selector
-          c[0][0] = dsig[0] * expf(fminf(fmaxf(h0r0, -15.f), 15.f)) * sel[0];
-          c[0][2] = dsig[1] * expf(fminf(fmaxf(h0r1, -15.f), 15.f)) * sel[1];
-        }
-        stage_tile<2>(ring, slot, L.dG, trow, nval, g, q, lane, c);
-        pack_bf16_a(c, dGA);
-      }
-      uint32_t dHA[4][4];
-      {
-        float c[8][4];
-        zero_c(c);
-        mma_layer_bf16<8, 1>(c, dGA, &B.base1T[0][0][0], 8, lane);
-        apply_mask(c, mkH);
-        stage_tile<8>(ring, slot, L.dH, trow, nval, g, q, lane, c);
-        pack_bf16_a(c, dHA);
-      }
-      {
-        float c[4][4];
-        zero_c(c);
-        mma_layer_bf16<4, 4>(c, dHA, &B.base0T[0][0][0], 4, lane);
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          const int l = nt * 4 + q;
-          float2* lt = gtab + ((size_t)l << grid.log2_size);
-          const float sc = W.scal[l];
-          scatter_level_runs<4>(lt, p[0][0], p[0][1], p[0][2], sc, mask, v0 ? c[nt][0] : 0.f, v0 ? c[nt][1] : 0.f, lane);
-          scatter_level_runs<4>(lt, p[1][0], p[1][1], p[1][2], sc, mask, v1 ? c[nt][2] : 0.f, v1 ? c[nt][3] : 0.f, lane);
-          if (pose) {
-            const float2* rt = reinterpret_cast<const float2*>(grid.table) + ((size_t)l << grid.log2_size);
-            if (v0) hash_level_pos_grad(rt, p[0][0], p[0][1], p[0][2], sc, mask, c[nt][0], c[nt][1], dp[0][0], dp[0][1], dp[0][2]);
-            if (v1) hash_level_pos_grad(rt, p[1][0], p[1][1], p[1][2], sc, mask, c[nt][2], c[nt][3], dp[1][0], dp[1][1], dp[1][2]);
-          }
-        }
-      }
-      if (pose) {
-        // the four q-lanes of a row hold the contributions of their four levels each
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-#pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            dp[h][j] += __shfl_xor_sync(kFull, dp[h][j], 1);
-            dp[h][j] += __shfl_xor_sync(kFull, dp[h][j], 2);
-          }
-          if (q == 0 && (h ? v1 : v0)) {
-            position_grad_to_world(m, ray_x(rc, mids[h]), ray_y(rc, mids[h]), ray_z(rc, mids[h]), sel[h], dp[h][0],
-                                   dp[h][1], dp[h][2]);
-            pg[0] += dp[h][0]; pg[1] += dp[h][1]; pg[2] += dp[h][2];
-            pg[3] = fmaf(mids[h], dp[h][0], pg[3]); pg[4] = fmaf(mids[h], dp[h][1], pg[4]);
-            pg[5] = fmaf(mids[h], dp[h][2], pg[5]);
-          }
-        }
-      }
-    }
-    if (pose) flush_ray_grad(gr, ray, pg[0], pg[1], pg[2], pg[3], pg[4], pg[5], lane);
-    // ---- per-ray epilogue
-    {
-      __syncwarp();
-      const float r0_ = ws.racc[lane], r1_ = ws.racc[lane + 32];
-      ray_epilogue<__nv_bfloat16>(m, rays, ray, lane, sh, app_lane, r0_, r1_, L, gr.field.appearance);
-      __syncwarp();
-    }
-  }
-  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");  // staged tiles have landed
-}
-
-// ------------------------------------------------------------------------------------
-// bf16 tensor-core weight-gradient GEMM: dW = dY^T X (+ db = column sums of dY) over 64-row tiles, fragments via
-// ldmatrix.trans, fed by the bulk-copy engine.  A 64-row tile of a staged matrix is one contiguous block of
-// global memory (rows are 128 / 96 / 64 / 32 / 16 bytes), so a tile of dY and a tile of X arrive in shared memory
-// as two cp.async.bulk copies that complete on an mbarrier - no per-thread address arithmetic, no register
-// staging - double buffered: the copies of tile i+1 are in flight while tile i is multiplied.  The 64-wide
-// matrices keep the chunk-swizzled layout stage_tile wrote them in, so the ldmatrix reads of the raw image are
-// bank-conflict free.
-// ------------------------------------------------------------------------------------
-struct alignas(128) WgradTmaSmem {
-  unsigned char dy[2][kWgradRows * 128];
-  unsigned char x[2][kWgradRows * 128];
-  unsigned char ones[kWgradRows * 16];  // [row][8] bf16, column 0 = 1: B operand of the bias-gradient tile
-  unsigned long long bar[2];
-};
-
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
-  unsigned done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(done)
-        : "r"(a), "r"(parity)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void bulk_load_tile(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-          (uint32_t)__cvta_generic_to_shared(sdst)),
-      "l"(gsrc), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
-      : "memory");
-}
-
-__global__ void __launch_bounds__(128) tnf_wgrad_kernel_tma(const __grid_constant__ WgradArgs args) {
-  extern __shared__ __align__(128) unsigned char wg_raw[];
-  WgradTmaSmem& S = *reinterpret_cast<WgradTmaSmem*>(wg_raw);
-  int cta_local, cta_count;
-  const WgradProblem& P = args.p[wgrad_problem_of(args, blockIdx.x, cta_local, cta_count)];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, q = lane & 3;
-  const int dyB = P.ldY * 2, xB = P.ldX * 2;  // bytes per row (bf16, or fp16 for the saved hash features)
-  const int MT = (P.N + 15) / 16;             // 16-wide blocks of output rows n; warp w owns block w
-  const int NT = P.K / 8;                     // 8-wide blocks of output columns k
-  const long long tiles = (P.rows + kWgradRows - 1) / kWgradRows;
-  const long long mine = cta_local < tiles ? (tiles - cta_local + cta_count - 1) / cta_count : 0;
-  if (tid < kWgradRows) *reinterpret_cast<uint4*>(&S.ones[tid * 16]) = make_uint4(0x00003F80u, 0u, 0u, 0u);
-  if (tid == 0) {
-    mbar_init(&S.bar[0], 1);
-    mbar_init(&S.bar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  }
-  __syncthreads();
-  auto issue = [&](long long i) {  // thread 0: both tiles of my i-th 64-row block into stage i & 1
-    const int st = (int)(i & 1);
-    const long long row0 = (cta_local + i * cta_count) * kWgradRows;
-    const long long left = P.rows - row0;
-    const unsigned nrows = (unsigned)(left < kWgradRows ? left : kWgradRows);
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-    mbar_expect_tx(&S.bar[st], nrows * (unsigned)(dyB + xB));
-    bulk_load_tile(S.dy[st], static_cast<const unsigned char*>(P.dY) + row0 * dyB, nrows * dyB, &S.bar[st]);
-    bulk_load_tile(S.x[st], static_cast<const unsigned char*>(P.X) + row0 * xB, nrows * xB, &S.bar[st]);
-  };
-  float acc[8][4];
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-  float accb[4] = {0.f, 0.f, 0.f, 0.f};
-  if (tid == 0 && mine > 0) issue(0);
-  for (long long i = 0; i < mine; ++i) {
-    const int st = (int)(i & 1);
-    if (tid == 0 && i + 1 < mine) issue(i + 1);  // stage st^1 was released by the barrier that ended iteration i-1
-    const long long row0 = (cta_local + i * cta_count) * kWgradRows;
-    const int nrows = (int)(P.rows - row0 < kWgradRows ? P.rows - row0 : kWgradRows);
-    unsigned char* sdy = S.dy[st];
-    unsigned char* sx = S.x[st];
-    if (nrows < kWgradRows) {  // ragged last block: rows the copy does not write must read as zero
-      for (int b = nrows * dyB + tid * 16; b < kWgradRows * dyB; b += 128 * 16)
-        *reinterpret_cast<uint4*>(sdy + b) = make_uint4(0u, 0u, 0u, 0u);
-      for (int b = nrows * xB + tid * 16; b < kWgradRows * xB; b += 128 * 16)
-        *reinterpret_cast<uint4*>(sx + b) = make_uint4(0u, 0u, 0u, 0u);
-    }
-    mbar_wait(&S.bar[st], (unsigned)((i >> 1) & 1));
-    if (P.x_f16) {  // saved hash features are fp16: convert the tile in place (bf16 mma operands)
-      for (int b = tid * 16; b < nrows * xB; b += 128 * 16) {
-        uint4 x = *reinterpret_cast<const uint4*>(sx + b);
-        const __half2* h = reinterpret_cast<const __half2*>(&x);
-        const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]),
-                     f3 = __half22float2(h[3]);
-        *reinterpret_cast<uint4*>(sx + b) = make_uint4(pack_bf162(f0.x, f0.y), pack_bf162(f1.x, f1.y),
-                                                       pack_bf162(f2.x, f2.y), pack_bf162(f3.x, f3.y));
-      }
-    }
-    if (P.x_f16 || nrows < kWgradRows) __syncthreads();
-    if (warp < MT) {
-      const int mi = lane >> 3, r = lane & 7;
-#pragma unroll
-      for (int ks = 0; ks < kWgradRows / 16; ++ks) {
-        uint32_t a[4];
-        {  // A = dY^T block: (rows ks*16 + {0,8}, cols n0 + warp*16 + {0,8})
-          const int row = ks * 16 + (mi >> 1) * 8 + r;
-          const int chunk = ((P.n0 >> 3) + warp * 2 + (mi & 1)) ^ (P.dy_swz ? (row & 7) : 0);
-          ldmatrix_x4_trans(a, sdy + row * dyB + chunk * 16);
-        }
-        const int rowb = ks * 16 + (mi & 1) * 8 + r;
-#pragma unroll
-        for (int np = 0; np < 4; ++np) {
-          if (2 * np < NT) {
-            uint32_t b[4];
-            const int chunk = ((P.xcol0 >> 3) + 2 * np + (mi >> 1)) ^ (P.x_swz ? (rowb & 7) : 0);
-            ldmatrix_x4_trans(b, sx + rowb * xB + chunk * 16);
-            mma_16816_bf16(acc[2 * np], a, make_uint2(b[0], b[1]));
-            mma_16816_bf16(acc[2 * np + 1], a, make_uint2(b[2], b[3]));
-          }
-        }
-        if (P.bias) {
-          uint32_t bb[2];
-          ldmatrix_x2_trans(bb, &S.ones[rowb * 16]);
-          mma_16816_bf16(accb, a, make_uint2(bb[0], bb[1]));
-        }
-      }
-    }
-    __syncthreads();  // every warp is done with stage st before iteration i+1 refills it
-  }
-  if (warp < MT) {
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      if (nt >= NT) continue;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int n = warp * 16 + g + (e >> 1) * 8;
-        const int k = nt * 8 + 2 * q + (e & 1) - P.k_skip;
-        if (n < P.n_valid && k >= 0 && acc[nt][e] != 0.f) atomicAdd(P.W + n * P.ldW + P.wcol0 + k, acc[nt][e]);
-      }
-    }
-    if (P.bias && q == 0) {
-      const int n = warp * 16 + g;
-      if (n < P.n_valid && accb[0] != 0.f) atomicAdd(P.bias + n, accb[0]);
-      if (n + 8 < P.n_valid && accb[2] != 0.f) atomicAdd(P.bias + n + 8, accb[2]);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------
 // weight-gradient GEMMs: dW[n][k] += sum_rows dY[row][n0+n] * X[row][k];  db[n] += sum_rows dY
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tnf_wgrad_kernel_fp32(const __grid_constant__ WgradArgs args) {
@@ -1630,13 +804,11 @@ int set_smem(K kernel, size_t bytes, const char* name) {
 }
 
 void add_problem(tnf::WgradArgs& a, const void* dY, int ldY, int n0, int N, int n_valid, const void* X, int ldX,
-                 int K, int k_skip, long long rows, float* W, int ldW, int wcol0, float* bias, int dy_swz = 0,
-                 int x_swz = 0, int x_f16 = 0, int xcol0 = 0) {
+                 int K, int k_skip, long long rows, float* W, int ldW, int wcol0, float* bias) {
   tnf::WgradProblem& p = a.p[a.n++];
   p.dY = dY; p.ldY = ldY; p.n0 = n0; p.N = N; p.n_valid = n_valid;
   p.X = X; p.ldX = ldX; p.K = K; p.k_skip = k_skip;
   p.rows = rows; p.W = W; p.ldW = ldW; p.wcol0 = wcol0; p.bias = bias;
-  p.dy_swz = dy_swz; p.x_swz = x_swz; p.x_f16 = x_f16; p.xcol0 = xcol0;
 }
 
 // CTAs per problem in proportion to the bytes it streams (rows x loaded columns): the 64x64 layers move 1.7x the
@@ -1660,36 +832,23 @@ int assign_wgrad_ctas(tnf::WgradArgs& a, int total_ctas) {
   return acc;
 }
 
-// the eight field layers (+ the two per-ray blocks of mlp_head.layers.0) as GEMM problems.
-// fp32 mode: plain row-major fp32 staging, dGeo = [Ns,128] (colour | thermal layer-0 gradients).
-// TC mode:   bf16 staging written by stage_tile (64-wide matrices chunk-swizzled), dGeo holds two
-//            [Ns,64] matrices back to back, X of base0 = the fp16 hash features saved by the forward.
-void field_problems(tnf::WgradArgs& a, const tnf::BwdLayout& L, const void* XF, bool tc, const TnfFieldGrad& g,
-                    long long Ns, long long R) {
+// the eight field layers (+ the two per-ray blocks of mlp_head.layers.0) as GEMM problems of the fp32 mode:
+// plain row-major fp32 staging, dGeo = [Ns,128] (colour | thermal layer-0 gradients).
+void field_problems(tnf::WgradArgs& a, const tnf::BwdLayout& L, const void* XF, const TnfFieldGrad& g, long long Ns,
+                    long long R) {
   using namespace tnf;
   a.n = 0;
-  const size_t es = tc ? 2 : 4;
-  auto off = [&](const unsigned char* p, size_t elems) { return static_cast<const void*>(p + elems * es); };
-  const int z = tc ? 1 : 0;  // swizzled 64-wide staging
-  add_problem(a, L.dH, kWX, 0, 64, 64, XF, kWXF, 32, 0, Ns, g.base0.weight, 32, 0, g.base0.bias, z, 0, z);
-  add_problem(a, L.dG, kWXG, 0, 16, 16, L.XH, kWXH, 64, 0, Ns, g.base1.weight, 64, 0, g.base1.bias, 0, z);
-  if (tc) {
-    add_problem(a, L.dGeo, kWX, 0, 64, 64, L.XG, kWXG, 16, 1, Ns, g.rgb0.weight, 63, 16, nullptr, 1);
-    add_problem(a, off(L.dGeo, (size_t)Ns * kWX), kWX, 0, 64, 64, L.XG, kWXG, 16, 1, Ns, g.th0.weight, 15, 0,
-                g.th0.bias, 1);
-  } else {
-    add_problem(a, L.dGeo, kWdGeo, 0, 64, 64, L.XG, kWXG, 16, 1, Ns, g.rgb0.weight, 63, 16, nullptr);
-    add_problem(a, L.dGeo, kWdGeo, 64, 64, 64, L.XG, kWXG, 16, 1, Ns, g.th0.weight, 15, 0, g.th0.bias);
-  }
-  add_problem(a, L.dA2, kWX, 0, 64, 64, L.XA1, kWX, 64, 0, Ns, g.rgb1.weight, 64, 0, g.rgb1.bias, z, z);
-  add_problem(a, L.dZ, kWdZ, 0, 8, 3, L.XA2, kWX, 64, 0, Ns, g.rgb2.weight, 64, 0, g.rgb2.bias, 0, z);
-  add_problem(a, L.dB2, kWX, 0, 64, 64, L.XB1, kWX, 64, 0, Ns, g.th1.weight, 64, 0, g.th1.bias, z, z);
-  add_problem(a, L.dT, kWdT, 0, 8, 1, L.XB2, kWX, 64, 0, Ns, g.th2.weight, 64, 0, g.th2.bias, 0, z);
+  auto off = [&](const unsigned char* p, size_t elems) { return static_cast<const void*>(p + elems * 4); };
+  add_problem(a, L.dH, kWX, 0, 64, 64, XF, kWXF, 32, 0, Ns, g.base0.weight, 32, 0, g.base0.bias);
+  add_problem(a, L.dG, kWXG, 0, 16, 16, L.XH, kWXH, 64, 0, Ns, g.base1.weight, 64, 0, g.base1.bias);
+  add_problem(a, L.dGeo, kWdGeo, 0, 64, 64, L.XG, kWXG, 16, 1, Ns, g.rgb0.weight, 63, 16, nullptr);
+  add_problem(a, L.dGeo, kWdGeo, 64, 64, 64, L.XG, kWXG, 16, 1, Ns, g.th0.weight, 15, 0, g.th0.bias);
+  add_problem(a, L.dA2, kWX, 0, 64, 64, L.XA1, kWX, 64, 0, Ns, g.rgb1.weight, 64, 0, g.rgb1.bias);
+  add_problem(a, L.dZ, kWdZ, 0, 8, 3, L.XA2, kWX, 64, 0, Ns, g.rgb2.weight, 64, 0, g.rgb2.bias);
+  add_problem(a, L.dB2, kWX, 0, 64, 64, L.XB1, kWX, 64, 0, Ns, g.th1.weight, 64, 0, g.th1.bias);
+  add_problem(a, L.dT, kWdT, 0, 8, 1, L.XB2, kWX, 64, 0, Ns, g.th2.weight, 64, 0, g.th2.bias);
   add_problem(a, L.dRay, kWdRay, 0, 64, 64, L.XRay, kWXRay, 16, 0, R, g.rgb0.weight, 63, 0, g.rgb0.bias);
-  if (tc)  // the TC kernel copies whole rows: the appearance block is columns 16..47 of the [R,48] rows
-    add_problem(a, L.dRay, kWdRay, 0, 64, 64, L.XRay, kWXRay, 32, 0, R, g.rgb0.weight, 63, 31, nullptr, 0, 0, 0, 16);
-  else
-    add_problem(a, L.dRay, kWdRay, 0, 64, 64, off(L.XRay, 16), kWXRay, 32, 0, R, g.rgb0.weight, 63, 31, nullptr);
+  add_problem(a, L.dRay, kWdRay, 0, 64, 64, off(L.XRay, 16), kWXRay, 32, 0, R, g.rgb0.weight, 63, 31, nullptr);
 }
 }  // namespace
 
@@ -1708,8 +867,10 @@ int tnf_backward_stage_mask(int mask) {
 size_t tnf_backward_workspace_bytes(const TnfModel* model, int64_t num_rays) {
   if (!model || num_rays <= 0) return 256;
   const long long Ns = (long long)num_rays * model->num_samples[TNF_NUM_PROP];
-  const bool tc = model->precision == TNF_PRECISION_TC_FP16;
-  return tnf::make_layout(nullptr, nullptr, Ns, num_rays, tc ? 2 : 4, false) + 256;
+  // tensor-core mode keeps every per-sample intermediate on chip (tnf_backward_tc.cu): only the work counter of
+  // the proposal kernel lives here.  fp32 mode stages the (X, dY) rows of the weight-gradient pass.
+  if (model->precision == TNF_PRECISION_TC_FP16) return 256;
+  return tnf::make_layout(nullptr, nullptr, Ns, num_rays, 4, false) + 256;
 }
 
 int tnf_render_backward(const TnfModel* model, const TnfRays* rays, const TnfSaved* saved, const TnfOutputGrads* gout,
@@ -1776,49 +937,27 @@ int tnf_render_backward(const TnfModel* model, const TnfRays* rays, const TnfSav
 
   // ---- field level
   const long long Ns = R * model->num_samples[TNF_NUM_PROP];
-  const bool tc = model->precision == TNF_PRECISION_TC_FP16;
-  tnf::BwdLayout L{};
-  tnf::make_layout(&L, static_cast<unsigned char*>(workspace), Ns, R, tc ? 2 : 4, false);
-  tnf::WgradArgs wa;
-  if (!tc) {
-    const size_t smem = sizeof(tnf::FieldBwdSmem32);
-    if (int rc = set_smem(tnf::tnf_backward_field_kernel_fp32, smem, "backward_field_fp32")) return rc;
-    const long long cap = sms;
+  if (model->precision == TNF_PRECISION_TC_FP16) {
     if (g_stage_mask & 2)
-      tnf::tnf_backward_field_kernel_fp32<<<(unsigned)(want < cap ? want : cap), tnf::kThreads, smem, stream>>>(
-          *model, *rays, *saved, *gout, *grads, L);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "backward_field launch: %s", cudaGetErrorString(e));
-    field_problems(wa, L, saved->field_features, false, grads->field, Ns, R);
-    const int grid = assign_wgrad_ctas(wa, sms * 2);
-    if (g_stage_mask & 4) tnf::tnf_wgrad_kernel_fp32<<<grid, 256, 0, stream>>>(wa);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(e));
-  } else {
-    const size_t smem = sizeof(tnf::FieldBwdSmemTC);
-    const long long cap = (long long)sms * 2;
-    const unsigned gridf = (unsigned)(want < cap ? want : cap);
-    if (grads->ray_origins) {
-      if (int rc = set_smem(tnf::tnf_backward_field_kernel_tc<true>, smem, "backward_field_tc")) return rc;
-      if (g_stage_mask & 2)
-        tnf::tnf_backward_field_kernel_tc<true><<<gridf, tnf::kThreads, smem, stream>>>(*model, *rays, *saved, *gout,
-                                                                                      *grads, L);
-    } else {
-      if (int rc = set_smem(tnf::tnf_backward_field_kernel_tc<false>, smem, "backward_field_tc")) return rc;
-      if (g_stage_mask & 2)
-        tnf::tnf_backward_field_kernel_tc<false><<<gridf, tnf::kThreads, smem, stream>>>(*model, *rays, *saved, *gout,
-                                                                                       *grads, L);
-    }
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "backward_field launch: %s", cudaGetErrorString(e));
-    field_problems(wa, L, saved->field_features, true, grads->field, Ns, R);
-    const size_t wsmem = sizeof(tnf::WgradTmaSmem);
-    if (int rc = set_smem(tnf::tnf_wgrad_kernel_tma, wsmem, "wgrad_tma")) return rc;
-    const int grid = assign_wgrad_ctas(wa, sms * 6);  // 33.8 KB of shared memory per CTA: six CTAs per SM
-    if (g_stage_mask & 4) tnf::tnf_wgrad_kernel_tma<<<grid, 128, wsmem, stream>>>(wa);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(e));
+      if (int rc = tnf::launch_backward_field_tc(*model, *rays, *saved, *gout, *grads, stream)) return rc;
+    return TNF_OK;
   }
+  tnf::BwdLayout L{};
+  tnf::make_layout(&L, static_cast<unsigned char*>(workspace), Ns, R, 4, false);
+  tnf::WgradArgs wa;
+  const size_t smem = sizeof(tnf::FieldBwdSmem32);
+  if (int rc = set_smem(tnf::tnf_backward_field_kernel_fp32, smem, "backward_field_fp32")) return rc;
+  const long long cap = sms;
+  if (g_stage_mask & 2)
+    tnf::tnf_backward_field_kernel_fp32<<<(unsigned)(want < cap ? want : cap), tnf::kThreads, smem, stream>>>(
+        *model, *rays, *saved, *gout, *grads, L);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "backward_field launch: %s", cudaGetErrorString(e));
+  field_problems(wa, L, saved->field_features, grads->field, Ns, R);
+  const int grid = assign_wgrad_ctas(wa, sms * 2);
+  if (g_stage_mask & 4) tnf::tnf_wgrad_kernel_fp32<<<grid, 256, 0, stream>>>(wa);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(e));
   return TNF_OK;
 }
 

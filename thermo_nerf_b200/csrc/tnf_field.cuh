@@ -100,8 +100,8 @@ __device__ __forceinline__ int frag_index(int kt, int nt, int lane, int NT) {
   return (NT & 1) ? (kt * NT + nt) * 32 + lane : ((kt * (NT >> 1) + (nt >> 1)) * 32 + lane) * 2 + (nt & 1);
 }
 template <typename V>
-__device__ inline void stage_frag(uint2* dst, int KT, int NT, const V& v, int tid) {
-  for (int i = tid; i < KT * NT * 32; i += kThreads) {
+__device__ inline void stage_frag(uint2* dst, int KT, int NT, const V& v, int tid, int nthreads = kThreads) {
+  for (int i = tid; i < KT * NT * 32; i += nthreads) {
     const int lane = i & 31, nt = (i >> 5) % NT, kt = (i >> 5) / NT;
     const int g = lane >> 2, q = lane & 3;
     const int n = nt * 8 + g, k = kt * 16 + 2 * q;
@@ -109,8 +109,8 @@ __device__ inline void stage_frag(uint2* dst, int KT, int NT, const V& v, int ti
         make_uint2(pack_half2(v(k, n), v(k + 1, n)), pack_half2(v(k + 8, n), v(k + 9, n)));
   }
 }
-__device__ inline void stage_vec(float* dst, const float* src, int n, int npad, int tid) {
-  for (int i = tid; i < npad; i += kThreads) dst[i] = i < n ? src[i] : 0.f;
+__device__ inline void stage_vec(float* dst, const float* src, int n, int npad, int tid, int nthreads = kThreads) {
+  for (int i = tid; i < npad; i += nthreads) dst[i] = i < n ? src[i] : 0.f;
 }
 
 __device__ inline void stage_common(FieldCommon& C, const TnfField& f, bool fold_appearance, int tid) {
@@ -143,22 +143,22 @@ __device__ inline void stage_field(FieldW32& W, const TnfField& f, int tid) {
   stage_vec(W.th2b, f.th2.bias, 1, 4, tid);
 }
 
-__device__ inline void stage_field(FieldWTC& W, const TnfField& f, int tid) {
-  stage_frag(&W.base0[0][0][0], 2, 8, ViewPlain{f.base0.weight, 32, 32, 64}, tid);
-  stage_frag(&W.base1[0][0][0], 4, 2, ViewPlain{f.base1.weight, 64, 64, 16}, tid);
+__device__ inline void stage_field(FieldWTC& W, const TnfField& f, int tid, int nthreads = kThreads) {
+  stage_frag(&W.base0[0][0][0], 2, 8, ViewPlain{f.base0.weight, 32, 32, 64}, tid, nthreads);
+  stage_frag(&W.base1[0][0][0], 4, 2, ViewPlain{f.base1.weight, 64, 64, 16}, tid, nthreads);
   stage_frag(&W.geo0[0][0][0], 1, 16,
-             ViewGeo0{ViewShift{f.rgb0.weight, 63, 16, 15, 64}, ViewShift{f.th0.weight, 15, 0, 15, 64}}, tid);
-  stage_frag(&W.rgb1[0][0][0], 4, 8, ViewPlain{f.rgb1.weight, 64, 64, 64}, tid);
-  stage_frag(&W.rgb2[0][0][0], 4, 1, ViewPlain{f.rgb2.weight, 64, 64, 3}, tid);
-  stage_frag(&W.th1[0][0][0], 4, 8, ViewPlain{f.th1.weight, 64, 64, 64}, tid);
-  stage_frag(&W.th2[0][0][0], 4, 1, ViewPlain{f.th2.weight, 64, 64, 1}, tid);
-  stage_vec(W.base0b, f.base0.bias, 64, 64, tid);
-  stage_vec(W.base1b, f.base1.bias, 16, 16, tid);
-  stage_vec(W.rgb1b, f.rgb1.bias, 64, 64, tid);
-  stage_vec(W.rgb2b, f.rgb2.bias, 3, 8, tid);
-  stage_vec(W.th0b, f.th0.bias, 64, 64, tid);
-  stage_vec(W.th1b, f.th1.bias, 64, 64, tid);
-  stage_vec(W.th2b, f.th2.bias, 1, 8, tid);
+             ViewGeo0{ViewShift{f.rgb0.weight, 63, 16, 15, 64}, ViewShift{f.th0.weight, 15, 0, 15, 64}}, tid, nthreads);
+  stage_frag(&W.rgb1[0][0][0], 4, 8, ViewPlain{f.rgb1.weight, 64, 64, 64}, tid, nthreads);
+  stage_frag(&W.rgb2[0][0][0], 4, 1, ViewPlain{f.rgb2.weight, 64, 64, 3}, tid, nthreads);
+  stage_frag(&W.th1[0][0][0], 4, 8, ViewPlain{f.th1.weight, 64, 64, 64}, tid, nthreads);
+  stage_frag(&W.th2[0][0][0], 4, 1, ViewPlain{f.th2.weight, 64, 64, 1}, tid, nthreads);
+  stage_vec(W.base0b, f.base0.bias, 64, 64, tid, nthreads);
+  stage_vec(W.base1b, f.base1.bias, 16, 16, tid, nthreads);
+  stage_vec(W.rgb1b, f.rgb1.bias, 64, 64, tid, nthreads);
+  stage_vec(W.rgb2b, f.rgb2.bias, 3, 8, tid, nthreads);
+  stage_vec(W.th0b, f.th0.bias, 64, 64, tid, nthreads);
+  stage_vec(W.th1b, f.th1.bias, 64, 64, tid, nthreads);
+  stage_vec(W.th2b, f.th2.bias, 1, 8, tid, nthreads);
   if (tid < TNF_MAX_LEVELS) W.scal[tid] = f.grid.scalings[tid];
 }
 

@@ -2,6 +2,8 @@
 // error string behind tnf_last_error() and model validation.
 #pragma once
 
+#include <cuda_runtime.h>
+
 #include <cstdarg>
 #include <cstdio>
 #include <cstdint>
@@ -24,6 +26,10 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 // defined in tnf_forward.cu
 int check_model(const TnfModel* m);
+
+// defined in tnf_backward_tc.cu: the tensor-core field backward (one launch, weight gradients in tensor memory)
+int launch_backward_field_tc(const TnfModel& m, const TnfRays& rays, const TnfSaved& sv, const TnfOutputGrads& go,
+                             const TnfModelGrad& gr, cudaStream_t stream);
 
 // cached per-thread device properties
 inline int num_sms() {

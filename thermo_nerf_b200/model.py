@@ -148,14 +148,20 @@ class ThermalNerfModel(nn.Module):
             hidden_dim_transient=cfg.hidden_dim_transient,
             use_average_appearance_embedding=cfg.use_average_appearance_embedding,
             appearance_embedding_dim=cfg.appearance_embed_dim, pass_thermal_gradients=cfg.pass_thermal_gradients,
-            thermal_head=cfg.thermal_head)
+            thermal_head=cfg.thermal_head, use_contraction=not cfg.disable_scene_contraction)
         self.camera_optimizer = CameraOptimizer(self.num_train_data, cfg.camera_optimizer_mode)
         self.proposal_networks = nn.ModuleList()
         for i in range(cfg.num_proposal_iterations):
             a = dict(cfg.proposal_net_args_list[min(i, len(cfg.proposal_net_args_list) - 1)])
             if a.pop("use_linear", False):
                 raise ValueError("use_linear proposal networks are not built into libtnf_b200")
-            self.proposal_networks.append(HashMLPDensityField(aabb, **a))
+            self.proposal_networks.append(HashMLPDensityField(aabb, use_contraction=not cfg.disable_scene_contraction, **a))
+        # density_fns / renderers of the reference's populate_modules (thermal_nerf_model.py:127-208): the fused
+        # kernel does not go through them, callers that compose the modules by hand can
+        self.density_fns = [net.density_fn for net in self.proposal_networks]
+        from .surface import ThermalRenderer
+
+        self.thermal_renderer = ThermalRenderer()
         # ProposalNetworkSampler state (annealing + update schedule)
         self._anneal = 1.0
         self._steps_since_update = 0

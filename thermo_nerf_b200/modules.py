@@ -10,7 +10,10 @@ with the ones a reference checkpoint carries after its ``_model.`` prefix (SURVE
 * ``HashMLPDensityField``     <- built at thermo_nerf/thermal_nerf/thermal_nerf_model.py:127-148
 * ``CameraOptimizer``         <- built at thermal_nerf_model.py:118-120 (nerfstudio SO3xR3)
 
-Calling ``forward`` on a container raises: there is deliberately no PyTorch fallback.
+The leaf containers (``HashEncoding``, ``MLP`` ...) raise from ``forward``: there is deliberately no PyTorch
+fallback.  The two field classes carry the reference's Field surface - ``get_density`` / ``get_outputs`` /
+``forward`` / ``density_fn`` (thermal_field.py:108-201) - backed by the stand-alone kernels of ``surface.py``
+(inference only; training and rendering go through the fused ``Model.get_outputs``).
 """
 
 from __future__ import annotations
@@ -146,8 +149,9 @@ class HashMLPDensityField(nn.Module):
 
     def __init__(self, aabb: Tensor, num_layers: int = 2, hidden_dim: int = 64, num_levels: int = 8,
                  max_res: int = 1024, base_res: int = 16, log2_hashmap_size: int = 18,
-                 features_per_level: int = 2) -> None:
+                 features_per_level: int = 2, use_contraction: bool = True) -> None:
         super().__init__()
+        self.use_contraction = bool(use_contraction)  # nerfstudio: spatial_distortion=SceneContraction(inf) or None
         if num_layers != 2 or hidden_dim != 16:
             raise ValueError("libtnf_b200 proposal kernels are built for num_layers=2, hidden_dim=16")
         if num_levels > 8:
@@ -157,8 +161,23 @@ class HashMLPDensityField(nn.Module):
         network = MLP(self.encoding.get_out_dim(), num_layers, hidden_dim, 1)
         self.mlp_base = _Seq(self.encoding, network)
 
-    def forward(self, *_):
-        _no_torch_path("HashMLPDensityField")
+    # nerfstudio DensityField surface (HashMLPDensityField.get_density / Field.density_fn / Field.forward)
+    def get_density(self, ray_samples):
+        from . import surface
+
+        surface._no_grad_surface(self, "get_density")
+        return surface.density_at(self, ray_samples.frustums.get_positions())[0], None
+
+    def density_fn(self, positions: Tensor, times: Optional[Tensor] = None) -> Tensor:
+        from . import surface
+
+        return surface.density_fn(self, positions, times)
+
+    def get_outputs(self, ray_samples, density_embedding: Optional[Tensor] = None) -> dict:
+        return {}
+
+    def forward(self, ray_samples, compute_normals: bool = False) -> dict:
+        return {FieldHeadNames.DENSITY: self.get_density(ray_samples)[0]}
 
 
 class ThermalNerfactoTField(nn.Module):
@@ -170,8 +189,9 @@ class ThermalNerfactoTField(nn.Module):
                  log2_hashmap_size: int = 19, num_layers_color: int = 3, features_per_level: int = 2,
                  hidden_dim_color: int = 64, hidden_dim_transient: int = 64, appearance_embedding_dim: int = 32,
                  use_average_appearance_embedding: bool = False, pass_thermal_gradients: bool = False,
-                 thermal_head: bool = True) -> None:
+                 thermal_head: bool = True, use_contraction: bool = True) -> None:
         super().__init__()
+        self.use_contraction = bool(use_contraction)  # nerfstudio: spatial_distortion=SceneContraction(inf) or None
         fixed = dict(num_layers=(num_layers, 2), hidden_dim=(hidden_dim, 64), geo_feat_dim=(geo_feat_dim, 15),
                      num_levels=(num_levels, 16), num_layers_color=(num_layers_color, 3),
                      hidden_dim_color=(hidden_dim_color, 64), hidden_dim_transient=(hidden_dim_transient, 64),
@@ -198,8 +218,26 @@ class ThermalNerfactoTField(nn.Module):
         self.training_iteration = 0
         self.pass_rgb_gradients = True  # thermal_field.py:106
 
-    def forward(self, *_):
-        _no_torch_path("ThermalNerfactoTField")
+    # the reference's Field surface (thermal_field.py:108-201), kernel backed (surface.py)
+    def get_density(self, ray_samples):
+        from . import surface
+
+        return surface.field_get_density(self, ray_samples)
+
+    def get_outputs(self, ray_samples, density_embedding: Optional[Tensor] = None) -> dict:
+        from . import surface
+
+        return surface.field_get_outputs(self, ray_samples, density_embedding)
+
+    def forward(self, ray_samples, compute_normals: bool = False) -> dict:
+        from . import surface
+
+        return surface.field_forward(self, ray_samples, compute_normals)
+
+    def density_fn(self, positions: Tensor, times: Optional[Tensor] = None) -> Tensor:
+        from . import surface
+
+        return surface.density_fn(self, positions, times)
 
 
 def exp_map_so3xr3(tangent: Tensor) -> Tensor:
