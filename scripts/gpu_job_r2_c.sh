@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_surface_gpu.py tests/test_train_gpu.py -x -q 2>&1 | tail -15
+timeout 600 python -m pytest tests/test_surface_gpu.py tests/test_train_gpu.py -q 2>&1 | tail -15
 echo "=== bench train"
 timeout 600 python bench.py --no-render --no-cpu-baseline 2>gpurun_out/bench_train_c.err > gpurun_out/bench_train_c.json; tail -3 gpurun_out/bench_train_c.err
 python - <<'PY'

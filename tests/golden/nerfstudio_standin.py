@@ -3,7 +3,8 @@ torchmetrics), so that THE REFERENCE'S OWN thermo-nerf modules - thermal_nerf_mo
 thermal_field_head.py, thermal_renderer.py, nerfacto_config/thermal_nerfacto.py - can be imported and executed
 in the build container by tests/golden/make_reference_wiring_golden.py.
 
-GENERATOR INFRASTRUCTURE ONLY (never imported by the product, the tests or the bench).
+TEST / GENERATOR INFRASTRUCTURE ONLY (never imported by the product or the bench; tests/test_plugin_*.py use it to build
+the reference's class hierarchy where nerfstudio itself cannot be installed).
 
 What this does and does not pin.  Every class here has nerfstudio's *interface* (constructor arguments, attribute and
 sub-module names, call signatures - as the reference's call sites use them) and the ORACLE's arithmetic behind it
@@ -447,6 +448,9 @@ class NerfactoModelConfig:
     appearance_embed_dim: int = 32
     average_init_density: float = 1.0
     camera_optimizer: CameraOptimizerConfig = field(default_factory=CameraOptimizerConfig)
+
+    def setup(self, **kwargs):  # nerfstudio InstantiateConfig.setup
+        return self._target(self, **kwargs)
 
 
 class NerfactoModel(nn.Module):

@@ -76,11 +76,24 @@ def test_unsupported_configurations_are_rejected():
 
 
 def test_parameter_containers_have_no_torch_fallback():
+    """Leaf containers raise from forward; the field classes' surface (get_density / get_outputs / forward /
+    density_fn, thermal_field.py:108-201) runs kernels only: on CPU tensors it fails loudly."""
+    from types import SimpleNamespace
+
     _, model = small_pair()
-    with pytest.raises(RuntimeError, match="no PyTorch fallback"):
-        model.field(torch.zeros(1, 3))
-    with pytest.raises(RuntimeError, match="no PyTorch fallback"):
-        model.proposal_networks[0](torch.zeros(1, 3))
+    for leaf in (model.field.mlp_base, model.field.mlp_head, model.field.mlp_thermal, model.field.field_head_thermal,
+                 model.field.embedding_appearance, model.proposal_networks[0].encoding):
+        with pytest.raises(RuntimeError, match="no PyTorch fallback"):
+            leaf(torch.zeros(1, 3))
+    pos = torch.zeros(4, 2, 3)
+    rs = SimpleNamespace(frustums=SimpleNamespace(get_positions=lambda: pos, directions=torch.ones(4, 2, 3)),
+                         camera_indices=torch.zeros(4, 2, 1, dtype=torch.int64))
+    for call in (lambda: model.field(rs), lambda: model.field.get_density(rs), lambda: model.field.density_fn(pos),
+                 lambda: model.field.get_outputs(rs, density_embedding=torch.zeros(4, 2, 15)),
+                 lambda: model.proposal_networks[0].density_fn(pos), lambda: model.density_fns[1](pos),
+                 lambda: model.thermal_renderer(torch.zeros(4, 2, 1), torch.zeros(4, 2, 1))):
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            call()
 
 
 def test_get_outputs_on_cpu_fails_loudly():

@@ -71,8 +71,9 @@ def test_field_surface_matches_oracle(contraction):
         oracle.train(training)
         model.train(training)
         with torch.no_grad():
-            ref = oracle.field.get_outputs(rs.frustums.directions.cpu(), rs.camera_indices.cpu()[..., 0], ref_geo,
-                                           training=training)
+            ref_rgb, ref_th = oracle.field.get_outputs(rs.frustums.directions.cpu(), rs.camera_indices.cpu()[..., 0],
+                                                       ref_geo, training=training)
+            ref = {"rgb": ref_rgb, "thermal": ref_th}
             out = model.field.get_outputs(rs, density_embedding=ref_geo.to(pos.device))
             fwd = model.field(rs)
         _close(out[FieldHeadNames.RGB], ref["rgb"], 2e-5, name=f"rgb training={training}")
@@ -106,31 +107,34 @@ def test_field_surface_error_behaviour():
         model.field(rs, compute_normals=True)
 
 
-def test_renderers_match_reference_vectors_and_oracle():
-    """ThermalRenderer / RGBTRenderer against the vectors the reference's own modules produced
-    (tests/golden/reference_renderers.pt, made by make_reference_renderer_golden.py)."""
+def test_renderers_match_the_reference_executed_vectors():
+    """ThermalRenderer / RGBTRenderer against the vectors the reference's OWN modules produced
+    (tests/golden/reference_renderers.pt, made by make_reference_renderer_golden.py from
+    thermo_nerf/thermal_nerf/thermal_renderer.py and thermo_nerf/rgb_concat/rgbt_renderer.py): train / eval mode,
+    NaN / inf and out-of-range samples, empty and opaque rays."""
     from pathlib import Path
 
     from thermo_nerf_b200.surface import RGBTRenderer, ThermalRenderer
 
     gold = torch.load(Path(__file__).parent / "golden" / "reference_renderers.pt", weights_only=False)
     checked = 0
-    for case in gold["cases"]:
-        vals, w = case["values"].cuda(), case["weights"].cuda()
-        for training in (True, False):
-            key = "train" if training else "eval"
-            if case["kind"] == "thermal":
-                r = ThermalRenderer().train(training)
-            else:
-                r = RGBTRenderer().train(training)
+    for kind, key, cls in (("thermal", "thermal", ThermalRenderer), ("rgbt", "rgbt", RGBTRenderer)):
+        for case in gold[kind]:
+            r = cls().train(bool(case["training"]))
             with torch.no_grad():
-                out = r(vals, w)
-            ref = case[key]
-            # the reference propagates NaN / inf samples in training mode; compare where the reference is finite
+                out = r(case[key].cuda(), case["weights"].cuda())
+            ref = case["out"]
+            # training mode propagates NaN / inf samples in the reference: compare where the reference is finite
             finite = torch.isfinite(ref)
-            _close(torch.where(finite.cuda(), out, torch.zeros_like(out)), torch.where(finite, ref, torch.zeros_like(ref)),
-                   2e-6, 2e-6, f"{case['kind']} {key}")
+            assert torch.equal(torch.isfinite(out).cpu() | ~finite, torch.ones_like(finite)), (kind, case["training"])
+            _close(torch.where(finite.cuda(), out, torch.zeros_like(out)),
+                   torch.where(finite, ref, torch.zeros_like(ref)), 2e-6, 2e-6, f"{kind} training={case['training']}")
             checked += 1
-    assert checked >= 4
+    fb = gold["thermal_forced_background"]  # a background_color argument is ignored (thermal_renderer.py:49)
+    with torch.no_grad():
+        out = ThermalRenderer(background_color="black").train()(fb["thermal"].cuda(), fb["weights"].cuda(),
+                                                               background_color="white")
+    _close(out, fb["out"], 2e-6, 2e-6, "forced background")
+    assert checked == 12
     with pytest.raises(NotImplementedError):
-        ThermalRenderer().eval()(vals, w, ray_indices=torch.zeros(1), num_rays=1)
+        ThermalRenderer().eval()(fb["thermal"].cuda(), fb["weights"].cuda(), ray_indices=torch.zeros(1), num_rays=1)

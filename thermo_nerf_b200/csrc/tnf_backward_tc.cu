@@ -137,8 +137,8 @@ __device__ inline void stage_field_bwd(FieldBwdWTC& W, const TnfModel& m, int ti
 constexpr int kProducers = 15;            // producer warps per CTA; warp kProducers issues the tcgen05.mma
 constexpr int kBwdThreads = (kProducers + 1) * 32;
 constexpr int kGrp = 256;                 // bytes of one 8-column group of a 16-sample bf16 tile
-constexpr int kBufGroups = 17;            // largest event: [X 8 | 1 | dY 8]
-constexpr int kNumBufs = 12;
+constexpr int kBufGroups = 31;            // largest event (EV_TRUNK): [XF 4 | 1 | dG 2 | dH 8 | dB1 8 | dA1 8]
+constexpr int kNumBufs = 7;
 constexpr int kTmemCols = 512;
 
 // tensor-memory columns of the accumulators (all M = 64: row m on lane (m % 16) + 32 * (m / 16))
@@ -154,7 +154,10 @@ enum {
   C_SB = 312,     // row sums: [dT 8 | dZ 8 | dG 16] against an all-ones A tile   32
   C_END = 344
 };
-enum { EV_TH2 = 0, EV_TH1, EV_TH0, EV_RGB2, EV_RGB1, EV_RGB0, EV_TRUNK, EV_COUNT };
+// One hand-off per head and one for the trunk: three events per 16-sample tile.
+//   EV_THERMAL / EV_COLOUR  [X1 8 | 1 | dY2 8 | X2 8 | dOut 1]   layers 1 and 2 of the head
+//   EV_TRUNK                [XF 4 | 1 | dG 2 | dH 8 | dB1 8 | dA1 8]  mlp_base + layer 0 of both heads
+enum { EV_THERMAL = 0, EV_COLOUR, EV_TRUNK, EV_COUNT };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -175,13 +178,17 @@ __device__ __forceinline__ bool mbar_test(unsigned long long* bar, unsigned pari
       : "memory");
   return done != 0;
 }
-__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+// The `completed` counter: written by the issuer after it has observed the commit barrier of a ticket (the
+// tensor core has finished reading that buffer by then; stores are not speculated, so a plain volatile store
+// behind the dependent branch suffices - st.release would add a MEMBAR.ALL.CTA to every retirement), read by
+// producers before they overwrite the buffer with generic stores.
+__device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) {
   uint32_t v;
-  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  asm volatile("ld.volatile.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(smem_u32(p)) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.cta.shared.u32 [%0], %1;\n" ::"r"(smem_u32(p)), "r"(v) : "memory");
+__device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) {
+  asm volatile("st.volatile.shared.u32 [%0], %1;\n" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
 constexpr long long kSpinLimit = 1ll << 32;  // ~2 s: a protocol error traps (the launch fails loudly), never hangs
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
@@ -286,12 +293,9 @@ static_assert(sizeof(FieldBwdSmemU) <= 227 * 1024, "FieldBwdSmemU exceeds the sh
 
 // Tickets are handed out in arrival order; ticket t uses buffer t % kNumBufs once ticket t - kNumBufs has retired.
 // Producers wait on the monotonic `completed` counter (a parity wait could be two ring laps behind and alias).
+// (No time-out here: the issuer traps when it sees no progress for kSpinLimit cycles, which ends the launch.)
 __device__ __forceinline__ void wait_retired(FieldBwdSmemU& S, const uint32_t upto) {  // until completed >= upto
-  const long long t0 = clock64();
-  while ((int32_t)(ld_acquire(&S.completed) - upto) < 0) {
-    if (clock64() - t0 > kSpinLimit) __trap();
-    __nanosleep(64);
-  }
+  while ((int32_t)(ld_volatile(&S.completed) - upto) < 0) __nanosleep(20);
 }
 __device__ __forceinline__ uint32_t acquire_ticket(FieldBwdSmemU& S, const int lane) {
   uint32_t t = 0;
@@ -411,50 +415,34 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
       uint32_t t = 0, c = 0;  // next ticket to issue, next ticket to retire
       long long last = clock64();
       while (c < total) {
-        bool progress = false;
-        if (c < t && mbar_test(&S.done[c % kNumBufs], (c / kNumBufs) & 1)) {
-          ++c;
-          st_release(&S.completed, c);
-          progress = true;
-        }
-        if (t < total && mbar_test(&S.full[t % kNumBufs], (t / kNumBufs) & 1)) {
+        // both probes are issued before either result is consumed: their latencies overlap
+        const bool can_retire = c < t, can_issue = t < total;
+        const bool retired = can_retire && mbar_test(&S.done[c % kNumBufs], (c / kNumBufs) & 1);
+        const bool filled = can_issue && mbar_test(&S.full[t % kNumBufs], (t / kNumBufs) & 1);
+        if (retired) st_volatile(&S.completed, ++c);
+        if (filled) {
           const int b = (int)(t % kNumBufs);
           tc_fence_after();
           const uint32_t hdr = *reinterpret_cast<volatile uint32_t*>(&S.hdr[b]);
           const int ev = (int)(hdr & 0xffu), w = (int)(hdr >> 8);
           const uint32_t buf = smem_u32(S.pool[b]);
-          switch (ev) {
-            case EV_TH2:  // [XB2 8 | dT 1]
-              umma(tmem, C_TH2, buf, buf + 8 * kGrp, 8, inited, 0);
-              umma(tmem, C_SB, ones, buf + 8 * kGrp, 8, inited, 1);
-              break;
-            case EV_TH1:  // [XB1 8 | 1 | dB2 8]
-              umma(tmem, C_TH1, buf + 9 * kGrp, buf, 72, inited, 2);
-              break;
-            case EV_TH0:  // [dB1 8]  x  private [XG | 1]
-              umma(tmem, C_TH0, buf, smem_u32(S.xgv[w]), 24, inited, 3);
-              break;
-            case EV_RGB2:  // [XA2 8 | dZ 1]
-              umma(tmem, C_RGB2, buf, buf + 8 * kGrp, 8, inited, 4);
-              umma(tmem, C_SB + 8, ones, buf + 8 * kGrp, 8, inited, 5);
-              break;
-            case EV_RGB1:  // [XA1 8 | 1 | dA2 8]
-              umma(tmem, C_RGB1, buf + 9 * kGrp, buf, 72, inited, 6);
-              break;
-            case EV_RGB0:  // [dA1 8]  x  private [XG | 1 | SH | appearance]
-              umma(tmem, C_RGB0, buf, smem_u32(S.xgv[w]), 72, inited, 7);
-              break;
-            default:  // EV_TRUNK: [XF 4 | 1 | dG 2 | dH 8], private XH
-              umma(tmem, C_BASE0, buf + 7 * kGrp, buf, 40, inited, 8);
-              umma(tmem, C_BASE1, smem_u32(S.xh[w]), buf + 5 * kGrp, 16, inited, 9);
-              umma(tmem, C_SB + 16, ones, buf + 5 * kGrp, 16, inited, 10);
-              break;
+          if (ev == EV_TRUNK) {  // [XF 4 | 1 | dG 2 | dH 8 | dB1 8 | dA1 8], private XH and [XG | 1 | SH | app]
+            const uint32_t xgv = smem_u32(S.xgv[w]);
+            umma(tmem, C_BASE0, buf + 7 * kGrp, buf, 40, inited, 0);
+            umma(tmem, C_BASE1, smem_u32(S.xh[w]), buf + 5 * kGrp, 16, inited, 1);
+            umma(tmem, C_SB + 16, ones, buf + 5 * kGrp, 16, inited, 2);
+            umma(tmem, C_TH0, buf + 15 * kGrp, xgv, 24, inited, 3);
+            umma(tmem, C_RGB0, buf + 23 * kGrp, xgv, 72, inited, 4);
+          } else {  // [X1 8 | 1 | dY2 8 | X2 8 | dOut 1]
+            const bool th = ev == EV_THERMAL;
+            umma(tmem, th ? C_TH1 : C_RGB1, buf + 9 * kGrp, buf, 72, inited, th ? 5 : 8);
+            umma(tmem, th ? C_TH2 : C_RGB2, buf + 17 * kGrp, buf + 25 * kGrp, 8, inited, th ? 6 : 9);
+            umma(tmem, th ? C_SB : C_SB + 8, ones, buf + 25 * kGrp, 8, inited, th ? 7 : 10);
           }
           tc_commit(&S.done[b]);
           ++t;
-          progress = true;
         }
-        if (progress) last = clock64();
+        if (retired || filled) last = clock64();
         else if (clock64() - last > kSpinLimit) __trap();
       }
     }
@@ -577,95 +565,103 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
         uint32_t dB1A[4][4];
         {
           float c[8][4];
-          uint32_t xb1[4][4];
+          uint32_t xb1[4][4], dy[4][4];
           init_bias(c, W.th0b, q);
           mma_layer<8, 1>(c, ga, &W.geo0[0][0][0], 8, 16, lane);
           const uint32_t mkB1 = relu_mask(c);
           act_pack<8, ACT_NONE>(c, xb1);
           init_bias(c, W.th1b, q);
           mma_layer<8, 4>(c, xb1, &W.th1[0][0][0], 0, 8, lane);
+          // x2 <- XB2 = sigmoid(.);  dy <- dB2pre = dtau w_th2 XB2 (1 - XB2)  (bf16 A fragments of the next product).
+          // Everything the hand-off stores is packed BEFORE the ticket is taken: between acquire and close only the
+          // stores remain (the issuer consumes tickets in order - a long fill would hold up every later ticket)
+          uint32_t x2[4][4];
 #pragma unroll
-          for (int nt = 0; nt < 8; ++nt)
+          for (int kt = 0; kt < 4; ++kt)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) c[nt][e] = sigmoid_fast(c[nt][e]);
-          {  // field_head_thermal: dW^T = XB2^T dT
+            for (int h = 0; h < 2; ++h) {
+              const int nt = 2 * kt + h;
+              float x[4], d[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                x[e] = sigmoid_fast(c[nt][e]);
+                d[e] = dtau[e >> 1] * B.th2w[nt * 8 + 2 * q + (e & 1)] * x[e] * (1.f - x[e]);
+              }
+              x2[kt][2 * h] = pack_bf162(x[0], x[1]);
+              x2[kt][2 * h + 1] = pack_bf162(x[2], x[3]);
+              dy[kt][2 * h] = pack_bf162(d[0], d[1]);
+              dy[kt][2 * h + 1] = pack_bf162(d[2], d[3]);
+            }
+#pragma unroll
+          for (int kt = 0; kt < 4; ++kt)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xb1[kt][j] = half2_to_bf162(xb1[kt][j]);
+          {  // mlp_thermal.layers.1: dW = dB2^T [XB1 | 1];  field_head_thermal: dW^T = XB2^T dT
+            const uint32_t d0 = pack_bf162(dtau[0], 0.f), d1 = pack_bf162(dtau[1], 0.f);
             const uint32_t tk = acquire_ticket(S, lane);
             unsigned char* buf = S.pool[tk % kNumBufs];
-            stage_c<8>(buf, c, lane);
-            stage_rows(buf + 8 * kGrp, g, q, pack_bf162(dtau[0], 0.f), 0u, pack_bf162(dtau[1], 0.f), 0u);
-            close_buf(S, tk, EV_TH2, warp, lane);
-          }
-#pragma unroll
-          for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              c[nt][e] = dtau[e >> 1] * B.th2w[nt * 8 + 2 * q + (e & 1)] * c[nt][e] * (1.f - c[nt][e]);
-          {  // mlp_thermal.layers.1: dW = dB2^T [XB1 | 1]
-            const uint32_t tk = acquire_ticket(S, lane);
-            unsigned char* buf = S.pool[tk % kNumBufs];
-            stage_a_f16<4>(buf, xb1, lane);
+            stage_a<4>(buf, xb1, lane);
             stage_ones(buf + 8 * kGrp, lane);
-            stage_c<8>(buf + 9 * kGrp, c, lane);
-            close_buf(S, tk, EV_TH1, warp, lane);
+            stage_a<4>(buf + 9 * kGrp, dy, lane);
+            stage_a<4>(buf + 17 * kGrp, x2, lane);
+            stage_rows(buf + 25 * kGrp, g, q, d0, 0u, d1, 0u);
+            close_buf(S, tk, EV_THERMAL, warp, lane);
           }
-          uint32_t dy[4][4];
-          pack_bf16_a(c, dy);
           zero_c(c);
           mma_layer_bf16<8, 4>(c, dy, &B.th1T[0][0][0], 8, lane);
           apply_mask(c, mkB1);
-          {  // mlp_thermal.layers.0: dW = dB1^T [XG | 1]
-            const uint32_t tk = acquire_ticket(S, lane);
-            stage_c<8>(S.pool[tk % kNumBufs], c, lane);
-            close_buf(S, tk, EV_TH0, warp, lane);
-          }
           pack_bf16_a(c, dB1A);
         }
         // ---- colour head forward + backward down to dA1pre
         uint32_t dA1A[4][4];
         {
           float c[8][4];
-          uint32_t xa1[4][4];
+          uint32_t xa1[4][4], dy[4][4];
           init_bias(c, ws.rayb, q);
           mma_layer<8, 1>(c, ga, &W.geo0[0][0][0], 0, 16, lane);
           const uint32_t mkA1 = relu_mask(c);
           act_pack<8, ACT_NONE>(c, xa1);
           init_bias(c, W.rgb1b, q);
           mma_layer<8, 4>(c, xa1, &W.rgb1[0][0][0], 0, 8, lane);
-          relu_mask(c);
-          {  // mlp_head.layers.2: dW^T = XA2^T dZ
-            const uint32_t tk = acquire_ticket(S, lane);
-            unsigned char* buf = S.pool[tk % kNumBufs];
-            stage_c<8>(buf, c, lane);
-            stage_rows(buf + 8 * kGrp, g, q, pack_bf162(dz[0][0], dz[0][1]), pack_bf162(dz[0][2], 0.f),
-                       pack_bf162(dz[1][0], dz[1][1]), pack_bf162(dz[1][2], 0.f));
-            close_buf(S, tk, EV_RGB2, warp, lane);
-          }
+          // x2 <- XA2 = relu(.);  dy <- dA2pre = (XA2 > 0) dz . W_rgb2   (packed before the ticket, as above)
+          uint32_t x2[4][4];
 #pragma unroll
-          for (int nt = 0; nt < 8; ++nt)
+          for (int kt = 0; kt < 4; ++kt)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int col = nt * 8 + 2 * q + (e & 1), h = e >> 1;
-              const float v = dz[h][0] * B.rgb2w[0][col] + dz[h][1] * B.rgb2w[1][col] + dz[h][2] * B.rgb2w[2][col];
-              c[nt][e] = c[nt][e] > 0.f ? v : 0.f;
+            for (int h = 0; h < 2; ++h) {
+              const int nt = 2 * kt + h;
+              float x[4], d[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int col = nt * 8 + 2 * q + (e & 1), r = e >> 1;
+                const float v = dz[r][0] * B.rgb2w[0][col] + dz[r][1] * B.rgb2w[1][col] + dz[r][2] * B.rgb2w[2][col];
+                d[e] = c[nt][e] > 0.f ? v : 0.f;
+                x[e] = fmaxf(c[nt][e], 0.f);
+              }
+              x2[kt][2 * h] = pack_bf162(x[0], x[1]);
+              x2[kt][2 * h + 1] = pack_bf162(x[2], x[3]);
+              dy[kt][2 * h] = pack_bf162(d[0], d[1]);
+              dy[kt][2 * h + 1] = pack_bf162(d[2], d[3]);
             }
-          {  // mlp_head.layers.1: dW = dA2^T [XA1 | 1]
+#pragma unroll
+          for (int kt = 0; kt < 4; ++kt)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xa1[kt][j] = half2_to_bf162(xa1[kt][j]);
+          {  // mlp_head.layers.1: dW = dA2^T [XA1 | 1];  mlp_head.layers.2: dW^T = XA2^T dZ
+            const uint32_t z00 = pack_bf162(dz[0][0], dz[0][1]), z01 = pack_bf162(dz[0][2], 0.f);
+            const uint32_t z10 = pack_bf162(dz[1][0], dz[1][1]), z11 = pack_bf162(dz[1][2], 0.f);
             const uint32_t tk = acquire_ticket(S, lane);
             unsigned char* buf = S.pool[tk % kNumBufs];
-            stage_a_f16<4>(buf, xa1, lane);
+            stage_a<4>(buf, xa1, lane);
             stage_ones(buf + 8 * kGrp, lane);
-            stage_c<8>(buf + 9 * kGrp, c, lane);
-            close_buf(S, tk, EV_RGB1, warp, lane);
+            stage_a<4>(buf + 9 * kGrp, dy, lane);
+            stage_a<4>(buf + 17 * kGrp, x2, lane);
+            stage_rows(buf + 25 * kGrp, g, q, z00, z01, z10, z11);
+            close_buf(S, tk, EV_COLOUR, warp, lane);
           }
-          uint32_t dy[4][4];
-          pack_bf16_a(c, dy);
           zero_c(c);
           mma_layer_bf16<8, 4>(c, dy, &B.rgb1T[0][0][0], 8, lane);
           apply_mask(c, mkA1);
-          {  // mlp_head.layers.0: dW = dA1^T [XG | 1 | SH | appearance]
-            const uint32_t tk = acquire_ticket(S, lane);
-            stage_c<8>(S.pool[tk % kNumBufs], c, lane);
-            close_buf(S, tk, EV_RGB0, warp, lane);
-          }
           pack_bf16_a(c, dA1A);
           // column sums over the 16 rows of the tile -> per-ray sum of dA1pre
 #pragma unroll
@@ -698,7 +694,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
           zero_c(c);
           mma_layer_bf16<8, 1>(c, dGA, &B.base1T[0][0][0], 8, lane);
           apply_mask(c, mkH);
-          {  // mlp_base layers: dW0 = dH^T [XF | 1], dW1^T = XH^T dG
+          pack_bf16_a(c, dHA);
+          {  // mlp_base: dW0 = dH^T [XF | 1], dW1^T = XH^T dG;  layer 0 of the heads: dB1^T [XG | 1],
+             // dA1^T [XG | 1 | SH | appearance]
             // the tile's saved hash features (16 rows x 4 chunks of 8 halves) are fetched BEFORE the ticket is
             // taken: the issuer consumes tickets in order, so nothing slow may sit between acquire and close
             uint4 xf[2];
@@ -719,11 +717,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
             }
             stage_ones(buf + 4 * kGrp, lane);
             stage_a<1>(buf + 5 * kGrp, dGA, lane);
-            stage_c<8>(buf + 7 * kGrp, c, lane);
+            stage_a<4>(buf + 7 * kGrp, dHA, lane);
+            stage_a<4>(buf + 15 * kGrp, dB1A, lane);
+            stage_a<4>(buf + 23 * kGrp, dA1A, lane);
             close_buf(S, tk, EV_TRUNK, warp, lane);
             trunk_ticket = tk + 1;
           }
-          pack_bf16_a(c, dHA);
         }
         {
           float c[4][4];
@@ -781,7 +780,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
   if (total_events > 0) {  // the issuer left its loop after the last ticket retired
     tc_fence_after();
     const int qd = warp & 3;  // a warp reaches the 32 tensor-memory lanes of its quadrant
-    for (int chunk = warp >> 2; chunk < C_END / 8; chunk += 4) {
+    for (int it = warp >> 2; it < C_END / 8; it += 4) {
+      // CTAs finish together and add to the same 14 336 addresses: each starts at a different column chunk so
+      // that the L2 atomic units do not see 148 adds to one address at the same moment
+      const int chunk = (it + (int)blockIdx.x) % (C_END / 8);
       uint32_t r[8];
       const uint32_t taddr = tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(chunk * 8);
       asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"

@@ -96,10 +96,16 @@ class ModelTensors:
             "rgb0": cls._lin(f.mlp_head.layers[0]),
             "rgb1": cls._lin(f.mlp_head.layers[1]),
             "rgb2": cls._lin(f.mlp_head.layers[2]),
-            "th0": cls._lin(f.mlp_thermal.layers[0]),
-            "th1": cls._lin(f.mlp_thermal.layers[1]),
-            "th2": cls._lin(f.field_head_thermal.net),
         }
+        if hasattr(f, "mlp_thermal"):
+            lin.update(th0=cls._lin(f.mlp_thermal.layers[0]), th1=cls._lin(f.mlp_thermal.layers[1]),
+                       th2=cls._lin(f.field_head_thermal.net))
+        else:
+            # a stock nerfstudio NerfactoField (nerfacto / thermal-nerfacto model types): the kernels always
+            # evaluate the thermal head, so it gets constant zeros that are neither parameters nor state
+            ref = lin["rgb0"].weight
+            z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=ref.device)  # noqa: E731
+            lin.update(th0=_Linear(z(64, 15), z(64)), th1=_Linear(z(64, 64), z(64)), th2=_Linear(z(1, 64), z(1)))
         expect = {"base0": (64, 32), "base1": (16, 64), "rgb0": (64, 63), "rgb1": (64, 64), "rgb2": (3, 64),
                   "th0": (64, 15), "th1": (64, 64), "th2": (1, 64)}
         for k, shp in expect.items():

@@ -25,21 +25,17 @@ from .rays import RayBundle
 
 
 @dataclass
-class ThermalNerfModelConfig:
-    """ThermalNerfModelConfig (thermal_nerf_model.py:46-56) + ThermalNerfactoModelConfig
-    (nerfacto_config/thermal_nerfacto.py:13-25) + the NerfactoModelConfig defaults they
-    inherit."""
+class ThermalNerfactoModelConfig:
+    """ThermalNerfactoModelConfig (nerfacto_config/thermal_nerfacto.py:13-25) + the NerfactoModelConfig defaults it
+    inherits: nerfacto on one image modality (the ``nerfacto`` / ``thermal-nerfacto`` ModelTypes of
+    train_eval_script.py:66-73) - sampler / field / renderers without the thermal head."""
 
-    _target: Type = field(default_factory=lambda: ThermalNerfModel)
+    _target: Type = field(default_factory=lambda: ThermalNerfactoModel)
     # ThermalNerfactoModelConfig
     max_temperature: float = 1.0
     min_temperature: float = 0.0
     cold: bool = False
     camera_optimizer_mode: Literal["off", "SO3xR3"] = "SO3xR3"
-    # ThermalNerfModelConfig
-    use_transient_embedding: bool = False
-    thermal_loss_weight: float = 1.0  # declared but unused by the reference (thermal_nerf_model.py:53 vs :321-324)
-    pass_thermal_gradients: bool = True
     # NerfactoModelConfig
     near_plane: float = 0.05
     far_plane: float = 1000.0
@@ -80,10 +76,22 @@ class ThermalNerfModelConfig:
     eval_num_rays_per_chunk: int = 1 << 16  # config_thermal_nerf.py:30
     # B200 specific
     precision: Literal["fp32", "tc_fp16"] = "tc_fp16"
-    thermal_head: bool = True  # False: plain nerfacto field (ThermalNerfactoModel, nerfacto_config/thermal_nerfacto.py)
+    thermal_head: bool = False  # the thermal head belongs to ThermalNerfModelConfig
 
     def setup(self, **kwargs) -> Any:
         return self._target(self, **kwargs)
+
+
+@dataclass
+class ThermalNerfModelConfig(ThermalNerfactoModelConfig):
+    """ThermalNerfModelConfig (thermal_nerf_model.py:46-56): a subclass of ThermalNerfactoModelConfig, as
+    train_eval_script.py:94 requires."""
+
+    _target: Type = field(default_factory=lambda: ThermalNerfModel)
+    use_transient_embedding: bool = False
+    thermal_loss_weight: float = 1.0  # declared but unused by the reference (thermal_nerf_model.py:53 vs :321-324)
+    pass_thermal_gradients: bool = True
+    thermal_head: bool = True
 
 
 @dataclass
@@ -108,15 +116,265 @@ class _SceneBox:
         self.aabb = aabb
 
 
-class ThermalNerfModel(nn.Module):
-    """ThermalNerfModel on libtnf_b200 (see module docstring)."""
+class KernelModelMixin:
+    """The kernel-backed part of the Model surface: ``forward`` / ``get_outputs`` / ``get_outputs_for_camera_ray_bundle``
+    / ``get_metrics_dict`` / ``get_loss_dict`` over libtnf_b200.  It only touches what nerfstudio's ``NerfactoModel``
+    and the reference's ``ThermalNerfModel`` expose (``config``, ``field``, ``proposal_networks``, ``camera_optimizer``,
+    ``scene_box``, ``device``, ``training`` and the ProposalNetworkSampler state), so the same code serves this
+    package's stand-alone model classes and the subclass of the reference's own class in ``nerfstudio_plugin.py``."""
 
-    config: ThermalNerfModelConfig
+    _tensors: Optional[F.ModelTensors] = None
 
-    def __init__(self, config: ThermalNerfModelConfig, metadata: dict, scene_box, num_train_data: int,
-                 **kwargs) -> None:
-        if config.thermal_head and "thermal" not in metadata.keys():  # thermal_nerf_model.py:75-76
-            raise ValueError("Thermal images not found in metadata.")
+    # ------------------------------------------------------------------ tensors of the path
+    def _apply(self, fn, *a, **k):  # parameters may move: re-resolve tensor references
+        self._tensors = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, state_dict, strict: bool = True, **k):  # type: ignore[override]
+        self._tensors = None
+        return super().load_state_dict(state_dict, strict=strict, **k)
+
+    def tensors(self) -> F.ModelTensors:
+        if self._tensors is None:
+            self._tensors = F.ModelTensors.from_module(self)
+        return self._tensors
+
+    # ------------------------------------------------------------------ ProposalNetworkSampler state
+    def _sampler_state(self):
+        """The object carrying ``_anneal`` / ``_steps_since_update`` / ``_step``: nerfstudio's ProposalNetworkSampler
+        when the model has one (the reference's populate_modules builds it, thermal_nerf_model.py:172-179), else
+        the model itself."""
+        return getattr(self, "proposal_sampler", None) or self
+
+    def _update_schedule(self, step: int) -> float:
+        sched = getattr(self._sampler_state(), "update_sched", None)
+        return float(sched(step)) if sched is not None else self.update_schedule(step)
+
+    def _precision(self) -> int:
+        return L.PRECISION_FP32 if getattr(self.config, "precision", "tc_fp16") == "fp32" else L.PRECISION_TC_FP16
+
+    def _has_thermal_head(self) -> bool:
+        return bool(getattr(self.config, "thermal_head", True))
+
+    def _appearance_mode(self) -> int:
+        if self.training:
+            return L.APPEARANCE_LOOKUP
+        return L.APPEARANCE_MEAN if self.config.use_average_appearance_embedding else L.APPEARANCE_ZEROS
+
+    def _collider_near(self) -> float:
+        # NearFarCollider(reset_near_plane=True): eval renders from t=0 (SURVEY A.2)
+        return self.config.near_plane if self.training else 0.0
+
+    def forward(self, ray_bundle) -> Dict[str, Any]:
+        """Model.forward: collider (thermal_nerf_model.py:182-184) then get_outputs.  The
+        NearFarCollider only writes two constants per ray, so they travel as kernel
+        arguments instead of [R,1] tensors (a caller-supplied nears/fars still wins)."""
+        return self.get_outputs(ray_bundle)
+
+    def _aabb_list(self) -> List[float]:
+        box = getattr(self, "_aabb_cache", None)
+        if box is None:  # host copy made once: a CUDA-resident aabb would otherwise cost a sync per call
+            box = [float(x) for x in torch.as_tensor(self.scene_box.aabb).reshape(-1).tolist()]
+            self._aabb_cache = box
+        return box
+
+    def _render_kwargs(self) -> Dict[str, Any]:
+        cfg = self.config
+        return dict(
+            num_samples=(*cfg.num_proposal_samples_per_ray, cfg.num_nerf_samples_per_ray),
+            near_plane=self._collider_near(), far_plane=cfg.far_plane, anneal=float(self._sampler_state()._anneal),
+            use_contraction=not cfg.disable_scene_contraction,
+            aabb=self._aabb_list(), appearance_mode=self._appearance_mode(), precision=self._precision())
+
+    def get_outputs(self, ray_bundle, depth_clip_chunk: int = 0) -> Dict[str, Any]:
+        """thermal_nerf_model.py:210-275 as one fused kernel launch (eval) or one autograd node over
+        tnf_render_forward / tnf_render_backward (training)."""
+        cfg = self.config
+        if self.training:
+            self.camera_optimizer.apply_to_raybundle(ray_bundle)
+        shape = tuple(ray_bundle.origins.shape[:-1])
+        o = ray_bundle.origins.reshape(-1, 3).contiguous().float()
+        d = ray_bundle.directions.reshape(-1, 3).contiguous().float()
+        R = o.shape[0]
+        cam = ray_bundle.camera_indices
+        if self.training and cam is None:
+            raise AttributeError("Camera indices are not provided.")  # thermal_field.py:113-114
+        nears = ray_bundle.nears.reshape(-1).contiguous().float() if ray_bundle.nears is not None else None
+        fars = ray_bundle.fars.reshape(-1).contiguous().float() if ray_bundle.fars is not None else None
+        cam_flat = cam.reshape(-1) if cam is not None else None
+        if self.training and torch.is_grad_enabled():
+            # ProposalNetworkSampler: the proposal densities only carry gradients on "updated" steps
+            st = self._sampler_state()
+            updated = st._steps_since_update > self._update_schedule(st._step) or st._step < 10
+            jitter = torch.rand((L.TNF_NUM_PROP + 1, R), device=o.device)
+            # origins / directions stay in the graph when the camera optimiser produced them: the backward then
+            # also returns dL/d origins, dL/d directions and autograd carries them into the pose deltas
+            res = F.render(self.tensors(), o, d, cam_flat, nears, fars, jitter, prop_grad=updated,
+                           detach_thermal_geo=not self.field.pass_thermal_gradients, **self._render_kwargs())
+            if updated:
+                st._steps_since_update = 0
+        else:
+            jitter = torch.rand((L.TNF_NUM_PROP + 1, R), device=o.device) if self.training else None
+            res = F.render_forward(self.tensors(), o, d, cam_flat, nears, fars, jitter, training=self.training,
+                                   depth_clip_chunk=depth_clip_chunk, return_samples=self.training,
+                                   **self._render_kwargs())
+        outputs: Dict[str, Any] = {
+            "rgb": res["rgb"].view(*shape, 3),
+            "accumulation": res["accumulation"].view(*shape, 1),
+            "depth": res["depth"].view(*shape, 1),
+            "expected_depth": res["expected_depth"].view(*shape, 1),
+        }
+        if self.training:
+            outputs["weights_list"] = res["weights_list"]
+            outputs["ray_samples_list"] = res["sdist_list"]  # spacing bins [R,S+1] per level (see DESIGN.md)
+        for i in range(cfg.num_proposal_iterations):
+            outputs[f"prop_depth_{i}"] = res[f"prop_depth_{i}"].view(*shape, 1)
+        if self._has_thermal_head():
+            outputs["thermal"] = res["thermal"].view(*shape, 1)
+        return outputs
+
+    @torch.no_grad()
+    def get_outputs_for_camera_ray_bundle(self, camera_ray_bundle) -> Dict[str, Tensor]:
+        """nerfstudio Model.get_outputs_for_camera_ray_bundle (called at renderer.py:185,
+        evaluator.py:79).  The reference loops over eval_num_rays_per_chunk slices; here the
+        whole image is ONE launch and the only chunk-dependent quantity (the expected-depth
+        clip range) is evaluated per chunk inside the kernel, so results are identical."""
+        input_device = camera_ray_bundle.directions.device
+        image_shape = tuple(camera_ray_bundle.origins.shape[:-1])
+        flat = RayBundle(
+            origins=camera_ray_bundle.origins.reshape(-1, 3).to(self.device),
+            directions=camera_ray_bundle.directions.reshape(-1, 3).to(self.device),
+            camera_indices=(camera_ray_bundle.camera_indices.reshape(-1, 1).to(self.device)
+                            if camera_ray_bundle.camera_indices is not None else None),
+            nears=camera_ray_bundle.nears.reshape(-1, 1).to(self.device) if camera_ray_bundle.nears is not None else None,
+            fars=camera_ray_bundle.fars.reshape(-1, 1).to(self.device) if camera_ray_bundle.fars is not None else None,
+        )
+        if flat.nears is None or flat.fars is None:
+            flat.nears, flat.fars = None, None  # constants are folded into the kernel arguments
+        was_training = self.training
+        outputs = KernelModelMixin.get_outputs(self, flat, depth_clip_chunk=self.config.eval_num_rays_per_chunk)
+        assert was_training == self.training
+        res = {}
+        for k, v in outputs.items():
+            if not isinstance(v, Tensor):
+                continue  # nerfstudio skips non-tensor outputs (weights_list etc.)
+            res[k] = v.view(*image_shape, -1).to(input_device)
+        # RenderedImageModality.RGB.value == "img" (rendered_image_modalities.py:5) while get_outputs emits
+        # "rgb": the alias lets the unchanged render_video_script.py default modalities work (SURVEY 3.3)
+        res["img"] = res["rgb"]
+        return res
+
+    @torch.no_grad()
+    def get_outputs_for_camera(self, cameras, camera_idx: int) -> Dict[str, Tensor]:
+        """``get_outputs_for_camera_ray_bundle(cameras.generate_rays(camera_indices=camera_idx))``
+        (renderer.py:183-187, evaluator.py:69-79) as one launch: the rays of a perspective camera are generated
+        inside the kernel, so no [H,W,3] origin/direction tensors are built, stored or re-read.  ``cameras``
+        exposes nerfstudio's ``Cameras`` attributes (camera_to_worlds, fx, fy, cx, cy, width, height).
+        Eval mode only (training batches are random pixels, not whole frames)."""
+        if self.training:
+            raise RuntimeError("get_outputs_for_camera is an eval-mode call")
+
+        def scalar(v):
+            v = v[camera_idx] if (torch.is_tensor(v) and v.dim() > 0) else v
+            return float(v)
+
+        c2w = cameras.camera_to_worlds[camera_idx].detach().to("cpu", torch.float32)
+        H, W = int(scalar(cameras.height)), int(scalar(cameras.width))
+        cam = F.pack_camera(c2w, scalar(cameras.fx), scalar(cameras.fy), scalar(cameras.cx), scalar(cameras.cy), W, H)
+        kw = self._render_kwargs()
+        res = F.render_forward(self.tensors(), None, None, camera=cam, training=False,
+                               depth_clip_chunk=self.config.eval_num_rays_per_chunk, **kw)
+        out = {k: v.view(H, W, -1) for k, v in res.items() if isinstance(v, Tensor)}
+        if not self._has_thermal_head():
+            out.pop("thermal", None)
+        out["img"] = out["rgb"]
+        return out
+
+    # ------------------------------------------------------------------ losses / metrics
+    def _fused_losses(self, outputs, batch) -> Dict[str, Tensor]:
+        """tnf_losses over the training outputs, evaluated once per step (metrics + loss dict share it)."""
+        cache = outputs.get("_b200_losses")
+        if cache is None:
+            # the reference keeps the thermal GT on the host and moves it here (thermal_dataset.py:18-20,
+            # thermal_nerf_model.py:319); non_blocking keeps that copy from draining the stream when the
+            # host tensor is pinned (a blocking .to() waits for the forward kernel before the loss can launch)
+            image = batch["image"].to(self.device, non_blocking=True)[..., :3].reshape(-1, 3).float()
+            if self._has_thermal_head():
+                thermal = batch["thermal"].to(self.device, non_blocking=True).reshape(-1).float()
+                pred_th = outputs["thermal"].reshape(-1)
+            else:  # nerfacto field: no thermal term (use_thermal_loss is False below); any [R] tensors do
+                thermal = pred_th = torch.zeros(image.shape[0], dtype=torch.float32, device=self.device)
+            w = outputs["weights_list"]
+            cache = F.losses(
+                {"rgb": outputs["rgb"].reshape(-1, 3), "thermal": pred_th,
+                 "weights_list": w, "sdist_list": outputs["ray_samples_list"]},
+                image, thermal, interlevel_mult=self.config.interlevel_loss_mult,
+                distortion_mult=self.config.distortion_loss_mult, use_rgb_loss=self.field.pass_rgb_gradients,
+                use_thermal_loss=self._has_thermal_head() and self.field.pass_thermal_gradients)
+            outputs["_b200_losses"] = cache
+        return cache
+
+    def get_metrics_dict(self, outputs, batch) -> Dict[str, Tensor]:
+        """NerfactoModel.get_metrics_dict (inherited by the reference): psnr, and in training the
+        distortion metric that get_loss_dict consumes (thermal_nerf_model.py:303-305)."""
+        metrics: Dict[str, Tensor] = {}
+        if self.training:
+            losses = self._fused_losses(outputs, batch)
+            metrics["distortion"] = losses["distortion_loss"] / self.config.distortion_loss_mult
+        with torch.no_grad():
+            if self.training and self.field.pass_rgb_gradients:
+                mse = losses["rgb_loss"].detach()  # the fused loss kernel already reduced MSE(rgb, gt)
+            else:
+                gt_rgb = batch["image"].to(self.device)
+                mse = torch.mean((outputs["rgb"].detach() - gt_rgb[..., :3]) ** 2)
+            metrics["psnr"] = -10.0 * torch.log10(mse)
+        cam_metrics = getattr(self.camera_optimizer, "get_metrics_dict", None)
+        if cam_metrics is not None:  # nerfstudio CameraOptimizer: camera_opt_translation / _rotation
+            cam_metrics(metrics)
+        return metrics
+
+    def get_loss_dict(self, outputs, batch, metrics_dict=None) -> Dict[str, Tensor]:
+        """thermal_nerf_model.py:277-326.  background_color="last_sample" makes
+        blend_background_for_loss_computation the identity on (pred, gt)."""
+        if self.training:
+            assert metrics_dict is not None and "distortion" in metrics_dict  # thermal_nerf_model.py:302
+            return dict(self._fused_losses(outputs, batch))
+        loss_dict: Dict[str, Tensor] = {}
+        image = batch["image"].to(self.device)[..., :3]
+        if self.field.pass_rgb_gradients:
+            loss_dict["rgb_loss"] = torch.nn.functional.mse_loss(image, outputs["rgb"])
+        if self._has_thermal_head() and self.field.pass_thermal_gradients:
+            loss_dict["thermal"] = torch.nn.functional.mse_loss(outputs["thermal"], batch["thermal"].to(self.device))
+        return loss_dict
+
+
+def check_supported_config(cfg) -> None:
+    """The options libtnf_b200 compiles; everything else raises instead of silently taking another path."""
+    if cfg.predict_normals or getattr(cfg, "use_transient_embedding", False) or cfg.use_gradient_scaling:
+        raise ValueError("predict_normals / use_transient_embedding / use_gradient_scaling are not on the "
+                         "thermal-nerf hot path and are not built into libtnf_b200")
+    if cfg.proposal_initial_sampler != "piecewise" or not cfg.use_single_jitter:
+        raise ValueError("libtnf_b200 implements the default piecewise initial sampler with single jitter")
+    if cfg.num_proposal_iterations != L.TNF_NUM_PROP or cfg.use_same_proposal_network:
+        raise ValueError("libtnf_b200 is built for 2 distinct proposal networks (nerfacto default)")
+    if cfg.background_color != "last_sample":
+        raise ValueError("libtnf_b200 implements background_color='last_sample' (nerfacto default)")
+    if getattr(cfg, "camera_optimizer_mode", "off") not in ("off", "SO3xR3"):
+        raise ValueError("libtnf_b200 supports camera_optimizer_mode 'off' or 'SO3xR3'")
+
+
+class ThermalNerfactoModel(KernelModelMixin, nn.Module):
+    """ThermalNerfactoModel (thermo_nerf/nerfacto_config/thermal_nerfacto.py:28-84) on libtnf_b200: the base class of
+    the hierarchy, as in the reference (``evaluator.py:76`` asserts ``isinstance(model, ThermalNerfactoModel)`` for
+    every model type).  Constructor without the thermal metadata requirement; with a plain
+    ``ThermalNerfactoModelConfig`` there is no "thermal" output and only the rgb / interlevel / distortion losses."""
+
+    config: ThermalNerfactoModelConfig
+
+    def __init__(self, config: ThermalNerfactoModelConfig, scene_box, num_train_data: int,
+                 metadata: Optional[dict] = None, **kwargs) -> None:
+        if config.thermal_head and not isinstance(self, ThermalNerfModel):
+            raise ValueError("ThermalNerfactoModel is the model without a thermal head (thermal_head=False)")
         super().__init__()
         self.config = config
         self.scene_box = scene_box if hasattr(scene_box, "aabb") else _SceneBox(torch.as_tensor(scene_box))
@@ -126,20 +384,12 @@ class ThermalNerfModel(nn.Module):
         self.min_temperature = config.min_temperature
         self.device_indicator_param = nn.Parameter(torch.empty(0))
         self.populate_modules()
-        self._tensors: Optional[F.ModelTensors] = None
+        self._tensors = None
 
     # ------------------------------------------------------------------ construction
     def populate_modules(self) -> None:
         cfg = self.config
-        if cfg.predict_normals or cfg.use_transient_embedding or cfg.use_gradient_scaling:
-            raise ValueError("predict_normals / use_transient_embedding / use_gradient_scaling are not on the "
-                             "thermal-nerf hot path and are not built into libtnf_b200")
-        if cfg.proposal_initial_sampler != "piecewise" or not cfg.use_single_jitter:
-            raise ValueError("libtnf_b200 implements the default piecewise initial sampler with single jitter")
-        if cfg.num_proposal_iterations != L.TNF_NUM_PROP or cfg.use_same_proposal_network:
-            raise ValueError("libtnf_b200 is built for 2 distinct proposal networks (nerfacto default)")
-        if cfg.background_color != "last_sample":
-            raise ValueError("libtnf_b200 implements background_color='last_sample' (nerfacto default)")
+        check_supported_config(cfg)
         aabb = torch.as_tensor(self.scene_box.aabb, dtype=torch.float32)
         self.field = ThermalNerfactoTField(
             aabb, num_images=self.num_train_data, hidden_dim=cfg.hidden_dim, num_levels=cfg.num_levels,
@@ -147,7 +397,8 @@ class ThermalNerfModel(nn.Module):
             log2_hashmap_size=cfg.log2_hashmap_size, hidden_dim_color=cfg.hidden_dim_color,
             hidden_dim_transient=cfg.hidden_dim_transient,
             use_average_appearance_embedding=cfg.use_average_appearance_embedding,
-            appearance_embedding_dim=cfg.appearance_embed_dim, pass_thermal_gradients=cfg.pass_thermal_gradients,
+            appearance_embedding_dim=cfg.appearance_embed_dim,
+            pass_thermal_gradients=getattr(cfg, "pass_thermal_gradients", False),
             thermal_head=cfg.thermal_head, use_contraction=not cfg.disable_scene_contraction)
         self.camera_optimizer = CameraOptimizer(self.num_train_data, cfg.camera_optimizer_mode)
         self.proposal_networks = nn.ModuleList()
@@ -171,19 +422,6 @@ class ThermalNerfModel(nn.Module):
     @property
     def device(self) -> torch.device:
         return self.device_indicator_param.device
-
-    def _apply(self, fn, *a, **k):  # parameters may move: re-resolve tensor references
-        self._tensors = None
-        return super()._apply(fn, *a, **k)
-
-    def load_state_dict(self, state_dict, strict: bool = True, **k):  # type: ignore[override]
-        self._tensors = None
-        return super().load_state_dict(state_dict, strict=strict, **k)
-
-    def tensors(self) -> F.ModelTensors:
-        if self._tensors is None:
-            self._tensors = F.ModelTensors.from_module(self)
-        return self._tensors
 
     # ------------------------------------------------------------------ nerfstudio Model surface
     def get_param_groups(self) -> Dict[str, List[nn.Parameter]]:
@@ -218,196 +456,6 @@ class ThermalNerfModel(nn.Module):
         callbacks.append(TrainingCallback([AFTER_TRAIN_ITERATION], 1, step_cb))
         return callbacks
 
-    def _precision(self) -> int:
-        return L.PRECISION_FP32 if self.config.precision == "fp32" else L.PRECISION_TC_FP16
-
-    def _appearance_mode(self) -> int:
-        if self.training:
-            return L.APPEARANCE_LOOKUP
-        return L.APPEARANCE_MEAN if self.config.use_average_appearance_embedding else L.APPEARANCE_ZEROS
-
-    def _collider_near(self) -> float:
-        # NearFarCollider(reset_near_plane=True): eval renders from t=0
-        return self.config.near_plane if self.training else 0.0
-
-    def forward(self, ray_bundle) -> Dict[str, Any]:
-        """Model.forward: collider (thermal_nerf_model.py:182-184) then get_outputs.  The
-        NearFarCollider only writes two constants per ray, so they travel as kernel
-        arguments instead of [R,1] tensors (a caller-supplied nears/fars still wins)."""
-        return self.get_outputs(ray_bundle)
-
-    def _aabb_list(self) -> List[float]:
-        box = getattr(self, "_aabb_cache", None)
-        if box is None:  # host copy made once: a CUDA-resident aabb would otherwise cost a sync per call
-            box = [float(x) for x in torch.as_tensor(self.scene_box.aabb).reshape(-1).tolist()]
-            self._aabb_cache = box
-        return box
-
-    def _render_kwargs(self) -> Dict[str, Any]:
-        cfg = self.config
-        return dict(
-            num_samples=(*cfg.num_proposal_samples_per_ray, cfg.num_nerf_samples_per_ray),
-            near_plane=self._collider_near(), far_plane=cfg.far_plane, anneal=self._anneal,
-            use_contraction=not cfg.disable_scene_contraction,
-            aabb=self._aabb_list(), appearance_mode=self._appearance_mode(), precision=self._precision())
-
-    def get_outputs(self, ray_bundle, depth_clip_chunk: int = 0) -> Dict[str, Any]:
-        """thermal_nerf_model.py:210-275 as one fused kernel launch (eval) or one autograd node over
-        tnf_render_forward / tnf_render_backward (training)."""
-        cfg = self.config
-        if self.training:
-            self.camera_optimizer.apply_to_raybundle(ray_bundle)
-        shape = tuple(ray_bundle.origins.shape[:-1])
-        o = ray_bundle.origins.reshape(-1, 3).contiguous().float()
-        d = ray_bundle.directions.reshape(-1, 3).contiguous().float()
-        R = o.shape[0]
-        cam = ray_bundle.camera_indices
-        if self.training and cam is None:
-            raise AttributeError("Camera indices are not provided.")  # thermal_field.py:113-114
-        nears = ray_bundle.nears.reshape(-1).contiguous().float() if ray_bundle.nears is not None else None
-        fars = ray_bundle.fars.reshape(-1).contiguous().float() if ray_bundle.fars is not None else None
-        cam_flat = cam.reshape(-1) if cam is not None else None
-        if self.training and torch.is_grad_enabled():
-            # ProposalNetworkSampler: the proposal densities only carry gradients on "updated" steps
-            updated = self._steps_since_update > self.update_schedule(self._step) or self._step < 10
-            jitter = torch.rand((L.TNF_NUM_PROP + 1, R), device=o.device)
-            # origins / directions stay in the graph when the camera optimiser produced them: the backward then
-            # also returns dL/d origins, dL/d directions and autograd carries them into the pose deltas
-            res = F.render(self.tensors(), o, d, cam_flat, nears, fars, jitter, prop_grad=updated,
-                           detach_thermal_geo=not self.field.pass_thermal_gradients, **self._render_kwargs())
-            if updated:
-                self._steps_since_update = 0
-        else:
-            jitter = torch.rand((L.TNF_NUM_PROP + 1, R), device=o.device) if self.training else None
-            res = F.render_forward(self.tensors(), o, d, cam_flat, nears, fars, jitter, training=self.training,
-                                   depth_clip_chunk=depth_clip_chunk, return_samples=self.training,
-                                   **self._render_kwargs())
-        outputs: Dict[str, Any] = {
-            "rgb": res["rgb"].view(*shape, 3),
-            "accumulation": res["accumulation"].view(*shape, 1),
-            "depth": res["depth"].view(*shape, 1),
-            "expected_depth": res["expected_depth"].view(*shape, 1),
-        }
-        if self.training:
-            outputs["weights_list"] = res["weights_list"]
-            outputs["ray_samples_list"] = res["sdist_list"]  # spacing bins [R,S+1] per level (see DESIGN.md)
-        for i in range(cfg.num_proposal_iterations):
-            outputs[f"prop_depth_{i}"] = res[f"prop_depth_{i}"].view(*shape, 1)
-        if cfg.thermal_head:
-            outputs["thermal"] = res["thermal"].view(*shape, 1)
-        return outputs
-
-    @torch.no_grad()
-    def get_outputs_for_camera_ray_bundle(self, camera_ray_bundle) -> Dict[str, Tensor]:
-        """nerfstudio Model.get_outputs_for_camera_ray_bundle (called at renderer.py:185,
-        evaluator.py:79).  The reference loops over eval_num_rays_per_chunk slices; here the
-        whole image is ONE launch and the only chunk-dependent quantity (the expected-depth
-        clip range) is evaluated per chunk inside the kernel, so results are identical."""
-        input_device = camera_ray_bundle.directions.device
-        image_shape = tuple(camera_ray_bundle.origins.shape[:-1])
-        flat = RayBundle(
-            origins=camera_ray_bundle.origins.reshape(-1, 3).to(self.device),
-            directions=camera_ray_bundle.directions.reshape(-1, 3).to(self.device),
-            camera_indices=(camera_ray_bundle.camera_indices.reshape(-1, 1).to(self.device)
-                            if camera_ray_bundle.camera_indices is not None else None),
-            nears=camera_ray_bundle.nears.reshape(-1, 1).to(self.device) if camera_ray_bundle.nears is not None else None,
-            fars=camera_ray_bundle.fars.reshape(-1, 1).to(self.device) if camera_ray_bundle.fars is not None else None,
-        )
-        if flat.nears is None or flat.fars is None:
-            flat.nears, flat.fars = None, None  # constants are folded into the kernel arguments
-        was_training = self.training
-        outputs = self.get_outputs(flat, depth_clip_chunk=self.config.eval_num_rays_per_chunk)
-        assert was_training == self.training
-        res = {}
-        for k, v in outputs.items():
-            if not isinstance(v, Tensor):
-                continue  # nerfstudio skips non-tensor outputs (weights_list etc.)
-            res[k] = v.view(*image_shape, -1).to(input_device)
-        # RenderedImageModality.RGB.value == "img" (rendered_image_modalities.py:5) while get_outputs emits
-        # "rgb": the alias lets the unchanged render_video_script.py default modalities work (SURVEY 3.3)
-        res["img"] = res["rgb"]
-        return res
-
-    @torch.no_grad()
-    def get_outputs_for_camera(self, cameras, camera_idx: int) -> Dict[str, Tensor]:
-        """``get_outputs_for_camera_ray_bundle(cameras.generate_rays(camera_indices=camera_idx))``
-        (renderer.py:183-187, evaluator.py:69-79) as one launch: the rays of a perspective camera are generated
-        inside the kernel, so no [H,W,3] origin/direction tensors are built, stored or re-read.  ``cameras``
-        exposes nerfstudio's ``Cameras`` attributes (camera_to_worlds, fx, fy, cx, cy, width, height).
-        Eval mode only (training batches are random pixels, not whole frames)."""
-        if self.training:
-            raise RuntimeError("get_outputs_for_camera is an eval-mode call")
-
-        def scalar(v):
-            v = v[camera_idx] if (torch.is_tensor(v) and v.dim() > 0) else v
-            return float(v)
-
-        c2w = cameras.camera_to_worlds[camera_idx].detach().to("cpu", torch.float32)
-        H, W = int(scalar(cameras.height)), int(scalar(cameras.width))
-        cam = F.pack_camera(c2w, scalar(cameras.fx), scalar(cameras.fy), scalar(cameras.cx), scalar(cameras.cy), W, H)
-        kw = self._render_kwargs()
-        res = F.render_forward(self.tensors(), None, None, camera=cam, training=False,
-                               depth_clip_chunk=self.config.eval_num_rays_per_chunk, **kw)
-        out = {k: v.view(H, W, -1) for k, v in res.items() if isinstance(v, Tensor)}
-        if not self.config.thermal_head:
-            out.pop("thermal", None)
-        out["img"] = out["rgb"]
-        return out
-
-    # ------------------------------------------------------------------ losses / metrics
-    def _fused_losses(self, outputs, batch) -> Dict[str, Tensor]:
-        """tnf_losses over the training outputs, evaluated once per step (metrics + loss dict share it)."""
-        cache = outputs.get("_b200_losses")
-        if cache is None:
-            # the reference keeps the thermal GT on the host and moves it here (thermal_dataset.py:18-20,
-            # thermal_nerf_model.py:319); non_blocking keeps that copy from draining the stream when the
-            # host tensor is pinned (a blocking .to() waits for the forward kernel before the loss can launch)
-            image = batch["image"].to(self.device, non_blocking=True)[..., :3].reshape(-1, 3).float()
-            if self.config.thermal_head:
-                thermal = batch["thermal"].to(self.device, non_blocking=True).reshape(-1).float()
-                pred_th = outputs["thermal"].reshape(-1)
-            else:  # nerfacto field: no thermal term (use_thermal_loss is False below); any [R] tensors do
-                thermal = pred_th = torch.zeros(image.shape[0], dtype=torch.float32, device=self.device)
-            w = outputs["weights_list"]
-            cache = F.losses(
-                {"rgb": outputs["rgb"].reshape(-1, 3), "thermal": pred_th,
-                 "weights_list": w, "sdist_list": outputs["ray_samples_list"]},
-                image, thermal, interlevel_mult=self.config.interlevel_loss_mult,
-                distortion_mult=self.config.distortion_loss_mult, use_rgb_loss=self.field.pass_rgb_gradients,
-                use_thermal_loss=self.field.pass_thermal_gradients)
-            outputs["_b200_losses"] = cache
-        return cache
-
-    def get_metrics_dict(self, outputs, batch) -> Dict[str, Tensor]:
-        """NerfactoModel.get_metrics_dict (inherited by the reference): psnr, and in training the
-        distortion metric that get_loss_dict consumes (thermal_nerf_model.py:303-305)."""
-        metrics: Dict[str, Tensor] = {}
-        if self.training:
-            losses = self._fused_losses(outputs, batch)
-            metrics["distortion"] = losses["distortion_loss"] / self.config.distortion_loss_mult
-        with torch.no_grad():
-            if self.training and self.field.pass_rgb_gradients:
-                mse = losses["rgb_loss"].detach()  # the fused loss kernel already reduced MSE(rgb, gt)
-            else:
-                gt_rgb = batch["image"].to(self.device)
-                mse = torch.mean((outputs["rgb"].detach() - gt_rgb[..., :3]) ** 2)
-            metrics["psnr"] = -10.0 * torch.log10(mse)
-        return metrics
-
-    def get_loss_dict(self, outputs, batch, metrics_dict=None) -> Dict[str, Tensor]:
-        """thermal_nerf_model.py:277-326.  background_color="last_sample" makes
-        blend_background_for_loss_computation the identity on (pred, gt)."""
-        if self.training:
-            assert metrics_dict is not None and "distortion" in metrics_dict  # thermal_nerf_model.py:302
-            return dict(self._fused_losses(outputs, batch))
-        loss_dict: Dict[str, Tensor] = {}
-        image = batch["image"].to(self.device)[..., :3]
-        if self.field.pass_rgb_gradients:
-            loss_dict["rgb_loss"] = torch.nn.functional.mse_loss(image, outputs["rgb"])
-        if self.field.pass_thermal_gradients:
-            loss_dict["thermal"] = torch.nn.functional.mse_loss(outputs["thermal"], batch["thermal"].to(self.device))
-        return loss_dict
-
     # ------------------------------------------------------------------ evaluation (Evaluator, evaluator.py:79-87)
     lpips: Optional[Callable[[Tensor, Tensor], Tensor]] = None  # LPIPS needs pretrained weights: plug a callable in
 
@@ -441,13 +489,8 @@ class ThermalNerfModel(nn.Module):
     def _lpips(self, gt: Tensor, pred: Tensor) -> float:
         return float(self.lpips(gt, pred)) if self.lpips is not None else float("nan")
 
-    def get_image_metrics_and_images(self, outputs: Dict[str, Tensor], batch: Dict[str, Tensor],
-                                     threshold: Optional[float] = None) -> Tuple[Dict[str, float], Dict[str, Tensor]]:
-        """thermal_nerf_model.py:328-398 on top of NerfactoModel.get_image_metrics_and_images: psnr / ssim / lpips of
-        the RGB image, psnr_thermal / ssim_thermal / lpips_thermal, mae_thermal and mae_thermal_foreground
-        (thermal_metrics.py), plus the side-by-side images the viewer logs.  Evaluation-only glue in plain PyTorch on
-        the already rendered [H,W,C] outputs.  LPIPS needs a pretrained network that is not shipped here: assign
-        ``model.lpips`` (e.g. torchmetrics' LearnedPerceptualImagePatchSimilarity) or the two lpips entries are NaN.
+    def _nerfacto_metrics_and_images(self, outputs, batch) -> Tuple[Dict[str, float], Dict[str, Tensor], Tensor, Tensor]:
+        """NerfactoModel.get_image_metrics_and_images: psnr / ssim / lpips of the colour image + the viewer panels.
         The accumulation / depth panels are grey-scale (nerfstudio's default colour maps come from matplotlib)."""
         dev = self.device
         gt_rgb = batch["image"].to(dev)[..., :3]
@@ -467,25 +510,18 @@ class ThermalNerfModel(nn.Module):
         g4, p4 = torch.moveaxis(gt_rgb, -1, 0)[None], torch.moveaxis(rgb, -1, 0)[None]
         metrics: Dict[str, float] = {"psnr": float(self.psnr(g4, p4)), "ssim": float(self.ssim(g4, p4)),
                                      "lpips": self._lpips(g4, p4)}
-        if not self.config.thermal_head:
-            # ThermalNerfactoModel.get_image_metrics_and_images (thermal_nerfacto.py:47-84): the "RGB" images are the
-            # thermal images, so the temperature MAE is taken on rgb
-            metrics["mae_foreground"] = float(self.mae_thermal(g4, p4, threshold=threshold))
-            metrics["mae"] = float(self.mae_thermal(g4, p4, threshold=None))
-            return metrics, images
-        # ThermalNerfModel reaches the method above through super() *without* its threshold
-        # (thermal_nerf_model.py:339), so both entries are the unthresholded MAE of the colour image
-        metrics["mae_foreground"] = metrics["mae"] = float(self.mae_thermal(g4, p4, threshold=None))
-        gt_th = batch["thermal"].to(dev)  # thermal_nerf_model.py:347 (the reference forgets the .to() at :355)
-        th = outputs["thermal"]
-        images["thermal"] = gray(th)
-        images["thermal_combined"] = torch.cat([gray(gt_th), gray(th)], dim=1)
-        gt4, th4 = torch.moveaxis(gt_th, -1, 0)[None], torch.moveaxis(th, -1, 0)[None]
-        metrics["psnr_thermal"] = float(self.psnr(gt4, th4))
-        metrics["ssim_thermal"] = float(self.ssim(gt4, th4))
-        metrics["lpips_thermal"] = self._lpips(torch.repeat_interleave(gt4, 3, dim=1), torch.repeat_interleave(th4, 3, dim=1))
-        metrics["mae_thermal_foreground"] = float(self.mae_thermal(gt4, th4, threshold=threshold))
-        metrics["mae_thermal"] = float(self.mae_thermal(gt4, th4, threshold=None))
+        return metrics, images, g4, p4
+
+    def get_image_metrics_and_images(self, outputs: Dict[str, Tensor], batch: Dict[str, Tensor],
+                                     threshold: Optional[float] = None) -> Tuple[Dict[str, float], Dict[str, Tensor]]:
+        """ThermalNerfactoModel.get_image_metrics_and_images (thermal_nerfacto.py:47-84): the "RGB" images are the
+        thermal images for the thermal-nerfacto method, so the temperature MAE is taken on rgb.  Evaluation-only glue
+        in plain PyTorch on the already rendered [H,W,C] outputs.  LPIPS needs a pretrained network that is not
+        shipped here: assign ``model.lpips`` (e.g. torchmetrics' LearnedPerceptualImagePatchSimilarity) or the lpips
+        entries are NaN."""
+        metrics, images, g4, p4 = self._nerfacto_metrics_and_images(outputs, batch)
+        metrics["mae_foreground"] = float(self.mae_thermal(g4, p4, threshold=threshold))
+        metrics["mae"] = float(self.mae_thermal(g4, p4, threshold=None))
         return metrics, images
 
     def mae_thermal(self, gt: Tensor, pred: Tensor, threshold: Optional[float] = None) -> Tensor:
@@ -497,22 +533,42 @@ class ThermalNerfModel(nn.Module):
         return torch.mean(torch.abs((gt * span + self.min_temperature) - (pred * span + self.min_temperature)))
 
 
-@dataclass
-class ThermalNerfactoModelConfig(ThermalNerfModelConfig):
-    """thermo_nerf/nerfacto_config/thermal_nerfacto.py:13-25: nerfacto on one image modality (the ``nerfacto`` and
-    ``thermal-nerfacto`` ModelTypes of train_eval_script.py:66-73) - the same sampler / field / renderers without the
-    thermal head, temperature MAE computed on the rendered rgb."""
+class ThermalNerfModel(ThermalNerfactoModel):
+    """ThermalNerfModel (thermo_nerf/thermal_nerf/thermal_nerf_model.py:60-393) on libtnf_b200: config :46-56, ctor
+    :67-84, populate_modules :86-208, get_outputs :210-275, get_loss_dict :277-326; a subclass of
+    ThermalNerfactoModel as in the reference.  Same names, argument meaning, output keys / shapes and error
+    behaviour; the arithmetic is one call into libtnf_b200.so."""
 
-    _target: Type = field(default_factory=lambda: ThermalNerfactoModel)
-    thermal_head: bool = False
+    config: ThermalNerfModelConfig
 
-
-class ThermalNerfactoModel(ThermalNerfModel):
-    """ThermalNerfactoModel (thermal_nerfacto.py:28-84) on libtnf_b200: constructor without the thermal metadata
-    requirement, no "thermal" output, rgb / interlevel / distortion losses only."""
-
-    def __init__(self, config: ThermalNerfactoModelConfig, scene_box, num_train_data: int, metadata: Optional[dict] = None,
+    def __init__(self, config: ThermalNerfModelConfig, metadata: dict, scene_box, num_train_data: int,
                  **kwargs) -> None:
-        if config.thermal_head:
-            raise ValueError("ThermalNerfactoModel is the model without a thermal head (thermal_head=False)")
-        super().__init__(config, metadata or {}, scene_box, num_train_data, **kwargs)
+        if config.thermal_head and "thermal" not in metadata.keys():  # thermal_nerf_model.py:75-76
+            raise ValueError("Thermal images not found in metadata.")
+        super().__init__(config, scene_box, num_train_data, metadata=metadata, **kwargs)
+
+    def get_image_metrics_and_images(self, outputs: Dict[str, Tensor], batch: Dict[str, Tensor],
+                                     threshold: Optional[float] = None) -> Tuple[Dict[str, float], Dict[str, Tensor]]:
+        """thermal_nerf_model.py:328-398 on top of the base class: psnr_thermal / ssim_thermal / lpips_thermal,
+        mae_thermal and mae_thermal_foreground (thermal_metrics.py), plus the side-by-side images the viewer logs."""
+        if not self.config.thermal_head:
+            return super().get_image_metrics_and_images(outputs, batch, threshold=threshold)
+        # the reference reaches the base method through super() *without* its threshold
+        # (thermal_nerf_model.py:339), so both colour-image entries are the unthresholded MAE
+        metrics, images = super().get_image_metrics_and_images(outputs, batch, threshold=None)
+        dev = self.device
+
+        def gray(t: Tensor) -> Tensor:
+            return t.repeat(1, 1, 3) if t.shape[-1] == 1 else t
+
+        gt_th = batch["thermal"].to(dev)  # thermal_nerf_model.py:347 (the reference forgets the .to() at :355)
+        th = outputs["thermal"]
+        images["thermal"] = gray(th)
+        images["thermal_combined"] = torch.cat([gray(gt_th), gray(th)], dim=1)
+        gt4, th4 = torch.moveaxis(gt_th, -1, 0)[None], torch.moveaxis(th, -1, 0)[None]
+        metrics["psnr_thermal"] = float(self.psnr(gt4, th4))
+        metrics["ssim_thermal"] = float(self.ssim(gt4, th4))
+        metrics["lpips_thermal"] = self._lpips(torch.repeat_interleave(gt4, 3, dim=1), torch.repeat_interleave(th4, 3, dim=1))
+        metrics["mae_thermal_foreground"] = float(self.mae_thermal(gt4, th4, threshold=threshold))
+        metrics["mae_thermal"] = float(self.mae_thermal(gt4, th4, threshold=None))
+        return metrics, images

@@ -74,11 +74,19 @@ class Renderer:
     @classmethod
     def from_pipeline_path(cls, model_path: Path, transforms_path: Path,
                            eval_num_rays_per_chunk: Optional[int] = None) -> "Renderer":
-        """renderer.py:116-141 builds a nerfstudio pipeline from ``config.yml`` + the last ``*.ckpt``.  That needs
-        nerfstudio (data managers, TrainerConfig); with it installed, register this package's model as the
-        method's ``_target`` (INTEGRATION.md) and construct ``Renderer(pipeline.model)``."""
-        raise ImportError("Renderer.from_pipeline_path needs nerfstudio's pipeline loader; build the pipeline with "
-                          "nerfstudio and pass pipeline.model to Renderer(model) (see INTEGRATION.md)")
+        """renderer.py:116-141: ``config.yml`` + the last ``*.ckpt`` of a training run -> a renderer on its model.
+        The pipeline (data manager, TrainerConfig unpickling, checkpoint layout) is nerfstudio's and the
+        reference's own loader builds it (``Renderer.extract_pipeline``, renderer.py:70-115);
+        ``nerfstudio_plugin.install()`` makes that loader construct the B200 model - also for runs trained with the
+        stock model, whose state_dict keys are the same.  Raises ImportError without nerfstudio + thermo_nerf."""
+        from . import nerfstudio_plugin
+
+        nerfstudio_plugin.install()  # raises ImportError naming what is missing
+        from thermo_nerf.render.renderer import Renderer as ReferenceRenderer  # type: ignore[import-not-found]
+
+        pipeline, _, _ = ReferenceRenderer.extract_pipeline(model_path=model_path, transforms_path=transforms_path,
+                                                            eval_num_rays_per_chunk=eval_num_rays_per_chunk)
+        return cls(pipeline.model)
 
     @staticmethod
     def load_cameras(load_camera_trajectory: Path, rendered_resolution_scaling_factor: float = 1.0) -> PinholeCameras:
