@@ -469,7 +469,45 @@ class NerfactoModel(nn.Module):
         return self.device_indicator_param.device
 
     def populate_modules(self) -> None:
-        raise NotImplementedError
+        """nerfstudio 1.1.5 NerfactoModel.populate_modules (the module tree ThermalNerfactoModel inherits for the
+        nerfacto / thermal-nerfacto model types; the reference's ThermalNerfModel overrides it, thermal_nerf_model.py:86-208)."""
+        cfg = self.config
+        distortion = None if cfg.disable_scene_contraction else SceneContraction(order=float("inf"))
+        self.field = NerfactoField(
+            self.scene_box.aabb, hidden_dim=cfg.hidden_dim, num_levels=cfg.num_levels, max_res=cfg.max_res,
+            base_res=cfg.base_res, features_per_level=cfg.features_per_level, log2_hashmap_size=cfg.log2_hashmap_size,
+            hidden_dim_color=cfg.hidden_dim_color, hidden_dim_transient=cfg.hidden_dim_transient,
+            spatial_distortion=distortion, num_images=self.num_train_data, use_pred_normals=cfg.predict_normals,
+            use_average_appearance_embedding=cfg.use_average_appearance_embedding,
+            appearance_embedding_dim=cfg.appearance_embed_dim if cfg.use_appearance_embedding else 0,
+            average_init_density=cfg.average_init_density, implementation=cfg.implementation)
+        self.camera_optimizer = cfg.camera_optimizer.setup(num_cameras=self.num_train_data, device="cpu")
+        self.density_fns = []
+        self.proposal_networks = nn.ModuleList()
+        for i in range(cfg.num_proposal_iterations):
+            a = cfg.proposal_net_args_list[min(i, len(cfg.proposal_net_args_list) - 1)]
+            net = HashMLPDensityField(self.scene_box.aabb, spatial_distortion=distortion, **a,
+                                      average_init_density=cfg.average_init_density, implementation=cfg.implementation)
+            self.proposal_networks.append(net)
+        self.density_fns.extend([net.density_fn for net in self.proposal_networks])
+
+        def update_schedule(step):
+            import numpy as np
+
+            return np.clip(np.interp(step, [0, cfg.proposal_warmup], [0, cfg.proposal_update_every]), 1,
+                           cfg.proposal_update_every)
+
+        self.proposal_sampler = ProposalNetworkSampler(
+            num_nerf_samples_per_ray=cfg.num_nerf_samples_per_ray,
+            num_proposal_samples_per_ray=cfg.num_proposal_samples_per_ray,
+            num_proposal_network_iterations=cfg.num_proposal_iterations, single_jitter=cfg.use_single_jitter,
+            update_sched=update_schedule, initial_sampler=None)
+        self.collider = NearFarCollider(near_plane=cfg.near_plane, far_plane=cfg.far_plane)
+        self.renderer_rgb = RGBRenderer(background_color=cfg.background_color)
+        self.renderer_accumulation = AccumulationRenderer()
+        self.renderer_depth = DepthRenderer(method="median")
+        self.renderer_expected_depth = DepthRenderer(method="expected")
+        self.rgb_loss = nn.MSELoss()
 
     def forward(self, ray_bundle: RayBundle):
         if self.collider is not None:
@@ -511,6 +549,11 @@ class NerfactoModel(nn.Module):
                 if torch.is_tensor(v):
                     chunks.setdefault(k, []).append(v)
         return {k: torch.cat(v).view(h, w, -1) for k, v in chunks.items()}
+
+    def get_param_groups(self):  # nerfstudio NerfactoModel.get_param_groups
+        groups = {"proposal_networks": list(self.proposal_networks.parameters()), "fields": list(self.field.parameters())}
+        self.camera_optimizer.get_param_groups(param_groups=groups)
+        return groups
 
     def get_metrics_dict(self, outputs, batch):
         metrics = {}

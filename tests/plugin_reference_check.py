@@ -62,6 +62,9 @@ def install_standins():
         m = types.ModuleType(name)
         m.__dict__.update(attrs)
         sys.modules[name] = m
+        parent, _, leaf = name.rpartition(".")
+        if parent:
+            setattr(sys.modules[parent], leaf, m)
     # recording stand-ins for the config classes (TrainerConfig, data managers, optimisers ...), with attribute access
     Cg.Recorded.__getattr__ = lambda self, n: self.__dict__["_kwargs"][n] if n in self.__dict__.get("_kwargs", {}) else (
         _ for _ in ()).throw(AttributeError(n))
@@ -69,8 +72,8 @@ def install_standins():
     def rec_setattr(self, n, v):
         if n in ("_args", "_kwargs"):
             object.__setattr__(self, n, v)
-        else:
-            self._kwargs[n] = v
+        else:  # dataclass subclasses of a recorded class never run Recorded.__init__
+            self.__dict__.setdefault("_kwargs", {})[n] = v
 
     Cg.Recorded.__setattr__ = rec_setattr
     sys.meta_path.append(Cg._Finder())
@@ -226,11 +229,11 @@ def main():
     check("renderer_frames_equal_reference_run", same)
     check("one_launch_per_frame_with_reference_chunking", all(c["chunk"] == 64 and c["rays"] == gold["hw"][0] * gold["hw"][1]
                                                               and c["near"] == 0.0 for c in calls), repr(calls[:2]))
-    r.render([Mod.RGB], cams)  # the stock model raises here ("img" vs "rgb", renderer.py:186-190); the alias fixes it
-    check("rgb_modality_renders", len(r._rendered_images[Mod.RGB]) == cams.size and gold["rgb_modality_error"] is not None)
     r.save_images(mods, Path("/nonexistent"))
     r.save_gif(mods, 2.5, Path("/nonexistent"))
     check("renderer_writes", len(written) > 0)
+    r.render([Mod.RGB], cams)  # the stock model raises here ("img" vs "rgb", renderer.py:186-190); the alias fixes it
+    check("rgb_modality_renders", len(r._rendered_images[Mod.RGB]) == cams.size and gold["rgb_modality_error"] is not None)
 
     # ---- the reference's Evaluator on the plugin model (isinstance at evaluator.py:76 included)
     import make_reference_evaluator_golden as Eg
