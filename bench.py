@@ -198,8 +198,9 @@ class OracleSchedule:
     def updated(self, step: int) -> bool:
         import numpy as np
 
-        sched = float(np.clip(np.interp(step, [0, 5000], [0, 5]), 1, 5))
-        return self.steps_since_update > sched or step < 10
+        prev = max(step - 1, 0)  # the sampler's _step is set by step_cb after an iteration: it lags by one
+        sched = float(np.clip(np.interp(prev, [0, 5000], [0, 5]), 1, 5))
+        return self.steps_since_update > sched or prev < 10
 
 
 def oracle_train_step(model, opts, batch, step: int, sched: "OracleSchedule" = None, scaler=None) -> float:

@@ -70,3 +70,43 @@ def test_save_round_trip_with_optimizer_state(tmp_path):
     assert load_nerfstudio_checkpoint(other, path) == 42
     for (k, a), (_, b) in zip(sorted(model.state_dict().items()), sorted(other.state_dict().items())):
         assert torch.equal(a, b), k
+
+
+REFERENCE_FIXTURE = "/root/reference/tests/data/vanilla_nerf/training-job/vanilla-nerf/date/nerfstudio_models/test_pipeline.ckpt"
+
+
+def test_foreign_keys_of_real_checkpoints_are_skipped_in_strict_mode():
+    """A genuine nerfstudio checkpoint carries metric networks (`_model.lpips.net.*`), derived `hash_offset` buffers and
+    the proposal encoder under two names (`encoding.*` and `mlp_base.0.*`): strict mode accepts those and still fails
+    on a missing or unexpected key of a module the model owns."""
+    model, trained = _small()
+    pipe = {"_model." + k: v.clone() for k, v in trained.state_dict().items()}
+    for i in range(20):  # the key pattern of the reference fixture
+        pipe[f"_model.lpips.net.lin{i % 5}.model.1.weight"] = torch.zeros(1, 8, 1, 1)
+    pipe["_model.field.mlp_base.encoder.hash_offset"] = torch.arange(16)
+    for i in range(2):
+        pipe[f"_model.proposal_networks.{i}.encoding.hash_offset"] = torch.arange(5)
+        pipe[f"_model.proposal_networks.{i}.mlp_base.0.hash_offset"] = torch.arange(5)
+        pipe[f"_model.proposal_networks.{i}.mlp_base.0.hash_table"] = pipe[f"_model.proposal_networks.{i}.encoding.hash_table"]
+        pipe[f"_model.proposal_networks.{i}.mlp_base.0.scalings"] = pipe[f"_model.proposal_networks.{i}.encoding.scalings"]
+    assert load_nerfstudio_checkpoint(model, {"step": 9, "pipeline": pipe}, strict=True) == 9
+    assert torch.equal(model.proposal_networks[1].encoding.hash_table, trained.proposal_networks[1].encoding.hash_table)
+    pipe["_model.field.mlp_extra.weight"] = torch.zeros(2)  # an unexpected key of an owned module still fails
+    with pytest.raises(KeyError):
+        load_nerfstudio_checkpoint(model, {"step": 9, "pipeline": pipe}, strict=True)
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(REFERENCE_FIXTURE), reason="needs the reference checkout")
+def test_envelope_of_the_reference_fixture_checkpoint():
+    """The reference's own fixture (a vanilla-NeRF run, so its field keys are not this model's): the envelope, the
+    `_model.` prefix and the step are read from the real file, and its LPIPS keys are the ones strict mode skips."""
+    from thermo_nerf_b200.checkpoint import _foreign
+
+    state, step = extract_model_state(REFERENCE_FIXTURE)
+    assert step == 1 and len(state) == 69
+    lp = [k for k in state if k.startswith("lpips.")]
+    assert len(lp) == 20 and all(_foreign(k) for k in lp)
+    assert any(k.startswith("field_coarse.mlp_base.layers.") for k in state)
+    model, _ = _small()
+    with pytest.raises(KeyError):  # a vanilla-NeRF checkpoint is not a ThermoNeRF one
+        load_nerfstudio_checkpoint(model, REFERENCE_FIXTURE)

@@ -355,7 +355,8 @@ def test_training_trajectory_tracks_oracle(precision, tol):
         gt_th = (0.5 + 0.4 * torch.cos(rays.directions[:, :1] * 5.0)).float()
         jitter = torch.rand((3, R, 1), generator=gen)
         # ---- oracle: what Trainer.train_iteration does around the reference model
-        updated = since_update > model.update_schedule(step) or step < 10
+        prev = max(step - 1, 0)  # the sampler's _step is set by step_cb AFTER an iteration: it lags by one
+        updated = since_update > model.update_schedule(prev) or prev < 10
         oracle.set_anneal_for_step(step)
         opt_f.zero_grad(); opt_p.zero_grad()
         out = oracle.get_outputs(rays, training=True, jitter=jitter, prop_grad=updated)

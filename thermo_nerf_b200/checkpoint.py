@@ -32,6 +32,18 @@ KEY_ALIASES = {
 }
 
 
+# model tensors a genuine nerfstudio checkpoint carries that are not part of the hot path and that this model does
+# not own: the metric networks registered on the nerfstudio Model (the reference fixture
+# tests/data/vanilla_nerf/.../test_pipeline.ckpt holds 20 `_model.lpips.net.*` entries), and derived buffers of the
+# hash encodings under either spelling of the proposal networks' encoder (`encoding.` and `mlp_base.0.`)
+IGNORED_PREFIXES = ("lpips.", "psnr.", "ssim.", "collider.", "renderer_", "normals_shader.")
+IGNORED_SUFFIXES = (".hash_offset",)
+
+
+def _foreign(key: str) -> bool:
+    return key.startswith(IGNORED_PREFIXES) or key.endswith(IGNORED_SUFFIXES)
+
+
 def extract_model_state(checkpoint: Union[str, Path, Mapping]) -> Tuple[Dict[str, Tensor], int]:
     """(model state_dict without the pipeline prefix, step) from a checkpoint path / loaded envelope / bare
     pipeline state_dict."""
@@ -52,7 +64,9 @@ def extract_model_state(checkpoint: Union[str, Path, Mapping]) -> Tuple[Dict[str
 
 def load_nerfstudio_checkpoint(model: torch.nn.Module, checkpoint: Union[str, Path, Mapping], strict: bool = True) -> int:
     """Load a ThermoNeRF (torch-implementation) nerfstudio checkpoint into ``model``; returns the training step.
-    Tensors of components outside the hot path that this model does not own are ignored only with strict=False."""
+    ``strict`` fails on missing or unexpected keys of the modules this model owns (field, proposal networks, camera
+    optimiser); tensors of components outside the hot path (``IGNORED_PREFIXES``: LPIPS / PSNR / SSIM metric networks,
+    ``*.hash_offset`` derived buffers) are skipped in either mode - every real nerfstudio checkpoint has them."""
     state, step = extract_model_state(checkpoint)
     if any(k.endswith(".params") or ".tcnn_encoding." in k for k in state):
         raise NotImplementedError(
@@ -60,10 +74,10 @@ def load_nerfstudio_checkpoint(model: torch.nn.Module, checkpoint: Union[str, Pa
             "libtnf_b200 follows the torch implementation's hash encoding and cannot reinterpret those tables")
     state = {KEY_ALIASES.get(k, k): v for k, v in state.items()}
     own = model.state_dict()
-    for k in ("field.mlp_base.encoder.hash_offset",) + tuple(
-            f"proposal_networks.{i}.encoding.hash_offset" for i in range(8)):
-        if k in state and k not in own:
-            state.pop(k)  # derived buffer (level * table size); recomputed from the config here
+    state = {k: v for k, v in state.items() if k in own or not _foreign(k)}
+    # nn.Sequential(encoding, mlp) registers the proposal encoder twice: `encoding.*` and `mlp_base.0.*`
+    state = {k: v for k, v in state.items()
+             if not (k not in own and ".mlp_base.0." in k and k.replace(".mlp_base.0.", ".encoding.") in state)}
     for k, v in state.items():
         if k in own and tuple(own[k].shape) != tuple(v.shape):
             raise ValueError(f"{k}: checkpoint shape {tuple(v.shape)} != model shape {tuple(own[k].shape)} "

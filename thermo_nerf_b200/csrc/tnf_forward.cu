@@ -664,6 +664,17 @@ int check_linear(const TnfLinear& l, const char* name) {
 }  // namespace
 
 namespace tnf {
+// The run-merged scatter identifies a grid cell by its floor coordinates packed into 11 bits each (HashCorners::k1):
+// unique for grid resolutions below 2048.  nerfacto's default field tops out at 2047; nerfacto-big / -huge
+// (max_res 4096 / 8192) would alias cells and corrupt hash-table gradients, so they are rejected here.
+static int check_scalings(const TnfHashGrid& g, const char* name) {
+  for (int l = 0; l < g.num_levels; ++l)
+    if (!(g.scalings[l] > 0.f) || !(g.scalings[l] < 2048.f))
+      return fail(TNF_ERR_UNSUPPORTED_CONFIG, "%s: scalings[%d]=%g outside (0, 2048): the kernels are built for "
+                  "max_res < 2048", name, l, (double)g.scalings[l]);
+  return TNF_OK;
+}
+
 int check_model(const TnfModel* m) {
   if (!m) return fail(TNF_ERR_INVALID_ARGUMENT, "model is null");
   for (int k = 0; k < TNF_NUM_PROP; ++k) {
@@ -676,6 +687,7 @@ int check_model(const TnfModel* m) {
       return fail(TNF_ERR_UNSUPPORTED_CONFIG, "prop[%d]: log2_size=%d not in [1,24]", k, n.grid.log2_size);
     if (int e = check_linear(n.l0, "prop.l0")) return e;
     if (int e = check_linear(n.l1, "prop.l1")) return e;
+    if (int e = check_scalings(n.grid, "prop.grid")) return e;
   }
   const TnfField& f = m->field;
   if (!f.grid.table) return fail(TNF_ERR_INVALID_ARGUMENT, "field.grid.table is null");
@@ -684,6 +696,7 @@ int check_model(const TnfModel* m) {
                 TNF_MAX_LEVELS);
   if (f.grid.log2_size < 1 || f.grid.log2_size > 24)
     return fail(TNF_ERR_UNSUPPORTED_CONFIG, "field: log2_size=%d not in [1,24]", f.grid.log2_size);
+  if (int e = check_scalings(f.grid, "field.grid")) return e;
   const TnfLinear* ls[] = {&f.base0, &f.base1, &f.rgb0, &f.rgb1, &f.rgb2, &f.th0, &f.th1, &f.th2};
   for (const TnfLinear* l : ls)
     if (int e = check_linear(*l, "field linear")) return e;

@@ -15,6 +15,8 @@
 #include <cstring>
 
 #include "tnf_device.cuh"
+#include <cstdlib>
+
 #include "tnf_host.h"
 
 namespace tnf {
@@ -110,9 +112,11 @@ __global__ void __launch_bounds__(256) tnf_peer_gather_kernel(const __grid_const
 
 // Flag barrier over peer-mapped words: rank r writes `epoch` into word [slot][r] of every rank's flag block
 // (release, system scope) and waits until every word of its own block reached `epoch` (acquire).
-// The wait is bounded (~2 s of SM clocks): a missing peer raises word [TNF_PEER_FLAG_TIMEOUT] instead of
-// hanging the GPU.
-__global__ void tnf_peer_barrier_kernel(const __grid_constant__ TnfPeerArena a, const int slot, const unsigned epoch) {
+// The wait is bounded (`limit` SM cycles; TNF_PEER_TIMEOUT_S seconds, default 60): a peer that never arrives is
+// FATAL - word [TNF_PEER_FLAG_TIMEOUT] is raised and the kernel traps, so the next CUDA call of this rank fails
+// instead of the step carrying on with stale or zeroed peer gradients (ranks would diverge silently).
+__global__ void tnf_peer_barrier_kernel(const __grid_constant__ TnfPeerArena a, const int slot, const unsigned epoch,
+                                        const long long limit) {
   const int t = threadIdx.x;
   if (t >= a.world_size) return;
   __threadfence_system();
@@ -124,9 +128,10 @@ __global__ void tnf_peer_barrier_kernel(const __grid_constant__ TnfPeerArena a, 
   for (;;) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(src) : "memory");
     if ((int)(seen - epoch) >= 0) break;
-    if (clock64() - t0 > 4000000000LL) {
+    if (clock64() - t0 > limit) {
       atomicAdd(a.flags[a.rank] + TNF_PEER_FLAG_TIMEOUT, 1u);
-      break;
+      __threadfence_system();
+      __trap();
     }
   }
   __threadfence_system();
@@ -234,7 +239,13 @@ int tnf_peer_barrier(const TnfPeerArena* arena, int32_t slot, uint32_t epoch, vo
   tnf::g_err[0] = 0;
   if (int rc = check_arena(arena)) return rc;
   if (slot < 0 || slot >= TNF_PEER_FLAG_SLOTS) return fail(TNF_ERR_INVALID_ARGUMENT, "slot=%d", slot);
-  tnf::tnf_peer_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream_)>>>(*arena, slot, epoch);
+  static long long limit = 0;
+  if (limit == 0) {  // seconds of SM clock at ~2 GHz; generous: a rank may be saving a checkpoint or evaluating
+    const char* v = getenv("TNF_PEER_TIMEOUT_S");
+    const double sec = v ? atof(v) : 60.0;
+    limit = (long long)((sec > 0.01 ? sec : 0.01) * 2.0e9);
+  }
+  tnf::tnf_peer_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream_)>>>(*arena, slot, epoch, limit);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "peer barrier launch: %s", cudaGetErrorString(e));
   return TNF_OK;

@@ -87,7 +87,15 @@ class TrainEngine:
         self.field_steps = 0         # Adam step counters (a tensor without gradient does not advance)
         self.prop_steps = 0
         self.steps_since_update = 0
+        self.sampler_step = 0        # ProposalNetworkSampler._step: the step of the PREVIOUS iteration (step_cb)
         self._ws: Optional[Tensor] = None
+        mode = getattr(getattr(model, "camera_optimizer", None), "mode", "off")
+        if mode != "off":
+            # the engine feeds origins / directions straight to the kernels: pose refinement lives in the
+            # autograd route (model(ray_bundle) ... FusedAdam), which applies the deltas and trains pose_adjustment
+            raise ValueError(f"TrainEngine does not train the camera optimiser (camera_optimizer_mode={mode!r}): build "
+                             "the model with camera_optimizer_mode='off' or use the plugin route, whose backward "
+                             "returns dL/d origins and dL/d directions")
 
     # ---- reference schedules -------------------------------------------------------------
     def anneal(self, step: int) -> float:
@@ -97,8 +105,11 @@ class TrainEngine:
         f = float(np.clip(step / n, 0, 1))
         return b * f / ((b - 1) * f + 1)
 
-    def prop_updated(self, step: int) -> bool:
-        return self.steps_since_update > self.model.update_schedule(step) or step < 10
+    def prop_updated(self, step: Optional[int] = None) -> bool:
+        """ProposalNetworkSampler.generate_ray_samples: the schedule and the `< 10` warm-up are evaluated with the
+        sampler's `_step`, which step_cb sets AFTER each iteration - i.e. with the previous iteration's step."""
+        s = self.sampler_step if step is None else step
+        return self.steps_since_update > self.model._update_schedule(s) or s < 10
 
     # ---- one iteration -------------------------------------------------------------------
     def step(self, origins: Tensor, directions: Tensor, camera_indices: Tensor, gt_rgb: Tensor, gt_thermal: Tensor,
@@ -109,7 +120,7 @@ class TrainEngine:
         R = int(origins.shape[0])
         if jitter is None:
             jitter = torch.rand((L.TNF_NUM_PROP + 1, R), device=self.device)
-        updated = self.prop_updated(step)
+        updated = self.prop_updated()
         kw = dict(num_samples=(*cfg.num_proposal_samples_per_ray, cfg.num_nerf_samples_per_ray),
                   near_plane=cfg.near_plane, far_plane=cfg.far_plane, anneal=self.anneal(step),
                   use_contraction=not cfg.disable_scene_contraction,
@@ -151,8 +162,9 @@ class TrainEngine:
             self._adam(slice(NUM_PROP_TENSORS, len(self.params)), lr, self.field_steps)
             if updated:
                 self._adam(slice(0, NUM_PROP_TENSORS), lr, self.prop_steps)
+        self.sampler_step = step      # ProposalNetworkSampler.step_cb (AFTER_TRAIN_ITERATION)
+        self.steps_since_update += 1
         self.step_count += 1
-        self.steps_since_update += 1  # ProposalNetworkSampler.step_cb (AFTER_TRAIN_ITERATION)
         return losses
 
     def _adam(self, sl: slice, lr: float, step: int) -> None:
@@ -162,10 +174,12 @@ class TrainEngine:
 
     def state_dict(self) -> Dict[str, object]:
         return {"step": self.step_count, "field_steps": self.field_steps, "prop_steps": self.prop_steps,
-                "steps_since_update": self.steps_since_update, "exp_avg": self.m_arena, "exp_avg_sq": self.v_arena}
+                "steps_since_update": self.steps_since_update, "sampler_step": self.sampler_step,
+                "exp_avg": self.m_arena, "exp_avg_sq": self.v_arena}
 
     def load_state_dict(self, sd: Dict[str, object]) -> None:
         self.step_count, self.field_steps = int(sd["step"]), int(sd["field_steps"])
         self.prop_steps, self.steps_since_update = int(sd["prop_steps"]), int(sd["steps_since_update"])
+        self.sampler_step = int(sd.get("sampler_step", max(self.step_count - 1, 0)))
         self.m_arena.copy_(sd["exp_avg"])
         self.v_arena.copy_(sd["exp_avg_sq"])

@@ -54,6 +54,9 @@ class HashEncoding(nn.Module):
         super().__init__()
         if features_per_level != 2:
             raise ValueError("libtnf_b200 kernels are built for features_per_level == 2")
+        if max_res >= 2048 + 1:  # the scatter's cell key packs grid coordinates into 11 bits (tnf_device.cuh)
+            raise ValueError(f"libtnf_b200 kernels are built for max_res <= 2048 (got {max_res}): nerfacto-big / -huge "
+                             "grids would alias cells in the hash-table gradient scatter")
         self.num_levels = num_levels
         self.min_res = min_res
         self.max_res = max_res
