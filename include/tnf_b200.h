@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define TNF_ABI_VERSION 7
+#define TNF_ABI_VERSION 8
 
 #define TNF_MAX_LEVELS 16      /* hash levels of the field grid (fixed: 16)          */
 #define TNF_MAX_PROP_LEVELS 8  /* max hash levels of a proposal density grid          */
@@ -73,6 +73,19 @@ typedef enum TnfPrecision {
 
 /* nerfstudio HashEncoding, torch layout: table [num_levels << log2_size, 2] fp32,
  * level-major; `scalings` is the registered buffer (host copy). */
+/* Which field head produces the temperature channel.
+ *   THERMAL  ThermalNerfModel: colour head 63-64-64-3 + thermal head 15-64-64-1, both composited with the
+ *            last sample as background (thermal_field.py:160-179, thermal_renderer.py:49).
+ *   CONCAT   ConcatNerfModel (the `concat_nerf` model type, train_eval_script.py:74-78): one 4-channel RGBT
+ *            colour head (rgb_concat/concat_field.py:65-75: field.rgb2 is [4,64] / [4]), no thermal head (its
+ *            tensors are ignored), RGBTRenderer with its default "random" background = plain weighted sum, no
+ *            background term (rgb_concat/rgbt_renderer.py:63-71).  out.rgb carries channels 0-2 and out.thermal
+ *            channel 3 of the 4-channel "rgb" output. */
+typedef enum TnfHeadMode {
+  TNF_HEAD_THERMAL = 0,
+  TNF_HEAD_CONCAT = 1
+} TnfHeadMode;
+
 typedef struct TnfHashGrid {
   const float* table;
   float scalings[TNF_MAX_LEVELS];
@@ -123,7 +136,7 @@ typedef struct TnfModel {
   int32_t precision;       /* TnfPrecision                                                    */
   int32_t detach_thermal_geo; /* 1: pass_thermal_gradients == False (thermal_field.py:173-175): the
                                  thermal head's gradient stops at the geo feature                */
-  int32_t _pad;
+  int32_t head_mode;       /* TnfHeadMode                                                      */
 } TnfModel;
 
 /* One perspective camera without distortion, as nerfstudio's Cameras holds it (the cameras the reference
@@ -321,6 +334,15 @@ typedef struct TnfLossArgs {
   float* g_rgb;                        /* [R,3] or NULL */
   float* g_thermal;                    /* [R]   or NULL */
   float* g_weights[TNF_NUM_PROP + 1];  /* [R,S_k] or NULL */
+  /* concat_nerf loss (rgb_concat/concat_nerfacto_model.py:197-233, rgbt_renderer.py:118-140): with concat != 0
+   * losses[0] = MSE over the 4 channels [rgb | thermal] of pred + noise * (1 - accumulation) against
+   * [gt_rgb | gt_thermal] (the renderer's "random" background is blended into the prediction only; `noise` is the
+   * caller's torch.rand_like(pred) draw), losses[3] = 0, and g_accumulation receives d losses[0] / d accumulation. */
+  int32_t concat;
+  int32_t _pad;
+  const float* accumulation;  /* [R]   */
+  const float* noise;         /* [R,4] */
+  float* g_accumulation;      /* [R] or NULL */
 } TnfLossArgs;
 
 int tnf_losses(const TnfLossArgs* args, void* stream);
@@ -434,6 +456,16 @@ int tnf_peer_adam_step(const TnfPeerArena* arena, float* exp_avg_shard, float* e
 int tnf_peer_adam_reduce(const TnfPeerArena* arena, float* exp_avg_shard, float* exp_avg_sq_shard,
                          const TnfAdamSegment* segments, int32_t num_segments, double beta1, double beta2, float eps,
                          void* stream);
+/* The same exchange through NVSwitch multicast (NVLS): `grads_multicast` / `params_multicast` are the multicast
+ * addresses of the gradient and parameter arenas (every rank's arena bound to one multicast object, e.g. by
+ * torch.distributed._symmetric_memory).  multimem.ld_reduce forms the sum over ranks inside the switch and
+ * multimem.st replicates the updated shard into every rank's parameters: each rank moves 1/N of the arena per
+ * direction instead of (N-1)/N.  Replaces DDP's all-reduce + the optimisers of config_thermal_nerf.py:32-45 like
+ * tnf_peer_adam_step; bracket it with the same two tnf_peer_barrier calls. */
+int tnf_peer_adam_multimem(const TnfPeerArena* arena, const float* grads_multicast, float* params_multicast,
+                           float* exp_avg_shard, float* exp_avg_sq_shard, const TnfAdamSegment* segments,
+                           int32_t num_segments, double beta1, double beta2, float eps, void* stream);
+
 int tnf_peer_gather_params(const TnfPeerArena* arena, const TnfAdamSegment* segments, int32_t num_segments,
                            void* stream);
 

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_plugin_gpu.py -q 2>&1 | tail -5
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -25
 echo "=== bench default"
 timeout 900 python bench.py 2>gpurun_out/bench_d.err > gpurun_out/bench_d.json; grep -E "Elapsed|Error|error" gpurun_out/bench_d.err | tail -5
 python - <<'PY'

@@ -291,6 +291,21 @@ def main():
     check("nerfacto_family", isinstance(m3, ThermalNerfactoModel) and not isinstance(m3, ThermalNerfModel)
           and float(t.field_linears["th2"].weight.abs().sum()) == 0.0 and not m3._has_thermal_head()
           and not any("thermal" in k for k in m3.state_dict()))
+    # ---- concat_nerf family: the reference's ConcatNerfModel / ConcatNerfactoTField / RGBTRenderer code builds the
+    #      modules, the kernels get head_mode = concat and a [4, 64] last colour layer
+    from thermo_nerf.rgb_concat.concat_nerfacto_model import ConcatNerfModel
+
+    ccfg = P.B200ConcatNerfModelConfig(**Wg.MINI)
+    m4 = ccfg.setup(scene_box=box, num_train_data=Wg.NUM_IMAGES)
+    from thermo_nerf_b200 import _lib as L
+
+    check("concat_family", isinstance(m4, ConcatNerfModel) and isinstance(m4, ThermalNerfactoModel) and m4._is_concat()
+          and tuple(m4.tensors().field_linears["rgb2"].weight.shape) == (4, 64)
+          and m4._render_kwargs()["head_mode"] == L.HEAD_CONCAT and not m4._has_thermal_head()
+          and type(m4).get_image_metrics_and_images is ConcatNerfModel.get_image_metrics_and_images)
+    from thermo_nerf.rgb_concat.config_concat_nerfacto import concat_nerf_config
+
+    check("install_swaps_concat_config", type(concat_nerf_config.pipeline.model) is P.B200ConcatNerfModelConfig)
 
 
 if __name__ == "__main__":

@@ -62,7 +62,8 @@ def test_engine_with_fused_exchange_trains():
 
     losses = {}
     for fused in (False, True):
-        _, model = make_pair(trained_like=False, precision="tc_fp16", log2_field=14, log2_prop=12)
+        _, model = make_pair(trained_like=False, precision="tc_fp16", log2_field=14, log2_prop=12,
+                             camera_optimizer_mode="off")
         model.train()
         eng = TrainEngine(model, peer_fused=fused)
         rays = make_synthetic_rays(1024, num_images=8, seed=5)
@@ -93,12 +94,13 @@ def _free_port() -> int:
         return s.getsockname()[1]
 
 
-def _worker(rank: int, world: int, port: int, q) -> None:
+def _worker(rank: int, world: int, port: int, q, backend: str = "auto") -> None:
     import torch.distributed as dist
 
     from thermo_nerf_b200.dist import PeerArena
 
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    os.environ["TNF_PEER_BACKEND"] = backend
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -122,35 +124,47 @@ def _worker(rank: int, world: int, port: int, q) -> None:
 
             F.adam_step([p_ref], [mean], [m_ref], [v_ref], [1e-2], step=step, eps=1e-15)
             torch.cuda.synchronize()
-            ok = ok and bool(torch.equal(arena.params, p_ref)) and arena.grads.abs().max().item() == 0.0
+            # peer loads sum in rank order like the reference below: bitwise.  The in-switch reduction (multimem) may
+            # sum in another order: exact for two ranks (one addition), last-bit differences beyond
+            exact = arena.gather != "multimem" or world == 2
+            same_p = torch.equal(arena.params, p_ref) if exact else torch.allclose(arena.params, p_ref, rtol=2e-6, atol=1e-7)
+            ok = ok and bool(same_p) and arena.grads.abs().max().item() == 0.0
             lo, hi = arena.shard * rank, arena.shard * (rank + 1)
-            ok = ok and bool(torch.equal(arena.exp_avg, m_ref[lo:hi]))
+            same_m = (torch.equal(arena.exp_avg, m_ref[lo:hi]) if exact
+                      else torch.allclose(arena.exp_avg, m_ref[lo:hi], rtol=2e-6, atol=1e-7))
+            ok = ok and bool(same_m)
+            if not exact:
+                p_ref.copy_(arena.params)  # keep following the kernel's own trajectory
         # every rank holds the same parameters
         chk = arena.params.double().sum().reshape(1)
         both = [torch.zeros_like(chk) for _ in range(world)]
         dist.all_gather(both, chk)
         same = all(float(b) == float(both[0]) for b in both)
-        q.put((rank, ok, same, arena.timeouts()))
+        q.put((rank, ok, same, arena.timeouts(), arena.gather, bool(arena.multicast)))
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 @pytest.mark.timeout(300)
-def test_world2_fused_exchange_matches_mean_then_adam():
+@pytest.mark.parametrize("backend", ["ipc", "auto"])
+def test_world2_fused_exchange_matches_mean_then_adam(backend):
+    """backend "ipc": our own CUDA-IPC mapping, peer loads / stores.  "auto": torch symmetric memory and, where the
+    NVSwitch multicast object exists, the in-switch reduction + broadcast (multimem.ld_reduce / multimem.st)."""
     import torch.multiprocessing as mp
 
-    world = 2
+    world = min(torch.cuda.device_count(), 8) if os.environ.get("TNF_TEST_ALL_GPUS") else 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, backend)) for r in range(world)]
     for p in procs:
         p.start()
     out = [q.get(timeout=120) for _ in range(world)]
     for p in procs:
         p.join(timeout=30)
         assert p.exitcode == 0
-    for rank, ok, same, timeouts in out:
-        assert ok, f"rank {rank}: fused result differs from mean-then-Adam"
+    for rank, ok, same, timeouts, gather, multicast in out:
+        assert ok, f"rank {rank}: fused result differs from mean-then-Adam ({gather})"
         assert same and timeouts == 0
+    print(f"backend={backend}: exchange flavour {out[0][4]}, multicast {out[0][5]}")

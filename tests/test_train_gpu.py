@@ -422,3 +422,36 @@ def test_backward_ragged_ray_and_sample_counts(precision):
         if err > (tol_t if k.endswith("hash_table") else tol_g):
             bad.append((k, err))
     assert not bad, bad
+
+
+def test_engine_step_from_host_batches_equals_the_device_step():
+    """TrainEngine.step_host (pinned host batch -> persistent device buffers -> step) is the same iteration as
+    TrainEngine.step on device tensors: identical losses and parameters for identical jitter draws."""
+    from thermo_nerf_b200.engine import TrainEngine
+
+    R = 256
+    rays = make_synthetic_rays(R, num_images=8, seed=21)
+    gt_rgb = (0.5 + 0.4 * torch.sin(rays.directions * 7.0)).float()
+    gt_th = (0.5 + 0.4 * torch.cos(rays.directions[:, 0] * 5.0)).float()
+    results = []
+    for host in (False, True):
+        _, model = make_pair(trained_like=False, precision="tc_fp16", log2_field=12, log2_prop=10,
+                             camera_optimizer_mode="off")
+        model.train()
+        eng = TrainEngine(model)
+        torch.manual_seed(5)
+        for _ in range(3):
+            if host:
+                batch = [t.pin_memory() for t in (rays.origins, rays.directions, rays.camera_indices.reshape(-1), gt_rgb, gt_th)]
+                ls = eng.step_host(*batch)
+            else:
+                ls = eng.step(rays.origins.cuda(), rays.directions.cuda(), rays.camera_indices.cuda().reshape(-1),
+                              gt_rgb.cuda(), gt_th.cuda())
+        torch.cuda.synchronize()
+        results.append((ls.cpu(), model.field.mlp_head.layers[1].weight.detach().cpu().clone()))
+    # hash-table gradients are summed with atomics: last-bit differences between two runs are expected
+    assert torch.allclose(results[0][0], results[1][0], rtol=1e-4, atol=1e-6)
+    assert torch.allclose(results[0][1], results[1][1], rtol=1e-3, atol=1e-5)
+    with pytest.raises(ValueError, match="camera optimiser"):
+        _, m2 = make_pair(trained_like=False, log2_field=12, log2_prop=10, camera_optimizer_mode="SO3xR3")
+        TrainEngine(m2)

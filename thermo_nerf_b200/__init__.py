@@ -7,7 +7,8 @@ binding of ``include/tnf_b200.h``), ``functional`` (tensor-level entry points),
 
 from . import _lib
 from .functional import ModelTensors, adam_step, losses, render, render_forward
-from .model import ThermalNerfactoModel, ThermalNerfactoModelConfig, ThermalNerfModel, ThermalNerfModelConfig
+from .model import (ConcatNerfModel, ConcatNerfModelConfig, ThermalNerfactoModel, ThermalNerfactoModelConfig,
+                    ThermalNerfModel, ThermalNerfModelConfig)
 from .optim import FusedAdam
 from .modules import (CameraOptimizer, FieldHeadNames, FieldHeadNamesT, HashMLPDensityField, ThermalFieldHead,
                       ThermalNerfactoTField)
@@ -17,7 +18,7 @@ from .data import DevicePixelSampler
 from .evaluator import Evaluator
 
 __all__ = [
-    "ModelTensors", "render_forward", "render", "losses", "adam_step", "FusedAdam", "ThermalNerfModel", "ThermalNerfModelConfig", "ThermalNerfactoModel", "ThermalNerfactoModelConfig", "CameraOptimizer",
+    "ModelTensors", "render_forward", "render", "losses", "adam_step", "FusedAdam", "ThermalNerfModel", "ThermalNerfModelConfig", "ThermalNerfactoModel", "ThermalNerfactoModelConfig", "ConcatNerfModel", "ConcatNerfModelConfig", "CameraOptimizer",
     "FieldHeadNames", "FieldHeadNamesT", "HashMLPDensityField", "ThermalFieldHead", "ThermalNerfactoTField",
     "PinholeCameras", "RayBundle", "orbit_cameras", "sphere_cameras", "Renderer", "RenderedImageModality", "DevicePixelSampler", "Evaluator",
 ]

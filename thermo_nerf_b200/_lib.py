@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 from typing import Optional
 
-TNF_ABI_VERSION = 7
+TNF_ABI_VERSION = 8
 TNF_MAX_LEVELS = 16
 TNF_MAX_PROP_LEVELS = 8
 TNF_MAX_SAMPLES = 256
@@ -26,6 +26,7 @@ TNF_ERR_CUDA = -4
 
 APPEARANCE_ZEROS, APPEARANCE_MEAN, APPEARANCE_LOOKUP = 0, 1, 2
 PRECISION_FP32, PRECISION_TC_FP16 = 0, 1
+HEAD_THERMAL, HEAD_CONCAT = 0, 1
 
 _fp = C.c_void_p  # device pointers cross the ABI as plain addresses
 
@@ -78,7 +79,7 @@ class TnfModel(C.Structure):
         ("appearance_mode", C.c_int32),
         ("precision", C.c_int32),
         ("detach_thermal_geo", C.c_int32),
-        ("_pad", C.c_int32),
+        ("head_mode", C.c_int32),
     ]
 
 
@@ -205,6 +206,11 @@ class TnfLossArgs(C.Structure):
         ("g_rgb", _fp),
         ("g_thermal", _fp),
         ("g_weights", _fp * (TNF_NUM_PROP + 1)),
+        ("concat", C.c_int32),
+        ("_pad", C.c_int32),
+        ("accumulation", _fp),
+        ("noise", _fp),
+        ("g_accumulation", _fp),
     ]
 
 
@@ -277,6 +283,7 @@ EXPORTED_SYMBOLS = (
     "tnf_peer_barrier",
     "tnf_peer_adam_step",
     "tnf_peer_adam_reduce",
+    "tnf_peer_adam_multimem",
     "tnf_peer_gather_params",
 )
 
@@ -389,6 +396,10 @@ def load() -> C.CDLL:
     lib.tnf_peer_adam_step.restype = C.c_int
     lib.tnf_peer_adam_step.argtypes = [C.POINTER(TnfPeerArena), C.c_void_p, C.c_void_p, C.POINTER(TnfAdamSegment),
                                        C.c_int32, C.c_double, C.c_double, C.c_float, C.c_void_p]
+    lib.tnf_peer_adam_multimem.restype = C.c_int
+    lib.tnf_peer_adam_multimem.argtypes = [C.POINTER(TnfPeerArena), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.POINTER(TnfAdamSegment), C.c_int32, C.c_double, C.c_double, C.c_float,
+                                           C.c_void_p]
     lib.tnf_peer_adam_reduce.restype = C.c_int
     lib.tnf_peer_adam_reduce.argtypes = lib.tnf_peer_adam_step.argtypes
     lib.tnf_peer_gather_params.restype = C.c_int

@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FieldBwdSmem32& S = *reinterpret_cast<FieldBwdSmem32*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  stage_field(S.fw, m.field, tid);
+  stage_field(S.fw, m.field, tid, kThreads, m.head_mode == TNF_HEAD_CONCAT ? 4 : 3);
   __syncthreads();
   const FieldW32& W = S.fw;
   FieldBwdScratch& ws = S.ws[warp];
@@ -590,8 +590,12 @@ __global__ void __launch_bounds__(kThreads, 1)
       const float sel = normalise_position(m, ray_x(rc, mid), ray_y(rc, mid), ray_z(rc, mid), px, py, pz);
       // upstream gradients of this sample (zero for padding lanes: every product below vanishes)
       const float dsig = active ? ws.dsig[ii] : 0.f;
-      const float dz[3] = {active ? ws.dzr[ii] : 0.f, active ? ws.dzg[ii] : 0.f, active ? ws.dzb[ii] : 0.f};
-      const float dtau = active ? ws.dtau[ii] : 0.f;
+      // ws.dtau: thermal head -> dL/d thermal_i; RGBT head (concat_nerf) -> dL/d(pre-sigmoid channel 3)
+      const bool concat = m.head_mode == TNF_HEAD_CONCAT;
+      const float dt = active ? ws.dtau[ii] : 0.f;
+      const float dz[4] = {active ? ws.dzr[ii] : 0.f, active ? ws.dzg[ii] : 0.f, active ? ws.dzb[ii] : 0.f,
+                           concat ? dt : 0.f};
+      const float dtau = concat ? 0.f : dt;
       // ---- forward recompute: F -> H -> G
       {
         const float4* fr = reinterpret_cast<const float4*>(F + row * 32);
@@ -650,10 +654,10 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
         for (int n = 0; n < 64; ++n) {
           const float4 w2 = *reinterpret_cast<const float4*>(W.rgb2t + n * 4);
-          y[n] = y[n] > 0.f ? dz[0] * w2.x + dz[1] * w2.y + dz[2] * w2.z : 0.f;
+          y[n] = y[n] > 0.f ? dz[0] * w2.x + dz[1] * w2.y + dz[2] * w2.z + dz[3] * w2.w : 0.f;
         }
         if (active) stage_row(L.dA2, row, kWX, 0, y);
-        float z8[8] = {dz[0], dz[1], dz[2], 0.f, 0.f, 0.f, 0.f, 0.f};
+        float z8[8] = {dz[0], dz[1], dz[2], dz[3], 0.f, 0.f, 0.f, 0.f};
         if (active) stage_row(L.dZ, row, kWdZ, 0, z8);
         dense_row_t<64, 64, true, false>(W.rgb1t, y, a);  // a: A1 -> dA1pre
         load_col(a, y);
@@ -835,7 +839,7 @@ int assign_wgrad_ctas(tnf::WgradArgs& a, int total_ctas) {
 // the eight field layers (+ the two per-ray blocks of mlp_head.layers.0) as GEMM problems of the fp32 mode:
 // plain row-major fp32 staging, dGeo = [Ns,128] (colour | thermal layer-0 gradients).
 void field_problems(tnf::WgradArgs& a, const tnf::BwdLayout& L, const void* XF, const TnfFieldGrad& g, long long Ns,
-                    long long R) {
+                    long long R, int nout) {
   using namespace tnf;
   a.n = 0;
   auto off = [&](const unsigned char* p, size_t elems) { return static_cast<const void*>(p + elems * 4); };
@@ -844,7 +848,7 @@ void field_problems(tnf::WgradArgs& a, const tnf::BwdLayout& L, const void* XF, 
   add_problem(a, L.dGeo, kWdGeo, 0, 64, 64, L.XG, kWXG, 16, 1, Ns, g.rgb0.weight, 63, 16, nullptr);
   add_problem(a, L.dGeo, kWdGeo, 64, 64, 64, L.XG, kWXG, 16, 1, Ns, g.th0.weight, 15, 0, g.th0.bias);
   add_problem(a, L.dA2, kWX, 0, 64, 64, L.XA1, kWX, 64, 0, Ns, g.rgb1.weight, 64, 0, g.rgb1.bias);
-  add_problem(a, L.dZ, kWdZ, 0, 8, 3, L.XA2, kWX, 64, 0, Ns, g.rgb2.weight, 64, 0, g.rgb2.bias);
+  add_problem(a, L.dZ, kWdZ, 0, 8, nout, L.XA2, kWX, 64, 0, Ns, g.rgb2.weight, 64, 0, g.rgb2.bias);
   add_problem(a, L.dB2, kWX, 0, 64, 64, L.XB1, kWX, 64, 0, Ns, g.th1.weight, 64, 0, g.th1.bias);
   add_problem(a, L.dT, kWdT, 0, 8, 1, L.XB2, kWX, 64, 0, Ns, g.th2.weight, 64, 0, g.th2.bias);
   add_problem(a, L.dRay, kWdRay, 0, 64, 64, L.XRay, kWXRay, 16, 0, R, g.rgb0.weight, 63, 0, g.rgb0.bias);
@@ -953,7 +957,7 @@ int tnf_render_backward(const TnfModel* model, const TnfRays* rays, const TnfSav
         *model, *rays, *saved, *gout, *grads, L);
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "backward_field launch: %s", cudaGetErrorString(e));
-  field_problems(wa, L, saved->field_features, grads->field, Ns, R);
+  field_problems(wa, L, saved->field_features, grads->field, Ns, R, model->head_mode == TNF_HEAD_CONCAT ? 4 : 3);
   const int grid = assign_wgrad_ctas(wa, sms * 2);
   if (g_stage_mask & 4) tnf::tnf_wgrad_kernel_fp32<<<grid, 256, 0, stream>>>(wa);
   e = cudaGetLastError();

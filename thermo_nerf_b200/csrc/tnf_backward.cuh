@@ -209,9 +209,11 @@ __device__ __forceinline__ void composite_backward(const TnfModel& m, FieldBwdSc
     sw += w;
   }
   sw = warp_sum(sw);
-  const float bgw = 1.f - sw;
+  // "last_sample" background (ThermalNerfModel) or none (concat_nerf: RGBTRenderer's "random" background)
+  const bool concat = m.head_mode == TNF_HEAD_CONCAT;
+  const float bgw = concat ? 0.f : 1.f - sw;
   const float* fl = fs + (S2 - 1) * 5;
-  const float lr = fl[1], lg = fl[2], lb = fl[3], lt = fl[4];
+  const float lr = concat ? 0.f : fl[1], lg = concat ? 0.f : fl[2], lb = concat ? 0.f : fl[3], lt = concat ? 0.f : fl[4];
   __syncwarp();
   // pass 2: dL/dw_i, then dL/d(delta*sigma)_i = gw_i (T_i - w_i) - sum_{j>i} gw_j w_j
   for (int i = lane; i < S2; i += 32) {
@@ -223,7 +225,8 @@ __device__ __forceinline__ void composite_backward(const TnfModel& m, FieldBwdSc
     ws.dzr[i] = gr_ * wc * f[1] * (1.f - f[1]);
     ws.dzg[i] = gg_ * wc * f[2] * (1.f - f[2]);
     ws.dzb[i] = gb_ * wc * f[3] * (1.f - f[3]);
-    ws.dtau[i] = gth * wc;
+    // dL/d thermal_i (thermal head, linear output) or, for the RGBT head, dL/d(pre-sigmoid channel 3)
+    ws.dtau[i] = concat ? gth * wc * f[4] * (1.f - f[4]) : gth * wc;
   }
   __syncwarp();
   float scarry = 0.f;

@@ -91,7 +91,7 @@ struct FieldBwdWTC {
   uint2 geoT[8][2][32];    // dG  = [dA1pre | dB1pre] . [W_rgb0[:,16:31] ; W_th0]   (column 0 = density slot = 0)
   uint2 base1T[1][8][32];  // dH  = dG . W_base1
   uint2 base0T[4][4][32];  // dF  = dHpre . W_base0
-  float rgb2w[3][64];
+  float rgb2w[4][64];      // row 3: the temperature channel of the RGBT head (concat_nerf), else zero
   float th2w[64];
 };
 struct ViewRows {  // V(k,n) = w[k*ld + n]
@@ -127,7 +127,8 @@ __device__ inline void stage_field_bwd(FieldBwdWTC& W, const TnfModel& m, int ti
                   nthreads);
   stage_frag_bf16(&W.base1T[0][0][0], 1, 8, ViewRows{f.base1.weight, 64, 16, 64}, tid, nthreads);
   stage_frag_bf16(&W.base0T[0][0][0], 4, 4, ViewRows{f.base0.weight, 32, 64, 32}, tid, nthreads);
-  for (int i = tid; i < 192; i += nthreads) W.rgb2w[i / 64][i % 64] = f.rgb2.weight[i];
+  const int nout = m.head_mode == TNF_HEAD_CONCAT ? 4 : 3;
+  for (int i = tid; i < 256; i += nthreads) W.rgb2w[i / 64][i % 64] = i < 64 * nout ? f.rgb2.weight[i] : 0.f;
   for (int i = tid; i < 64; i += nthreads) W.th2w[i] = f.th2.weight[i];
 }
 
@@ -327,7 +328,8 @@ __device__ __forceinline__ long long cta_ray_count(const long long R) {
 }
 
 // accumulator element (row m of the M = 64 tile, absolute column) -> gradient tensor
-__device__ __forceinline__ void store_grad(const TnfFieldGrad& g, const int col, const int row, const float v) {
+__device__ __forceinline__ void store_grad(const TnfFieldGrad& g, const int col, const int row, const float v,
+                                           const int nout) {
   if (v == 0.f) return;
   if (col < C_RGB1) {
     const int c = col - C_TH1;
@@ -357,11 +359,11 @@ __device__ __forceinline__ void store_grad(const TnfFieldGrad& g, const int col,
     if (col == C_TH2) atomicAdd(g.th2.weight + row, v);
   } else if (col < C_SB) {
     const int c = col - C_RGB2;
-    if (c < 3) atomicAdd(g.rgb2.weight + c * 64 + row, v);
+    if (c < nout) atomicAdd(g.rgb2.weight + c * 64 + row, v);
   } else if (row == 0) {
     const int c = col - C_SB;
     if (c == 0) atomicAdd(g.th2.bias, v);
-    else if (c >= 8 && c < 11) atomicAdd(g.rgb2.bias + (c - 8), v);
+    else if (c >= 8 && c < 8 + nout) atomicAdd(g.rgb2.bias + (c - 8), v);
     else if (c >= 16) atomicAdd(g.base1.bias + (c - 16), v);
   }
 }
@@ -377,7 +379,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   FieldBwdSmemU& S = *reinterpret_cast<FieldBwdSmemU*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  stage_field(S.fw, m.field, tid, kBwdThreads);
+  stage_field(S.fw, m.field, tid, kBwdThreads, m.head_mode == TNF_HEAD_CONCAT ? 4 : 3);
   stage_field_bwd(S.bw, m, tid, kBwdThreads);
   for (int i = tid; i < 8 * 16; i += kBwdThreads)
     *reinterpret_cast<uint4*>(S.ones + i * 16) = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
@@ -523,9 +525,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
         // rows past the end of the ray carry zero upstream gradients: every dY row of theirs is zero, so the
         // (finite) duplicate X rows contribute nothing to the weight gradients
         const float dsig[2] = {v0 ? ws.dsig[i0] : 0.f, v1 ? ws.dsig[i1] : 0.f};
-        const float dtau[2] = {v0 ? ws.dtau[i0] : 0.f, v1 ? ws.dtau[i1] : 0.f};
-        const float dz[2][3] = {{v0 ? ws.dzr[i0] : 0.f, v0 ? ws.dzg[i0] : 0.f, v0 ? ws.dzb[i0] : 0.f},
-                                {v1 ? ws.dzr[i1] : 0.f, v1 ? ws.dzg[i1] : 0.f, v1 ? ws.dzb[i1] : 0.f}};
+        // ws.dtau: thermal head -> dL/d thermal_i; RGBT head (concat_nerf) -> dL/d(pre-sigmoid channel 3), which
+        // joins the colour head's output gradient while the thermal head sees none
+        const bool concat = m.head_mode == TNF_HEAD_CONCAT;
+        const float dt0 = v0 ? ws.dtau[i0] : 0.f, dt1 = v1 ? ws.dtau[i1] : 0.f;
+        const float dtau[2] = {concat ? 0.f : dt0, concat ? 0.f : dt1};
+        const float dz[2][4] = {{v0 ? ws.dzr[i0] : 0.f, v0 ? ws.dzg[i0] : 0.f, v0 ? ws.dzb[i0] : 0.f, concat ? dt0 : 0.f},
+                                {v1 ? ws.dzr[i1] : 0.f, v1 ? ws.dzg[i1] : 0.f, v1 ? ws.dzb[i1] : 0.f, concat ? dt1 : 0.f}};
         // ---- saved hash features -> A fragments (fp16)
         uint32_t a0[2][4];
 #pragma unroll
@@ -634,7 +640,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int col = nt * 8 + 2 * q + (e & 1), r = e >> 1;
-                const float v = dz[r][0] * B.rgb2w[0][col] + dz[r][1] * B.rgb2w[1][col] + dz[r][2] * B.rgb2w[2][col];
+                const float v = dz[r][0] * B.rgb2w[0][col] + dz[r][1] * B.rgb2w[1][col] + dz[r][2] * B.rgb2w[2][col] +
+                                dz[r][3] * B.rgb2w[3][col];
                 d[e] = c[nt][e] > 0.f ? v : 0.f;
                 x[e] = fmaxf(c[nt][e], 0.f);
               }
@@ -648,8 +655,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 #pragma unroll
             for (int j = 0; j < 4; ++j) xa1[kt][j] = half2_to_bf162(xa1[kt][j]);
           {  // mlp_head.layers.1: dW = dA2^T [XA1 | 1];  mlp_head.layers.2: dW^T = XA2^T dZ
-            const uint32_t z00 = pack_bf162(dz[0][0], dz[0][1]), z01 = pack_bf162(dz[0][2], 0.f);
-            const uint32_t z10 = pack_bf162(dz[1][0], dz[1][1]), z11 = pack_bf162(dz[1][2], 0.f);
+            const uint32_t z00 = pack_bf162(dz[0][0], dz[0][1]), z01 = pack_bf162(dz[0][2], dz[0][3]);
+            const uint32_t z10 = pack_bf162(dz[1][0], dz[1][1]), z11 = pack_bf162(dz[1][2], dz[1][3]);
             const uint32_t tk = acquire_ticket(S, lane);
             unsigned char* buf = S.pool[tk % kNumBufs];
             stage_a<4>(buf, xa1, lane);
@@ -792,7 +799,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
       asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
       if (lane < 16) {  // M = 64: rows 16 qd .. 16 qd + 15 sit on the first 16 lanes of the quadrant
 #pragma unroll
-        for (int j = 0; j < 8; ++j) store_grad(gr.field, chunk * 8 + j, qd * 16 + lane, __uint_as_float(r[j]));
+        for (int j = 0; j < 8; ++j)
+          store_grad(gr.field, chunk * 8 + j, qd * 16 + lane, __uint_as_float(r[j]), m.head_mode == TNF_HEAD_CONCAT ? 4 : 3);
       }
     }
   }

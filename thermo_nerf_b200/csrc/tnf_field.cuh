@@ -125,37 +125,37 @@ __device__ inline void stage_common(FieldCommon& C, const TnfField& f, bool fold
   }
 }
 
-__device__ inline void stage_field(FieldW32& W, const TnfField& f, int tid) {
+__device__ inline void stage_field(FieldW32& W, const TnfField& f, int tid, int /*nthreads*/ = kThreads, int nout = 3) {
   stage_t(W.base0t, 32, 64, ViewPlain{f.base0.weight, 32, 32, 64}, tid);
   stage_t(W.base1t, 64, 16, ViewPlain{f.base1.weight, 64, 64, 16}, tid);
   stage_t(W.rgb0geo_t, 16, 64, ViewShift{f.rgb0.weight, 63, 16, 15, 64}, tid);
   stage_t(W.rgb1t, 64, 64, ViewPlain{f.rgb1.weight, 64, 64, 64}, tid);
-  stage_t(W.rgb2t, 64, 4, ViewPlain{f.rgb2.weight, 64, 64, 3}, tid);
+  stage_t(W.rgb2t, 64, 4, ViewPlain{f.rgb2.weight, 64, 64, nout}, tid);  // nout = 4: RGBT head (concat_nerf)
   stage_t(W.th0t, 16, 64, ViewShift{f.th0.weight, 15, 0, 15, 64}, tid);
   stage_t(W.th1t, 64, 64, ViewPlain{f.th1.weight, 64, 64, 64}, tid);
   stage_vec(W.base0b, f.base0.bias, 64, 64, tid);
   stage_vec(W.base1b, f.base1.bias, 16, 16, tid);
   stage_vec(W.rgb1b, f.rgb1.bias, 64, 64, tid);
-  stage_vec(W.rgb2b, f.rgb2.bias, 3, 4, tid);
+  stage_vec(W.rgb2b, f.rgb2.bias, nout, 4, tid);
   stage_vec(W.th0b, f.th0.bias, 64, 64, tid);
   stage_vec(W.th1b, f.th1.bias, 64, 64, tid);
   stage_vec(W.th2, f.th2.weight, 64, 64, tid);
   stage_vec(W.th2b, f.th2.bias, 1, 4, tid);
 }
 
-__device__ inline void stage_field(FieldWTC& W, const TnfField& f, int tid, int nthreads = kThreads) {
+__device__ inline void stage_field(FieldWTC& W, const TnfField& f, int tid, int nthreads = kThreads, int nout = 3) {
   stage_frag(&W.base0[0][0][0], 2, 8, ViewPlain{f.base0.weight, 32, 32, 64}, tid, nthreads);
   stage_frag(&W.base1[0][0][0], 4, 2, ViewPlain{f.base1.weight, 64, 64, 16}, tid, nthreads);
   stage_frag(&W.geo0[0][0][0], 1, 16,
              ViewGeo0{ViewShift{f.rgb0.weight, 63, 16, 15, 64}, ViewShift{f.th0.weight, 15, 0, 15, 64}}, tid, nthreads);
   stage_frag(&W.rgb1[0][0][0], 4, 8, ViewPlain{f.rgb1.weight, 64, 64, 64}, tid, nthreads);
-  stage_frag(&W.rgb2[0][0][0], 4, 1, ViewPlain{f.rgb2.weight, 64, 64, 3}, tid, nthreads);
+  stage_frag(&W.rgb2[0][0][0], 4, 1, ViewPlain{f.rgb2.weight, 64, 64, nout}, tid, nthreads);
   stage_frag(&W.th1[0][0][0], 4, 8, ViewPlain{f.th1.weight, 64, 64, 64}, tid, nthreads);
   stage_frag(&W.th2[0][0][0], 4, 1, ViewPlain{f.th2.weight, 64, 64, 1}, tid, nthreads);
   stage_vec(W.base0b, f.base0.bias, 64, 64, tid, nthreads);
   stage_vec(W.base1b, f.base1.bias, 16, 16, tid, nthreads);
   stage_vec(W.rgb1b, f.rgb1.bias, 64, 64, tid, nthreads);
-  stage_vec(W.rgb2b, f.rgb2.bias, 3, 8, tid, nthreads);
+  stage_vec(W.rgb2b, f.rgb2.bias, nout, 8, tid, nthreads);
   stage_vec(W.th0b, f.th0.bias, 64, 64, tid, nthreads);
   stage_vec(W.th1b, f.th1.bias, 64, 64, tid, nthreads);
   stage_vec(W.th2b, f.th2.bias, 1, 8, tid, nthreads);

@@ -222,8 +222,8 @@ __device__ __forceinline__ void field_level(const TnfModel& m, Smem<TNF_PRECISIO
       store_col(a, y);
       dense_col<64, 4, ACT_SIGMOID>(W.rgb2t, W.rgb2b, a, rgb);
     }
-    float th;
-    {
+    float th = rgb[3];  // concat_nerf: the fourth channel of the RGBT colour head (sigmoid applied)
+    if (m.head_mode == TNF_HEAD_THERMAL) {
       float y[64];
       dense_col<16, 64, ACT_RELU>(W.th0t, W.th0b, geo, y);
       store_col(a, y);
@@ -324,8 +324,9 @@ __device__ __forceinline__ void field_level(const TnfModel& m, Smem<TNF_PRECISIO
       init_bias(rgb, W.rgb2b, q);
       mma_layer<1, 4>(rgb, hid, &W.rgb2[0][0][0], 0, 1, lane);
     }
-    float th[1][4];
-    {
+    float th[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+    const bool concat = m.head_mode == TNF_HEAD_CONCAT;
+    if (!concat) {
       float c[8][4];
       init_bias(c, W.th0b, q);
       mma_layer<8, 1>(c, ga, &W.geo0[0][0][0], 8, 16, lane);
@@ -341,17 +342,21 @@ __device__ __forceinline__ void field_level(const TnfModel& m, Smem<TNF_PRECISIO
         ws.sigma[r0] = expf(dba0) * sel[0];
         ws.r[r0] = sigmoid_fast(rgb[0][0]);
         ws.g[r0] = sigmoid_fast(rgb[0][1]);
-        ws.th[r0] = th[0][0];
+        if (!concat) ws.th[r0] = th[0][0];
       }
       if (r1 < S2) {
         ws.sigma[r1] = expf(dba1) * sel[1];
         ws.r[r1] = sigmoid_fast(rgb[0][2]);
         ws.g[r1] = sigmoid_fast(rgb[0][3]);
-        ws.th[r1] = th[0][2];
+        if (!concat) ws.th[r1] = th[0][2];
       }
     } else if (q == 1) {
       if (r0 < S2) ws.b[r0] = sigmoid_fast(rgb[0][0]);
       if (r1 < S2) ws.b[r1] = sigmoid_fast(rgb[0][2]);
+      if (concat) {  // RGBT head: channel 3 is the temperature (rgb_concat/concat_field.py:65-75)
+        if (r0 < S2) ws.th[r0] = sigmoid_fast(rgb[0][1]);
+        if (r1 < S2) ws.th[r1] = sigmoid_fast(rgb[0][3]);
+      }
     }
   }
   __syncwarp();
@@ -403,7 +408,7 @@ __global__ void __launch_bounds__(kThreads, MINB)
       }
       S.fc.app_const[lane] = e;
     }
-    stage_field(S.fw, m.field, tid);
+    stage_field(S.fw, m.field, tid, kThreads, m.head_mode == TNF_HEAD_CONCAT ? 4 : 3);
     __syncthreads();
     stage_common(S.fc, m.field, !lookup, tid);
   }
@@ -543,7 +548,9 @@ __global__ void __launch_bounds__(kThreads, MINB)
     if (lane == 0) {
       float lr = ws.r[S2 - 1], lg = ws.g[S2 - 1], lb = ws.b[S2 - 1], lt = ws.th[S2 - 1];
       if (!train) { lr = nan_to_num(lr); lg = nan_to_num(lg); lb = nan_to_num(lb); lt = nan_to_num(lt); }
-      const float bgw = 1.f - sw;  // background_color = "last_sample" (thermal_renderer.py:49)
+      // background_color = "last_sample" (thermal_renderer.py:49); concat_nerf: RGBTRenderer's default "random"
+      // background adds nothing to the composite (rgbt_renderer.py:63-71)
+      const float bgw = m.head_mode == TNF_HEAD_CONCAT ? 0.f : 1.f - sw;
       float r = sr + lr * bgw, g = sg + lg * bgw, b = sb + lb * bgw, t = st + lt * bgw;
       if (!train) {
         r = fminf(fmaxf(r, 0.f), 1.f); g = fminf(fmaxf(g, 0.f), 1.f);
@@ -712,6 +719,8 @@ int check_model(const TnfModel* m) {
   }
   if (m->precision != TNF_PRECISION_FP32 && m->precision != TNF_PRECISION_TC_FP16)
     return fail(TNF_ERR_INVALID_ARGUMENT, "precision=%d", m->precision);
+  if (m->head_mode != TNF_HEAD_THERMAL && m->head_mode != TNF_HEAD_CONCAT)
+    return fail(TNF_ERR_INVALID_ARGUMENT, "head_mode=%d", m->head_mode);
   return TNF_OK;
 }
 }  // namespace tnf

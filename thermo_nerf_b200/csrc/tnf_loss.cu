@@ -46,14 +46,33 @@ __global__ void __launch_bounds__(kThreads) tnf_losses_kernel(const __grid_const
   for (long long ray = (long long)blockIdx.x * kWarpsPerCta + warp; ray < R;
        ray += (long long)gridDim.x * kWarpsPerCta) {
     // ---- MSE terms
-    if (a.use_rgb_loss && lane < 3) {
+    if (a.concat) {
+      // ConcatNerfModel: MSE over the 4 RGBT channels of pred + noise (1 - accumulation)
+      // (rgbt_renderer.py:134-140 blends the random background into the prediction only)
+      float d = 0.f, n = 0.f;
+      if (lane < 4) {
+        const float one_minus_acc = 1.f - a.accumulation[ray];
+        const float p = lane < 3 ? a.rgb[ray * 3 + lane] : a.thermal[ray];
+        const float gt = lane < 3 ? a.gt_rgb[ray * 3 + lane] : a.gt_thermal[ray];
+        n = a.noise[ray * 4 + lane];
+        d = p + n * one_minus_acc - gt;
+        l_rgb += d * d;
+        const float g = a.grad_scale * 2.f * d * invR * 0.25f;
+        if (lane < 3) { if (a.g_rgb) a.g_rgb[ray * 3 + lane] = g; }
+        else if (a.g_thermal) a.g_thermal[ray] = g;
+      }
+      float ga = -(a.grad_scale * 2.f * d * invR * 0.25f) * n;  // d/d accumulation
+      ga += __shfl_xor_sync(kFull, ga, 1);
+      ga += __shfl_xor_sync(kFull, ga, 2);
+      if (lane == 0 && a.g_accumulation) a.g_accumulation[ray] = ga;
+    } else if (a.use_rgb_loss && lane < 3) {
       const float d = a.rgb[ray * 3 + lane] - a.gt_rgb[ray * 3 + lane];
       l_rgb += d * d;
       if (a.g_rgb) a.g_rgb[ray * 3 + lane] = a.grad_scale * 2.f * d * invR * (1.f / 3.f);
     } else if (!a.use_rgb_loss && lane < 3 && a.g_rgb) {
       a.g_rgb[ray * 3 + lane] = 0.f;
     }
-    if (lane == 0) {
+    if (lane == 0 && !a.concat) {
       if (a.use_thermal_loss) {
         const float d = a.thermal[ray] - a.gt_thermal[ray];
         l_th += d * d;
@@ -151,10 +170,11 @@ __global__ void __launch_bounds__(kThreads) tnf_losses_kernel(const __grid_const
   l_dist = warp_sum(l_dist);
   l_th = warp_sum(l_th);
   if (lane == 0) {
-    if (a.use_rgb_loss) atomicAdd(a.losses + 0, l_rgb * invR * (1.f / 3.f));
+    if (a.concat) atomicAdd(a.losses + 0, l_rgb * invR * 0.25f);
+    else if (a.use_rgb_loss) atomicAdd(a.losses + 0, l_rgb * invR * (1.f / 3.f));
     atomicAdd(a.losses + 1, a.interlevel_mult * l_inter * invR);
     atomicAdd(a.losses + 2, a.distortion_mult * l_dist * invR);
-    if (a.use_thermal_loss) atomicAdd(a.losses + 3, l_th * invR);
+    if (a.use_thermal_loss && !a.concat) atomicAdd(a.losses + 3, l_th * invR);
   }
 }
 
@@ -173,8 +193,10 @@ extern "C" int tnf_losses(const TnfLossArgs* args, void* stream_) {
     if (a.num_samples[k] < 1 || a.num_samples[k] > lim)
       return fail(TNF_ERR_UNSUPPORTED_CONFIG, "num_samples[%d]=%d not in [1,%d]", k, a.num_samples[k], lim);
   }
+  if (a.concat && (!a.rgb || !a.gt_rgb || !a.thermal || !a.gt_thermal || !a.accumulation || !a.noise))
+    return fail(TNF_ERR_INVALID_ARGUMENT, "concat loss needs rgb, thermal, gt_rgb, gt_thermal, accumulation and noise");
   if (a.use_rgb_loss && (!a.rgb || !a.gt_rgb)) return fail(TNF_ERR_INVALID_ARGUMENT, "rgb/gt_rgb is null");
-  if (a.use_thermal_loss && (!a.thermal || !a.gt_thermal))
+  if (a.use_thermal_loss && !a.concat && (!a.thermal || !a.gt_thermal))
     return fail(TNF_ERR_INVALID_ARGUMENT, "thermal/gt_thermal is null");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   cudaError_t e = cudaMemsetAsync(a.losses, 0, 4 * sizeof(float), stream);

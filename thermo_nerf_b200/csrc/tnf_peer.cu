@@ -87,6 +87,61 @@ __global__ void __launch_bounds__(256) tnf_peer_adam_kernel(const __grid_constan
   }
 }
 
+// NVLS flavour: the same exchange through the NVSwitch multicast objects of the gradient and the parameter arenas.
+//   reduce-scatter  multimem.ld_reduce.add: ONE load returns the sum of this element over all ranks, formed inside
+//                   the switch - a rank receives 1/N of the arena instead of (N-1)/N of it
+//   all-gather      multimem.st: ONE store is replicated by the switch into every rank's parameter arena - a rank
+//                   sends 1/N of the arena instead of (N-1)/N of it
+// Both directions of every link carry data at the same time (reduce traffic towards the owner, broadcast traffic
+// away from it) and a chunk is stored as soon as it is updated, so the whole exchange is one pass over the shard.
+// The switch's summation order differs from the rank-order sum of tnf_peer_adam_kernel (last-bit differences);
+// every rank still receives the owner's one result, so the replicas stay bit-identical.
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float* mc) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];\n"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(mc)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void multimem_st(float* mc, const float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+    tnf_peer_adam_multimem_kernel(const __grid_constant__ PeerAdamArgs A, const float* __restrict__ grads_mc,
+                                  float* __restrict__ params_mc) {
+  const long long n4 = (A.shard_end - A.shard_begin) >> 2;
+  const int me = A.a.rank;
+  float4* __restrict__ M = reinterpret_cast<float4*>(A.m);
+  float4* __restrict__ V = reinterpret_cast<float4*>(A.v);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long e = A.shard_begin + 4 * i;
+    int s = 0;
+    while (s + 1 < A.nseg && e >= A.seg_end[s]) ++s;
+    if (!A.seg_active[s]) continue;
+    float4 g = multimem_ld_reduce_add(grads_mc + e);
+    g.x *= A.inv_world; g.y *= A.inv_world; g.z *= A.inv_world; g.w *= A.inv_world;
+    float4 p = *reinterpret_cast<const float4*>(A.a.params[me] + e);
+    float4 m = M[i], v = V[i];
+    // never-touched entries: the update is exactly zero and every rank already holds the same value
+    if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f && m.x == 0.f && m.y == 0.f && m.z == 0.f && m.w == 0.f &&
+        v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f)
+      continue;
+    const float ss = A.seg_step_size[s], ib = A.seg_inv_sqrt_bc2[s];
+    peer_adam_one(p.x, g.x, m.x, v.x, A, ss, ib);
+    peer_adam_one(p.y, g.y, m.y, v.y, A, ss, ib);
+    peer_adam_one(p.z, g.z, m.z, v.z, A, ss, ib);
+    peer_adam_one(p.w, g.w, m.w, v.w, A, ss, ib);
+    M[i] = m;
+    V[i] = v;
+    multimem_st(params_mc + e, p);
+  }
+}
+
 // all-gather, pull flavour: every rank copies the other ranks' freshly updated shards out of their owners'
 // parameter arenas (peer loads run at the NVLink rate; see DESIGN.md for the measured push / pull comparison)
 __global__ void __launch_bounds__(256) tnf_peer_gather_kernel(const __grid_constant__ TnfPeerArena a,
@@ -253,7 +308,18 @@ int tnf_peer_barrier(const TnfPeerArena* arena, int32_t slot, uint32_t epoch, vo
 
 static int peer_adam_impl(const TnfPeerArena* arena, float* exp_avg_shard, float* exp_avg_sq_shard,
                           const TnfAdamSegment* segments, int32_t num_segments, double beta1, double beta2, float eps,
-                          int phase, void* stream_);
+                          int phase, void* stream_, const float* grads_mc = nullptr, float* params_mc = nullptr);
+
+int tnf_peer_adam_multimem(const TnfPeerArena* arena, const float* grads_multicast, float* params_multicast,
+                           float* exp_avg_shard, float* exp_avg_sq_shard, const TnfAdamSegment* segments,
+                           int32_t num_segments, double beta1, double beta2, float eps, void* stream_) {
+  if (!grads_multicast || !params_multicast || !tnf::aligned16(grads_multicast) || !tnf::aligned16(params_multicast)) {
+    tnf::g_err[0] = 0;
+    return tnf::fail(TNF_ERR_INVALID_ARGUMENT, "multicast addresses null or not 16-byte aligned");
+  }
+  return peer_adam_impl(arena, exp_avg_shard, exp_avg_sq_shard, segments, num_segments, beta1, beta2, eps, 3, stream_,
+                        grads_multicast, params_multicast);
+}
 
 int tnf_peer_adam_step(const TnfPeerArena* arena, float* exp_avg_shard, float* exp_avg_sq_shard,
                        const TnfAdamSegment* segments, int32_t num_segments, double beta1, double beta2, float eps,
@@ -272,10 +338,11 @@ int tnf_peer_gather_params(const TnfPeerArena* arena, const TnfAdamSegment* segm
   return peer_adam_impl(arena, nullptr, nullptr, segments, num_segments, 0.9, 0.999, 0.f, 2, stream_);
 }
 
-// phase 0: reduce + Adam + push to all ranks; 1: reduce + Adam, own copy only; 2: pull the other ranks' shards
+// phase 0: reduce + Adam + push to all ranks; 1: reduce + Adam, own copy only; 2: pull the other ranks' shards;
+// 3: reduce + Adam + broadcast through the NVSwitch multicast objects
 static int peer_adam_impl(const TnfPeerArena* arena, float* exp_avg_shard, float* exp_avg_sq_shard,
                           const TnfAdamSegment* segments, int32_t num_segments, double beta1, double beta2, float eps,
-                          int phase, void* stream_) {
+                          int phase, void* stream_, const float* grads_mc, float* params_mc) {
   using tnf::fail;
   tnf::g_err[0] = 0;
   if (int rc = check_arena(arena)) return rc;
@@ -328,6 +395,9 @@ static int peer_adam_impl(const TnfPeerArena* arena, float* exp_avg_shard, float
   if (blocks > cap) blocks = cap;
   if (phase == 2)
     tnf::tnf_peer_gather_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream_)>>>(*arena, A);
+  else if (phase == 3)
+    tnf::tnf_peer_adam_multimem_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream_)>>>(A, grads_mc,
+                                                                                                       params_mc);
   else
     tnf::tnf_peer_adam_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream_)>>>(A);
   const cudaError_t e = cudaGetLastError();

@@ -131,9 +131,97 @@ class PeerArena:
         self.numel = (int(numel) + pad - 1) // pad * pad
         self.shard = self.numel // self.world
         self.device = dev
-        # one cudaMalloc of our own per rank: [gradients | parameters | flag block].  (Tensors of the caching
-        # allocator sit inside larger segments, and the IPC handle has to name an allocation's base.)
         arena_bytes = self.numel * 4
+        self._mapped: dict = {}  # rank -> base pointer of that rank's allocation mapped for this device (IPC path)
+        self._symm = None         # (tensor, handle) of the symmetric-memory path
+        self.multicast = 0        # multicast base address of the allocation (NVSwitch / NVLS), 0 = none
+        import os
+
+        backend = os.environ.get("TNF_PEER_BACKEND", "auto")
+        if backend not in ("auto", "symm", "ipc"):
+            raise ValueError("TNF_PEER_BACKEND must be 'auto', 'symm' or 'ipc'")
+        bases = None
+        if self.world > 1 and backend in ("auto", "symm"):
+            bases = self._setup_symmetric(dev, group, arena_bytes, strict=(backend == "symm"))
+        if bases is None:
+            bases = self._setup_ipc(dev, group, arena_bytes)
+        ptrs = [(b, b + arena_bytes, b + 2 * arena_bytes) for b in bases]
+        a = L.TnfPeerArena()
+        for r, (g, p, f) in enumerate(ptrs):
+            a.grads[r], a.params[r], a.flags[r] = g, p, f
+        a.world_size, a.rank, a.numel = self.world, self.rank, self.numel
+        self.struct = a
+        self.exp_avg = torch.zeros(self.shard, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(self.shard, dtype=torch.float32, device=dev)
+        self._epoch = [0] * L.TNF_PEER_FLAG_SLOTS
+        self.timing: Optional[list] = None
+        import os
+
+        # all-gather flavour: "push" (everything in one kernel) or "pull" (owners keep their shard, peers copy it out).
+        # Measured (profiles/r1_peer_exchange_phases.json): push wins on 2 GPUs, the owner-balanced pull on 8.
+        # "multimem": reduction and broadcast inside the NVSwitch (needs the multicast object of the symmetric path).
+        self.gather = os.environ.get("TNF_PEER_GATHER", "auto")
+        if self.gather == "auto":
+            self.gather = "multimem" if self.multicast else ("pull" if self.world >= 4 else "push")
+        if self.gather not in ("push", "pull", "multimem"):
+            raise ValueError("TNF_PEER_GATHER must be 'auto', 'push', 'pull' or 'multimem'")
+        if self.gather == "multimem" and not self.multicast:
+            raise RuntimeError("TNF_PEER_GATHER=multimem needs NVSwitch multicast (symmetric-memory backend)")
+        if self.world > 1:
+            # self-test of the mappings in both directions: one barrier round must complete without a time-out
+            self.barrier(0)
+            torch.cuda.synchronize(dev)
+            if self.timeouts() != 0:
+                raise RuntimeError("peer flag barrier timed out: the IPC mappings are not reachable")
+
+    def _setup_symmetric(self, dev, group, arena_bytes: int, strict: bool):
+        """[gradients | parameters | flag block] as ONE torch symmetric-memory allocation: torch.distributed maps every
+        rank's buffer into this process and, on NVSwitch systems, binds them to a multicast object - plumbing only;
+        the exchange itself is our kernel (peer loads / stores, or multimem.ld_reduce / multimem.st on the multicast
+        address).  Returns the per-rank base addresses, or None when symmetric memory is unavailable on any rank."""
+        L = self._L
+        err, buf, hdl = "", None, None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            words = 2 * self.numel + L.TNF_PEER_FLAG_WORDS
+            with torch.cuda.device(dev):
+                buf = symm_mem.empty(words, dtype=torch.float32, device=dev)
+                buf.zero_()
+                torch.cuda.synchronize(dev)
+                hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+            bases = [int(p) for p in hdl.buffer_ptrs]
+            if len(bases) != self.world or bases[self.rank] != buf.data_ptr():
+                raise RuntimeError("symmetric memory returned unexpected buffer pointers")
+        except Exception as e:  # noqa: BLE001 - reported collectively below
+            err = repr(e)
+        ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            if strict:
+                raise RuntimeError("PeerArena: TNF_PEER_BACKEND=symm but symmetric memory is unavailable"
+                                   + (f" (this rank: {err})" if err else ""))
+            return None
+        self._symm = (buf, hdl)
+        self._base = bases[self.rank]
+        self.grads = buf[:self.numel]
+        self.params = buf[self.numel:2 * self.numel]
+        self.flags = buf[2 * self.numel:].view(torch.int32)
+        mc = 0
+        try:
+            mc = int(hdl.multicast_ptr or 0)
+        except Exception:  # noqa: BLE001
+            mc = 0
+        # every rank must agree (the multicast kernel is collective)
+        flag = torch.tensor([1 if mc else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        self.multicast = mc if int(flag.item()) == 1 else 0
+        return bases
+
+    def _setup_ipc(self, dev, group, arena_bytes: int):
+        """One cudaMalloc of our own per rank, shared through CUDA IPC handles (tensors of the caching allocator sit
+        inside larger segments, and an IPC handle has to name an allocation's base)."""
+        L, C = self._L, self._C
         total_bytes = 2 * arena_bytes + L.TNF_PEER_FLAG_WORDS * 4
         handle = C.create_string_buffer(L.TNF_IPC_HANDLE_BYTES)
         base = C.c_void_p()
@@ -143,7 +231,6 @@ class PeerArena:
         self.grads = _wrap_device_memory(self._base, (self.numel,), "<f4", dev, self)
         self.params = _wrap_device_memory(self._base + arena_bytes, (self.numel,), "<f4", dev, self)
         self.flags = _wrap_device_memory(self._base + 2 * arena_bytes, (L.TNF_PEER_FLAG_WORDS,), "<i4", dev, self)
-        self._mapped: dict = {}  # rank -> base pointer of that rank's allocation mapped for this device
         bases = [self._base] * self.world
         if self.world > 1:
             gathered: List[object] = [None] * self.world
@@ -170,31 +257,7 @@ class PeerArena:
                 self.close()
                 raise RuntimeError("PeerArena: mapping the peers' memory failed on at least one rank"
                                    + (f" (this rank: {err})" if err else ""))
-        ptrs = [(b, b + arena_bytes, b + 2 * arena_bytes) for b in bases]
-        a = L.TnfPeerArena()
-        for r, (g, p, f) in enumerate(ptrs):
-            a.grads[r], a.params[r], a.flags[r] = g, p, f
-        a.world_size, a.rank, a.numel = self.world, self.rank, self.numel
-        self.struct = a
-        self.exp_avg = torch.zeros(self.shard, dtype=torch.float32, device=dev)
-        self.exp_avg_sq = torch.zeros(self.shard, dtype=torch.float32, device=dev)
-        self._epoch = [0] * L.TNF_PEER_FLAG_SLOTS
-        self.timing: Optional[list] = None
-        import os
-
-        # all-gather flavour: "push" (everything in one kernel) or "pull" (owners keep their shard, peers copy it out).
-        # Measured (profiles/r1_peer_exchange_phases.json): push wins on 2 GPUs, the owner-balanced pull on 8.
-        self.gather = os.environ.get("TNF_PEER_GATHER", "auto")
-        if self.gather == "auto":
-            self.gather = "pull" if self.world >= 4 else "push"
-        if self.gather not in ("push", "pull"):
-            raise ValueError("TNF_PEER_GATHER must be 'auto', 'push' or 'pull'")
-        if self.world > 1:
-            # self-test of the mappings in both directions: one barrier round must complete without a time-out
-            self.barrier(0)
-            torch.cuda.synchronize(dev)
-            if self.timeouts() != 0:
-                raise RuntimeError("peer flag barrier timed out: the IPC mappings are not reachable")
+        return bases
 
     def close(self) -> None:
         """Unmap the peers' allocations (the own allocation lives as long as tensors view it)."""
@@ -227,10 +290,16 @@ class PeerArena:
         if ev:
             ev[1].record()
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        fn = self.lib.tnf_peer_adam_step if self.gather == "push" else self.lib.tnf_peer_adam_reduce
         with torch.cuda.device(self.device):
-            L.check(fn(C.byref(self.struct), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), segs, len(segments),
-                       float(beta1), float(beta2), float(eps), C.c_void_p(stream)))
+            if self.gather == "multimem":
+                L.check(self.lib.tnf_peer_adam_multimem(
+                    C.byref(self.struct), C.c_void_p(self.multicast), C.c_void_p(self.multicast + 4 * self.numel),
+                    self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), segs, len(segments), float(beta1),
+                    float(beta2), float(eps), C.c_void_p(stream)))
+            else:
+                fn = self.lib.tnf_peer_adam_step if self.gather == "push" else self.lib.tnf_peer_adam_reduce
+                L.check(fn(C.byref(self.struct), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), segs,
+                           len(segments), float(beta1), float(beta2), float(eps), C.c_void_p(stream)))
         if ev:
             ev[2].record()
         self.barrier(1)  # push: every shard has landed everywhere; pull: every owner holds its updated shard

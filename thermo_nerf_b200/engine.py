@@ -126,7 +126,8 @@ class TrainEngine:
                   use_contraction=not cfg.disable_scene_contraction,
                   aabb=self.model._aabb_list(),
                   appearance_mode=L.APPEARANCE_LOOKUP, precision=self.model._precision(),
-                  detach_thermal_geo=not self.model.field.pass_thermal_gradients)
+                  detach_thermal_geo=not self.model.field.pass_thermal_gradients,
+                  head_mode=L.HEAD_CONCAT if self.model._is_concat() else L.HEAD_THERMAL)
         cam = camera_indices.reshape(-1)
         res = F.render_forward(self.tensors, origins, directions, cam, None, None, jitter, training=True,
                                return_samples=True, save_for_backward=True, **kw)
@@ -134,7 +135,10 @@ class TrainEngine:
             res["weights_list"], res["sdist_list"], res["rgb"], res["thermal"], gt_rgb, gt_thermal,
             interlevel_mult=cfg.interlevel_loss_mult, distortion_mult=cfg.distortion_loss_mult,
             use_rgb_loss=self.model.field.pass_rgb_gradients, use_thermal_loss=self.model.field.pass_thermal_gradients,
-            prop_grad=updated)
+            prop_grad=updated,
+            # concat_nerf: gt_thermal is channel 3 of the RGBT image, the random background is drawn here
+            concat_accumulation=res["accumulation"] if self.model._is_concat() else None,
+            concat_noise=torch.rand((R, 4), device=self.device) if self.model._is_concat() else None)
         grads = list(self.grads)
         if not updated:
             grads[:NUM_PROP_TENSORS] = [None] * NUM_PROP_TENSORS
@@ -143,7 +147,8 @@ class TrainEngine:
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         res["_workspace"] = self._ws
         F.render_backward(self.tensors, res["_model_struct"], origins, directions, cam, None, None, jitter, res,
-                          {"rgb": g["rgb"], "thermal": g["thermal"], "weights_list": g["weights_list"]}, grads)
+                          {"rgb": g["rgb"], "thermal": g["thermal"], "accumulation": g.get("accumulation"),
+                           "weights_list": g["weights_list"]}, grads)
         lr = exponential_decay_lr(step, self.lr, self.lr_final, self.lr_max_steps)
         self.field_steps += 1
         if updated:
@@ -166,6 +171,23 @@ class TrainEngine:
         self.steps_since_update += 1
         self.step_count += 1
         return losses
+
+    def step_host(self, origins: Tensor, directions: Tensor, camera_indices: Tensor, gt_rgb: Tensor,
+                  gt_thermal: Tensor) -> Tensor:
+        """One iteration from a HOST batch (what ``datamanager.next_train`` hands the trainer, pipeline_tracking.py:47-59):
+        the five tensors - pinned for the copies to be asynchronous - go into persistent device buffers on the current
+        stream, then :meth:`step` runs.  Returns the 4 losses on the device; the caller decides when to read them."""
+        R = int(origins.shape[0])
+        bufs = getattr(self, "_host_batch", None)
+        if bufs is None or bufs[0].shape[0] != R:
+            dev = self.device
+            bufs = (torch.empty((R, 3), dtype=torch.float32, device=dev), torch.empty((R, 3), dtype=torch.float32, device=dev),
+                    torch.empty((R,), dtype=torch.int64, device=dev), torch.empty((R, 3), dtype=torch.float32, device=dev),
+                    torch.empty((R,), dtype=torch.float32, device=dev))
+            self._host_batch = bufs
+        for d, h in zip(bufs, (origins, directions, camera_indices.reshape(-1), gt_rgb, gt_thermal.reshape(-1))):
+            d.copy_(h, non_blocking=True)
+        return self.step(*bufs)
 
     def _adam(self, sl: slice, lr: float, step: int) -> None:
         n = len(self.params[sl])

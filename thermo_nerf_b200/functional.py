@@ -109,8 +109,11 @@ class ModelTensors:
         expect = {"base0": (64, 32), "base1": (16, 64), "rgb0": (64, 63), "rgb1": (64, 64), "rgb2": (3, 64),
                   "th0": (64, 15), "th1": (64, 64), "th2": (1, 64)}
         for k, shp in expect.items():
-            if tuple(lin[k].weight.shape) != shp:
-                raise ValueError(f"{k}: weight shape {tuple(lin[k].weight.shape)} != {shp} (fixed architecture)")
+            got = tuple(lin[k].weight.shape)
+            if k == "rgb2" and got == (4, 64):
+                continue  # the RGBT colour head of the concat_nerf model type (rgb_concat/concat_field.py:65-75)
+            if got != shp:
+                raise ValueError(f"{k}: weight shape {got} != {shp} (fixed architecture)")
         for i in range(len(props)):
             if tuple(l0[i].weight.shape) != (16, 2 * prop_grids[i].num_levels) or tuple(l1[i].weight.shape) != (1, 16):
                 raise ValueError("proposal MLP must be grid -> 16 -> 1")
@@ -132,7 +135,7 @@ class ModelTensors:
 
     def pack(self, *, num_samples: Sequence[int], training: bool, near_plane: float, far_plane: float,
              anneal: float, use_contraction: bool, aabb: Optional[Sequence[float]], appearance_mode: int,
-             precision: int, detach_thermal_geo: bool = False) -> L.TnfModel:
+             precision: int, detach_thermal_geo: bool = False, head_mode: int = L.HEAD_THERMAL) -> L.TnfModel:
         """Fresh ``TnfModel`` for one call.  The pointer part is validated and filled once per set of
         tensor addresses and memcpy'd afterwards (this runs every training step)."""
         plist = self.param_list()
@@ -165,6 +168,10 @@ class ModelTensors:
         m.appearance_mode = int(appearance_mode)
         m.precision = int(precision)
         m.detach_thermal_geo = int(bool(detach_thermal_geo))
+        m.head_mode = int(head_mode)
+        nout = int(self.field_linears["rgb2"].weight.shape[0])
+        if nout != (4 if m.head_mode == L.HEAD_CONCAT else 3):
+            raise ValueError(f"head_mode={m.head_mode} does not match a colour head with {nout} outputs")
         return m
 
     # ------------------------------------------------------------------ autograd plumbing
@@ -256,6 +263,7 @@ def render_forward(
     out: Optional[Dict[str, Tensor]] = None,
     save_for_backward: bool = False,
     detach_thermal_geo: bool = False,
+    head_mode: int = L.HEAD_THERMAL,
     camera: Optional[L.TnfCamera] = None,
     first_pixel: int = 0,
     num_pixels: Optional[int] = None,
@@ -312,7 +320,7 @@ def render_forward(
     model = tensors.pack(num_samples=num_samples, training=training, near_plane=near_plane, far_plane=far_plane,
                          anneal=anneal, use_contraction=use_contraction, aabb=aabb,
                          appearance_mode=appearance_mode, precision=precision,
-                         detach_thermal_geo=detach_thermal_geo)
+                         detach_thermal_geo=detach_thermal_geo, head_mode=head_mode)
 
     res: Dict[str, object] = {}
     outs = L.TnfOutputs()
@@ -548,9 +556,13 @@ def losses_forward_backward(weights_list: Sequence[Tensor], sdist_list: Sequence
                             thermal: Tensor, gt_rgb: Tensor, gt_thermal: Tensor, *, interlevel_mult: float = 1.0,
                             distortion_mult: float = 0.002, use_rgb_loss: bool = True,
                             use_thermal_loss: bool = True, grad_scale: float = 1.0, want_grads: bool = True,
-                            prop_grad: bool = True):
+                            prop_grad: bool = True, concat_accumulation: Optional[Tensor] = None,
+                            concat_noise: Optional[Tensor] = None):
     """``tnf_losses``: returns (losses[4] device tensor in LOSS_NAMES order, grads dict or None).
-    grads: d(loss)/d(input) * grad_scale for rgb [R,3], thermal [R], weights_list[k] [R,S_k]."""
+    grads: d(loss)/d(input) * grad_scale for rgb [R,3], thermal [R], weights_list[k] [R,S_k].
+    With ``concat_accumulation`` [R] and ``concat_noise`` [R,4] the colour term is the concat_nerf loss
+    (rgb_concat/concat_nerfacto_model.py:197-233): MSE over the 4 RGBT channels of pred + noise (1 - accumulation);
+    grads then also carry "accumulation" [R]."""
     lib = L.load()
     R = int(rgb.shape[0])
     dev = rgb.device
@@ -576,6 +588,13 @@ def losses_forward_backward(weights_list: Sequence[Tensor], sdist_list: Sequence
     a.interlevel_mult, a.distortion_mult = float(interlevel_mult), float(distortion_mult)
     a.use_rgb_loss, a.use_thermal_loss = int(bool(use_rgb_loss)), int(bool(use_thermal_loss))
     a.grad_scale = float(grad_scale)
+    concat = concat_accumulation is not None
+    if concat:
+        if concat_noise is None:
+            raise ValueError("the concat loss needs the random-background draw (torch.rand_like(pred), [R,4])")
+        a.concat = 1
+        a.accumulation = f32(concat_accumulation.reshape(R), "accumulation").data_ptr()
+        a.noise = f32(concat_noise.reshape(R, 4), "noise").data_ptr()
     losses = torch.empty(4, dtype=torch.float32, device=dev)
     a.losses = losses.data_ptr()
     grads = None
@@ -583,6 +602,9 @@ def losses_forward_backward(weights_list: Sequence[Tensor], sdist_list: Sequence
         grads = {"rgb": torch.empty((R, 3), dtype=torch.float32, device=dev),
                  "thermal": torch.empty((R,), dtype=torch.float32, device=dev), "weights_list": []}
         a.g_rgb, a.g_thermal = grads["rgb"].data_ptr(), grads["thermal"].data_ptr()
+        if concat:
+            grads["accumulation"] = torch.empty((R,), dtype=torch.float32, device=dev)
+            a.g_accumulation = grads["accumulation"].data_ptr()
         for k in range(L.TNF_NUM_PROP + 1):
             if k < L.TNF_NUM_PROP and not prop_grad:
                 grads["weights_list"].append(None)
@@ -603,15 +625,18 @@ class _LossFn(torch.autograd.Function):
     backward scales the stashed gradients by the upstream scalars."""
 
     @staticmethod
-    def forward(ctx, cfg: dict, rgb, thermal, w0, w1, w2, sd0, sd1, sd2, gt_rgb, gt_thermal):
+    def forward(ctx, cfg: dict, rgb, thermal, w0, w1, w2, sd0, sd1, sd2, gt_rgb, gt_thermal, accumulation=None,
+                noise=None):
         prop_grad = bool(ctx.needs_input_grad[3] or ctx.needs_input_grad[4])
         losses, g = losses_forward_backward([w0, w1, w2], [sd0, sd1, sd2], rgb, thermal, gt_rgb, gt_thermal,
                                             interlevel_mult=cfg["interlevel_mult"],
                                             distortion_mult=cfg["distortion_mult"], use_rgb_loss=cfg["use_rgb_loss"],
-                                            use_thermal_loss=cfg["use_thermal_loss"], prop_grad=prop_grad)
+                                            use_thermal_loss=cfg["use_thermal_loss"], prop_grad=prop_grad,
+                                            concat_accumulation=accumulation, concat_noise=noise)
         ctx.g = g
         ctx.set_materialize_grads(False)
-        ctx.shapes = (rgb.shape, thermal.shape, w0.shape, w1.shape, w2.shape)
+        ctx.shapes = (rgb.shape, thermal.shape, w0.shape, w1.shape, w2.shape,
+                      None if accumulation is None else accumulation.shape)
         return losses[0], losses[1], losses[2], losses[3]
 
     @staticmethod
@@ -619,24 +644,34 @@ class _LossFn(torch.autograd.Function):
         g = ctx.g
         s = ctx.shapes
         gw = g["weights_list"]
+        concat = s[5] is not None
+
         def sc(t, u, shape):
             return None if (t is None or u is None) else (t * u).view(shape)
 
-        return (None, sc(g["rgb"], u_rgb, s[0]), sc(g["thermal"], u_th, s[1]), sc(gw[0], u_inter, s[2]),
-                sc(gw[1], u_inter, s[3]), sc(gw[2], u_dist, s[4]), None, None, None, None, None)
+        # concat_nerf: the temperature channel and the accumulation feed losses[0] (the 4-channel colour term)
+        return (None, sc(g["rgb"], u_rgb, s[0]), sc(g["thermal"], u_rgb if concat else u_th, s[1]),
+                sc(gw[0], u_inter, s[2]), sc(gw[1], u_inter, s[3]), sc(gw[2], u_dist, s[4]), None, None, None, None,
+                None, sc(g.get("accumulation"), u_rgb, s[5]) if concat else None, None)
 
 
 def losses(outputs: Dict[str, object], gt_rgb: Tensor, gt_thermal: Tensor, *, interlevel_mult: float = 1.0,
-           distortion_mult: float = 0.002, use_rgb_loss: bool = True, use_thermal_loss: bool = True
-           ) -> Dict[str, Tensor]:
+           distortion_mult: float = 0.002, use_rgb_loss: bool = True, use_thermal_loss: bool = True,
+           concat_noise: Optional[Tensor] = None) -> Dict[str, Tensor]:
     """Differentiable loss dict of get_loss_dict (thermal_nerf_model.py:277-326) from the training outputs
-    of :func:`render`."""
+    of :func:`render`.  ``concat_noise`` [R,4] selects the concat_nerf loss (one 4-channel colour term with the
+    random background blended into the prediction, rgb_concat/concat_nerfacto_model.py:197-233; no "thermal" entry);
+    ``outputs`` must then carry "accumulation"."""
     w, sd = outputs["weights_list"], outputs["sdist_list"]
     cfg = dict(interlevel_mult=interlevel_mult, distortion_mult=distortion_mult, use_rgb_loss=use_rgb_loss,
                use_thermal_loss=use_thermal_loss)
+    extra = () if concat_noise is None else (outputs["accumulation"], concat_noise)
     vals = _LossFn.apply(cfg, outputs["rgb"], outputs["thermal"], w[0], w[1], w[2], sd[0], sd[1], sd[2], gt_rgb,
-                         gt_thermal)
+                         gt_thermal, *extra)
     out = dict(zip(LOSS_NAMES, vals))
+    if concat_noise is not None:
+        out.pop("thermal")
+        return out
     if not use_rgb_loss:
         out.pop("rgb_loss")
     if not use_thermal_loss:

@@ -77,6 +77,7 @@ class ThermalNerfactoModelConfig:
     # B200 specific
     precision: Literal["fp32", "tc_fp16"] = "tc_fp16"
     thermal_head: bool = False  # the thermal head belongs to ThermalNerfModelConfig
+    concat_head: bool = False   # the 4-channel RGBT colour head belongs to ConcatNerfModelConfig
 
     def setup(self, **kwargs) -> Any:
         return self._target(self, **kwargs)
@@ -156,6 +157,10 @@ class KernelModelMixin:
     def _has_thermal_head(self) -> bool:
         return bool(getattr(self.config, "thermal_head", True))
 
+    def _is_concat(self) -> bool:
+        """ConcatNerfModel (rgb_concat/concat_nerfacto_model.py): 4-channel RGBT colour head, no thermal head."""
+        return bool(getattr(self.config, "concat_head", False))
+
     def _appearance_mode(self) -> int:
         if self.training:
             return L.APPEARANCE_LOOKUP
@@ -184,7 +189,8 @@ class KernelModelMixin:
             num_samples=(*cfg.num_proposal_samples_per_ray, cfg.num_nerf_samples_per_ray),
             near_plane=self._collider_near(), far_plane=cfg.far_plane, anneal=float(self._sampler_state()._anneal),
             use_contraction=not cfg.disable_scene_contraction,
-            aabb=self._aabb_list(), appearance_mode=self._appearance_mode(), precision=self._precision())
+            aabb=self._aabb_list(), appearance_mode=self._appearance_mode(), precision=self._precision(),
+            head_mode=L.HEAD_CONCAT if self._is_concat() else L.HEAD_THERMAL)
 
     def get_outputs(self, ray_bundle, depth_clip_chunk: int = 0) -> Dict[str, Any]:
         """thermal_nerf_model.py:210-275 as one fused kernel launch (eval) or one autograd node over
@@ -218,8 +224,11 @@ class KernelModelMixin:
             res = F.render_forward(self.tensors(), o, d, cam_flat, nears, fars, jitter, training=self.training,
                                    depth_clip_chunk=depth_clip_chunk, return_samples=self.training,
                                    **self._render_kwargs())
+        rgb = res["rgb"].view(*shape, 3)
+        if self._is_concat():  # "rgb" is the 4-channel RGBT image (the kernel returns channel 3 as `thermal`)
+            rgb = torch.cat([rgb, res["thermal"].view(*shape, 1)], dim=-1)
         outputs: Dict[str, Any] = {
-            "rgb": res["rgb"].view(*shape, 3),
+            "rgb": rgb,
             "accumulation": res["accumulation"].view(*shape, 1),
             "depth": res["depth"].view(*shape, 1),
             "expected_depth": res["expected_depth"].view(*shape, 1),
@@ -285,6 +294,8 @@ class KernelModelMixin:
         res = F.render_forward(self.tensors(), None, None, camera=cam, training=False,
                                depth_clip_chunk=self.config.eval_num_rays_per_chunk, **kw)
         out = {k: v.view(H, W, -1) for k, v in res.items() if isinstance(v, Tensor)}
+        if self._is_concat():
+            out["rgb"] = torch.cat([out["rgb"], out["thermal"]], dim=-1)
         if not self._has_thermal_head():
             out.pop("thermal", None)
         out["img"] = out["rgb"]
@@ -298,7 +309,20 @@ class KernelModelMixin:
             # the reference keeps the thermal GT on the host and moves it here (thermal_dataset.py:18-20,
             # thermal_nerf_model.py:319); non_blocking keeps that copy from draining the stream when the
             # host tensor is pinned (a blocking .to() waits for the forward kernel before the loss can launch)
-            image = batch["image"].to(self.device, non_blocking=True)[..., :3].reshape(-1, 3).float()
+            full = batch["image"].to(self.device, non_blocking=True)
+            image = full[..., :3].reshape(-1, 3).float()
+            if self._is_concat():
+                # ConcatNerfModel.get_loss_dict (concat_nerfacto_model.py:197-211): the batch image is RGBT; the
+                # renderer's "random" background is blended into the prediction only (rgbt_renderer.py:134-140)
+                pred = outputs["rgb"].reshape(-1, 4)
+                noise = torch.rand_like(pred)
+                cache = F.losses(
+                    {"rgb": pred[:, :3], "thermal": pred[:, 3], "accumulation": outputs["accumulation"].reshape(-1),
+                     "weights_list": outputs["weights_list"], "sdist_list": outputs["ray_samples_list"]},
+                    image, full[..., 3].reshape(-1).float(), interlevel_mult=self.config.interlevel_loss_mult,
+                    distortion_mult=self.config.distortion_loss_mult, concat_noise=noise)
+                outputs["_b200_losses"] = cache
+                return cache
             if self._has_thermal_head():
                 thermal = batch["thermal"].to(self.device, non_blocking=True).reshape(-1).float()
                 pred_th = outputs["thermal"].reshape(-1)
@@ -322,7 +346,10 @@ class KernelModelMixin:
             losses = self._fused_losses(outputs, batch)
             metrics["distortion"] = losses["distortion_loss"] / self.config.distortion_loss_mult
         with torch.no_grad():
-            if self.training and self.field.pass_rgb_gradients:
+            if self._is_concat():  # psnr over the four RGBT channels, without the loss's random background
+                gt = batch["image"].to(self.device)
+                mse = torch.mean((outputs["rgb"].detach() - gt.reshape(outputs["rgb"].shape)) ** 2)
+            elif self.training and self.field.pass_rgb_gradients:
                 mse = losses["rgb_loss"].detach()  # the fused loss kernel already reduced MSE(rgb, gt)
             else:
                 gt_rgb = batch["image"].to(self.device)
@@ -338,8 +365,16 @@ class KernelModelMixin:
         blend_background_for_loss_computation the identity on (pred, gt)."""
         if self.training:
             assert metrics_dict is not None and "distortion" in metrics_dict  # thermal_nerf_model.py:302
-            return dict(self._fused_losses(outputs, batch))
+            loss_dict = dict(self._fused_losses(outputs, batch))
+            cam_loss = getattr(self.camera_optimizer, "get_loss_dict", None)
+            if self._is_concat() and cam_loss is not None:  # only ConcatNerfModel adds it (concat_nerfacto_model.py:231)
+                cam_loss(loss_dict)
+            return loss_dict
         loss_dict: Dict[str, Tensor] = {}
+        if self._is_concat():  # concat_nerfacto_model.py:197-211 outside training: the blended colour term only
+            image = batch["image"].to(self.device)
+            pred = outputs["rgb"] + torch.rand_like(outputs["rgb"]) * (1.0 - outputs["accumulation"])
+            return {"rgb_loss": torch.nn.functional.mse_loss(image.reshape(pred.shape), pred)}
         image = batch["image"].to(self.device)[..., :3]
         if self.field.pass_rgb_gradients:
             loss_dict["rgb_loss"] = torch.nn.functional.mse_loss(image, outputs["rgb"])
@@ -375,6 +410,8 @@ class ThermalNerfactoModel(KernelModelMixin, nn.Module):
                  metadata: Optional[dict] = None, **kwargs) -> None:
         if config.thermal_head and not isinstance(self, ThermalNerfModel):
             raise ValueError("ThermalNerfactoModel is the model without a thermal head (thermal_head=False)")
+        if config.concat_head and not isinstance(self, ConcatNerfModel):
+            raise ValueError("the RGBT colour head (concat_head=True) belongs to ConcatNerfModel")
         super().__init__()
         self.config = config
         self.scene_box = scene_box if hasattr(scene_box, "aabb") else _SceneBox(torch.as_tensor(scene_box))
@@ -399,7 +436,8 @@ class ThermalNerfactoModel(KernelModelMixin, nn.Module):
             use_average_appearance_embedding=cfg.use_average_appearance_embedding,
             appearance_embedding_dim=cfg.appearance_embed_dim,
             pass_thermal_gradients=getattr(cfg, "pass_thermal_gradients", False),
-            thermal_head=cfg.thermal_head, use_contraction=not cfg.disable_scene_contraction)
+            thermal_head=cfg.thermal_head, use_contraction=not cfg.disable_scene_contraction,
+            rgb_out_dim=4 if cfg.concat_head else 3)
         self.camera_optimizer = CameraOptimizer(self.num_train_data, cfg.camera_optimizer_mode)
         self.proposal_networks = nn.ModuleList()
         for i in range(cfg.num_proposal_iterations):
@@ -519,6 +557,8 @@ class ThermalNerfactoModel(KernelModelMixin, nn.Module):
         in plain PyTorch on the already rendered [H,W,C] outputs.  LPIPS needs a pretrained network that is not
         shipped here: assign ``model.lpips`` (e.g. torchmetrics' LearnedPerceptualImagePatchSimilarity) or the lpips
         entries are NaN."""
+        if self._is_concat():
+            return self._concat_metrics_and_images(outputs, batch, threshold)
         metrics, images, g4, p4 = self._nerfacto_metrics_and_images(outputs, batch)
         metrics["mae_foreground"] = float(self.mae_thermal(g4, p4, threshold=threshold))
         metrics["mae"] = float(self.mae_thermal(g4, p4, threshold=None))
@@ -571,4 +611,52 @@ class ThermalNerfModel(ThermalNerfactoModel):
         metrics["lpips_thermal"] = self._lpips(torch.repeat_interleave(gt4, 3, dim=1), torch.repeat_interleave(th4, 3, dim=1))
         metrics["mae_thermal_foreground"] = float(self.mae_thermal(gt4, th4, threshold=threshold))
         metrics["mae_thermal"] = float(self.mae_thermal(gt4, th4, threshold=None))
+        return metrics, images
+
+
+@dataclass
+class ConcatNerfModelConfig(ThermalNerfactoModelConfig):
+    """ConcatNerfModelConfig (thermo_nerf/rgb_concat/concat_nerfacto_model.py:52-57): the ``concat_nerf`` model type
+    of train_eval_script.py:74-78."""
+
+    _target: Type = field(default_factory=lambda: ConcatNerfModel)
+    concat_head: bool = True
+
+
+class ConcatNerfModel(ThermalNerfactoModel):
+    """ConcatNerfModel (rgb_concat/concat_nerfacto_model.py:60-324) on libtnf_b200: the ablation baseline that
+    renders temperature as a fourth colour channel.  One RGBT colour head 63-64-64-4 (concat_field.py:65-75), no
+    thermal head; ``outputs["rgb"]`` is [*, 4]; RGBTRenderer with its default "random" background, i.e. the plain
+    weighted sum (rgbt_renderer.py:63-71); the training loss blends ``rand_like(pred) (1 - accumulation)`` into the
+    prediction (:197-211); evaluation metrics are taken on channel 3 (:250-296)."""
+
+    config: ConcatNerfModelConfig
+
+    def populate_modules(self) -> None:
+        super().populate_modules()
+        from .surface import RGBTRenderer
+
+        self.renderer_rgb = RGBTRenderer()
+
+    def _concat_metrics_and_images(self, outputs, batch, threshold=None):
+        dev = self.device
+        gt = batch["image"].to(dev)
+        pred = outputs["rgb"]
+
+        def gray(t: Tensor) -> Tensor:
+            return t.repeat(1, 1, 3) if t.shape[-1] == 1 else t
+
+        depth = outputs["depth"]
+        near, far = float(depth.min()), float(depth.max())
+        images = {"img": torch.cat([gt, pred], dim=1), "accumulation": gray(outputs["accumulation"]),
+                  "depth": gray(torch.clip((depth - near) / (far - near + 1e-10), 0, 1))}
+        for i in range(self.config.num_proposal_iterations):
+            pd = outputs[f"prop_depth_{i}"]
+            images[f"prop_depth_{i}"] = gray(torch.clip((pd - float(pd.min())) / (float(pd.max() - pd.min()) + 1e-10), 0, 1))
+        g4 = torch.moveaxis(gt, -1, 0)[None][:, 3, :, :].unsqueeze(0)      # concat_nerfacto_model.py:270-271
+        p4 = torch.moveaxis(pred, -1, 0)[None][:, 3, :, :].unsqueeze(0)
+        metrics = {"psnr": float(self.psnr(g4, p4)), "ssim": float(self.ssim(g4, p4)),
+                   "lpips": self._lpips(torch.repeat_interleave(g4, 3, dim=1), torch.repeat_interleave(p4, 3, dim=1)),
+                   "mae_thermal_foreground": float(self.mae_thermal(g4, p4, threshold=threshold)),
+                   "mae_thermal": float(self.mae_thermal(g4, p4, threshold=None))}
         return metrics, images

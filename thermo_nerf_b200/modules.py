@@ -192,8 +192,12 @@ class ThermalNerfactoTField(nn.Module):
                  log2_hashmap_size: int = 19, num_layers_color: int = 3, features_per_level: int = 2,
                  hidden_dim_color: int = 64, hidden_dim_transient: int = 64, appearance_embedding_dim: int = 32,
                  use_average_appearance_embedding: bool = False, pass_thermal_gradients: bool = False,
-                 thermal_head: bool = True, use_contraction: bool = True) -> None:
+                 thermal_head: bool = True, use_contraction: bool = True, rgb_out_dim: int = 3) -> None:
         super().__init__()
+        if rgb_out_dim not in (3, 4):
+            raise ValueError("the colour head has 3 outputs, or 4 for the RGBT head of concat_nerf")
+        if rgb_out_dim == 4 and thermal_head:
+            raise ValueError("the RGBT field (rgb_concat/concat_field.py) has no separate thermal head")
         self.use_contraction = bool(use_contraction)  # nerfstudio: spatial_distortion=SceneContraction(inf) or None
         fixed = dict(num_layers=(num_layers, 2), hidden_dim=(hidden_dim, 64), geo_feat_dim=(geo_feat_dim, 15),
                      num_levels=(num_levels, 16), num_layers_color=(num_layers_color, 3),
@@ -209,7 +213,9 @@ class ThermalNerfactoTField(nn.Module):
         self.mlp_base = MLPWithHashEncoding(num_levels, base_res, max_res, log2_hashmap_size, num_layers,
                                             hidden_dim, 1 + geo_feat_dim)
         self.embedding_appearance = Embedding(num_images, appearance_embedding_dim)
-        self.mlp_head = MLP(16 + geo_feat_dim + appearance_embedding_dim, num_layers_color, hidden_dim_color, 3)
+        # rgb_out_dim = 4: ConcatNerfactoTField (rgb_concat/concat_field.py:65-75), temperature = colour channel 3
+        self.mlp_head = MLP(16 + geo_feat_dim + appearance_embedding_dim, num_layers_color, hidden_dim_color,
+                            rgb_out_dim)
         self.mlp_thermal = MLP(geo_feat_dim, 2, 64, hidden_dim_transient)
         self.field_head_thermal = ThermalFieldHead(in_dim=self.mlp_thermal.get_out_dim())
         self.thermal_head = bool(thermal_head)

@@ -7,6 +7,8 @@ unchanged on the sm_100a kernels.
   ``train_eval_script.py:94`` asserts, and ``isinstance(model, ThermalNerfactoModel)`` of ``evaluator.py:76`` holds)
 * ``B200ThermalNerfactoModel`` / ``...Config``           <- thermo_nerf/nerfacto_config/thermal_nerfacto.py (the
   ``nerfacto`` / ``thermal-nerfacto`` model types of train_eval_script.py:66-73)
+* ``B200ConcatNerfModel`` / ``...Config``                <- thermo_nerf/rgb_concat/concat_nerfacto_model.py (the
+  ``concat_nerf`` model type, train_eval_script.py:74-78)
 * ``b200_thermal_nerf_config`` / ``b200_thermalnerfacto_config``: the reference's method configs
   (thermal_nerf/config_thermal_nerf.py:17-48, nerfacto_config/config_nerfacto.py:14-53) with the model swapped
 * ``install()``: swaps the model configs inside the reference's module-level ``TrainerConfig`` objects and makes
@@ -53,10 +55,12 @@ def _bind_field_surface(model) -> None:
 
 def make_plugin_classes(ref_model: type, ref_config: type, *, name: str = "B200ThermalNerfModel",
                         field_head_names: Any = None, field_head_names_t: Any = None,
-                        thermal_head: bool = True) -> Tuple[type, type]:
+                        thermal_head: bool = True, concat_head: bool = False) -> Tuple[type, type]:
     """(model class, config class) deriving from the given reference classes.  ``thermal_head=False`` for the
-    ThermalNerfactoModel family, whose field is a stock NerfactoField (no "thermal" output, no thermal loss)."""
-    has_thermal_head = bool(thermal_head)
+    ThermalNerfactoModel family, whose field is a stock NerfactoField (no "thermal" output, no thermal loss);
+    ``concat_head=True`` for ConcatNerfModel (4-channel RGBT colour head, rgb_concat/)."""
+    has_thermal_head = bool(thermal_head) and not concat_head
+    is_concat = bool(concat_head)
 
     class _Model(KernelModelMixin, ref_model):  # type: ignore[misc, valid-type]
         def populate_modules(self) -> None:
@@ -77,6 +81,9 @@ def make_plugin_classes(ref_model: type, ref_config: type, *, name: str = "B200T
 
         def _has_thermal_head(self) -> bool:
             return has_thermal_head
+
+        def _is_concat(self) -> bool:
+            return is_concat
 
     _Model.__name__ = _Model.__qualname__ = name
     _Model.__doc__ = f"{ref_model.__name__} on libtnf_b200 (see thermo_nerf_b200.nerfstudio_plugin)."
@@ -125,9 +132,21 @@ if AVAILABLE:
     B200ThermalNerfactoModel, B200ThermalNerfactoModelConfig = make_plugin_classes(
         _RefNerfactoModel, _RefNerfactoConfig, name="B200ThermalNerfactoModel", field_head_names=_FHN,
         thermal_head=False)
+    _plugin_classes = [B200ThermalNerfModel, B200ThermalNerfModelConfig, B200ThermalNerfactoModel,
+                       B200ThermalNerfactoModelConfig]
+    try:  # the concat_nerf baseline (imports nerfacc through rgbt_renderer.py)
+        from thermo_nerf.rgb_concat.concat_nerfacto_model import (  # type: ignore[import-not-found]
+            ConcatNerfModel as _RefConcatModel,
+            ConcatNerfModelConfig as _RefConcatConfig,
+        )
+
+        B200ConcatNerfModel, B200ConcatNerfModelConfig = make_plugin_classes(
+            _RefConcatModel, _RefConcatConfig, name="B200ConcatNerfModel", field_head_names=_FHN, concat_head=True)
+        _plugin_classes += [B200ConcatNerfModel, B200ConcatNerfModelConfig]
+    except Exception:  # pragma: no cover - nerfacc missing
+        _RefConcatModel = _RefConcatConfig = None
     # pickled-YAML config.yml files name the classes by module path: keep them importable from here
-    for _c in (B200ThermalNerfModel, B200ThermalNerfModelConfig, B200ThermalNerfactoModel,
-               B200ThermalNerfactoModelConfig):
+    for _c in _plugin_classes:
         _c.__module__ = __name__
 
 
@@ -186,6 +205,11 @@ def install() -> None:
                                                                     B200ThermalNerfModelConfig)
     ref_nerfacto_mod.thermalnerfacto_config.pipeline.model = upgrade_config(
         ref_nerfacto_mod.thermalnerfacto_config.pipeline.model, B200ThermalNerfactoModelConfig)
+    if _RefConcatConfig is not None:
+        from thermo_nerf.rgb_concat import config_concat_nerfacto as ref_concat_mod  # type: ignore[import-not-found]
+
+        ref_concat_mod.concat_nerf_config.pipeline.model = upgrade_config(
+            ref_concat_mod.concat_nerf_config.pipeline.model, B200ConcatNerfModelConfig)
     stock_setup = _RefNerfactoConfig.setup
 
     def setup(self, **kwargs):
@@ -193,6 +217,8 @@ def install() -> None:
             return upgrade_config(self, B200ThermalNerfModelConfig).setup(**kwargs)
         if type(self) is _RefNerfactoConfig:
             return upgrade_config(self, B200ThermalNerfactoModelConfig).setup(**kwargs)
+        if _RefConcatConfig is not None and type(self) is _RefConcatConfig:
+            return upgrade_config(self, B200ConcatNerfModelConfig).setup(**kwargs)
         return stock_setup(self, **kwargs)
 
     _RefNerfactoConfig.setup = setup  # ThermalNerfModelConfig inherits it
