@@ -569,10 +569,13 @@ def bench_train(ctx) -> dict:
                    "final_losses": dict(zip(F.LOSS_NAMES, final_losses))},
         "clocks": clocks,
         "exchange": ("none (1 GPU)" if world == 1 else
-                     (("peer-memory fused reduce-scatter + Adam + all-gather (tnf_peer_adam_step)"
-                       if engine.arena.gather == "push" else
-                       "peer-memory fused reduce-scatter + Adam (tnf_peer_adam_reduce), pull all-gather "
-                       "(tnf_peer_gather_params)")
+                     ({"push": "peer-memory fused reduce-scatter + Adam + all-gather (tnf_peer_adam_step)",
+                       "pull": "peer-memory fused reduce-scatter + Adam (tnf_peer_adam_reduce), pull all-gather "
+                               "(tnf_peer_gather_params)",
+                       "multimem": "NVSwitch multicast: in-switch reduction (multimem.ld_reduce) + Adam + broadcast "
+                                   "(multimem.st) in one kernel (tnf_peer_adam_multimem)"}[engine.arena.gather]
+                      + (", arenas mapped by torch symmetric memory" if engine.arena._symm is not None
+                         else ", arenas mapped by CUDA IPC")
                       if engine.arena is not None else "NCCL all-reduce (mean) + tnf_adam_step")),
         "gpu_launches": None,
         "exchange_phases_ms": engine.arena.timing_summary() if engine.arena is not None else None,
@@ -595,7 +598,7 @@ def bench_train(ctx) -> dict:
     # (the counter memset of the proposal backward and, for world > 1, NCCL's all-reduce kernel are not ours)
     per_step = 4 + (1 if args.precision == "fp32" else 0)
     if engine.arena is not None:  # peer exchange: 2 barrier kernels + fused Adam (+ gather kernel when pulling)
-        line["gpu_launches"] = int(args.steps * (per_step + (3 if engine.arena.gather == "push" else 4)) + prop_steps_timed)
+        line["gpu_launches"] = int(args.steps * (per_step + (4 if engine.arena.gather == "pull" else 3)) + prop_steps_timed)
     else:
         line["gpu_launches"] = int(args.steps * (per_step + 1) + prop_steps_timed * 2)
     if roofline:

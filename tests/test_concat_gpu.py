@@ -101,7 +101,7 @@ def test_concat_loss_and_gradients_match_oracle_autograd(precision, rel_tol, cos
     sum(ld.values()).backward()
     torch.cuda.synchronize()
     for k in ld:
-        a, b = float(ld[k]), float(ref_ld[k])
+        a, b = float(ld[k].detach()), float(ref_ld[k].detach())
         assert abs(a - b) <= (5e-4 if precision == "fp32" else 2e-2) * max(abs(b), 1e-3), (k, a, b)
     ref_grads = dict(oracle.named_parameters())
     checked = 0

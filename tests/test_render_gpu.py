@@ -42,7 +42,7 @@ def test_eval_forward_fp32_matches_oracle(trained_like, contiguous):
     with torch.no_grad():
         ref = oracle.get_outputs(rays, training=False)
     out = _run(model, rays)
-    compare_outputs(out, ref, FP32_TOL)
+    compare_outputs(out, ref, FP32_TOL, thermal_contrast=trained_like)
     assert out["rgb"].shape == (1024, 3) and out["thermal"].shape == (1024, 1)
     assert out["rgb"].dtype == torch.float32
 
@@ -53,7 +53,7 @@ def test_eval_forward_tensor_core_matches_oracle():
     with torch.no_grad():
         ref = oracle.get_outputs(rays, training=False)
     out = _run(model, rays)
-    compare_outputs(out, ref, TC_TOL, median_bad_frac=0.05)
+    compare_outputs(out, ref, TC_TOL, median_bad_frac=0.05, thermal_contrast=True)
     mse = torch.mean((out["rgb"].cpu() - ref["rgb"]) ** 2).item()
     psnr = -10 * torch.log10(torch.tensor(mse + 1e-20)).item()
     assert psnr >= 40.0, psnr

@@ -117,28 +117,45 @@ __global__ void __launch_bounds__(256)
   const int me = A.a.rank;
   float4* __restrict__ M = reinterpret_cast<float4*>(A.m);
   float4* __restrict__ V = reinterpret_cast<float4*>(A.v);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long e = A.shard_begin + 4 * i;
-    int s = 0;
-    while (s + 1 < A.nseg && e >= A.seg_end[s]) ++s;
-    if (!A.seg_active[s]) continue;
-    float4 g = multimem_ld_reduce_add(grads_mc + e);
-    g.x *= A.inv_world; g.y *= A.inv_world; g.z *= A.inv_world; g.w *= A.inv_world;
-    float4 p = *reinterpret_cast<const float4*>(A.a.params[me] + e);
-    float4 m = M[i], v = V[i];
-    // never-touched entries: the update is exactly zero and every rank already holds the same value
-    if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f && m.x == 0.f && m.y == 0.f && m.z == 0.f && m.w == 0.f &&
-        v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f)
-      continue;
-    const float ss = A.seg_step_size[s], ib = A.seg_inv_sqrt_bc2[s];
-    peer_adam_one(p.x, g.x, m.x, v.x, A, ss, ib);
-    peer_adam_one(p.y, g.y, m.y, v.y, A, ss, ib);
-    peer_adam_one(p.z, g.z, m.z, v.z, A, ss, ib);
-    peer_adam_one(p.w, g.w, m.w, v.w, A, ss, ib);
-    M[i] = m;
-    V[i] = v;
-    multimem_st(params_mc + e, p);
+  constexpr int U = 4;  // switch reductions in flight per thread: the round trip through the NVSwitch is long
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += U * stride) {
+    float4 g[U];
+    int seg[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      seg[u] = -1;
+      if (i >= n4) continue;
+      const long long e = A.shard_begin + 4 * i;
+      int s = 0;
+      while (s + 1 < A.nseg && e >= A.seg_end[s]) ++s;
+      if (!A.seg_active[s]) continue;
+      seg[u] = s;
+      g[u] = multimem_ld_reduce_add(grads_mc + e);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (seg[u] < 0) continue;
+      const long long i = i0 + u * stride;
+      const long long e = A.shard_begin + 4 * i;
+      float4 gg = g[u];
+      gg.x *= A.inv_world; gg.y *= A.inv_world; gg.z *= A.inv_world; gg.w *= A.inv_world;
+      float4 p = *reinterpret_cast<const float4*>(A.a.params[me] + e);
+      float4 m = M[i], v = V[i];
+      // never-touched entries: the update is exactly zero and every rank already holds the same value
+      if (gg.x == 0.f && gg.y == 0.f && gg.z == 0.f && gg.w == 0.f && m.x == 0.f && m.y == 0.f && m.z == 0.f &&
+          m.w == 0.f && v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f)
+        continue;
+      const float ss = A.seg_step_size[seg[u]], ib = A.seg_inv_sqrt_bc2[seg[u]];
+      peer_adam_one(p.x, gg.x, m.x, v.x, A, ss, ib);
+      peer_adam_one(p.y, gg.y, m.y, v.y, A, ss, ib);
+      peer_adam_one(p.z, gg.z, m.z, v.z, A, ss, ib);
+      peer_adam_one(p.w, gg.w, m.w, v.w, A, ss, ib);
+      M[i] = m;
+      V[i] = v;
+      multimem_st(params_mc + e, p);
+    }
   }
 }
 

@@ -162,7 +162,13 @@ class PeerArena:
         # "multimem": reduction and broadcast inside the NVSwitch (needs the multicast object of the symmetric path).
         self.gather = os.environ.get("TNF_PEER_GATHER", "auto")
         if self.gather == "auto":
-            self.gather = "multimem" if self.multicast else ("pull" if self.world >= 4 else "push")
+            # measured on B200 (profiles/): two GPUs - the push kernel (half the arena per direction either way, and
+            # plain peer stores run faster than switch reductions); from four GPUs up the in-switch reduction moves
+            # 1/N instead of (N-1)/N of the arena per rank and direction
+            if self.world >= 4:
+                self.gather = "multimem" if self.multicast else "pull"
+            else:
+                self.gather = "push"
         if self.gather not in ("push", "pull", "multimem"):
             raise ValueError("TNF_PEER_GATHER must be 'auto', 'push', 'pull' or 'multimem'")
         if self.gather == "multimem" and not self.multicast:
