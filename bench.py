@@ -125,12 +125,15 @@ def build_b200_model(device, precision: str, camera_optimizer_mode: str = "off")
 
 
 def frame_bundles(n_frames: int, device, rank: int, world: int):
-    """Distinct orbit frames; rank r renders frames r, r+world, ... (frames shard with no collective)."""
+    """``n_frames`` distinct orbit views per rank.  Frames shard with no collective (rank r renders frames r, r+world,
+    ... of a trajectory, thermo_nerf_b200.dist.shard_frames); for the scaling measurement every rank gets the SAME
+    views as the single-GPU run: the cost of a frame depends on the view (measured 21.6 - 28 ms over an orbit of the
+    synthetic scene), so striping different views over the ranks would report the scene's load imbalance through the
+    max over ranks rather than anything about the system."""
     from thermo_nerf_b200 import orbit_cameras
-    from thermo_nerf_b200.dist import shard_frames
 
-    cams = orbit_cameras(max(n_frames * world, 1), hw=HW, focal=FOCAL, device=device)
-    return [cams.generate_rays(i) for i in shard_frames(n_frames * world, rank, world)]
+    cams = orbit_cameras(max(n_frames, 1), hw=HW, focal=FOCAL, device=device)
+    return [cams.generate_rays(i) for i in range(n_frames)]
 
 
 class L2Flusher:
@@ -920,10 +923,8 @@ def bench_render(ctx) -> dict:
     #      modalities of render_video_script.py - one camera per step: the camera (72 B of kernel arguments) goes
     #      in, the two uint8 frames come back to pinned host memory
     from thermo_nerf_b200 import PinholeCameras, RenderedImageModality, Renderer, orbit_cameras
-    from thermo_nerf_b200.dist import shard_frames
-
-    all_cams = orbit_cameras(n_distinct * world, hw=HW, focal=FOCAL)
-    mine = shard_frames(n_distinct * world, rank, world)
+    all_cams = orbit_cameras(n_distinct, hw=HW, focal=FOCAL)
+    mine = range(n_distinct)  # the same views on every rank, see frame_bundles
     one = [PinholeCameras(all_cams.camera_to_worlds[i:i + 1], all_cams.fx, all_cams.fy, all_cams.cx, all_cams.cy,
                           all_cams.width, all_cams.height) for i in mine]
     g = torch.Generator().manual_seed(5)
@@ -947,7 +948,8 @@ def bench_render(ctx) -> dict:
         "data": "synthetic",
         "config": {"workload": "render 800x800 ThermoScenes-shaped frame per step (640000 rays, samples 256/96/48, "
                                "eval chunk 65536), rgb+thermal+depth+accumulation in one pass; frames shard "
-                               "round-robin over ranks, no collective",
+                               "over ranks with no collective (every rank renders the same 4 views: equal work per "
+                               "rank, frame cost depends on the view)",
                    "l2": "flushed between timed iterations (256 MiB write)", "rays_per_second": value * 1e6,
                    "weights": "random trained-like, full-size tables (field 2^19x16, proposals 2^17x5)"},
         "clocks": clocks, "gpu_launches": 2 * args.steps,  # forward + depth-clip pass per frame (device-resident loop)

@@ -155,6 +155,10 @@ class PeerArena:
         self.exp_avg_sq = torch.zeros(self.shard, dtype=torch.float32, device=dev)
         self._epoch = [0] * L.TNF_PEER_FLAG_SLOTS
         self.timing: Optional[list] = None
+        # the gradient arena is cleared on a side stream so that the memset overlaps the next forward (which never
+        # touches it); whoever writes gradients next calls wait_zeroed() first
+        self._zero_stream: Optional[torch.cuda.Stream] = None
+        self._zero_done: Optional[torch.cuda.Event] = None
         import os
 
         # all-gather flavour: "push" (everything in one kernel) or "pull" (owners keep their shard, peers copy it out).
@@ -280,9 +284,11 @@ class PeerArena:
                                                     self._C.c_void_p(stream)))
 
     def adam_step(self, segments: Sequence[tuple], beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-15,
-                  zero_grads: bool = True) -> None:
+                  zero_grads: bool = True, async_zero: bool = False) -> None:
         """``segments`` = [(begin, end, lr, step, active), ...] covering [0, numel).  Runs
-        barrier -> fused reduce-scatter/Adam/all-gather -> barrier (-> zero this rank's gradient arena)."""
+        barrier -> fused reduce-scatter/Adam/all-gather -> barrier (-> zero this rank's gradient arena).
+        ``async_zero``: clear the arena on a side stream instead (the caller must :meth:`wait_zeroed` before the
+        next kernel that accumulates gradients) - TrainEngine does, so that the memset runs beside the forward."""
         L, C = self._L, self._C
         segs = (L.TnfAdamSegment * len(segments))()
         for i, (b, e, lr, step, active) in enumerate(segments):
@@ -316,11 +322,29 @@ class PeerArena:
             # which this rank reaches after its pull has completed (stream order)
         if ev:
             ev[3].record()
-        if zero_grads:
+        if zero_grads and not async_zero:
             self.grads.zero_()
+        elif zero_grads:
+            if self._zero_stream is None:
+                self._zero_stream = torch.cuda.Stream(self.device)
+            main = torch.cuda.current_stream(self.device)
+            landed = torch.cuda.Event()
+            landed.record(main)  # after barrier(1): every peer has finished reading this rank's gradients
+            self._zero_stream.wait_event(landed)
+            with torch.cuda.stream(self._zero_stream):
+                self.grads.zero_()
+                self._zero_done = torch.cuda.Event()
+                self._zero_done.record(self._zero_stream)
         if ev:
             ev[4].record()
             self.timing.append(ev)
+
+    def wait_zeroed(self) -> None:
+        """Orders the current stream after the asynchronous clearing of the gradient arena started by the last
+        :meth:`adam_step`.  Call before launching anything that accumulates into ``grads``."""
+        if self._zero_done is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._zero_done)
+            self._zero_done = None
 
     def timing_summary(self) -> Optional[dict]:
         """Median milliseconds of the four phases of adam_step (measurement aid: PeerArena.timing = [] enables it)."""

@@ -146,6 +146,8 @@ class TrainEngine:
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         res["_workspace"] = self._ws
+        if self.arena is not None:
+            self.arena.wait_zeroed()  # the previous step's memset of the gradient arena ran beside this forward
         F.render_backward(self.tensors, res["_model_struct"], origins, directions, cam, None, None, jitter, res,
                           {"rgb": g["rgb"], "thermal": g["thermal"], "accumulation": g.get("accumulation"),
                            "weights_list": g["weights_list"]}, grads)
@@ -158,7 +160,7 @@ class TrainEngine:
             # one kernel: mean over ranks (peer loads) + Adam on the owned shard + parameter broadcast (peer stores)
             self.arena.adam_step([(0, self.prop_end, lr, max(self.prop_steps, 1), updated),
                                   (self.prop_end, self.arena.numel, lr, self.field_steps, True)],
-                                 beta1=self.betas[0], beta2=self.betas[1], eps=self.eps)
+                                 beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, async_zero=True)
         else:
             if self.world_size > 1:
                 # DDP semantics: average over ranks.  The proposal part of the arena is all zeros on
