@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define TNF_ABI_VERSION 8
+#define TNF_ABI_VERSION 9
 
 #define TNF_MAX_LEVELS 16      /* hash levels of the field grid (fixed: 16)          */
 #define TNF_MAX_PROP_LEVELS 8  /* max hash levels of a proposal density grid          */
@@ -200,6 +200,15 @@ int tnf_render_forward(const TnfModel* model, const TnfRays* rays, const TnfOutp
                        int64_t depth_clip_chunk, void* workspace, size_t workspace_bytes,
                        void* stream);
 
+/* tnf_render_forward whose field level additionally waits for `field_params_ready` (a cudaEvent_t, or NULL for no
+ * wait) on `stream`: in training mode the call is two launches - the proposal levels (proposal-network parameters
+ * only) and the field level + compositing - and the event is waited for between them, so a parameter exchange of the
+ * field network (tnf_peer_adam_range on another stream) may still be in flight while the proposal pass runs.  When the
+ * call is a single launch (eval, fp32 mode) the wait comes first. */
+int tnf_render_forward_staged(const TnfModel* model, const TnfRays* rays, const TnfOutputs* out,
+                              int64_t depth_clip_chunk, void* workspace, size_t workspace_bytes, void* stream,
+                              void* field_params_ready);
+
 /* Cameras.generate_rays for `num_pixels` pixels of one camera starting at first_pixel (row-major):
  * origins/directions [n,3], directions_norm [n] (the RayBundle metadata entry; may be NULL).
  * Replaces cameras.generate_rays(camera_indices=i) at thermo_nerf/render/renderer.py:183 and
@@ -276,6 +285,16 @@ size_t tnf_backward_workspace_bytes(const TnfModel* model, int64_t num_rays);
 int tnf_render_backward(const TnfModel* model, const TnfRays* rays, const TnfSaved* saved,
                         const TnfOutputGrads* gout, const TnfModelGrad* grads, void* workspace,
                         size_t workspace_bytes, void* stream);
+
+/* tnf_render_backward with the two levels in the other order - field level first, then the proposal levels (their
+ * gradients are disjoint: the interlevel loss sees the field's weights detached) - and `field_grads_done` (a
+ * cudaEvent_t; NULL = plain tnf_render_backward) recorded on `stream` between them: a multi-GPU trainer starts the
+ * exchange of the field gradients (tnf_peer_adam_range on another stream) while the proposal kernel still runs.
+ * `reserve_ctas`: CTA slots of 256 threads x 64 registers the proposal kernel leaves free for that exchange kernel
+ * (its grid shrinks; the work units are handed out by a device counter, so nothing else changes). */
+int tnf_render_backward_staged(const TnfModel* model, const TnfRays* rays, const TnfSaved* saved,
+                               const TnfOutputGrads* gout, const TnfModelGrad* grads, void* workspace,
+                               size_t workspace_bytes, void* stream, void* field_grads_done, int32_t reserve_ctas);
 
 /* ---- Field / Renderer plugin surface: the per-module entry points of the reference's
  * ThermalNerfactoTField and ThermalRenderer for callers that compose the modules by hand (viewer density
@@ -400,9 +419,9 @@ int tnf_sample_batch(const TnfDataset* dataset, const float* rand, int64_t num_r
  * access enabled from the current device (tnf_peer_enable_access).
  * ------------------------------------------------------------------------------------ */
 #define TNF_MAX_PEERS 16
-#define TNF_PEER_FLAG_SLOTS 2       /* independent barrier slots                                   */
-#define TNF_PEER_FLAG_TIMEOUT 32    /* word of a rank's own flag block that counts timed-out waits */
-#define TNF_PEER_FLAG_WORDS 64      /* uint32 words per flag block (zero-initialised by the owner) */
+#define TNF_PEER_FLAG_SLOTS 4       /* independent barrier slots (TNF_MAX_PEERS words each)        */
+#define TNF_PEER_FLAG_TIMEOUT 64    /* word of a rank's own flag block that counts timed-out waits */
+#define TNF_PEER_FLAG_WORDS 128     /* uint32 words per flag block (zero-initialised by the owner) */
 #define TNF_MAX_ADAM_SEGMENTS 4
 
 typedef struct TnfPeerArena {
@@ -468,6 +487,22 @@ int tnf_peer_adam_multimem(const TnfPeerArena* arena, const float* grads_multica
 
 int tnf_peer_gather_params(const TnfPeerArena* arena, const TnfAdamSegment* segments, int32_t num_segments,
                            void* stream);
+
+/* The fused exchange over the slice [range_begin, range_end) of the arenas only, sharded over the ranks on its own
+ * (rank r owns the r-th of world_size equal parts of the slice; the slice's length must be a multiple of
+ * 4 * world_size).  exp_avg / exp_avg_sq hold the state of this rank's part of THIS slice.  `flavour`:
+ * TNF_PEER_PUSH = the kernel of tnf_peer_adam_step, TNF_PEER_MULTIMEM = the kernel of tnf_peer_adam_multimem (needs
+ * the two multicast addresses, ignored otherwise).  `max_ctas` > 0 bounds the grid so that the exchange can share
+ * the SMs with a compute kernel running beside it on another stream.
+ * Why slices: the proposal networks and the field are separate optimizer groups of config_thermal_nerf.py:32-45 and
+ * the next iteration's proposal pass reads only the former, so the trainer exchanges the proposal slice first and
+ * lets the (seven times larger) field slice travel while that pass already runs; see tnf_render_forward_staged. */
+#define TNF_PEER_PUSH 0
+#define TNF_PEER_MULTIMEM 3
+int tnf_peer_adam_range(const TnfPeerArena* arena, int32_t flavour, int64_t range_begin, int64_t range_end,
+                        int32_t max_ctas, const float* grads_multicast, float* params_multicast,
+                        float* exp_avg_shard, float* exp_avg_sq_shard, const TnfAdamSegment* segments,
+                        int32_t num_segments, double beta1, double beta2, float eps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -41,7 +41,7 @@ def test_every_declared_symbol_is_exported(lib):
 def test_abi_version_and_error_string(lib):
     from thermo_nerf_b200 import _lib
 
-    assert lib.tnf_version() == _lib.TNF_ABI_VERSION == 8
+    assert lib.tnf_version() == _lib.TNF_ABI_VERSION == 9
     assert isinstance(lib.tnf_last_error(), bytes)
 
 

@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 from typing import Optional
 
-TNF_ABI_VERSION = 8
+TNF_ABI_VERSION = 9
 TNF_MAX_LEVELS = 16
 TNF_MAX_PROP_LEVELS = 8
 TNF_MAX_SAMPLES = 256
@@ -230,9 +230,11 @@ class TnfAdamTensor(C.Structure):
 
 
 TNF_MAX_PEERS = 16
-TNF_PEER_FLAG_SLOTS = 2
-TNF_PEER_FLAG_TIMEOUT = 32
-TNF_PEER_FLAG_WORDS = 64
+TNF_PEER_FLAG_SLOTS = 4
+TNF_PEER_FLAG_TIMEOUT = 64
+TNF_PEER_FLAG_WORDS = 128
+TNF_PEER_PUSH = 0
+TNF_PEER_MULTIMEM = 3
 TNF_MAX_ADAM_SEGMENTS = 4
 TNF_IPC_HANDLE_BYTES = 64
 
@@ -264,6 +266,8 @@ EXPORTED_SYMBOLS = (
     "tnf_last_error",
     "tnf_forward_workspace_bytes",
     "tnf_render_forward",
+    "tnf_render_forward_staged",
+    "tnf_render_backward_staged",
     "tnf_generate_rays",
     "tnf_postprocess_frame",
     "tnf_sample_batch",
@@ -284,6 +288,7 @@ EXPORTED_SYMBOLS = (
     "tnf_peer_adam_step",
     "tnf_peer_adam_reduce",
     "tnf_peer_adam_multimem",
+    "tnf_peer_adam_range",
     "tnf_peer_gather_params",
 )
 
@@ -332,6 +337,8 @@ def load() -> C.CDLL:
         C.c_size_t,
         C.c_void_p,
     ]
+    lib.tnf_render_forward_staged.restype = C.c_int
+    lib.tnf_render_forward_staged.argtypes = lib.tnf_render_forward.argtypes + [C.c_void_p]
     lib.tnf_generate_rays.restype = C.c_int
     lib.tnf_generate_rays.argtypes = [C.POINTER(TnfCamera), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p]
@@ -354,6 +361,8 @@ def load() -> C.CDLL:
         C.c_size_t,
         C.c_void_p,
     ]
+    lib.tnf_render_backward_staged.restype = C.c_int
+    lib.tnf_render_backward_staged.argtypes = lib.tnf_render_backward.argtypes + [C.c_void_p, C.c_int32]
     lib.tnf_backward_stage_mask.restype = C.c_int
     lib.tnf_backward_stage_mask.argtypes = [C.c_int]
     lib.tnf_field_density.restype = C.c_int
@@ -400,6 +409,10 @@ def load() -> C.CDLL:
     lib.tnf_peer_adam_multimem.argtypes = [C.POINTER(TnfPeerArena), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.POINTER(TnfAdamSegment), C.c_int32, C.c_double, C.c_double, C.c_float,
                                            C.c_void_p]
+    lib.tnf_peer_adam_range.restype = C.c_int
+    lib.tnf_peer_adam_range.argtypes = [C.POINTER(TnfPeerArena), C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(TnfAdamSegment), C.c_int32,
+                                        C.c_double, C.c_double, C.c_float, C.c_void_p]
     lib.tnf_peer_adam_reduce.restype = C.c_int
     lib.tnf_peer_adam_reduce.argtypes = lib.tnf_peer_adam_step.argtypes
     lib.tnf_peer_gather_params.restype = C.c_int

@@ -879,6 +879,12 @@ size_t tnf_backward_workspace_bytes(const TnfModel* model, int64_t num_rays) {
 
 int tnf_render_backward(const TnfModel* model, const TnfRays* rays, const TnfSaved* saved, const TnfOutputGrads* gout,
                         const TnfModelGrad* grads, void* workspace, size_t workspace_bytes, void* stream_) {
+  return tnf_render_backward_staged(model, rays, saved, gout, grads, workspace, workspace_bytes, stream_, nullptr, 0);
+}
+
+int tnf_render_backward_staged(const TnfModel* model, const TnfRays* rays, const TnfSaved* saved,
+                               const TnfOutputGrads* gout, const TnfModelGrad* grads, void* workspace,
+                               size_t workspace_bytes, void* stream_, void* field_grads_done, int32_t reserve_ctas) {
   tnf::g_err[0] = 0;
   if (int e = tnf::check_model(model)) return e;
   if (!rays || !saved || !gout) return fail(TNF_ERR_INVALID_ARGUMENT, "rays/saved/gout is null");
@@ -910,7 +916,8 @@ int tnf_render_backward(const TnfModel* model, const TnfRays* rays, const TnfSav
 
   // ---- proposal levels: (level, ray) units handed out by a device counter (last 8 bytes of the workspace)
   const bool do_prop = (grads->prop[0].table && gout->weights[0]) || (grads->prop[1].table && gout->weights[1]);
-  if (do_prop && (g_stage_mask & 1)) {
+  auto launch_prop = [&]() -> int {
+    if (!(do_prop && (g_stage_mask & 1))) return TNF_OK;
     unsigned long long* counter =
         reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(workspace) + need - 16);
     e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
@@ -922,7 +929,11 @@ int tnf_render_backward(const TnfModel* model, const TnfRays* rays, const TnfSav
     for (int k = 0; k < TNF_NUM_PROP; ++k)
       if (grads->prop[k].table && gout->weights[k]) units += R;
     const long long wantu = (units + tnf::kWarpsPerCta - 1) / tnf::kWarpsPerCta;
-    const long long cap = (long long)sms * 2;
+    // two CTAs per SM fill the register file; `reserve_ctas` slots of 256 threads x 64 registers (half a CTA of this
+    // kernel each) stay free for a kernel on another stream.  Units come from a device counter: fewer CTAs just
+    // take more units each.
+    long long cap = (long long)sms * 2 - (reserve_ctas > 0 ? (reserve_ctas + 1) / 2 : 0);
+    if (cap < sms) cap = sms;
     const unsigned grid = (unsigned)(wantu < cap ? wantu : cap);
 #define TNF_LAUNCH_PROP(TC_, NLC_)                                                                              \
   do {                                                                                                          \
@@ -937,14 +948,26 @@ int tnf_render_backward(const TnfModel* model, const TnfRays* rays, const TnfSav
 #undef TNF_LAUNCH_PROP
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "backward_prop launch: %s", cudaGetErrorString(e));
-  }
+    return TNF_OK;
+  };
+  // The two levels write disjoint gradients (the interlevel loss sees the field's weights detached).  Default order:
+  // proposal, field.  Staged: field first, the event recorded, then proposal - the caller starts exchanging the field
+  // gradients with the other GPUs while the proposal kernel still runs.
+  auto field_done = [&]() -> int {
+    if (!field_grads_done) return TNF_OK;
+    const cudaError_t re = cudaEventRecord(static_cast<cudaEvent_t>(field_grads_done), stream);
+    if (re != cudaSuccess) return fail(TNF_ERR_CUDA, "cudaEventRecord: %s", cudaGetErrorString(re));
+    return launch_prop();
+  };
+  if (!field_grads_done)
+    if (int rc = launch_prop()) return rc;
 
   // ---- field level
   const long long Ns = R * model->num_samples[TNF_NUM_PROP];
   if (model->precision == TNF_PRECISION_TC_FP16) {
     if (g_stage_mask & 2)
       if (int rc = tnf::launch_backward_field_tc(*model, *rays, *saved, *gout, *grads, stream)) return rc;
-    return TNF_OK;
+    return field_done();
   }
   tnf::BwdLayout L{};
   tnf::make_layout(&L, static_cast<unsigned char*>(workspace), Ns, R, 4, false);
@@ -962,7 +985,7 @@ int tnf_render_backward(const TnfModel* model, const TnfRays* rays, const TnfSav
   if (g_stage_mask & 4) tnf::tnf_wgrad_kernel_fp32<<<grid, 256, 0, stream>>>(wa);
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(TNF_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(e));
-  return TNF_OK;
+  return field_done();
 }
 
 }  // extern "C"

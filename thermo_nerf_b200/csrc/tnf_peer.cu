@@ -325,7 +325,8 @@ int tnf_peer_barrier(const TnfPeerArena* arena, int32_t slot, uint32_t epoch, vo
 
 static int peer_adam_impl(const TnfPeerArena* arena, float* exp_avg_shard, float* exp_avg_sq_shard,
                           const TnfAdamSegment* segments, int32_t num_segments, double beta1, double beta2, float eps,
-                          int phase, void* stream_, const float* grads_mc = nullptr, float* params_mc = nullptr);
+                          int phase, void* stream_, const float* grads_mc = nullptr, float* params_mc = nullptr,
+                          long long range_begin = 0, long long range_end = -1, int max_ctas = 0);
 
 int tnf_peer_adam_multimem(const TnfPeerArena* arena, const float* grads_multicast, float* params_multicast,
                            float* exp_avg_shard, float* exp_avg_sq_shard, const TnfAdamSegment* segments,
@@ -350,6 +351,22 @@ int tnf_peer_adam_reduce(const TnfPeerArena* arena, float* exp_avg_shard, float*
   return peer_adam_impl(arena, exp_avg_shard, exp_avg_sq_shard, segments, num_segments, beta1, beta2, eps, 1, stream_);
 }
 
+int tnf_peer_adam_range(const TnfPeerArena* arena, int32_t flavour, int64_t range_begin, int64_t range_end,
+                        int32_t max_ctas, const float* grads_multicast, float* params_multicast,
+                        float* exp_avg_shard, float* exp_avg_sq_shard, const TnfAdamSegment* segments,
+                        int32_t num_segments, double beta1, double beta2, float eps, void* stream_) {
+  tnf::g_err[0] = 0;
+  if (flavour != TNF_PEER_PUSH && flavour != TNF_PEER_MULTIMEM)
+    return tnf::fail(TNF_ERR_INVALID_ARGUMENT, "flavour=%d (TNF_PEER_PUSH or TNF_PEER_MULTIMEM)", flavour);
+  if (flavour == TNF_PEER_MULTIMEM && (!grads_multicast || !params_multicast || !tnf::aligned16(grads_multicast) ||
+                                       !tnf::aligned16(params_multicast)))
+    return tnf::fail(TNF_ERR_INVALID_ARGUMENT, "multicast addresses null or not 16-byte aligned");
+  if (range_end < range_begin || range_begin < 0)
+    return tnf::fail(TNF_ERR_INVALID_ARGUMENT, "range [%lld,%lld)", (long long)range_begin, (long long)range_end);
+  return peer_adam_impl(arena, exp_avg_shard, exp_avg_sq_shard, segments, num_segments, beta1, beta2, eps, flavour,
+                        stream_, grads_multicast, params_multicast, range_begin, range_end, max_ctas);
+}
+
 int tnf_peer_gather_params(const TnfPeerArena* arena, const TnfAdamSegment* segments, int32_t num_segments,
                            void* stream_) {
   return peer_adam_impl(arena, nullptr, nullptr, segments, num_segments, 0.9, 0.999, 0.f, 2, stream_);
@@ -359,7 +376,8 @@ int tnf_peer_gather_params(const TnfPeerArena* arena, const TnfAdamSegment* segm
 // 3: reduce + Adam + broadcast through the NVSwitch multicast objects
 static int peer_adam_impl(const TnfPeerArena* arena, float* exp_avg_shard, float* exp_avg_sq_shard,
                           const TnfAdamSegment* segments, int32_t num_segments, double beta1, double beta2, float eps,
-                          int phase, void* stream_, const float* grads_mc, float* params_mc) {
+                          int phase, void* stream_, const float* grads_mc, float* params_mc, long long range_begin,
+                          long long range_end, int max_ctas) {
   using tnf::fail;
   tnf::g_err[0] = 0;
   if (int rc = check_arena(arena)) return rc;
@@ -376,8 +394,15 @@ static int peer_adam_impl(const TnfPeerArena* arena, float* exp_avg_shard, float
     return fail(TNF_ERR_INVALID_ARGUMENT, "num_segments=%d not in [1,%d]", num_segments, TNF_MAX_ADAM_SEGMENTS);
   tnf::PeerAdamArgs A;
   A.a = *arena;
-  const long long shard = arena->numel / W;
-  A.shard_begin = shard * arena->rank;
+  if (range_end < 0) range_end = arena->numel;
+  if (range_begin < 0 || range_end > arena->numel || range_begin > range_end || (range_begin & 3) ||
+      (range_end - range_begin) % (4LL * W) != 0)
+    return fail(TNF_ERR_INVALID_ARGUMENT, "range [%lld,%lld): must lie in the arena, start on a multiple of 4 and "
+                "have a length that is a multiple of 4*world_size", range_begin, range_end);
+  if (phase == 2 && (range_begin != 0 || range_end != arena->numel))
+    return fail(TNF_ERR_INVALID_ARGUMENT, "the pull all-gather works on the whole arena");
+  const long long shard = (range_end - range_begin) / W;
+  A.shard_begin = range_begin + shard * arena->rank;
   A.shard_end = A.shard_begin + shard;
   A.m = exp_avg_shard;
   A.v = exp_avg_sq_shard;
@@ -408,7 +433,7 @@ static int peer_adam_impl(const TnfPeerArena* arena, float* exp_avg_shard, float
   const long long n4 = phase == 2 ? (((shard >> 2) + 255) / 256) * 256 * (W - 1) : (shard >> 2);
   if (n4 == 0) return TNF_OK;
   long long blocks = (n4 + 255) / 256;
-  const long long cap = (long long)tnf::num_sms() * 8;
+  const long long cap = max_ctas > 0 ? (long long)max_ctas : (long long)tnf::num_sms() * 8;
   if (blocks > cap) blocks = cap;
   if (phase == 2)
     tnf::tnf_peer_gather_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream_)>>>(*arena, A);

@@ -17,6 +17,11 @@ import torch.distributed as dist
 from torch import Tensor
 
 
+def peer_padding(world_size: int) -> int:
+    """Slices of a PeerArena are sharded in runs of 4 floats per rank: their lengths are multiples of this."""
+    return 4 * int(world_size)
+
+
 def world_info(group=None) -> tuple:
     """(rank, world_size), (0, 1) when torch.distributed is not initialised."""
     if dist.is_available() and dist.is_initialized():
@@ -114,7 +119,10 @@ class PeerArena:
     the per-step exchange is our kernel reading and writing peer memory.  world_size 1 degenerates to a
     local fused Adam, which is what the single-GPU tests exercise."""
 
-    def __init__(self, numel: int, device, group=None) -> None:
+    def __init__(self, numel: int, device, group=None, split: Optional[int] = None) -> None:
+        """``split``: boundary between two slices of the arena that are exchanged separately
+        (:meth:`adam_step_pipelined`): [0, split) and [split, numel), each sharded over the ranks on its own; it must be
+        a multiple of 4 * world_size (:func:`peer_padding`)."""
         import ctypes as C
 
         from . import _lib as L
@@ -151,8 +159,15 @@ class PeerArena:
             a.grads[r], a.params[r], a.flags[r] = g, p, f
         a.world_size, a.rank, a.numel = self.world, self.rank, self.numel
         self.struct = a
+        # Adam state of the part(s) of the arena this rank owns: one shard of the whole arena, or - with `split` -
+        # this rank's part of [0, split) followed by its part of [split, numel)
         self.exp_avg = torch.zeros(self.shard, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(self.shard, dtype=torch.float32, device=dev)
+        self.split = None if split is None else int(split)
+        if self.split is not None and (self.split % pad or not 0 <= self.split <= self.numel):
+            raise ValueError(f"split={split} must be a multiple of 4*world_size={pad} inside the arena")
+        self._side: Optional[torch.cuda.Stream] = None
+        self._field_ready: Optional[torch.cuda.Event] = None
         self._epoch = [0] * L.TNF_PEER_FLAG_SLOTS
         self.timing: Optional[list] = None
         # the gradient arena is cleared on a side stream so that the memset overlaps the next forward (which never
@@ -275,10 +290,10 @@ class PeerArena:
             self.lib.tnf_peer_close_handle(self._C.c_void_p(base))
         self._mapped = {}
 
-    def barrier(self, slot: int) -> None:
+    def barrier(self, slot: int, stream: Optional["torch.cuda.Stream"] = None) -> None:
         """Stream-ordered barrier over all ranks (flag words in peer memory; no NCCL call)."""
         self._epoch[slot] += 1
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        stream = (stream if stream is not None else torch.cuda.current_stream(self.device)).cuda_stream
         with torch.cuda.device(self.device):
             self._L.check(self.lib.tnf_peer_barrier(self._C.byref(self.struct), slot, self._epoch[slot],
                                                     self._C.c_void_p(stream)))
@@ -338,6 +353,98 @@ class PeerArena:
         if ev:
             ev[4].record()
             self.timing.append(ev)
+
+    def owned_ranges(self) -> list:
+        """[(begin, end), ...] of the arena whose Adam state this rank holds, in the order of ``exp_avg``."""
+        if self.split is None:
+            return [(self.shard * self.rank, self.shard * (self.rank + 1))]
+        a, b = self.split // self.world, (self.numel - self.split) // self.world
+        return [(a * self.rank, a * (self.rank + 1)), (self.split + b * self.rank, self.split + b * (self.rank + 1))]
+
+    def _exchange_range(self, lo: int, hi: int, state_off: int, segs, nseg: int, beta1, beta2, eps, stream,
+                        max_ctas: int) -> None:
+        L, C = self._L, self._C
+        flavour = L.TNF_PEER_MULTIMEM if self.gather == "multimem" else L.TNF_PEER_PUSH
+        with torch.cuda.device(self.device):
+            L.check(self.lib.tnf_peer_adam_range(
+                C.byref(self.struct), flavour, lo, hi, max_ctas,
+                C.c_void_p(self.multicast or None), C.c_void_p((self.multicast + 4 * self.numel) if self.multicast else None),
+                self.exp_avg.data_ptr() + 4 * state_off, self.exp_avg_sq.data_ptr() + 4 * state_off, segs, nseg,
+                float(beta1), float(beta2), float(eps), C.c_void_p(stream.cuda_stream)))
+
+    def adam_step_pipelined(self, segments: Sequence[tuple], beta1: float = 0.9, beta2: float = 0.999,
+                            eps: float = 1e-15, side_ctas: int = 0,
+                            tail_grads_event: Optional["torch.cuda.Event"] = None) -> None:
+        """The exchange as two slices with the second one off the critical path (``split`` must be set; push and
+        multimem flavours).
+
+        side stream   [wait for the gradients of [split, numel)] -> barrier -> [split, numel) exchanged -> barrier
+                      -> event (:meth:`field_ready_event`) -> gradient arena cleared (:meth:`wait_zeroed`)
+        this stream   barrier -> [0, split) exchanged -> barrier          (only when one of its segments is active)
+
+        The side stream starts behind ``tail_grads_event`` when given (recorded by tnf_render_backward_staged between
+        the field level and the proposal levels), else behind this stream's first barrier.
+
+        TrainEngine's use: [0, split) are the proposal networks, [split, numel) the field.  The field slice - 7/8 of
+        the bytes - crosses the NVSwitch while the proposal backward still runs (update steps) and while the next
+        iteration's proposal pass, which reads the proposal networks only, already runs; the next field level waits
+        for the event (tnf_render_forward_staged)."""
+        if self.split is None or self.gather not in ("push", "multimem"):
+            raise RuntimeError("adam_step_pipelined needs PeerArena(split=...) and the push or multimem flavour")
+        L = self._L
+        segs = (L.TnfAdamSegment * len(segments))()
+        head_active = False
+        for i, (b, e, lr, step, active) in enumerate(segments):
+            segs[i].begin, segs[i].end, segs[i].lr = int(b), int(e), float(lr)
+            segs[i].step, segs[i].active = int(step), int(bool(active))
+            head_active = head_active or (bool(active) and int(b) < self.split)
+        head_active = head_active and self.split > 0
+        main = torch.cuda.current_stream(self.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.device)
+        side = self._side
+        if tail_grads_event is not None:
+            side.wait_event(tail_grads_event)
+            self.barrier(3, stream=side)  # every rank's gradients of the big slice are complete
+            if head_active:
+                self.barrier(0)           # ... and, on this stream, those of the small slice
+        else:
+            self.barrier(0)  # every rank's backward has written its gradient arena
+            start = torch.cuda.Event()
+            start.record(main)
+            side.wait_event(start)
+        a = self.split // self.world
+        # side stream: the big slice
+        self._exchange_range(self.split, self.numel, a, segs, len(segments), beta1, beta2, eps, side, side_ctas)
+        self.barrier(2, stream=side)  # every rank's part of the slice has landed everywhere
+        self._field_ready = torch.cuda.Event()
+        self._field_ready.record(side)
+        # current stream: the small slice, needed first
+        if head_active:
+            self._exchange_range(0, self.split, 0, segs, len(segments), beta1, beta2, eps, main, 0)
+            self.barrier(1)
+        # the gradients may be cleared once every peer has read them: the side stream's barrier covers the big
+        # slice, the barrier above the small one (nobody reads it on a step without active head segments).  The
+        # clearing also has to come after this rank's own backward (the proposal kernel may still be running)
+        head_done = torch.cuda.Event()
+        head_done.record(main)
+        side.wait_event(head_done)
+        with torch.cuda.stream(side):
+            self.grads.zero_()
+            self._zero_done = torch.cuda.Event()
+            self._zero_done.record(side)
+
+    def wait_params(self) -> None:
+        """Orders the current stream after a still pending exchange of [split, numel) (for readers of the parameters
+        other than the staged forward, e.g. an evaluation render between two training iterations)."""
+        if self._field_ready is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._field_ready)
+
+    def field_ready_event(self) -> Optional["torch.cuda.Event"]:
+        """Event of the last :meth:`adam_step_pipelined` after which [split, numel) of the parameters is up to date on
+        every rank (None when nothing is pending); handing it out clears it."""
+        ev, self._field_ready = self._field_ready, None
+        return ev
 
     def wait_zeroed(self) -> None:
         """Orders the current stream after the asynchronous clearing of the gradient arena started by the last

@@ -16,6 +16,7 @@ same numbers through the plugin API; this class is the launch-lean fast path the
 
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -24,7 +25,7 @@ from torch import Tensor
 
 from . import _lib as L
 from . import functional as F
-from .dist import PeerArena, allreduce_mean_
+from .dist import PeerArena, allreduce_mean_, peer_padding, world_info
 
 NUM_PROP_TENSORS = 5 * L.TNF_NUM_PROP  # leading entries of ModelTensors.param_list()
 
@@ -49,12 +50,19 @@ class TrainEngine:
         self.device = dev
         # flat arenas (each tensor 16-byte aligned): gradients, exp_avg, exp_avg_sq
         offs, total = [], 0
-        for p in self.params:
+        # peer-fused exchange: the proposal slice and the field slice are sharded over the ranks separately, so the
+        # field slice starts on a multiple of 4 * world_size
+        world = world_info(process_group)[1] if peer_fused else 1
+        for i, p in enumerate(self.params):
+            if i == NUM_PROP_TENSORS and peer_fused:
+                total = (total + peer_padding(world) - 1) // peer_padding(world) * peer_padding(world)
             offs.append(total)
             total += (p.numel() + 3) // 4 * 4
         self.offsets, self.total = offs, total
         self.prop_end = offs[NUM_PROP_TENSORS]  # [0, prop_end): proposal networks, [prop_end, total): field
         self.arena: Optional[PeerArena] = None
+        # TNF_PEER_PIPELINE=0: the exchange as one block on the critical path (the two-barrier form of round 1)
+        self.pipelined = os.environ.get("TNF_PEER_PIPELINE", "1") != "0"
 
         def views(arena):
             return [arena[o:o + p.numel()].view_as(p) for o, p in zip(offs, self.params)]
@@ -63,7 +71,9 @@ class TrainEngine:
             # multi-GPU exchange fused with Adam over NVLink peer memory (tnf_peer_adam_step): parameters move
             # into a peer-mapped arena (every rank writes its updated shard into everybody's copy), the gradient
             # arena is peer-mapped too, and the Adam state exists only for the shard this rank owns
-            self.arena = PeerArena(total, dev, process_group)
+            self.arena = PeerArena(total, dev, process_group, split=self.prop_end)
+            self.pipelined = self.pipelined and self.arena.world > 1 and self.arena.gather in ("push", "multimem")
+            model._peer_arena = self.arena  # model.tensors() orders other readers after a pending exchange
             with torch.no_grad():
                 for v, p in zip(views(self.arena.params), self.params):
                     v.copy_(p)
@@ -89,6 +99,18 @@ class TrainEngine:
         self.steps_since_update = 0
         self.sampler_step = 0        # ProposalNetworkSampler._step: the step of the PREVIOUS iteration (step_cb)
         self._ws: Optional[Tensor] = None
+        self._field_done: Optional[torch.cuda.Event] = None
+        # CTAs (256 threads, <= 64 registers) of the field-slice exchange, which shares the SMs with the proposal
+        # backward (told to leave that many slots free) and with the next proposal pass (512 CTAs at 4096 rays in
+        # 4 x 148 slots).  64 CTAs keep 1 MB of switch reductions in flight; two ranks move four times the bytes per
+        # rank with plain peer loads and want more
+        # Measured (profiles/r2_exchange_pipeline.json): 8 GPUs, in-switch reduction - 64 CTAs started under the
+        # proposal backward: 0.717 ms / step (0.796 started after it, 0.830 with 296 CTAs, 0.846 unpipelined);
+        # 2 GPUs, peer loads / stores, 34 MB per rank and direction - 296 CTAs started after the backward: 0.765 ms
+        # (0.795 started under it: the proposal kernel then runs on half its CTAs; 0.799 unpipelined)
+        self._side_ctas = int(os.environ.get("TNF_PEER_SIDE_CTAS", 64 if world >= 4 else 296))
+        # start the field exchange under the proposal backward (1) or after the whole backward (0)
+        self._early = os.environ.get("TNF_PEER_EARLY", "1" if world >= 4 else "0") != "0"
         mode = getattr(getattr(model, "camera_optimizer", None), "mode", "off")
         if mode != "off":
             # the engine feeds origins / directions straight to the kernels: pose refinement lives in the
@@ -129,8 +151,11 @@ class TrainEngine:
                   detach_thermal_geo=not self.model.field.pass_thermal_gradients,
                   head_mode=L.HEAD_CONCAT if self.model._is_concat() else L.HEAD_THERMAL)
         cam = camera_indices.reshape(-1)
+        # pipelined exchange: the previous iteration's field slice may still be in flight - the proposal levels
+        # start now, the field level waits for the event
+        ready = self.arena.field_ready_event() if self.arena is not None else None
         res = F.render_forward(self.tensors, origins, directions, cam, None, None, jitter, training=True,
-                               return_samples=True, save_for_backward=True, **kw)
+                               return_samples=True, save_for_backward=True, field_ready_event=ready, **kw)
         losses, g = F.losses_forward_backward(
             res["weights_list"], res["sdist_list"], res["rgb"], res["thermal"], gt_rgb, gt_thermal,
             interlevel_mult=cfg.interlevel_loss_mult, distortion_mult=cfg.distortion_loss_mult,
@@ -146,21 +171,33 @@ class TrainEngine:
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         res["_workspace"] = self._ws
+        field_done = None
         if self.arena is not None:
             self.arena.wait_zeroed()  # the previous step's memset of the gradient arena ran beside this forward
+            if self.pipelined and self._early:
+                # field level first, event, proposal levels: the field gradients start travelling under the latter
+                if self._field_done is None:
+                    self._field_done = torch.cuda.Event()
+                    self._field_done.record()  # creates the handle the kernel launcher re-records
+                field_done = self._field_done
         F.render_backward(self.tensors, res["_model_struct"], origins, directions, cam, None, None, jitter, res,
                           {"rgb": g["rgb"], "thermal": g["thermal"], "accumulation": g.get("accumulation"),
-                           "weights_list": g["weights_list"]}, grads)
+                           "weights_list": g["weights_list"]}, grads, field_grads_event=field_done,
+                          reserve_ctas=self._side_ctas if field_done is not None else 0)
         lr = exponential_decay_lr(step, self.lr, self.lr_final, self.lr_max_steps)
         self.field_steps += 1
         if updated:
             self.prop_steps += 1
             self.steps_since_update = 0
         if self.arena is not None:
-            # one kernel: mean over ranks (peer loads) + Adam on the owned shard + parameter broadcast (peer stores)
-            self.arena.adam_step([(0, self.prop_end, lr, max(self.prop_steps, 1), updated),
-                                  (self.prop_end, self.arena.numel, lr, self.field_steps, True)],
-                                 beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, async_zero=True)
+            # one kernel per slice: mean over ranks + Adam on the owned shard + parameter broadcast
+            segs = [(0, self.prop_end, lr, max(self.prop_steps, 1), updated),
+                    (self.prop_end, self.arena.numel, lr, self.field_steps, True)]
+            if self.pipelined:
+                self.arena.adam_step_pipelined(segs, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
+                                               side_ctas=self._side_ctas, tail_grads_event=field_done)
+            else:
+                self.arena.adam_step(segs, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, async_zero=True)
         else:
             if self.world_size > 1:
                 # DDP semantics: average over ranks.  The proposal part of the arena is all zeros on
@@ -197,6 +234,8 @@ class TrainEngine:
                     beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, zero_grads=True)
 
     def state_dict(self) -> Dict[str, object]:
+        if self.arena is not None:
+            self.arena.wait_params()
         return {"step": self.step_count, "field_steps": self.field_steps, "prop_steps": self.prop_steps,
                 "steps_since_update": self.steps_since_update, "sampler_step": self.sampler_step,
                 "exp_avg": self.m_arena, "exp_avg_sq": self.v_arena}

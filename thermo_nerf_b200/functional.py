@@ -267,6 +267,7 @@ def render_forward(
     camera: Optional[L.TnfCamera] = None,
     first_pixel: int = 0,
     num_pixels: Optional[int] = None,
+    field_ready_event: Optional["torch.cuda.Event"] = None,
 ) -> Dict[str, object]:
     """One call of ``tnf_render_forward`` over R rays (flat).  Returns the output dict of
     ThermalNerfModel.get_outputs (thermal_nerf_model.py:245-275): rgb [R,3], thermal,
@@ -365,8 +366,14 @@ def render_forward(
     ws = torch.empty((ws_bytes + 3) // 4, dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
     with torch.cuda.device(dev):
-        rc = lib.tnf_render_forward(C.byref(model), C.byref(rays), C.byref(outs), chunk, ws.data_ptr(), ws_bytes,
-                                    C.c_void_p(stream))
+        if field_ready_event is not None:
+            # tnf_render_forward_staged: the field level waits for the event (a parameter exchange of the field
+            # network still in flight on another stream); the proposal levels start right away
+            rc = lib.tnf_render_forward_staged(C.byref(model), C.byref(rays), C.byref(outs), chunk, ws.data_ptr(),
+                                               ws_bytes, C.c_void_p(stream), C.c_void_p(field_ready_event.cuda_event))
+        else:
+            rc = lib.tnf_render_forward(C.byref(model), C.byref(rays), C.byref(outs), chunk, ws.data_ptr(), ws_bytes,
+                                        C.c_void_p(stream))
     L.check(rc)
     del keep  # inputs stay alive until the launch is enqueued; stream order protects them afterwards
     return res
@@ -397,9 +404,13 @@ def _workspace_for(model_struct: L.TnfModel, R: int, dev: torch.device) -> Tenso
 def render_backward(tensors: ModelTensors, model_struct: L.TnfModel, origins: Tensor, directions: Tensor,
                     camera_indices: Optional[Tensor], nears: Optional[Tensor], fars: Optional[Tensor],
                     jitter: Optional[Tensor], saved: Dict[str, object], grad_outputs: Dict[str, Optional[Tensor]],
-                    grads: Sequence[Optional[Tensor]], ray_grads: Optional[Tuple[Tensor, Tensor]] = None) -> None:
+                    grads: Sequence[Optional[Tensor]], ray_grads: Optional[Tuple[Tensor, Tensor]] = None,
+                    field_grads_event: Optional["torch.cuda.Event"] = None, reserve_ctas: int = 0) -> None:
     """``tnf_render_backward``: accumulates into ``grads`` (``ModelTensors.param_list`` order) and, when
-    ``ray_grads`` = (d origins, d directions) is given, into those [R,3] buffers (camera-optimiser path)."""
+    ``ray_grads`` = (d origins, d directions) is given, into those [R,3] buffers (camera-optimiser path).
+    ``field_grads_event`` (an event that has been recorded once, so that its handle exists): the field level runs
+    first and the event is re-recorded behind it, before the proposal levels, whose kernel leaves ``reserve_ctas``
+    CTA slots free (``tnf_render_backward_staged``)."""
     lib = L.load()
     R = int(origins.shape[0])
     dev = origins.device
@@ -436,8 +447,13 @@ def render_backward(tensors: ModelTensors, model_struct: L.TnfModel, origins: Te
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
     with torch.cuda.device(dev):
-        rc = lib.tnf_render_backward(C.byref(model_struct), C.byref(rays), C.byref(sv), C.byref(go), C.byref(gstruct),
-                                     ws.data_ptr(), ws.numel(), C.c_void_p(stream))
+        if field_grads_event is not None:
+            rc = lib.tnf_render_backward_staged(C.byref(model_struct), C.byref(rays), C.byref(sv), C.byref(go),
+                                                C.byref(gstruct), ws.data_ptr(), ws.numel(), C.c_void_p(stream),
+                                                C.c_void_p(field_grads_event.cuda_event), int(reserve_ctas))
+        else:
+            rc = lib.tnf_render_backward(C.byref(model_struct), C.byref(rays), C.byref(sv), C.byref(go),
+                                         C.byref(gstruct), ws.data_ptr(), ws.numel(), C.c_void_p(stream))
     L.check(rc)
     del keep
 

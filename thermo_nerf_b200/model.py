@@ -136,6 +136,11 @@ class KernelModelMixin:
         return super().load_state_dict(state_dict, strict=strict, **k)
 
     def tensors(self) -> F.ModelTensors:
+        arena = self.__dict__.get("_peer_arena")
+        if arena is not None:
+            # a TrainEngine with the pipelined multi-GPU exchange owns the parameters: a field slice may still be in
+            # flight on its side stream - readers that come through here (eval renders, the autograd route) wait for it
+            arena.wait_params()
         if self._tensors is None:
             self._tensors = F.ModelTensors.from_module(self)
         return self._tensors
