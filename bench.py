@@ -371,8 +371,16 @@ def main() -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def gather_ranks(obj):
+        """[obj of rank 0, obj of rank 1, ...] on every rank (small python objects: per-rank time and clocks)."""
+        if world == 1:
+            return [obj]
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
     ctx = dict(args=args, rank=rank, world=world, local=local, device=device, barrier=barrier,
-               max_over_ranks=max_over_ranks)
+               max_over_ranks=max_over_ranks, gather_ranks=gather_ranks)
     line = bench_train(ctx) if args.mode == "train" else bench_render(ctx)
     if rank == 0:
         emit(line)
@@ -423,7 +431,9 @@ def bench_train(ctx) -> dict:
     barrier()
     prop_steps_timed = engine.prop_steps - prop_steps_before
     clocks = sampler.stop()
+    my_ms = e0.elapsed_time(e1) / args.steps
     ms_per_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    ranks = ctx["gather_ranks"]({"ms_per_step": my_ms, "sm_mhz": clocks["sm_mhz"], "reasons": clocks["reasons"]})
     value = world * R / (ms_per_step * 1e-3)
     final_losses = [float(x) for x in losses.tolist()]
 
@@ -570,7 +580,7 @@ def bench_train(ctx) -> dict:
                          f"{n_distinct} distinct ray batches cycle",
                    "weights": "random trained-like init, full-size tables (field 2^19x16, proposals 2^17x5)",
                    "final_losses": dict(zip(F.LOSS_NAMES, final_losses))},
-        "clocks": clocks,
+        "clocks": clocks, "ranks": ranks,
         "exchange": ("none (1 GPU)" if world == 1 else
                      ({"push": "peer-memory fused reduce-scatter + Adam + all-gather (tnf_peer_adam_step)",
                        "pull": "peer-memory fused reduce-scatter + Adam (tnf_peer_adam_reduce), pull all-gather "
@@ -596,11 +606,22 @@ def bench_train(ctx) -> dict:
                     "get_metrics_dict -> get_loss_dict -> loss.backward() -> FusedAdam.step -> D2H loss; bound by "
                     "PyTorch's per-call host time (autograd engine, tensor bookkeeping), not by the kernels"},
     }
-    # launches of OUR kernels per engine step: forward + clip + losses + backward_field (+ the fp32 mode's
+    # launches of OUR kernels per engine step: forward (proposal launch + field launch in tensor-core mode, one fused
+    # launch in fp32 mode or with TNF_FORWARD_SPLIT=0) + clip + losses + backward_field (+ the fp32 mode's
     # weight-gradient pass) + adam, and backward_prop + a second adam launch on update steps
-    # (the counter memset of the proposal backward and, for world > 1, NCCL's all-reduce kernel are not ours)
-    per_step = 4 + (1 if args.precision == "fp32" else 0)
-    if engine.arena is not None:  # peer exchange: 2 barrier kernels + fused Adam (+ gather kernel when pulling)
+    # (memsets and, on the NCCL path, the all-reduce kernel are not ours)
+    fwd = 2 if (args.precision == "tc_fp16" and os.environ.get("TNF_FORWARD_SPLIT", "4") != "0") else 1
+    per_step = fwd + 3 + (1 if args.precision == "fp32" else 0)
+    if engine.arena is not None and engine.pipelined:
+        # field slice: 2 barrier kernels + exchange kernel every step; proposal slice on update steps: backward_prop +
+        # exchange kernel + closing barrier, + its opening barrier when the field slice started early (otherwise that
+        # barrier is the field slice's too)
+        line["gpu_launches"] = int(args.steps * (per_step + 3) + prop_steps_timed * (4 if engine._early else 3))
+        line["exchange"] += (" - pipelined (tnf_peer_adam_range): proposal slice on the critical path, field slice on a "
+                             f"side stream ({engine._side_ctas} CTAs) started "
+                             + ("under the proposal backward" if engine._early else "after the backward")
+                             + ", next field level waits for it (tnf_render_forward_staged)")
+    elif engine.arena is not None:  # unpipelined peer exchange: 2 barrier kernels + fused Adam (+ gather kernel when pulling)
         line["gpu_launches"] = int(args.steps * (per_step + (4 if engine.arena.gather == "pull" else 3)) + prop_steps_timed)
     else:
         line["gpu_launches"] = int(args.steps * (per_step + 1) + prop_steps_timed * 2)
@@ -737,7 +758,8 @@ def kernel_breakdown(engine, batches, device) -> dict:
     # median: the interval between two events also contains any host stall between the launches (GC pause,
     # allocator growth), which an average would book as kernel time
     out = {k + "_ms": sorted(v)[len(v) // 2] for k, v in acc.items()}
-    out["note"] = ("one kernel per entry (forward includes the 3 us depth-clip pass; in tensor-core mode the field "
+    out["note"] = ("one kernel per entry, except forward: proposal launch + field launch in tensor-core mode, plus the 3 us "
+                   "depth-clip pass; in tensor-core mode the field "
                    "backward accumulates the weight gradients in tensor memory - there is no separate weight-gradient "
                    "kernel); the proposal backward runs only on the sampler's update steps (every 2nd step in the first "
                    "1000 iterations, every 6th after 5000)")
@@ -847,8 +869,11 @@ def bench_render(ctx) -> dict:
         evs[i][1].record()
     barrier()
     clocks = sampler.stop()
+    my_ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
     ms_total = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs))
     ms_per_step = ms_total / args.steps
+    # every rank renders the same views: what differs between them is the GPU (clocks under an 8-GPU load, binning)
+    ranks = ctx["gather_ranks"]({"ms_per_step": my_ms, "sm_mhz": clocks["sm_mhz"], "reasons": clocks["reasons"]})
     value = world * rays_per_step / (ms_per_step * 1e-3) / 1e6
 
     # ---- dominant kernel alone (roofline): tnf_render_forward on device-resident flat rays
@@ -952,7 +977,7 @@ def bench_render(ctx) -> dict:
                                "rank, frame cost depends on the view)",
                    "l2": "flushed between timed iterations (256 MiB write)", "rays_per_second": value * 1e6,
                    "weights": "random trained-like, full-size tables (field 2^19x16, proposals 2^17x5)"},
-        "clocks": clocks, "gpu_launches": 2 * args.steps,  # forward + depth-clip pass per frame (device-resident loop)
+        "clocks": clocks, "ranks": ranks, "gpu_launches": 2 * args.steps,  # forward + depth-clip pass per frame (device-resident loop)
         "e2e": {"value": e2e_val, "unit": "Mpix/s", "h2d_bytes_per_step": h2d_cam, "d2h_bytes_per_step": d2h,
                 "note": "Renderer.render([RGB, THERMAL], one camera): rays generated in the kernel from the camera, "
                         "uint8 conversion + colour map on the device, two uint8 frames D2H into pinned memory"},
