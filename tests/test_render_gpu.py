@@ -205,3 +205,32 @@ def test_nerfacto_variant_matches_the_full_model_without_thermal():
     torch.cuda.synchronize()
     assert float(m.field.mlp_head.layers[2].weight.grad.abs().sum()) > 0
     assert float(m.field.mlp_thermal.layers[0].weight.abs().sum()) == 0.0  # still the constant zeros
+
+
+def test_large_eval_calls_in_two_launches_equal_the_fused_launch():
+    """Eval calls of >= 16384 rays run as proposal launch + field launch (the bins cross a scratch buffer): every
+    output bit for bit what the single fused launch gives, for tensor rays and for camera-generated rays."""
+    from thermo_nerf_b200 import _lib as L
+    from thermo_nerf_b200 import functional as F
+    from thermo_nerf_b200 import orbit_cameras
+
+    _, model = make_pair(trained_like=True, precision="tc_fp16")
+    rays = make_synthetic_rays(20000, num_images=8, seed=12)
+    o, d = rays.origins.cuda(), rays.directions.cuda()
+    cams = orbit_cameras(2, hw=160, focal=222.2)
+    cam = F.pack_camera(cams.camera_to_worlds[1], cams.fx, cams.fy, cams.cx, cams.cy, 160, 160)
+    kw = dict(near_plane=0.0, far_plane=1000.0, appearance_mode=L.APPEARANCE_MEAN, precision=L.PRECISION_TC_FP16,
+              depth_clip_chunk=4096)
+    got = {}
+    old = F._EVAL_SPLIT
+    try:
+        for split in (True, False):
+            F._EVAL_SPLIT = split
+            got[split] = (F.render_forward(model.tensors(), o, d, **kw),
+                          F.render_forward(model.tensors(), None, None, camera=cam, **kw))
+    finally:
+        F._EVAL_SPLIT = old
+    torch.cuda.synchronize()
+    for a, b in zip(got[True], got[False]):
+        for k in ("rgb", "thermal", "depth", "expected_depth", "accumulation", "prop_depth_0", "prop_depth_1"):
+            assert torch.equal(a[k], b[k]), k

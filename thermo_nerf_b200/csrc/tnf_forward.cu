@@ -761,7 +761,7 @@ int split_mode() {
   if (mode < 0) {
     const char* v = getenv("TNF_FORWARD_SPLIT");
     mode = v ? atoi(v) : 4;
-    if (mode != 0 && mode != 3 && mode != 4) mode = 4;
+    if (mode != 0 && mode != 3 && mode != 4 && mode != 5) mode = 4;
   }
   return mode;
 }
@@ -837,6 +837,10 @@ int tnf_render_forward_staged(const TnfModel* model, const TnfRays* rays, const 
     if (int wrc = wait_field()) return wrc;
   if (split == 4) {
     rc = launch_forward<TNF_PRECISION_TC_FP16, PHASE_PROP, 4>(*model, *rays, *out, chunk, cmin, cmax, stream);
+    if (rc == TNF_OK) rc = wait_field();
+    if (rc == TNF_OK) rc = launch_forward<TNF_PRECISION_TC_FP16, PHASE_FIELD, 2>(*model, *rays, *out, chunk, cmin, cmax, stream);
+  } else if (split == 5) {
+    rc = launch_forward<TNF_PRECISION_TC_FP16, PHASE_PROP, 5>(*model, *rays, *out, chunk, cmin, cmax, stream);
     if (rc == TNF_OK) rc = wait_field();
     if (rc == TNF_OK) rc = launch_forward<TNF_PRECISION_TC_FP16, PHASE_FIELD, 2>(*model, *rays, *out, chunk, cmin, cmax, stream);
   } else if (split == 3) {

@@ -11,6 +11,7 @@ on a stock ThermoNeRF model and on ``thermo_nerf_b200.model.ThermalNerfModel``.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -240,6 +241,11 @@ class ModelTensors:
 _OUT_KEYS = ("rgb", "thermal", "depth", "expected_depth", "accumulation", "prop_depth_0", "prop_depth_1")
 
 
+# TNF_EVAL_SPLIT=0: eval calls as one fused launch whatever their size
+_EVAL_SPLIT = os.environ.get("TNF_EVAL_SPLIT", "1") != "0"
+_EVAL_SPLIT_MIN_RAYS = 16384
+
+
 def render_forward(
     tensors: ModelTensors,
     origins: Optional[Tensor],
@@ -350,6 +356,12 @@ def render_forward(
             wl.append(w)
             sl.append(sd)
         res["weights_list"], res["sdist_list"] = wl, sl
+    elif precision == L.PRECISION_TC_FP16 and _EVAL_SPLIT and R >= _EVAL_SPLIT_MIN_RAYS:
+        # two-launch form for large eval calls as well (proposal levels at twice the occupancy, then the field level):
+        # the 49 spacing bins of the last level cross HBM once (196 B per ray) in a scratch buffer of this call
+        scratch = torch.empty((R, int(num_samples[-1]) + 1), dtype=torch.float32, device=dev)
+        outs.sdist[L.TNF_NUM_PROP] = scratch.data_ptr()
+        keep.append(scratch)
     if save_for_backward:
         if not (return_samples and training):
             raise ValueError("save_for_backward needs training=True and return_samples=True")
