@@ -18,7 +18,7 @@
 // matrices straight from the mma C-fragment registers, bank-conflict free.  Any run of adjacent groups is an
 // operand, so [X | 1] (bias gradient as one more column) or [XG | 1 | SH | appearance] are just adjacent tiles.
 //
-// Producer -> issuer hand-off: a ring of kNumBufs 4.25 KB buffers; a producer takes a ticket (shared-memory
+// Producer -> issuer hand-off: a ring of kNumBufs (7) buffers of kBufGroups (31) 256-byte column groups = 7.75 KB; a producer takes a ticket (shared-memory
 // atomic), waits until the ticket that used the buffer before has retired, fills it, fences generic -> async
 // proxy and arrives on the buffer's "full" mbarrier.  The issuer consumes tickets in order, commits each to the
 // buffer's "done" mbarrier (tcgen05.commit), observes those completions in order and publishes a monotonic

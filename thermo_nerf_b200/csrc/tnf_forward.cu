@@ -755,13 +755,13 @@ int launch_forward(const TnfModel& m, const TnfRays& r, const TnfOutputs& o, lon
 
 // Training forward in tensor-core mode (needs out.sdist[2]).  0: one fused launch; 3 / 4: proposal launch at that many
 // CTAs per SM + field launch.  Measured on B200 at 4096 rays (profiles/r2_forward_split.json): 4 -> 0.212 ms,
-// 0 -> 0.221 ms, 3 -> 0.229 ms; TNF_FORWARD_SPLIT overrides.
+// 0 -> 0.221 ms, 3 -> 0.229 ms (5 CTAs per SM = 48 registers, 136 B of spills: 0.236 ms); TNF_FORWARD_SPLIT overrides.
 int split_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char* v = getenv("TNF_FORWARD_SPLIT");
     mode = v ? atoi(v) : 4;
-    if (mode != 0 && mode != 3 && mode != 4 && mode != 5) mode = 4;
+    if (mode != 0 && mode != 3 && mode != 4) mode = 4;
   }
   return mode;
 }
@@ -837,10 +837,6 @@ int tnf_render_forward_staged(const TnfModel* model, const TnfRays* rays, const 
     if (int wrc = wait_field()) return wrc;
   if (split == 4) {
     rc = launch_forward<TNF_PRECISION_TC_FP16, PHASE_PROP, 4>(*model, *rays, *out, chunk, cmin, cmax, stream);
-    if (rc == TNF_OK) rc = wait_field();
-    if (rc == TNF_OK) rc = launch_forward<TNF_PRECISION_TC_FP16, PHASE_FIELD, 2>(*model, *rays, *out, chunk, cmin, cmax, stream);
-  } else if (split == 5) {
-    rc = launch_forward<TNF_PRECISION_TC_FP16, PHASE_PROP, 5>(*model, *rays, *out, chunk, cmin, cmax, stream);
     if (rc == TNF_OK) rc = wait_field();
     if (rc == TNF_OK) rc = launch_forward<TNF_PRECISION_TC_FP16, PHASE_FIELD, 2>(*model, *rays, *out, chunk, cmin, cmax, stream);
   } else if (split == 3) {
