@@ -2,7 +2,10 @@
 """Per-source-line profile from an ncu report: joins `ncu --page source --csv` (SASS rows with executed
 instruction counts and stall samples) with `nvdisasm -g` line info of the same kernel, by instruction order.
 
-    python scripts/ncu_lines.py REPORT.ncu-rep KERNEL_REGEX CUBIN MANGLED_SUBSTR [top_n]
+    python scripts/ncu_lines.py REPORT.ncu-rep KERNEL_REGEX CUBIN MANGLED_SUBSTR [top_n] [NAME_SUBSTR]
+
+KERNEL_REGEX matches the base function name only (ncu); NAME_SUBSTR picks the instance whose full name (template
+arguments included, e.g. "(int)1, (int)1, (int)4") contains it.
 """
 import csv, re, subprocess, sys, collections
 
@@ -19,7 +22,8 @@ for r in rows:
     if cur is None: continue
     if cur["hdr"] is None: cur["hdr"] = r; continue
     cur["rows"].append(r)
-t = tables[0]
+want = sys.argv[6] if len(sys.argv) > 6 else ""
+t = next(x for x in tables if want in x["name"])
 h = {n: i for i, n in enumerate(t["hdr"])}
 sass = subprocess.run(["nvdisasm", "-g", cubin], capture_output=True, text=True).stdout.splitlines()
 # locate function
