@@ -628,12 +628,18 @@ def bench_train(ctx) -> dict:
     if roofline:
         line["roofline"] = roofline
         line["breakdown_ms"] = breakdown
-    if rank == 0 and world == 1 and not args.no_render:
-        line["render"] = quick_render(model, device, not args.no_torch_cuda_baseline)
+    if not args.no_render:
+        # every rank renders the same views (frames shard with no collective); aggregate = world * pixels / slowest rank
+        r = quick_render(model, device, world == 1 and not args.no_torch_cuda_baseline, ctx)
+        if rank == 0:
+            line["render"] = r
     if rank == 0 and world == 1 and not args.no_torch_cuda_baseline:
         del engine, model2, opts
         torch.cuda.empty_cache()
         line["torch_cuda_baseline"] = torch_cuda_train_baseline(device, args.rays, value)
+        if args.rays != 8192:
+            # BASELINE configs[2] / the per-GPU shape of configs[3]: ours and the PyTorch-CUDA baseline at 8192 rays
+            line["rays_8192"] = train_at_8192(device, args.precision)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_train(min(args.ref_rays, 4096))
     return line
@@ -701,6 +707,35 @@ def torch_cuda_train_baseline(device, rays: int, ours_rays_per_s: float) -> dict
     return out
 
 
+def train_at_8192(device, precision: str) -> dict:
+    """Device-resident training rate at 8192 rays per batch (one GPU) next to the PyTorch-CUDA baseline of the same
+    batch size: a short run (20 + 100 iterations); the full contract run is `bench.py --rays 8192`."""
+    from thermo_nerf_b200.engine import TrainEngine
+
+    R = 8192
+    try:
+        model = build_b200_model(device, precision)
+        model.train()
+        engine = TrainEngine(model, world_size=1)
+        batches = train_batches(4, R, device, 0)
+        for i in range(20):
+            engine.step(*batches[i % 4])
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(100):
+            engine.step(*batches[i % 4])
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 100
+        value = R / (ms * 1e-3)
+        del engine, model, batches
+        torch.cuda.empty_cache()
+        return {"value": value, "unit": "rays/s", "ms_per_step": ms, "rays_per_batch": R, "steps": 100,
+                "torch_cuda_baseline": torch_cuda_train_baseline(device, R, value)}
+    except Exception as e:  # context only
+        return {"error": repr(e)[:300]}
+
+
 def kernel_breakdown(engine, batches, device) -> dict:
     """Times every kernel of one iteration with CUDA events on the launching stream (median of 11).  The three
     backward kernels share one C entry point; tnf_backward_stage_mask runs them one at a time."""
@@ -766,7 +801,7 @@ def kernel_breakdown(engine, batches, device) -> dict:
     return out
 
 
-def quick_render(model, device, with_torch_baseline: bool = True) -> dict:
+def quick_render(model, device, with_torch_baseline: bool = True, ctx=None) -> dict:
     """The second headline metric inside the default line (BASELINE configs[4] shape, so that the driver's record
     carries it): 800x800 frames in eval mode - device-resident value, roofline of the forward kernel on algorithmic
     bytes, end to end through Renderer.render([RGB, THERMAL], camera) with uint8 frames on the host, and the
@@ -788,11 +823,13 @@ def quick_render(model, device, with_torch_baseline: bool = True) -> dict:
             b.record()
             evs.append((a, b))
         torch.cuda.synchronize()
-    ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
-    value = HW * HW / (ms * 1e-3) / 1e6
+    world = ctx["world"] if ctx else 1
+    slowest = ctx["max_over_ranks"] if ctx else (lambda x: x)
+    ms = slowest(sum(a.elapsed_time(b) for a, b in evs) / len(evs))
+    value = world * HW * HW / (ms * 1e-3) / 1e6
     peak, peak_src = hbm_peak()
-    achieved = HW * HW * ALGO_BYTES_PER_RAY / (ms * 1e-3) / 1e9
-    out = {"metric": "render_mpix_per_s", "value": value, "unit": "Mpix/s", "ms_per_frame": ms,
+    achieved = HW * HW * ALGO_BYTES_PER_RAY / (ms * 1e-3) / 1e9  # per GPU
+    out = {"metric": "render_mpix_per_s", "value": value, "unit": "Mpix/s", "ms_per_frame": ms, "n_gpus": world,
            "workload": "800x800 frame, rgb+thermal+depth+accumulation in one pass, L2 flushed between frames; "
                        "full contract run: bench.py --mode render",
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -814,7 +851,8 @@ def quick_render(model, device, with_torch_baseline: bool = True) -> dict:
         t0 = time.perf_counter()
         renderer.render(mods, one[i % 2], thermal_color_map=lut)
         t += time.perf_counter() - t0
-    out["e2e"] = {"value": HW * HW * 4 / t / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": 72,
+    t = slowest(t)
+    out["e2e"] = {"value": world * HW * HW * 4 / t / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": 72,
                   "d2h_bytes_per_step": 2 * HW * HW * 3,
                   "note": "Renderer.render([RGB, THERMAL], one camera): rays generated in the kernel, uint8 + colour map "
                           "on the device, two uint8 frames D2H"}
