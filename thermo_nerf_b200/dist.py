@@ -111,13 +111,17 @@ def _wrap_device_memory(ptr: int, shape: tuple, typestr: str, device, owner) -> 
 
 
 class PeerArena:
-    """Flat gradient + parameter arenas of every rank mapped into this process (CUDA IPC over NVLink peer
-    memory), for ``tnf_peer_adam_step``: the gradient mean over ranks fused with Adam in one kernel
-    (reduce-scatter -> Adam on the owned shard -> all-gather), bracketed by two flag barriers.
+    """Flat gradient + parameter arenas of every rank mapped into this process - torch symmetric memory (with the
+    NVSwitch multicast object when there is one) or our own CUDA-IPC mapping - for the gradient mean over ranks fused
+    with Adam in one kernel: reduce-scatter -> Adam on the owned shard -> all-gather, by peer loads / stores
+    (``tnf_peer_adam_step``) or inside the switch (``tnf_peer_adam_multimem``), bracketed by flag barriers.
 
-    ``torch.distributed`` is only the plumbing here (it carries the IPC handles once, at construction);
-    the per-step exchange is our kernel reading and writing peer memory.  world_size 1 degenerates to a
-    local fused Adam, which is what the single-GPU tests exercise."""
+    :meth:`adam_step` runs it as one block on the current stream; :meth:`adam_step_pipelined` exchanges two slices of
+    the arena separately, the large one on a side stream (``tnf_peer_adam_range``).
+
+    ``torch.distributed`` is only the plumbing here (it maps the buffers once, at construction); the per-step exchange
+    is our kernel reading and writing peer memory.  world_size 1 degenerates to a local fused Adam, which is what the
+    single-GPU tests exercise."""
 
     def __init__(self, numel: int, device, group=None, split: Optional[int] = None) -> None:
         """``split``: boundary between two slices of the arena that are exchanged separately

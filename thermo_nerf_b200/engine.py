@@ -2,7 +2,13 @@
 
     forward (tnf_render_forward, training) -> losses + their gradients (tnf_losses)
     -> backward (tnf_render_backward, into one flat gradient arena)
-    -> [NCCL all-reduce(mean) of the arena, world_size > 1] -> Adam (tnf_adam_step, zeroes the arena)
+    -> Adam (tnf_adam_step, zeroes the arena)
+
+With several GPUs (``peer_fused=True``) the last two lines become the pipelined exchange of DESIGN.md section 6: the
+field level of the backward first, its gradients reduced inside the NVSwitch, Adam on the shard this rank owns and the
+result multicast to every rank (tnf_peer_adam_range) on a side stream, under the proposal backward and the next
+iteration's proposal pass; the proposal networks' slice on the critical path.  ``peer_fused=False`` keeps the
+baseline: one NCCL all-reduce(mean) of the arena, then tnf_adam_step.
 
 It reproduces what nerfstudio's ``Trainer.train_iteration`` does around the reference model
 (SURVEY 3.1): the proposal-weight anneal and the proposal update schedule
