@@ -5,7 +5,13 @@ views; a freshly initialised student is trained on the teacher's train views wit
 the fused engine, and evaluated on the held-out views exactly as the reference's Evaluator does
 (evaluator.py:47-106: PSNR of rgb, thermal_metrics.mae_thermal of the de-normalised thermal image).
 
-    python scripts/quality_synthetic.py [--steps 3000] [--precision tc_fp16|fp32]  -> one JSON line
+    python scripts/quality_synthetic.py [--steps 3000] [--precision tc_fp16|fp32|oracle_fp32|oracle_fp16]  -> one JSON line
+
+``oracle_*``: the student is the PyTorch restatement of the reference (oracle port) trained eagerly on the GPU with
+torch.optim.Adam on the same batches, schedule and learning-rate decay - fp32, or fp16 autocast + GradScaler as the
+reference's mixed_precision=True - and evaluated through the same fp32 render of its weights.  It answers whether
+the B200 path's arithmetic (fp16 forward / bf16 backward operands in tensor-core mode) costs quality against the
+reference's own arithmetic, not just against the path's fp32 mode.
 """
 import argparse
 import json
@@ -62,13 +68,40 @@ def main():
     train_ids = [i for i in range(n_train + n_test) if i not in test_ids]
     sampler = DevicePixelSampler(rgb[train_ids], th[train_ids], cams.camera_to_worlds[train_ids], cams.fx, cams.fy,
                                  cams.cx, cams.cy, device="cuda", seed=0)
-    student = build(2, args.precision, len(train_ids), False).train()
-    eng = TrainEngine(student)
+    oracle_arm = args.precision.startswith("oracle")
+    student = build(2, "fp32" if oracle_arm else args.precision, len(train_ids), False).train()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for step in range(args.steps):
-        rb, batch = sampler.sample(args.rays)
-        eng.step(rb.origins, rb.directions, rb.camera_indices.reshape(-1), batch["image"], batch["thermal"].reshape(-1))
+    if oracle_arm:
+        sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+        from bench import OracleSchedule, oracle_train_step
+        from oracle import OracleConfig, OracleThermalNerf
+        from thermo_nerf_b200.engine import exponential_decay_lr
+
+        om = OracleThermalNerf(OracleConfig(camera_optimizer_mode="off"), len(train_ids), seed=0)
+        missing, unexpected = om.load_state_dict(student.state_dict(), strict=False)  # the student's initialisation
+        assert not [k for k in missing if "camera_optimizer" not in k], missing
+        om = om.cuda().train()
+        field = [p for n, p in om.named_parameters() if n.startswith("field.")]
+        props = [p for n, p in om.named_parameters() if n.startswith("proposal_networks.")]
+        opts = [torch.optim.Adam(field, lr=1e-2, eps=1e-15), torch.optim.Adam(props, lr=1e-2, eps=1e-15)]
+        scaler = torch.amp.GradScaler("cuda") if args.precision == "oracle_fp16" else None
+        sched = OracleSchedule()
+        for step in range(args.steps):
+            rb, batch = sampler.sample(args.rays)
+            for op in opts:
+                for g in op.param_groups:
+                    g["lr"] = exponential_decay_lr(step)
+            oracle_train_step(om, opts, (rb.origins, rb.directions, rb.camera_indices.reshape(-1), batch["image"],
+                                         batch["thermal"].reshape(-1)), step, sched, scaler)
+        student.load_state_dict(om.state_dict(), strict=False)
+        student._tensors = None
+    else:
+        eng = TrainEngine(student)
+        for step in range(args.steps):
+            rb, batch = sampler.sample(args.rays)
+            eng.step(rb.origins, rb.directions, rb.camera_indices.reshape(-1), batch["image"],
+                     batch["thermal"].reshape(-1))
     torch.cuda.synchronize()
     train_s = time.perf_counter() - t0
     student.eval()

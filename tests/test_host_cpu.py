@@ -279,3 +279,20 @@ def test_product_package_never_touches_the_oracle_or_the_reference():
     assert not any(isinstance(n, ast.ImportFrom) and (n.module or "").startswith("oracle") for n in top)
     assert "/root/reference" not in (root / "bench.py").read_text()
     assert "/root/reference" not in (root / "__graft_entry__.py").read_text()
+
+
+def test_arena_layout_aligns_tensors_and_slices():
+    """TrainEngine's flat arenas: 16-byte aligned tensors, no overlap, and the field slice starting on a multiple of
+    4 * world_size so that both slices shard evenly over the ranks (tnf_peer_adam_range)."""
+    from thermo_nerf_b200.engine import arena_layout
+
+    numels = [5 * 2 ** 17 * 2, 160, 16, 16, 1] * 2 + [16 * 2 ** 19 * 2, 2048, 64, 1024, 16, 100 * 32, 4033, 64, 7]
+    for world in (1, 2, 3, 4, 8, 16):
+        offs, total = arena_layout(numels, 10, world)
+        assert all(o % 4 == 0 for o in offs)
+        for i in range(len(numels) - 1):
+            assert offs[i] + numels[i] <= offs[i + 1]
+        assert offs[-1] + numels[-1] <= total
+        assert offs[10] % (4 * world) == 0
+        # the head slice is padded by less than one shard granule, nothing else moves
+        assert offs[10] - (offs[9] + (numels[9] + 3) // 4 * 4) < 4 * world

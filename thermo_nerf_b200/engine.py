@@ -42,6 +42,21 @@ def exponential_decay_lr(step: int, lr_init: float = 1e-2, lr_final: float = 1e-
     return float(np.exp(np.log(lr_init) * (1 - t) + np.log(lr_final) * t))
 
 
+def arena_layout(numels, num_head_tensors: int, world_size: int = 1):
+    """Offsets (in floats) of the tensors in the flat gradient / parameter / Adam-state arenas and the arena's length.
+    Every tensor starts on a multiple of 4 floats (16-byte vector accesses).  The first ``num_head_tensors`` tensors
+    (the proposal networks) and the rest (the field) form two slices that the multi-GPU exchange shards over the ranks
+    separately: the second slice starts on a multiple of 4 * world_size, and PeerArena pads the total to one."""
+    pad = peer_padding(world_size)
+    offs, total = [], 0
+    for i, n in enumerate(numels):
+        if i == num_head_tensors:
+            total = (total + pad - 1) // pad * pad
+        offs.append(total)
+        total += (int(n) + 3) // 4 * 4
+    return offs, total
+
+
 class TrainEngine:
     def __init__(self, model, *, lr: float = 1e-2, lr_final: float = 1e-4, lr_max_steps: int = 200000,
                  betas=(0.9, 0.999), eps: float = 1e-15, process_group=None, world_size: int = 1,
@@ -55,15 +70,8 @@ class TrainEngine:
             raise RuntimeError("TrainEngine needs the model on a CUDA device; there is no CPU path")
         self.device = dev
         # flat arenas (each tensor 16-byte aligned): gradients, exp_avg, exp_avg_sq
-        offs, total = [], 0
-        # peer-fused exchange: the proposal slice and the field slice are sharded over the ranks separately, so the
-        # field slice starts on a multiple of 4 * world_size
         world = world_info(process_group)[1] if peer_fused else 1
-        for i, p in enumerate(self.params):
-            if i == NUM_PROP_TENSORS and peer_fused:
-                total = (total + peer_padding(world) - 1) // peer_padding(world) * peer_padding(world)
-            offs.append(total)
-            total += (p.numel() + 3) // 4 * 4
+        offs, total = arena_layout([p.numel() for p in self.params], NUM_PROP_TENSORS, world if peer_fused else 1)
         self.offsets, self.total = offs, total
         self.prop_end = offs[NUM_PROP_TENSORS]  # [0, prop_end): proposal networks, [prop_end, total): field
         self.arena: Optional[PeerArena] = None
