@@ -8,9 +8,15 @@
 
 One "step" = one pass of the hot path over one batch of synthetic ThermoScenes-shaped rays:
   --mode train  : (default) one full training iteration at 4096 rays/batch per GPU
-                  (BASELINE.json configs[1]; metric training rays/s = world * rays / iteration time)
+                  (BASELINE.json configs[1]; metric training rays/s = world * rays / iteration time).
+                  The line also carries `render` (configs[4] shape: 800x800 frames, Mpix/s, roofline, e2e - on every
+                  rank when N > 1), `torch_cuda_baseline` (the reference's PyTorch path on the same GPU, fp32 and fp16
+                  autocast + GradScaler), `rays_8192` (configs[2] / the per-GPU shape of configs[3], with its own
+                  PyTorch-CUDA baseline), `cpu_baseline`, and for N > 1 `ranks`, `param_checksum_all_ranks_equal`,
+                  `exchange_barrier_timeouts`.
   --mode render : one 800x800 frame (640 000 rays) through get_outputs_for_camera_ray_bundle
                   (BASELINE.json configs[4]; metric render Mpix/s, 1 ray = 1 pixel)
+  --rays 8192   : the full contract run at 8192 rays per batch per GPU
 Weights are random "trained-like" (no datasets/checkpoints offline); data is synthetic.
 Prints ONE JSON line on rank 0 (contract in the task statement).
 """
