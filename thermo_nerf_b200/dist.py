@@ -180,18 +180,18 @@ class PeerArena:
         self._zero_done: Optional[torch.cuda.Event] = None
         import os
 
-        # all-gather flavour: "push" (everything in one kernel) or "pull" (owners keep their shard, peers copy it out).
-        # Measured (profiles/r1_peer_exchange_phases.json): push wins on 2 GPUs, the owner-balanced pull on 8.
-        # "multimem": reduction and broadcast inside the NVSwitch (needs the multicast object of the symmetric path).
+        # exchange flavour: "push" (peer loads + peer stores in one kernel), "pull" (owners keep their shard, peers copy
+        # it out in a second kernel; round 1's choice for 8 GPUs, profiles/r1_peer_exchange_phases.json) or "multimem"
+        # (reduction and broadcast inside the NVSwitch; needs the multicast object of the symmetric path).
         self.gather = os.environ.get("TNF_PEER_GATHER", "auto")
         if self.gather == "auto":
             # measured on B200 (profiles/): two GPUs - the push kernel (half the arena per direction either way, and
             # plain peer stores run faster than switch reductions); from four GPUs up the in-switch reduction moves
             # 1/N instead of (N-1)/N of the arena per rank and direction
-            if self.world >= 4:
-                self.gather = "multimem" if self.multicast else "pull"
-            else:
-                self.gather = "push"
+            # without a multicast object (no NVSwitch, or the CUDA-IPC mapping) the push kernel: unpipelined it is on a
+            # par with the pull flavour at 8 GPUs (0.946 / 0.964 ms per step), and unlike pull it can be pipelined
+            # (4 GPUs, pipelined push: 0.82 ms against 1.00 ms for the unpipelined pull of round 1)
+            self.gather = "multimem" if (self.world >= 4 and self.multicast) else "push"
         if self.gather not in ("push", "pull", "multimem"):
             raise ValueError("TNF_PEER_GATHER must be 'auto', 'push', 'pull' or 'multimem'")
         if self.gather == "multimem" and not self.multicast:

@@ -122,9 +122,10 @@ class TrainEngine:
         # proposal backward: 0.717 ms / step (0.796 started after it, 0.830 with 296 CTAs, 0.846 unpipelined);
         # 2 GPUs, peer loads / stores, 34 MB per rank and direction - 296 CTAs started after the backward: 0.765 ms
         # (0.795 started under it: the proposal kernel then runs on half its CTAs; 0.799 unpipelined)
-        self._side_ctas = int(os.environ.get("TNF_PEER_SIDE_CTAS", 64 if world >= 4 else 296))
+        switch = self.arena is not None and self.arena.gather == "multimem"  # in-switch reduction: 1/N of the bytes per rank
+        self._side_ctas = int(os.environ.get("TNF_PEER_SIDE_CTAS", 64 if switch else 296))
         # start the field exchange under the proposal backward (1) or after the whole backward (0)
-        self._early = os.environ.get("TNF_PEER_EARLY", "1" if world >= 4 else "0") != "0"
+        self._early = os.environ.get("TNF_PEER_EARLY", "1" if switch else "0") != "0"
         mode = getattr(getattr(model, "camera_optimizer", None), "mode", "off")
         if mode != "off":
             # the engine feeds origins / directions straight to the kernels: pose refinement lives in the
